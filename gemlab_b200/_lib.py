@@ -1,0 +1,89 @@
+"""ctypes loader of libgemlab_cuda.so (the C ABI in include/gemlab_cuda.h).
+
+The product path has NO CPU fallback: if the shared library is missing this module raises, and if no sm_100 device is
+usable `Context()` raises (GL_ERR_NO_DEVICE).  Nothing here imports the oracle.
+"""
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libgemlab_cuda.so"
+
+
+class GlArgs(C.Structure):
+    """struct gl_args (mirrors integ::CommonArgs, src/integ/common_args.rs:5-43)."""
+
+    _fields_ = [
+        ("ngauss", C.c_int32), ("axisymmetric", C.c_int32), ("clear", C.c_int32), ("reserved", C.c_int32),
+        ("alpha", C.c_double), ("ii0", C.c_uint32), ("jj0", C.c_uint32), ("nrow", C.c_uint32), ("ncol", C.c_uint32),
+        ("ksi", C.c_double * 3),
+    ]
+
+
+class GlCoef(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("location", C.c_int32), ("data", C.c_void_p), ("markers", C.c_void_p),
+                ("nrecord", C.c_uint64)]
+
+
+class GlOut(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("location", C.c_int32), ("reserved", C.c_int32), ("capacity", C.c_uint64)]
+
+
+# every symbol include/gemlab_cuda.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "gl_ctx_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "gl_ctx_destroy": (None, [_P]),
+    "gl_ctx_set_stream": (C.c_int, [_P, _P]),
+    "gl_ctx_sync": (C.c_int, [_P]),
+    "gl_last_error": (C.c_char_p, [_P]),
+    "gl_last_error_cell": (C.c_uint64, [_P]),
+    "gl_status_string": (C.c_char_p, [C.c_int]),
+    "gl_ctx_launch_count": (C.c_uint64, [_P]),
+    "gl_kind_nnode": (C.c_int, [C.c_int]),
+    "gl_kind_geo_ndim": (C.c_int, [C.c_int]),
+    "gl_kind_class": (C.c_int, [C.c_int]),
+    "gl_kind_from_name": (C.c_int, [C.c_char_p]),
+    "gl_kind_name": (C.c_char_p, [C.c_int]),
+    "gl_kind_supported": (C.c_int, [C.c_int]),
+    "gl_gauss_rule": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),
+    "gl_shape_eval": (C.c_int, [C.c_int, _P, _P, _P]),
+    "gl_mesh_upload": (C.c_int, [_P, C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, C.POINTER(_P)]),
+    "gl_mesh_upload_homogeneous": (C.c_int, [_P, C.c_int, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, C.POINTER(_P)]),
+    "gl_mesh_update_coords": (C.c_int, [_P, _P, _P, C.c_int]),
+    "gl_mesh_free": (None, [_P, _P]),
+    "gl_mesh_ncell": (C.c_uint64, [_P]),
+    "gl_mesh_npoint": (C.c_uint64, [_P]),
+    "gl_mesh_ndim": (C.c_int, [_P]),
+    "gl_op_out_size": (C.c_uint64, [C.c_int, C.c_int, C.c_int]),
+    "gl_op_coef_size": (C.c_uint64, [C.c_int, C.c_int]),
+    "gl_out_total": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(C.c_uint64)]),
+    "gl_out_offsets": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), _P]),
+    "gl_integ": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlOut)]),
+    "gl_jacobian": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlOut)]),
+    "gl_args_default": (None, [C.POINTER(GlArgs)]),
+    "gl_lin_elasticity": (None, [C.c_double, C.c_double, C.c_int, C.c_int, _P]),
+    "gl_bench_fp64_peak": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+}
+for _name in ("gl_mat_10_bdb", "gl_mat_01_nsn", "gl_mat_03_btb", "gl_vec_01_ns", "gl_vec_02_nv", "gl_vec_03_bv",
+              "gl_vec_04_bt", "gl_mat_10_gdg", "gl_vec_10_gs"):
+    SYMBOLS[_name] = (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlOut)])
+
+_lib = None
+
+
+def lib():
+    """Loads libgemlab_cuda.so; raises if it has not been built (python __graft_entry__.py or make -C gemlab_b200/csrc)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib

@@ -1,0 +1,863 @@
+// gl_api.cu -- C ABI of libgemlab_cuda (see include/gemlab_cuda.h): context, device mesh, batched integ entry points.
+//
+// Host-side responsibilities (everything the reference does once per CELL in Rust is done here once per CALL):
+//   * Mesh -> structure of arrays on the device, bucketed by GeoKind (replaces Mesh::set_pad's AoS pointer chase,
+//     src/mesh/mesh.rs:448-456);
+//   * reference-element tables N, L, w per (kind, rule) (replaces the fn_interp / fn_deriv calls per Gauss point);
+//   * CommonArgs validation with the reference's error strings (src/integ/mat_10_bdb.rs:126-136 and siblings);
+//   * coefficient closures turned into data records (UNIFORM / PER_MARKER / PER_CELL / PER_GAUSS);
+//   * output placement: element blocks in original cell-id order, column-major, tight or (nrow, ncol, ii0, jj0);
+//   * host-buffer calls are pipelined in chunks: kernel(chunk k+1) overlaps the D2H copy of chunk k.
+// There is deliberately NO CPU fallback: without a usable sm_100 device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "gl_internal.hpp"
+
+using namespace gl;
+
+namespace {
+
+int fail(gl_ctx *ctx, int status, const char *detail = nullptr) {
+    if (ctx) {
+        ctx->last_status = status;
+        ctx->last_error = status_string(status);
+        if (detail && status >= GL_ERR_INVALID_ARG) {
+            ctx->last_error += ": ";
+            ctx->last_error += detail;
+        }
+    }
+    return status;
+}
+
+int cuda_fail(gl_ctx *ctx, cudaError_t e, const char *what) {
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    return fail(ctx, GL_ERR_CUDA, buf);
+}
+
+#define CUDA_TRY(ctx, call)                                   \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+// size classes of the element blocks
+enum { SZ_NDOF2 = 0, SZ_NNODE2 = 1, SZ_NNODE = 2, SZ_NDOF = 3, SZ_ONE = 4 };
+
+int op_size_class(int op) {
+    switch (op) {
+    case GL_OP_MAT_10_BDB: return SZ_NDOF2;
+    case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: return SZ_NNODE2;
+    case GL_OP_VEC_01_NS: case GL_OP_VEC_03_BV: return SZ_NNODE;
+    case GL_OP_VEC_02_NV: case GL_OP_VEC_04_BT: return SZ_NDOF;
+    case GL_OP_JACOBIAN: return SZ_ONE;
+    default: return -1;
+    }
+}
+
+bool op_is_matrix(int op) { return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB; }
+
+bool op_uses_gradient(int op) {
+    // the reference calls Scratchpad::calc_gradient for these (mat_01_nsn too, src/integ/mat_01_nsn.rs:76)
+    return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV ||
+           op == GL_OP_VEC_04_BT;
+}
+
+// rows / cols actually integrated for a cell of `kind`
+void op_extent(int op, int kind, int ndim, unsigned &size_r, unsigned &size_c) {
+    const unsigned nnode = (unsigned)kind_nnode(kind), ndof = nnode * (unsigned)ndim;
+    switch (op_size_class(op)) {
+    case SZ_NDOF2: size_r = ndof; size_c = ndof; break;
+    case SZ_NNODE2: size_r = nnode; size_c = nnode; break;
+    case SZ_NNODE: size_r = nnode; size_c = 1; break;
+    case SZ_NDOF: size_r = ndof; size_c = 1; break;
+    default: size_r = 1; size_c = 1; break;
+    }
+}
+
+struct BlockDims {
+    unsigned nrow, ncol, size_r, size_c;
+    uint64_t block() const { return (uint64_t)nrow * ncol; }
+};
+
+// resolves the element block of (op, kind) under args; returns the reference's dimension errors
+int block_dims(int op, int kind, int ndim, const gl_args *a, BlockDims &bd) {
+    op_extent(op, kind, ndim, bd.size_r, bd.size_c);
+    const bool mat = op_is_matrix(op);
+    const unsigned ii0 = a->ii0, jj0 = mat ? a->jj0 : 0;
+    bd.nrow = a->nrow ? a->nrow : ii0 + bd.size_r;
+    bd.ncol = mat ? (a->ncol ? a->ncol : jj0 + bd.size_c) : 1;
+    if (bd.nrow < ii0 + bd.size_r) {
+        switch (op) {
+        case GL_OP_MAT_10_BDB: return GL_ERR_NROW_KK_NDOF;
+        case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: return GL_ERR_NROW_KK_NNODE;
+        case GL_OP_VEC_01_NS: return GL_ERR_A_LEN;
+        case GL_OP_VEC_02_NV: return GL_ERR_B_LEN;
+        case GL_OP_VEC_03_BV: return GL_ERR_C_LEN;
+        case GL_OP_VEC_04_BT: return GL_ERR_D_LEN;
+        default: return GL_ERR_INVALID_ARG;
+        }
+    }
+    if (mat && bd.ncol < jj0 + bd.size_c) return op == GL_OP_MAT_10_BDB ? GL_ERR_NCOL_KK_NDOF : GL_ERR_NCOL_KK_NNODE;
+    return GL_OK;
+}
+
+uint64_t coef_len(int op, int ndim) {
+    const uint64_t ns = 2 * (uint64_t)ndim;
+    switch (op) {
+    case GL_OP_MAT_10_BDB: return ns * ns;
+    case GL_OP_MAT_01_NSN: case GL_OP_VEC_01_NS: return 1;
+    case GL_OP_MAT_03_BTB: case GL_OP_VEC_04_BT: return ns;
+    case GL_OP_VEC_02_NV: case GL_OP_VEC_03_BV: return (uint64_t)ndim;
+    default: return 0;
+    }
+}
+
+// bucket-local sub-range [lo, hi) of original ids [b, e)
+void bucket_range(const gl_mesh *mesh, const gl_mesh_bucket &bk, uint64_t b, uint64_t e, uint64_t &lo, uint64_t &hi) {
+    if (bk.h_cell_ids.empty()) { // identity (homogeneous mesh)
+        lo = std::min<uint64_t>(b, bk.ncell);
+        hi = std::min<uint64_t>(e, bk.ncell);
+        (void)mesh;
+        return;
+    }
+    lo = (uint64_t)(std::lower_bound(bk.h_cell_ids.begin(), bk.h_cell_ids.end(), (uint32_t)b) - bk.h_cell_ids.begin());
+    hi = (uint64_t)(std::lower_bound(bk.h_cell_ids.begin(), bk.h_cell_ids.end(), (uint32_t)std::min<uint64_t>(e, 0xffffffffull)) - bk.h_cell_ids.begin());
+    if (e > 0xffffffffull) hi = bk.ncell;
+}
+
+// exclusive prefix of block sizes over the whole (mixed) mesh, cached by the args that shape the block
+const std::vector<uint64_t> *mesh_prefix(gl_mesh *mesh, int op, const gl_args *a, int *key_out, int *status) {
+    *status = GL_OK;
+    const int cls = op_size_class(op);
+    // key: size class + offsets (explicit nrow/ncol make every block equal; handled by the caller)
+    const int key = cls | ((int)(a->ii0 & 0xfff) << 4) | ((int)(a->jj0 & 0xfff) << 16);
+    *key_out = key;
+    auto it = mesh->h_prefix.find(key);
+    if (it != mesh->h_prefix.end()) return &it->second;
+    uint64_t per_kind[GL_NKIND];
+    for (int k = 0; k < GL_NKIND; k++) {
+        BlockDims bd;
+        gl_args tight = *a;
+        tight.nrow = 0;
+        tight.ncol = 0;
+        block_dims(op, k, mesh->ndim, &tight, bd);
+        per_kind[k] = bd.block();
+    }
+    std::vector<uint64_t> pre(mesh->ncell + 1);
+    uint64_t acc = 0;
+    for (uint64_t e = 0; e < mesh->ncell; e++) {
+        pre[e] = acc;
+        acc += per_kind[mesh->h_kinds[e]];
+    }
+    pre[mesh->ncell] = acc;
+    auto ins = mesh->h_prefix.emplace(key, std::move(pre));
+    return &ins.first->second;
+}
+
+RuleTable *get_rule(gl_ctx *ctx, int kind, int ngauss, int *status) {
+    auto key = std::make_pair(kind, ngauss);
+    auto it = ctx->rules.find(key);
+    if (it != ctx->rules.end()) {
+        *status = GL_OK;
+        return it->second.get();
+    }
+    int ng = 0;
+    const double *data = nullptr;
+    *status = gauss_rule(kind, ngauss, &ng, &data);
+    if (*status) return nullptr;
+    if (!kind_supported(kind)) {
+        *status = GL_ERR_KIND_UNSUPPORTED;
+        return nullptr;
+    }
+    auto rt = std::make_unique<RuleTable>();
+    rt->kind = kind;
+    rt->ng = ng;
+    rt->nnode = kind_nnode(kind);
+    rt->gd = kind_geo_ndim(kind);
+    const int nn = rt->nnode, gd = rt->gd;
+    rt->host.assign((size_t)ng * (1 + nn + nn * gd), 0.0);
+    double *w = rt->host.data(), *N = w + ng, *L = N + (size_t)ng * nn;
+    for (int p = 0; p < ng; p++) {
+        w[p] = data[p * 4 + 3];
+        shape_eval(kind, data + p * 4, N + (size_t)p * nn, L + (size_t)p * nn * gd);
+    }
+    if (cudaMalloc(&rt->dev, rt->host.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(rt->dev, rt->host.data(), rt->host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        *status = GL_ERR_CUDA;
+        return nullptr;
+    }
+    RuleTable *raw = rt.get();
+    ctx->rules[key] = std::move(rt);
+    return raw;
+}
+
+int ensure_buffer(gl_ctx *ctx, double **buf, size_t *have, size_t need) {
+    if (*have >= need) return GL_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    CUDA_TRY(ctx, cudaMalloc(buf, need));
+    *have = need;
+    return GL_OK;
+}
+
+struct CoefResolved {
+    const double *dev = nullptr; // nullptr => uniform record in `uniform`
+    uint64_t cell_stride = 0, gp_stride = 0;
+    bool per_marker = false;
+    double uniform[36] = {0};
+    int len = 0;
+};
+
+} // namespace
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+
+extern "C" {
+
+int gl_ctx_create(int device, void *stream, gl_ctx **out) {
+    if (!out) return GL_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return GL_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GL_ERR_NO_DEVICE;
+    if (prop.major != 10) return GL_ERR_NO_DEVICE; // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return GL_ERR_CUDA;
+    gl_ctx *ctx = new gl_ctx();
+    ctx->device = device;
+    ctx->stream = stream;
+    if (cudaMalloc(&ctx->d_err_cell, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_err_cell, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_rule_tmp, sizeof(double) * GL_NKIND * (1 + MAX_NNODE + 3 * MAX_NNODE)) != cudaSuccess) {
+        delete ctx;
+        return GL_ERR_CUDA;
+    }
+    *ctx->h_err_cell = NO_ERR_CELL;
+    cudaMemcpy(ctx->d_err_cell, ctx->h_err_cell, sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    cudaStream_t cs;
+    if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return GL_ERR_CUDA;
+    }
+    ctx->copy_stream = cs;
+    for (int i = 0; i < 4; i++) {
+        cudaEvent_t ev;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        ctx->ev[i] = ev;
+    }
+    *out = ctx;
+    return GL_OK;
+}
+
+void gl_ctx_destroy(gl_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize((cudaStream_t)ctx->stream);
+    for (auto &kv : ctx->rules)
+        if (kv.second->dev) cudaFree(kv.second->dev);
+    if (ctx->d_err_cell) cudaFree(ctx->d_err_cell);
+    if (ctx->h_err_cell) cudaFreeHost(ctx->h_err_cell);
+    if (ctx->d_rule_tmp) cudaFree(ctx->d_rule_tmp);
+    for (int i = 0; i < 2; i++)
+        if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    if (ctx->d_coef) cudaFree(ctx->d_coef);
+    if (ctx->copy_stream) cudaStreamDestroy((cudaStream_t)ctx->copy_stream);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev[i]) cudaEventDestroy((cudaEvent_t)ctx->ev[i]);
+    delete ctx;
+}
+
+int gl_ctx_set_stream(gl_ctx *ctx, void *stream) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    ctx->stream = stream;
+    return GL_OK;
+}
+
+int gl_ctx_sync(gl_ctx *ctx) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_err_cell, ctx->d_err_cell, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)ctx->stream));
+    if (*ctx->h_err_cell != NO_ERR_CELL) {
+        ctx->last_error_cell = *ctx->h_err_cell;
+        *ctx->h_err_cell = NO_ERR_CELL;
+        CUDA_TRY(ctx, cudaMemcpy(ctx->d_err_cell, ctx->h_err_cell, sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        return fail(ctx, GL_ERR_ZERO_DET);
+    }
+    return GL_OK;
+}
+
+const char *gl_last_error(const gl_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t gl_last_error_cell(const gl_ctx *ctx) { return ctx ? ctx->last_error_cell : NO_ERR_CELL; }
+const char *gl_status_string(int status) { return status_string(status); }
+uint64_t gl_ctx_launch_count(const gl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int gl_kind_nnode(int kind) { return kind_nnode(kind); }
+int gl_kind_geo_ndim(int kind) { return kind_geo_ndim(kind); }
+int gl_kind_class(int kind) { return kind_class(kind); }
+int gl_kind_from_name(const char *name) { return name ? kind_from_name(name) : -1; }
+const char *gl_kind_name(int kind) { return kind_name(kind); }
+int gl_kind_supported(int kind) { return kind_supported(kind) ? 1 : 0; }
+int gl_gauss_rule(int kind, int ngauss, int *npoint, const double **data) {
+    if (!npoint || !data) return GL_ERR_INVALID_ARG;
+    return gauss_rule(kind, ngauss, npoint, data);
+}
+int gl_shape_eval(int kind, const double *ksi, double *nn, double *ll) {
+    if (!ksi || !nn || !ll) return GL_ERR_INVALID_ARG;
+    return shape_eval(kind, ksi, nn, ll);
+}
+
+void gl_args_default(gl_args *a) {
+    if (!a) return;
+    std::memset(a, 0, sizeof(*a));
+    a->clear = 1;
+    a->alpha = 1.0;
+}
+
+void gl_lin_elasticity(double young, double poisson, int two_dim, int plane_stress, double *dd) {
+    lin_elasticity(young, poisson, two_dim, plane_stress, dd);
+}
+
+uint64_t gl_op_out_size(int op, int kind, int ndim) {
+    if (op_size_class(op) < 0 || kind < 0 || kind >= GL_NKIND) return 0;
+    unsigned r, c;
+    op_extent(op, kind, ndim, r, c);
+    return (uint64_t)r * c;
+}
+
+uint64_t gl_op_coef_size(int op, int ndim) { return coef_len(op, ndim); }
+
+// =====================================================================================================
+// mesh
+// =====================================================================================================
+
+static int finish_mesh_upload(gl_ctx *ctx, gl_mesh *mesh, const std::vector<double> &soa) {
+    CUDA_TRY(ctx, cudaMalloc(&mesh->d_coords, soa.size() * sizeof(double)));
+    CUDA_TRY(ctx, cudaMemcpy(mesh->d_coords, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return GL_OK;
+}
+
+static void coords_to_soa(int ndim, uint64_t npoint, const double *coords, std::vector<double> &soa) {
+    soa.resize((size_t)ndim * npoint);
+    for (uint64_t i = 0; i < npoint; i++)
+        for (int j = 0; j < ndim; j++) soa[(size_t)j * npoint + i] = coords[i * ndim + j];
+}
+
+static int build_markers(gl_ctx *ctx, gl_mesh *mesh, const int32_t *markers, std::vector<uint32_t> &marker_idx) {
+    (void)ctx;
+    marker_idx.clear();
+    if (!markers) {
+        mesh->marker_values = {0};
+        return GL_OK;
+    }
+    std::vector<int32_t> uniq(markers, markers + mesh->ncell);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    mesh->marker_values = uniq;
+    if (uniq.size() > 1) {
+        marker_idx.resize(mesh->ncell);
+        for (uint64_t e = 0; e < mesh->ncell; e++)
+            marker_idx[e] = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), markers[e]) - uniq.begin());
+    }
+    return GL_OK;
+}
+
+int gl_mesh_upload(gl_ctx *ctx, int ndim, uint64_t npoint, const double *coords, uint64_t ncell, const uint8_t *kinds,
+                   const int32_t *markers, const uint64_t *conn_off, const uint64_t *conn, gl_mesh **out) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    if (!out || !coords || !kinds || !conn_off || !conn) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (ndim < 2 || ndim > 3) return fail(ctx, GL_ERR_SPACE_NDIM);
+    if (npoint == 0 || npoint > 0xffffffffull || ncell > 0xffffffffull) return fail(ctx, GL_ERR_MESH, "npoint/ncell must fit in 32 bits");
+    cudaSetDevice(ctx->device);
+    // validate and count per kind
+    uint64_t count[GL_NKIND] = {0};
+    for (uint64_t e = 0; e < ncell; e++) {
+        const int k = kinds[e];
+        if (k >= GL_NKIND || !kind_supported(k)) return fail(ctx, GL_ERR_KIND_UNSUPPORTED);
+        if (kind_geo_ndim(k) > ndim) return fail(ctx, GL_ERR_MESH, "geo_ndim cannot be greater than space_ndim");
+        if (conn_off[e + 1] - conn_off[e] != (uint64_t)kind_nnode(k)) return fail(ctx, GL_ERR_MESH, "cell connectivity length != nnode");
+        count[k]++;
+    }
+    auto mesh = std::make_unique<gl_mesh>();
+    mesh->ndim = ndim;
+    mesh->npoint = npoint;
+    mesh->ncell = ncell;
+    mesh->device = ctx->device;
+    int nkinds = 0;
+    for (int k = 0; k < GL_NKIND; k++) nkinds += count[k] ? 1 : 0;
+    mesh->homogeneous = nkinds <= 1;
+    std::vector<uint32_t> marker_idx;
+    build_markers(ctx, mesh.get(), markers, marker_idx);
+    if (!mesh->homogeneous) mesh->h_kinds.assign(kinds, kinds + ncell);
+    for (int k = 0; k < GL_NKIND; k++) {
+        if (!count[k]) continue;
+        gl_mesh_bucket bk;
+        bk.kind = k;
+        bk.nnode = kind_nnode(k);
+        bk.ncell = count[k];
+        std::vector<uint32_t> ids;
+        ids.reserve(count[k]);
+        for (uint64_t e = 0; e < ncell; e++)
+            if (kinds[e] == k) ids.push_back((uint32_t)e);
+        std::vector<uint32_t> soa((size_t)bk.nnode * bk.ncell);
+        for (uint64_t c = 0; c < bk.ncell; c++) {
+            const uint64_t *pts = conn + conn_off[ids[c]];
+            for (int m = 0; m < bk.nnode; m++) {
+                if (pts[m] >= npoint) return fail(ctx, GL_ERR_MESH, "point id out of range");
+                soa[(size_t)m * bk.ncell + c] = (uint32_t)pts[m];
+            }
+        }
+        CUDA_TRY(ctx, cudaMalloc(&bk.d_conn, soa.size() * sizeof(uint32_t)));
+        CUDA_TRY(ctx, cudaMemcpy(bk.d_conn, soa.data(), soa.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (!marker_idx.empty()) {
+            std::vector<uint32_t> mi(bk.ncell);
+            for (uint64_t c = 0; c < bk.ncell; c++) mi[c] = marker_idx[ids[c]];
+            CUDA_TRY(ctx, cudaMalloc(&bk.d_marker_idx, mi.size() * sizeof(uint32_t)));
+            CUDA_TRY(ctx, cudaMemcpy(bk.d_marker_idx, mi.data(), mi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        if (!mesh->homogeneous) {
+            CUDA_TRY(ctx, cudaMalloc(&bk.d_cell_ids, ids.size() * sizeof(uint32_t)));
+            CUDA_TRY(ctx, cudaMemcpy(bk.d_cell_ids, ids.data(), ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            bk.h_cell_ids = std::move(ids);
+        }
+        mesh->buckets.push_back(std::move(bk));
+    }
+    std::vector<double> soa;
+    coords_to_soa(ndim, npoint, coords, soa);
+    int st = finish_mesh_upload(ctx, mesh.get(), soa);
+    if (st) return st;
+    *out = mesh.release();
+    return GL_OK;
+}
+
+int gl_mesh_upload_homogeneous(gl_ctx *ctx, int ndim, uint64_t npoint, const double *coords, uint64_t ncell, int kind,
+                               const int32_t *markers, const uint32_t *conn, gl_mesh **out) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    if (!out || !coords || !conn) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (ndim < 2 || ndim > 3) return fail(ctx, GL_ERR_SPACE_NDIM);
+    if (!kind_supported(kind)) return fail(ctx, GL_ERR_KIND_UNSUPPORTED);
+    if (kind_geo_ndim(kind) > ndim) return fail(ctx, GL_ERR_MESH, "geo_ndim cannot be greater than space_ndim");
+    if (npoint == 0 || npoint > 0xffffffffull || ncell > 0xffffffffull) return fail(ctx, GL_ERR_MESH, "npoint/ncell must fit in 32 bits");
+    cudaSetDevice(ctx->device);
+    auto mesh = std::make_unique<gl_mesh>();
+    mesh->ndim = ndim;
+    mesh->npoint = npoint;
+    mesh->ncell = ncell;
+    mesh->device = ctx->device;
+    mesh->homogeneous = true;
+    std::vector<uint32_t> marker_idx;
+    build_markers(ctx, mesh.get(), markers, marker_idx);
+    gl_mesh_bucket bk;
+    bk.kind = kind;
+    bk.nnode = kind_nnode(kind);
+    bk.ncell = ncell;
+    const int nn = bk.nnode;
+    std::vector<uint32_t> soa((size_t)nn * ncell);
+    for (uint64_t c = 0; c < ncell; c++)
+        for (int m = 0; m < nn; m++) {
+            const uint32_t pid = conn[c * nn + m];
+            if (pid >= npoint) return fail(ctx, GL_ERR_MESH, "point id out of range");
+            soa[(size_t)m * ncell + c] = pid;
+        }
+    if (ncell) {
+        CUDA_TRY(ctx, cudaMalloc(&bk.d_conn, soa.size() * sizeof(uint32_t)));
+        CUDA_TRY(ctx, cudaMemcpy(bk.d_conn, soa.data(), soa.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (!marker_idx.empty()) {
+            CUDA_TRY(ctx, cudaMalloc(&bk.d_marker_idx, marker_idx.size() * sizeof(uint32_t)));
+            CUDA_TRY(ctx, cudaMemcpy(bk.d_marker_idx, marker_idx.data(), marker_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+    }
+    mesh->buckets.push_back(std::move(bk));
+    std::vector<double> csoa;
+    coords_to_soa(ndim, npoint, coords, csoa);
+    int st = finish_mesh_upload(ctx, mesh.get(), csoa);
+    if (st) return st;
+    *out = mesh.release();
+    return GL_OK;
+}
+
+int gl_mesh_update_coords(gl_ctx *ctx, gl_mesh *mesh, const double *coords, int location) {
+    if (!ctx || !mesh || !coords) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    if (location != GL_HOST) return fail(ctx, GL_ERR_INVALID_ARG, "gl_mesh_update_coords takes host AoS coordinates");
+    cudaSetDevice(ctx->device);
+    std::vector<double> soa;
+    coords_to_soa(mesh->ndim, mesh->npoint, coords, soa);
+    CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(mesh->d_coords, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return GL_OK;
+}
+
+void gl_mesh_free(gl_ctx *ctx, gl_mesh *mesh) {
+    if (!mesh) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize((cudaStream_t)ctx->stream);
+    }
+    if (mesh->d_coords) cudaFree(mesh->d_coords);
+    for (auto &bk : mesh->buckets) {
+        if (bk.d_conn) cudaFree(bk.d_conn);
+        if (bk.d_cell_ids) cudaFree(bk.d_cell_ids);
+        if (bk.d_marker_idx) cudaFree(bk.d_marker_idx);
+        for (auto &kv : bk.d_out_off)
+            if (kv.second) cudaFree(kv.second);
+    }
+    delete mesh;
+}
+
+uint64_t gl_mesh_ncell(const gl_mesh *mesh) { return mesh ? mesh->ncell : 0; }
+uint64_t gl_mesh_npoint(const gl_mesh *mesh) { return mesh ? mesh->npoint : 0; }
+int gl_mesh_ndim(const gl_mesh *mesh) { return mesh ? mesh->ndim : 0; }
+
+// =====================================================================================================
+// output layout
+// =====================================================================================================
+
+static int range_layout(const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, const gl_args *a, uint64_t *total,
+                        uint64_t *off /* may be null */) {
+    gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
+    if (!mesh || !a || op_size_class(op) < 0) return GL_ERR_INVALID_ARG;
+    if (b > e || e > mesh->ncell) return GL_ERR_CELL_RANGE;
+    const bool explicit_block = a->nrow != 0 || (op_is_matrix(op) && a->ncol != 0);
+    if (mesh->homogeneous || explicit_block) {
+        // all blocks equal (for explicit dims every kind in range must fit; checked at launch)
+        uint64_t blk = 0;
+        if (!mesh->buckets.empty()) {
+            BlockDims bd;
+            int st = block_dims(op, mesh->buckets[0].kind, mesh->ndim, a, bd);
+            if (st) return st;
+            blk = bd.block();
+        }
+        if (total) *total = blk * (e - b);
+        if (off)
+            for (uint64_t i = 0; i <= e - b; i++) off[i] = i * blk;
+        return GL_OK;
+    }
+    int key, st;
+    const std::vector<uint64_t> *pre = mesh_prefix(mesh, op, a, &key, &st);
+    if (st) return st;
+    if (total) *total = (*pre)[e] - (*pre)[b];
+    if (off)
+        for (uint64_t i = 0; i <= e - b; i++) off[i] = (*pre)[b + i] - (*pre)[b];
+    return GL_OK;
+}
+
+int gl_out_total(const gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a, uint64_t *total) {
+    if (!total) return GL_ERR_INVALID_ARG;
+    return range_layout(mesh, op, b, e, a, total, nullptr);
+}
+
+int gl_out_offsets(const gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a, uint64_t *off) {
+    if (!off) return GL_ERR_INVALID_ARG;
+    return range_layout(mesh, op, b, e, a, nullptr, off);
+}
+
+// =====================================================================================================
+// integration
+// =====================================================================================================
+
+// launches the kernels that integrate original cells [b, e) into the DEVICE buffer d_out (block of cell b at d_out[0])
+static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a,
+                        const CoefResolved &cr, uint64_t coef_begin, double *d_out) {
+    if (b == e) return GL_OK;
+    const bool explicit_block = a->nrow != 0 || (op_is_matrix(op) && a->ncol != 0);
+    const std::vector<uint64_t> *pre = nullptr;
+    int key = 0;
+    if (!mesh->homogeneous && !explicit_block) {
+        int st;
+        pre = mesh_prefix(mesh, op, a, &key, &st);
+        if (st) return fail(ctx, st);
+    }
+    for (auto &bk : mesh->buckets) {
+        uint64_t lo, hi;
+        bucket_range(mesh, bk, b, e, lo, hi);
+        if (lo >= hi) continue;
+        const int gd = kind_geo_ndim(bk.kind);
+        BlockDims bd;
+        int st = block_dims(op, bk.kind, mesh->ndim, a, bd);
+        if (st) return fail(ctx, st);
+        if (op == GL_OP_MAT_10_BDB || op == GL_OP_VEC_04_BT)
+            if (a->axisymmetric && mesh->ndim != 2) return fail(ctx, GL_ERR_AXISYM_NDIM);
+        if (op_uses_gradient(op) && gd != mesh->ndim) return fail(ctx, GL_ERR_GRADIENT_NDIM);
+
+        IntegParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.coords = mesh->d_coords;
+        p.npoint = mesh->npoint;
+        p.conn = bk.d_conn;
+        p.ncell_k = bk.ncell;
+        p.cell_ids = bk.d_cell_ids;
+        p.lo = lo;
+        p.hi = hi;
+        p.cell_begin = b;
+        p.coef_begin = coef_begin;
+        p.op = op;
+        p.axisym = a->axisymmetric ? 1 : 0;
+        p.clear = a->clear ? 1 : 0;
+        p.alpha = a->alpha;
+        p.nnode = bk.nnode;
+        if (op == GL_OP_JACOBIAN) {
+            // one-point "rule" at args->ksi: w = 1 | N | L
+            double tmp[1 + MAX_NNODE + 3 * MAX_NNODE];
+            tmp[0] = 1.0;
+            st = shape_eval(bk.kind, a->ksi, tmp + 1, tmp + 1 + bk.nnode);
+            if (st) return fail(ctx, st);
+            double *dst = ctx->d_rule_tmp + (size_t)bk.kind * (1 + MAX_NNODE + 3 * MAX_NNODE);
+            CUDA_TRY(ctx, cudaMemcpyAsync(dst, tmp, sizeof(double) * (1 + bk.nnode + bk.nnode * gd), cudaMemcpyHostToDevice,
+                                          (cudaStream_t)ctx->stream));
+            p.rule = dst;
+            p.ng = 1;
+        } else {
+            RuleTable *rt = get_rule(ctx, bk.kind, a->ngauss, &st);
+            if (!rt) return fail(ctx, st);
+            p.rule = rt->dev;
+            p.ng = rt->ng;
+        }
+        // coefficient
+        p.coef_len = cr.len;
+        std::memcpy(p.coef_uniform, cr.uniform, sizeof(p.coef_uniform));
+        p.coef = cr.dev;
+        p.coef_cell_stride = cr.cell_stride;
+        p.coef_gp_stride = cr.gp_stride;
+        p.coef_index = cr.per_marker ? bk.d_marker_idx : nullptr;
+        if (cr.dev && cr.gp_stride && cr.cell_stride == 0) p.coef_cell_stride = (uint64_t)p.ng * cr.gp_stride; // PER_GAUSS
+        // output
+        p.out = d_out;
+        p.nrow = bd.nrow;
+        p.ncol = bd.ncol;
+        p.ii0 = a->ii0;
+        p.jj0 = op_is_matrix(op) ? a->jj0 : 0;
+        p.size_r = bd.size_r;
+        p.size_c = bd.size_c;
+        p.err_cell = ctx->d_err_cell;
+        if (pre) {
+            auto it = bk.d_out_off.find(key);
+            if (it == bk.d_out_off.end()) {
+                std::vector<unsigned long long> offs(bk.ncell);
+                for (uint64_t c = 0; c < bk.ncell; c++) offs[c] = (*pre)[bk.h_cell_ids[c]];
+                unsigned long long *d = nullptr;
+                CUDA_TRY(ctx, cudaMalloc(&d, offs.size() * sizeof(unsigned long long)));
+                CUDA_TRY(ctx, cudaMemcpy(d, offs.data(), offs.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+                it = bk.d_out_off.emplace(key, d).first;
+            }
+            p.out_off = it->second;
+            p.out_base = (*pre)[b];
+        }
+        int nl = 0;
+        if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
+        if (nl == 0) {
+            p.cells_per_cta = generic_pick_cells_per_cta(mesh->ndim, gd, p.nnode, p.ng, op);
+            nl = launch_generic(p, mesh->ndim, gd, ctx->stream);
+        }
+        if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
+        ctx->launches += (uint64_t)nl;
+    }
+    return GL_OK;
+}
+
+static int resolve_coef(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *coef,
+                        CoefResolved &cr) {
+    const uint64_t len = coef_len(op, mesh->ndim);
+    cr.len = (int)len;
+    if (len == 0) return GL_OK; // GL_OP_JACOBIAN
+    if (!coef || !coef->data) return fail(ctx, GL_ERR_COEF, "coefficient data is required");
+    switch (coef->mode) {
+    case GL_COEF_UNIFORM:
+        if (coef->location != GL_HOST) return fail(ctx, GL_ERR_COEF, "UNIFORM coefficient must be a host record");
+        std::memcpy(cr.uniform, coef->data, len * sizeof(double));
+        return GL_OK;
+    case GL_COEF_PER_MARKER: {
+        if (coef->location != GL_HOST || !coef->markers || coef->nrecord == 0)
+            return fail(ctx, GL_ERR_COEF, "PER_MARKER needs host records and a host marker list");
+        const size_t nm = mesh->marker_values.size();
+        std::vector<double> table(nm * len, 0.0);
+        for (size_t k = 0; k < nm; k++) {
+            bool found = false;
+            for (uint64_t r = 0; r < coef->nrecord && !found; r++)
+                if (coef->markers[r] == mesh->marker_values[k]) {
+                    std::memcpy(&table[k * len], coef->data + r * len, len * sizeof(double));
+                    found = true;
+                }
+            if (!found) return fail(ctx, GL_ERR_COEF, "a cell marker has no coefficient record");
+        }
+        if (nm == 1) {
+            std::memcpy(cr.uniform, table.data(), len * sizeof(double));
+            return GL_OK;
+        }
+        int st = ensure_buffer(ctx, &ctx->d_coef, &ctx->coef_bytes, table.size() * sizeof(double));
+        if (st) return st;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coef, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                      (cudaStream_t)ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)ctx->stream)); // `table` is a local
+        cr.dev = ctx->d_coef;
+        cr.cell_stride = len;
+        cr.gp_stride = 0;
+        cr.per_marker = true;
+        return GL_OK;
+    }
+    case GL_COEF_PER_CELL:
+    case GL_COEF_PER_GAUSS: {
+        const bool per_gauss = coef->mode == GL_COEF_PER_GAUSS;
+        uint64_t nrec = e - b;
+        if (per_gauss) {
+            // every kind in the range must use the same number of Gauss points
+            int ng_common = -1;
+            for (auto &bk : mesh->buckets) {
+                uint64_t lo, hi;
+                bucket_range(mesh, bk, b, e, lo, hi);
+                if (lo >= hi) continue;
+                int ng = 0, st;
+                const double *data;
+                st = gauss_rule(bk.kind, a->ngauss, &ng, &data);
+                if (st) return fail(ctx, st);
+                if (ng_common >= 0 && ng != ng_common)
+                    return fail(ctx, GL_ERR_COEF, "PER_GAUSS needs one rule size for all kinds in the range");
+                ng_common = ng;
+            }
+            nrec *= (uint64_t)std::max(ng_common, 1);
+            cr.gp_stride = len;
+            cr.cell_stride = 0; // filled per bucket as ng * len
+        } else {
+            cr.gp_stride = 0;
+            cr.cell_stride = len;
+        }
+        if (coef->location == GL_DEVICE) {
+            cr.dev = coef->data;
+        } else {
+            int st = ensure_buffer(ctx, &ctx->d_coef, &ctx->coef_bytes, nrec * len * sizeof(double));
+            if (st) return st;
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coef, coef->data, nrec * len * sizeof(double), cudaMemcpyHostToDevice,
+                                          (cudaStream_t)ctx->stream));
+            cr.dev = ctx->d_coef;
+        }
+        return GL_OK;
+    }
+    default:
+        return fail(ctx, GL_ERR_COEF, "unknown coefficient mode");
+    }
+}
+
+int gl_integ(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *coef,
+             gl_out *out) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
+    if (!mesh || !a || !out) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    if (op_size_class(op) < 0) return fail(ctx, GL_ERR_INVALID_ARG, "unknown op");
+    if (mesh->device != ctx->device) return fail(ctx, GL_ERR_INVALID_ARG, "mesh belongs to another device");
+    if (b > e || e > mesh->ncell) return fail(ctx, GL_ERR_CELL_RANGE);
+    cudaSetDevice(ctx->device);
+    uint64_t total = 0;
+    int st = range_layout(mesh, op, b, e, a, &total, nullptr);
+    if (st) return fail(ctx, st);
+    if (e > b && (!out->ptr || out->capacity < total)) return fail(ctx, GL_ERR_OUT_CAPACITY);
+    CoefResolved cr;
+    st = resolve_coef(ctx, mesh, op, b, e, a, coef, cr);
+    if (st) return st;
+    if (b == e) return GL_OK;
+
+    if (out->location == GL_DEVICE) return launch_range(ctx, mesh, op, b, e, a, cr, b, out->ptr);
+
+    // ---- host output: pipeline chunks through two device staging buffers --------------------------------
+    const size_t chunk_target = (size_t)128 << 20;
+    const size_t avg_block = (size_t)std::max<uint64_t>(total / (e - b), 1) * sizeof(double);
+    uint64_t cells_per_chunk = std::max<uint64_t>(chunk_target / avg_block, 1);
+    // staging must hold the largest chunk; blocks may be unequal on mixed meshes, so size by the real layout
+    std::vector<uint64_t> cut{b};
+    while (cut.back() < e) cut.push_back(std::min(e, cut.back() + cells_per_chunk));
+    size_t max_bytes = 0;
+    std::vector<uint64_t> chunk_total(cut.size() - 1), chunk_off(cut.size() - 1);
+    uint64_t run = 0;
+    for (size_t k = 0; k + 1 < cut.size(); k++) {
+        uint64_t t = 0;
+        st = range_layout(mesh, op, cut[k], cut[k + 1], a, &t, nullptr);
+        if (st) return fail(ctx, st);
+        chunk_total[k] = t;
+        chunk_off[k] = run;
+        run += t;
+        max_bytes = std::max(max_bytes, (size_t)t * sizeof(double));
+    }
+    if (ctx->stage_bytes < max_bytes) {
+        for (int i = 0; i < 2; i++) {
+            if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+            ctx->d_stage[i] = nullptr;
+        }
+        ctx->stage_bytes = 0;
+        for (int i = 0; i < 2; i++) CUDA_TRY(ctx, cudaMalloc(&ctx->d_stage[i], max_bytes));
+        ctx->stage_bytes = max_bytes;
+    }
+    cudaStream_t s_compute = (cudaStream_t)ctx->stream, s_copy = (cudaStream_t)ctx->copy_stream;
+    cudaEvent_t ev_kernel[2] = {(cudaEvent_t)ctx->ev[0], (cudaEvent_t)ctx->ev[1]};
+    cudaEvent_t ev_copy[2] = {(cudaEvent_t)ctx->ev[2], (cudaEvent_t)ctx->ev[3]};
+    for (size_t k = 0; k + 1 < cut.size(); k++) {
+        const int buf = (int)(k & 1);
+        if (k >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(s_compute, ev_copy[buf], 0));
+        if (!a->clear)
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[buf], out->ptr + chunk_off[k], chunk_total[k] * sizeof(double),
+                                          cudaMemcpyHostToDevice, s_compute));
+        st = launch_range(ctx, mesh, op, cut[k], cut[k + 1], a, cr, b, ctx->d_stage[buf]);
+        if (st) {
+            cudaStreamSynchronize(s_copy);
+            cudaStreamSynchronize(s_compute);
+            return st;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ev_kernel[buf], s_compute));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(s_copy, ev_kernel[buf], 0));
+        CUDA_TRY(ctx, cudaMemcpyAsync(out->ptr + chunk_off[k], ctx->d_stage[buf], chunk_total[k] * sizeof(double),
+                                      cudaMemcpyDeviceToHost, s_copy));
+        CUDA_TRY(ctx, cudaEventRecord(ev_copy[buf], s_copy));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(s_copy));
+    return gl_ctx_sync(ctx);
+}
+
+int gl_mat_10_bdb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_10_BDB, b, e, a, c, o);
+}
+int gl_mat_01_nsn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_01_NSN, b, e, a, c, o);
+}
+int gl_mat_03_btb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_03_BTB, b, e, a, c, o);
+}
+int gl_vec_01_ns(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_VEC_01_NS, b, e, a, c, o);
+}
+int gl_vec_02_nv(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_VEC_02_NV, b, e, a, c, o);
+}
+int gl_vec_03_bv(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_VEC_03_BV, b, e, a, c, o);
+}
+int gl_vec_04_bt(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_VEC_04_BT, b, e, a, c, o);
+}
+int gl_jacobian(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_JACOBIAN, b, e, a, nullptr, o);
+}
+int gl_mat_10_gdg(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_10_BDB, b, e, a, c, o);
+}
+int gl_vec_10_gs(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_VEC_03_BV, b, e, a, c, o);
+}
+
+int gl_bench_fp64_peak(gl_ctx *ctx, int kind, int iters, double *tflops) {
+    if (!ctx || !tflops) return GL_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    int st = bench_fp64(kind, iters, ctx->stream, tflops);
+    if (st < 0) return cuda_fail(ctx, cudaGetLastError(), "fp64 micro-benchmark");
+    ctx->launches += (uint64_t)st;
+    return GL_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,138 @@
+// gl_internal.hpp -- internal declarations of libgemlab_cuda (not part of the C ABI)
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/gemlab_cuda.h"
+
+namespace gl {
+
+// GeoKind ordinals, GeoKind::VALUES order (src/shapes/enums.rs:1467-1493)
+enum {
+    GL_LIN2 = 0, GL_LIN3, GL_LIN4, GL_LIN5,
+    GL_TRI3, GL_TRI6, GL_TRI10, GL_TRI15,
+    GL_QUA4, GL_QUA8, GL_QUA9, GL_QUA12, GL_QUA16, GL_QUA17,
+    GL_TET4, GL_TET10, GL_TET20,
+    GL_HEX8, GL_HEX20, GL_HEX32,
+    GL_NKIND
+};
+
+constexpr int MAX_NNODE = 32;
+constexpr double ZERO_DETERMINANT = 1e-15; // russell_lab::mat_inverse threshold
+constexpr unsigned long long NO_ERR_CELL = ~0ull;
+
+// ---- host shapes / rules (gl_shapes.cpp) ---------------------------------------------------------
+int kind_nnode(int kind);
+int kind_geo_ndim(int kind);
+int kind_class(int kind);
+const char *kind_name(int kind);
+int kind_from_name(const char *name);
+bool kind_supported(int kind);
+int shape_eval(int kind, const double *ksi, double *nn, double *ll);
+int gauss_rule(int kind, int ngauss, int *npoint, const double **data);
+const char *status_string(int status);
+void lin_elasticity(double young, double poisson, int two_dim, int plane_stress, double *dd);
+
+// ---- device-side parameter block of the integration kernels ---------------------------------------
+// Reference-element table of one (kind, rule): doubles laid out as  w[ng] | N[ng][nnode] | L[ng][nnode][gd]
+struct RuleTable {
+    int kind = 0, ng = 0, nnode = 0, gd = 0;
+    std::vector<double> host;
+    double *dev = nullptr;
+    size_t ndoubles() const { return host.size(); }
+};
+
+struct IntegParams {
+    // mesh (structure of arrays)
+    const double *coords;     // [sd][npoint]
+    unsigned long long npoint;
+    const uint32_t *conn;     // [nnode][ncell_k]  (bucket of one GeoKind)
+    unsigned long long ncell_k;
+    const uint32_t *cell_ids; // bucket-local index -> original cell id; nullptr = identity
+    unsigned long long lo, hi;      // bucket-local sub-range to integrate
+    unsigned long long cell_begin;  // original id of the first cell written at out[0] (chunk start)
+    unsigned long long coef_begin;  // original id that coefficient record 0 belongs to (start of the call's range)
+    // reference element
+    const double *rule;
+    int ng, nnode;
+    // CommonArgs
+    int op, axisym, clear;
+    double alpha;
+    // coefficient records
+    const double *coef;       // device pointer (PER_MARKER / PER_CELL / PER_GAUSS) or nullptr (UNIFORM, in coef_uniform)
+    unsigned long long coef_cell_stride, coef_gp_stride; // in doubles
+    const uint32_t *coef_index; // PER_MARKER: bucket-local cell -> record index; nullptr otherwise
+    int coef_len;
+    double coef_uniform[36];
+    // output
+    double *out;
+    const unsigned long long *out_off; // bucket-local cell -> absolute block offset (mixed meshes); nullptr = homogeneous
+    unsigned long long out_base;       // subtracted from out_off (offset of cell_begin)
+    unsigned int nrow, ncol, ii0, jj0; // element block (ncol = 1 for vectors)
+    unsigned int size_r, size_c;       // extent actually integrated (ndof / nnode, ...)
+    // failure reporting: smallest original id of a cell with |det J| <= 1e-15
+    unsigned long long *err_cell;
+    // tile
+    int cells_per_cta;
+};
+
+// launchers (gl_kernels_generic.cu, gl_kernels_hex8.cu, ...); return the number of kernels launched or < 0 on CUDA error
+int launch_generic(const IntegParams &p, int sd, int gd, void *stream);
+size_t generic_smem_bytes(int sd, int gd, int nnode, int ng, int op, int cells_per_cta);
+int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op);
+
+// tuned kernels; return 0 if the configuration is not covered (caller falls back to the generic kernel)
+int launch_hex8_bdb(const IntegParams &p, void *stream);
+
+// micro-benchmarks
+int bench_fp64(int kind, int iters, void *stream, double *tflops);
+
+} // namespace gl
+
+// ---- opaque handles ---------------------------------------------------------------------------------
+struct gl_mesh_bucket {
+    int kind = 0, nnode = 0;
+    uint64_t ncell = 0;
+    std::vector<uint32_t> h_cell_ids; // empty => identity (homogeneous mesh)
+    uint32_t *d_cell_ids = nullptr;
+    uint32_t *d_conn = nullptr;       // [nnode][ncell]
+    uint32_t *d_marker_idx = nullptr; // [ncell] index into mesh->marker_values; nullptr if the mesh has one marker
+    std::map<int, unsigned long long *> d_out_off; // size-class -> absolute block offsets (mixed meshes, lazy)
+};
+
+struct gl_mesh {
+    int ndim = 0;
+    uint64_t npoint = 0, ncell = 0;
+    double *d_coords = nullptr; // [ndim][npoint]
+    bool homogeneous = true;
+    std::vector<gl_mesh_bucket> buckets;
+    std::vector<uint8_t> h_kinds;        // per cell (mixed meshes only)
+    std::vector<int32_t> marker_values;  // sorted unique markers
+    std::map<int, std::vector<uint64_t>> h_prefix; // size-class -> exclusive prefix of block sizes (mixed meshes, lazy)
+    int device = 0;
+};
+
+struct gl_ctx {
+    int device = 0;
+    void *stream = nullptr;
+    int last_status = 0;
+    std::string last_error;
+    uint64_t last_error_cell = gl::NO_ERR_CELL;
+    uint64_t launches = 0;
+    unsigned long long *d_err_cell = nullptr;
+    unsigned long long *h_err_cell = nullptr; // pinned
+    std::map<std::pair<int, int>, std::unique_ptr<gl::RuleTable>> rules; // (kind, ngauss) -> table
+    // scratch for host<->device staging
+    double *d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    double *d_coef = nullptr;
+    size_t coef_bytes = 0;
+    double *d_rule_tmp = nullptr; // for GL_OP_JACOBIAN tables
+    void *copy_stream = nullptr;
+    void *ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};

@@ -1,0 +1,340 @@
+"""Batched `integ` entry points -- host-side mirror of gemlab::integ for a Mesh plus a cell range.
+
+The reference integrates ONE cell per call: `integ::mat_10_bdb(&mut kk, &mut CommonArgs{pad, gauss, ..}, |dd,p,N,B| ..)`
+(src/integ/mat_10_bdb.rs:121; siblings mat_01_nsn.rs:48, mat_03_btb.rs:50, vec_01_ns.rs:83, vec_02_nv.rs:85,
+vec_03_bv.rs:84, vec_04_bt.rs:93) inside a user loop `for cell in &mesh.cells { mesh.set_pad(..); integ::X(..) }`.
+Here the same functions take the whole mesh and a cell range and run on the GPU through the C ABI
+(include/gemlab_cuda.h); names, argument meaning and error strings follow the reference:
+
+    ctx   = Context(device=0)                       # one per GPU
+    dmesh = ctx.upload(mesh)                        # SoA device mesh (replaces Mesh::set_pad's gather)
+    args  = CommonArgs()                            # clear=True, axisymmetric=False, alpha=1, ii0=jj0=0, ngauss=None
+    kk    = integ.mat_10_bdb(ctx, dmesh, (0, ncell), args, Coef.uniform(dd))
+
+Outputs: element e of the range occupies out[off[e-begin] : off[e-begin]+size], column-major inside the element.
+`out` may be None (a new numpy array is returned), a numpy array (host path, copies inside the call) or a CUDA
+torch tensor (device path, asynchronous on the ctx stream).  PyTorch is plumbing only (device memory, streams).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import GlArgs, GlCoef, GlOut, lib
+from .geo import GemlabError, GeoKind
+from .mesh import Mesh
+
+GL_HOST, GL_DEVICE = 0, 1
+OPS = {"mat_10_bdb": 0, "mat_01_nsn": 1, "mat_03_btb": 2, "vec_01_ns": 3, "vec_03_bv": 4, "vec_02_nv": 5,
+       "vec_04_bt": 6, "jacobian": 8}
+COEF_UNIFORM, COEF_PER_MARKER, COEF_PER_CELL, COEF_PER_GAUSS = 0, 1, 2, 3
+
+
+class CommonArgs:
+    """gemlab::integ::CommonArgs (src/integ/common_args.rs:5-43) without pad/gauss (implied by the mesh and `ngauss`)."""
+
+    def __init__(self, ngauss=None, clear=True, axisymmetric=False, alpha=1.0, ii0=0, jj0=0, nrow=0, ncol=0):
+        self.ngauss = ngauss          # None = Gauss::new(kind), else Gauss::new_sized(kind.class(), ngauss)
+        self.clear = clear
+        self.axisymmetric = axisymmetric
+        self.alpha = alpha
+        self.ii0 = ii0
+        self.jj0 = jj0
+        self.nrow = nrow              # 0 = tight element blocks
+        self.ncol = ncol
+        self.ksi = (0.0, 0.0, 0.0)    # integ.jacobian only
+
+    def _c(self):
+        a = GlArgs()
+        a.ngauss = 0 if self.ngauss is None else int(self.ngauss)
+        a.axisymmetric = int(bool(self.axisymmetric))
+        a.clear = int(bool(self.clear))
+        a.alpha = float(self.alpha)
+        a.ii0, a.jj0, a.nrow, a.ncol = int(self.ii0), int(self.jj0), int(self.nrow), int(self.ncol)
+        for i in range(3):
+            a.ksi[i] = float(self.ksi[i]) if i < len(self.ksi) else 0.0
+        return a
+
+
+class Coef:
+    """Coefficient data replacing the reference's per-Gauss-point closures (see struct gl_coef)."""
+
+    def __init__(self, mode, data, markers=None):
+        self.mode = mode
+        self.data = data
+        self.markers = None if markers is None else np.ascontiguousarray(markers, dtype=np.int32)
+
+    @staticmethod
+    def uniform(record):
+        """One record for every cell and Gauss point (e.g. `dd.set_tensor(1.0, model.get_modulus())`)."""
+        return Coef(COEF_UNIFORM, np.asarray(record, dtype=np.float64))
+
+    @staticmethod
+    def per_marker(markers, records):
+        return Coef(COEF_PER_MARKER, np.asarray(records, dtype=np.float64), markers)
+
+    @staticmethod
+    def per_cell(records):
+        """records[(e - cell_begin)] ; numpy array (host) or CUDA torch tensor (device)."""
+        return Coef(COEF_PER_CELL, records)
+
+    @staticmethod
+    def per_gauss(records):
+        """records[(e - cell_begin) * ngauss + p]."""
+        return Coef(COEF_PER_GAUSS, records)
+
+
+def mandel_matrix(dd):
+    """Flattens an (ns, ns) Mandel matrix (Tensor4::matrix()) COLUMN-major as the ABI expects."""
+    return np.asarray(dd, dtype=np.float64).ravel(order="F").copy()
+
+
+def lin_elasticity(young, poisson, two_dim, plane_stress=False):
+    """LinElasticity::new(E, nu, two_dim, plane_stress).get_modulus().matrix() -> (ns, ns)."""
+    ns = 4 if two_dim else 6
+    dd = np.zeros(ns * ns)
+    lib().gl_lin_elasticity(float(young), float(poisson), int(two_dim), int(plane_stress), dd.ctypes.data)
+    return dd.reshape(ns, ns, order="F")
+
+
+def _is_torch_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+class DeviceMesh:
+    """Handle of a mesh resident on one GPU (struct gl_mesh)."""
+
+    def __init__(self, ctx, handle, ndim, ncell, npoint, kinds):
+        self.ctx = ctx
+        self._h = handle
+        self.ndim = ndim
+        self.ncell = ncell
+        self.npoint = npoint
+        self.kinds = kinds  # host copy (uint8) -- used for sizes only
+
+    def free(self):
+        if self._h:
+            lib().gl_mesh_free(self.ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One per GPU (struct gl_ctx).  `stream` is a raw cudaStream_t handle; by default torch's current stream of that
+    device is used so that torch.cuda.Event timings bracket the kernels."""
+
+    def __init__(self, device=0, stream=None):
+        self.device = int(device)
+        if stream is None:
+            try:
+                import torch
+
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+            except Exception:
+                stream = 0
+        h = C.c_void_p()
+        st = lib().gl_ctx_create(self.device, C.c_void_p(stream), C.byref(h))
+        if st:
+            raise GemlabError(st)
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib().gl_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _raise(self, status):
+        msg = lib().gl_last_error(self._h).decode("utf-8")
+        cell = lib().gl_last_error_cell(self._h)
+        raise GemlabError(status, msg or None, None if cell == 0xFFFFFFFFFFFFFFFF else cell)
+
+    def set_stream(self, stream):
+        lib().gl_ctx_set_stream(self._h, C.c_void_p(stream))
+
+    def sync(self):
+        st = lib().gl_ctx_sync(self._h)
+        if st:
+            self._raise(st)
+
+    def launch_count(self):
+        return int(lib().gl_ctx_launch_count(self._h))
+
+    def upload(self, mesh):
+        """Mesh -> device SoA (gl_mesh_upload); replaces the per-cell Mesh::set_pad gather (src/mesh/mesh.rs:448-456)."""
+        if not isinstance(mesh, Mesh):
+            raise TypeError("expected a gemlab_b200.Mesh")
+        h = C.c_void_p()
+        if mesh.is_homogeneous() and mesh.ncell > 0 and mesh.npoint < 2**32:
+            conn32 = np.ascontiguousarray(mesh.conn, dtype=np.uint32)
+            st = lib().gl_mesh_upload_homogeneous(self._h, mesh.ndim, mesh.npoint, mesh.coords.ctypes.data, mesh.ncell,
+                                                  int(mesh.kinds[0]), mesh.markers.ctypes.data, conn32.ctypes.data,
+                                                  C.byref(h))
+        else:
+            st = lib().gl_mesh_upload(self._h, mesh.ndim, mesh.npoint, mesh.coords.ctypes.data, mesh.ncell,
+                                      mesh.kinds.ctypes.data, mesh.markers.ctypes.data, mesh.conn_off.ctypes.data,
+                                      mesh.conn.ctypes.data, C.byref(h))
+        if st:
+            self._raise(st)
+        return DeviceMesh(self, h, mesh.ndim, mesh.ncell, mesh.npoint, mesh.kinds.copy())
+
+    def fp64_peak(self, kind="dfma", iters=4096):
+        """Measured FP64 peak of this device in TFLOP/s (kind: 'dfma' or 'dmma')."""
+        t = C.c_double()
+        st = lib().gl_bench_fp64_peak(self._h, 0 if kind == "dfma" else 1, int(iters), C.byref(t))
+        if st:
+            self._raise(st)
+        return t.value
+
+
+def out_total(dmesh, op, cell_range, args):
+    b, e = _range(dmesh, cell_range)
+    a = args._c()
+    total = C.c_uint64()
+    st = lib().gl_out_total(dmesh._h, OPS[op], b, e, C.byref(a), C.byref(total))
+    if st:
+        raise GemlabError(st)
+    return total.value
+
+
+def out_offsets(dmesh, op, cell_range, args):
+    """off[0..n]: start of every element block of the range (gl_out_offsets)."""
+    b, e = _range(dmesh, cell_range)
+    a = args._c()
+    off = np.zeros(e - b + 1, dtype=np.uint64)
+    st = lib().gl_out_offsets(dmesh._h, OPS[op], b, e, C.byref(a), off.ctypes.data)
+    if st:
+        raise GemlabError(st)
+    return off
+
+
+def _range(dmesh, cell_range):
+    if cell_range is None:
+        return 0, dmesh.ncell
+    if isinstance(cell_range, range):
+        if cell_range.step != 1:
+            raise ValueError("cell range must be contiguous")
+        return cell_range.start, cell_range.stop
+    b, e = cell_range
+    return int(b), int(e)
+
+
+def _integ(op, ctx, dmesh, cell_range, args, coef, out):
+    b, e = _range(dmesh, cell_range)
+    a = args._c()
+    total = C.c_uint64()
+    st = lib().gl_out_total(dmesh._h, OPS[op], b, e, C.byref(a), C.byref(total))
+    if st:
+        raise GemlabError(st)
+    total = total.value
+    keep = []
+    # coefficient
+    c = GlCoef()
+    cptr = None
+    if coef is not None:
+        c.mode = coef.mode
+        if _is_torch_tensor(coef.data):
+            if not coef.data.is_cuda:
+                raise ValueError("coefficient tensor must be a CUDA tensor or a numpy array")
+            t = coef.data.contiguous()
+            keep.append(t)
+            c.location, c.data = GL_DEVICE, t.data_ptr()
+        else:
+            arr = np.ascontiguousarray(coef.data, dtype=np.float64)
+            keep.append(arr)
+            c.location, c.data = GL_HOST, arr.ctypes.data
+        if coef.markers is not None:
+            c.markers = coef.markers.ctypes.data
+            c.nrecord = coef.markers.shape[0]
+        cptr = C.byref(c)
+    # output
+    o = GlOut()
+    result = out
+    if out is None:
+        result = np.empty(total, dtype=np.float64) if args.clear else np.zeros(total, dtype=np.float64)
+        o.ptr, o.location, o.capacity = result.ctypes.data, GL_HOST, total
+    elif _is_torch_tensor(out):
+        if not out.is_contiguous():
+            raise ValueError("output tensor must be contiguous")
+        o.ptr, o.capacity = out.data_ptr(), out.numel()
+        o.location = GL_DEVICE if out.is_cuda else GL_HOST
+    else:
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
+            raise ValueError("output must be a contiguous float64 numpy array")
+        o.ptr, o.location, o.capacity = out.ctypes.data, GL_HOST, out.size
+    st = lib().gl_integ(ctx._h, dmesh._h, OPS[op], b, e, C.byref(a), cptr, C.byref(o))
+    if st:
+        ctx._raise(st)
+    return result
+
+
+def mat_10_bdb(ctx, dmesh, cell_range, args, coef, out=None):
+    """K = int B.D.B (stiffness), ndof x ndof per cell -- integ::mat_10_bdb (src/integ/mat_10_bdb.rs:121-233)."""
+    return _integ("mat_10_bdb", ctx, dmesh, cell_range, args, coef, out)
+
+
+mat_10_gdg = mat_10_bdb  # legacy (gemlab <= 1.x) name used by BASELINE.json
+
+
+def mat_01_nsn(ctx, dmesh, cell_range, args, coef, out=None):
+    """K = int N s N, nnode x nnode -- integ::mat_01_nsn (src/integ/mat_01_nsn.rs:48-102)."""
+    return _integ("mat_01_nsn", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_03_btb(ctx, dmesh, cell_range, args, coef, out=None):
+    """K = int B.T.B, nnode x nnode -- integ::mat_03_btb (src/integ/mat_03_btb.rs:50-131)."""
+    return _integ("mat_03_btb", ctx, dmesh, cell_range, args, coef, out)
+
+
+def vec_01_ns(ctx, dmesh, cell_range, args, coef, out=None):
+    """a = int N s, nnode -- integ::vec_01_ns (src/integ/vec_01_ns.rs:83-130)."""
+    return _integ("vec_01_ns", ctx, dmesh, cell_range, args, coef, out)
+
+
+def vec_02_nv(ctx, dmesh, cell_range, args, coef, out=None):
+    """b = int N v, ndof -- integ::vec_02_nv (src/integ/vec_02_nv.rs:85-140)."""
+    return _integ("vec_02_nv", ctx, dmesh, cell_range, args, coef, out)
+
+
+def vec_03_bv(ctx, dmesh, cell_range, args, coef, out=None):
+    """c = int B.w, nnode -- integ::vec_03_bv (src/integ/vec_03_bv.rs:84-141)."""
+    return _integ("vec_03_bv", ctx, dmesh, cell_range, args, coef, out)
+
+
+vec_10_gs = vec_03_bv  # legacy name used by BASELINE.json
+
+
+def vec_04_bt(ctx, dmesh, cell_range, args, coef, out=None):
+    """d = int B.sigma, ndof -- integ::vec_04_bt (src/integ/vec_04_bt.rs:93-170)."""
+    return _integ("vec_04_bt", ctx, dmesh, cell_range, args, coef, out)
+
+
+def jacobian(ctx, dmesh, cell_range, ksi, out=None):
+    """det J (SOLID), |J| (CABLE) or -1 (SHELL) of every cell at the reference point ksi --
+    the Scratchpad::calc_jacobian loop of Mesh::check_jacobian (src/mesh/check.rs:43-60)."""
+    args = CommonArgs()
+    args.ksi = tuple(ksi)
+    return _integ("jacobian", ctx, dmesh, cell_range, args, None, out)
+
+
+def partition(ncell, world_size, rank):
+    """Contiguous cell range of `rank`: [floor(r*ncell/G), floor((r+1)*ncell/G)); the concatenation of
+    the ranks' outputs in rank order equals the single-GPU output."""
+    return (rank * ncell) // world_size, ((rank + 1) * ncell) // world_size
+
+
+def op_out_size(op, kind, ndim):
+    return int(lib().gl_op_out_size(OPS[op], int(GeoKind(kind)), int(ndim)))
+
+
+def op_coef_size(op, ndim):
+    return int(lib().gl_op_coef_size(OPS[op], int(ndim)))

@@ -1,0 +1,244 @@
+/*
+ * gemlab_cuda.h -- C ABI of libgemlab_cuda: batched, B200-native (sm_100a) Gauss-quadrature
+ * integration of element matrices and vectors over a cell range of a gemlab mesh.
+ *
+ * This is the drop-in boundary for gemlab's per-cell integration path.  The reference
+ * (cpmech/gemlab v2.4.0, pure Rust) exposes no FFI for this path: its boundary is the generic Rust
+ * signature `integ::X(out, &mut CommonArgs, closure)` called once per cell by user code
+ * (examples/integ_mom_inertia_disk.rs:21-33, pmsim-style assemblers).  Each entry point below names the
+ * reference item it replaces (paths relative to the reference tree).  A `gemlab-cuda` Rust crate binds these
+ * symbols (gemlab-cuda/src/ffi.rs) and offers `integ::batch::*` taking `&Mesh` + a
+ * cell range.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is either a HOST pointer or a raw CUDA DEVICE pointer, as
+ *     stated by the accompanying `location` field.  No torch / C++ types cross this boundary.
+ *   - all functions return 0 on success or a stable nonzero gl_status; gl_last_error(ctx) returns
+ *     the reference's own StrError string for that status (tests compare the strings).
+ *   - GeoKind ordinals follow GeoKind::VALUES (src/shapes/enums.rs:1467-1493).
+ *   - matrices are COLUMN-MAJOR (russell_lab::Matrix storage): K(ii,jj) at ii + jj*nrow, with the
+ *     reference's index layout ii = ii0 + i + m*space_ndim, jj = jj0 + j + n*space_ndim
+ *     (src/integ/mat_10_bdb.rs:31-46).
+ *   - a ctx belongs to ONE device and ONE host thread at a time (Send, not Sync); calls are
+ *     stream-ordered on the ctx stream and asynchronous when every buffer is a device buffer;
+ *     gl_ctx_sync() waits and reports device-side failures (zero Jacobian determinant).
+ *   - there is no CPU fallback: every entry point fails with GL_ERR_CUDA when no sm_100 device is
+ *     usable.
+ */
+#ifndef GEMLAB_CUDA_H
+#define GEMLAB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GL_API
+#else
+#define GL_API __attribute__((visibility("default")))
+#endif
+
+typedef struct gl_ctx gl_ctx;   /* one per GPU: stream, reference-element tables, scratch buffers */
+typedef struct gl_mesh gl_mesh; /* device-resident SoA mesh, bucketed by GeoKind */
+
+typedef enum gl_status {
+    GL_OK = 0,
+    GL_ERR_XXT_NOT_SET = 1,   /* "all components of the coordinates matrix must be set first" (scratchpad_calc_jacobian.rs:104) */
+    GL_ERR_ZERO_DET = 2,      /* "cannot compute inverse due to zero determinant" (russell_lab::mat_inverse) */
+    GL_ERR_GRADIENT_NDIM = 3, /* "calc_gradient requires that geo_ndim = space_ndim" (scratchpad_calc_gradient.rs:82) */
+    GL_ERR_NROW_KK_NDOF = 4,  /* "nrow(K) must be >= ii0 + nnode * space_ndim" (mat_10_bdb.rs:129) */
+    GL_ERR_NCOL_KK_NDOF = 5,  /* "ncol(K) must be >= jj0 + nnode * space_ndim" (mat_10_bdb.rs:132) */
+    GL_ERR_AXISYM_NDIM = 6,   /* "axisymmetric requires space_ndim = 2" (mat_10_bdb.rs:135) */
+    GL_ERR_NROW_KK_NNODE = 7, /* "nrow(K) must be >= ii0 + nnode" (mat_01_nsn.rs:57) */
+    GL_ERR_NCOL_KK_NNODE = 8, /* "ncol(K) must be >= jj0 + nnode" (mat_01_nsn.rs:60) */
+    GL_ERR_A_LEN = 9,         /* "a.len() must be >= ii0 + nnode" (vec_01_ns.rs:91) */
+    GL_ERR_B_LEN = 10,        /* "b.len() must be >= ii0 + nnode * space_ndim" (vec_02_nv.rs:93) */
+    GL_ERR_C_LEN = 11,        /* "c.len() must be >= ii0 + nnode" (vec_03_bv.rs:92) */
+    GL_ERR_D_LEN = 12,        /* "d.len() must be >= ii0 + nnode * space_ndim" (vec_04_bt.rs:100) */
+    GL_ERR_GAUSS_LIN = 13,    /* "requested number of integration points is not available for Lin class" (gauss.rs:197) */
+    GL_ERR_GAUSS_TRI = 14,
+    GL_ERR_GAUSS_QUA = 15,
+    GL_ERR_GAUSS_TET = 16,
+    GL_ERR_GAUSS_HEX = 17,
+    GL_ERR_KIND_UNSUPPORTED = 18, /* GeoKind has no device tables yet */
+    GL_ERR_SPACE_NDIM = 20,       /* "space_ndim must be 2 or 3" (scratchpad.rs:153) */
+    /* errors of the batched boundary itself (no reference counterpart) */
+    GL_ERR_INVALID_ARG = 100,
+    GL_ERR_CELL_RANGE = 101,
+    GL_ERR_OUT_CAPACITY = 102,
+    GL_ERR_COEF = 103,
+    GL_ERR_MESH = 104,
+    GL_ERR_CUDA = 200,
+    GL_ERR_NO_DEVICE = 201
+} gl_status;
+
+/* integration cases; numbering follows the reference's file names (src/integ/mod.rs:304-353) */
+typedef enum gl_op {
+    GL_OP_MAT_10_BDB = 0, /* integ::mat_10_bdb  K = int B.D.B       (src/integ/mat_10_bdb.rs:121)  ndof x ndof */
+    GL_OP_MAT_01_NSN = 1, /* integ::mat_01_nsn  K = int N s N       (src/integ/mat_01_nsn.rs:48)   nnode x nnode */
+    GL_OP_MAT_03_BTB = 2, /* integ::mat_03_btb  K = int B.T.B       (src/integ/mat_03_btb.rs:50)   nnode x nnode */
+    GL_OP_VEC_01_NS = 3,  /* integ::vec_01_ns   a = int N s         (src/integ/vec_01_ns.rs:83)    nnode */
+    GL_OP_VEC_03_BV = 4,  /* integ::vec_03_bv   c = int B.w         (src/integ/vec_03_bv.rs:84)    nnode */
+    GL_OP_VEC_02_NV = 5,  /* integ::vec_02_nv   b = int N v         (src/integ/vec_02_nv.rs:85)    ndof */
+    GL_OP_VEC_04_BT = 6,  /* integ::vec_04_bt   d = int B.sigma     (src/integ/vec_04_bt.rs:93)    ndof */
+    GL_OP_JACOBIAN = 8    /* Scratchpad::calc_jacobian at one ksi (scratchpad_calc_jacobian.rs:101; Mesh::check_jacobian, mesh/check.rs:43-60)  1 */
+} gl_op;
+
+typedef enum gl_location { GL_HOST = 0, GL_DEVICE = 1 } gl_location;
+
+/* Mirrors integ::CommonArgs (src/integ/common_args.rs:5-43); pad and gauss are implied by the mesh
+ * (one Scratchpad per cell, gathered by Mesh::set_pad, src/mesh/mesh.rs:448-456) and by `ngauss`. */
+typedef struct gl_args {
+    int32_t ngauss;       /* 0 = Gauss::new(kind) default rule; else Gauss::new_sized(kind.class(), ngauss) (gauss.rs:87,189) */
+    int32_t axisymmetric; /* CommonArgs.axisymmetric: integrate over 1 radian, r = sum N.x0 */
+    int32_t clear;        /* CommonArgs.clear: 1 = zero-fill the element block first, 0 = accumulate into `out` */
+    int32_t reserved;
+    double alpha;         /* CommonArgs.alpha (e.g. plane-stress thickness) */
+    uint32_t ii0, jj0;    /* CommonArgs.ii0 / jj0: offsets inside each element's block */
+    uint32_t nrow, ncol;  /* per-element block dims; 0 = tight (nrow = ii0 + size, ncol = jj0 + size; vectors use nrow only) */
+    double ksi[3];        /* GL_OP_JACOBIAN only: the reference point */
+} gl_args;
+
+/* The reference takes the coefficient as a closure evaluated at every Gauss point
+ * (FnMut(&mut Tensor4, p, &N, &B), mat_10_bdb.rs:121-124, and siblings).  A device cannot call a host closure, so the
+ * batched boundary takes the coefficient as DATA.  One record is:
+ *   mat_10_bdb : D as the ns x ns Mandel matrix `dd.matrix()`, column-major, ns = 2*space_ndim
+ *   mat_03_btb, vec_04_bt : the Mandel vector `tt.vector()` (ns)
+ *   mat_01_nsn, vec_01_ns : the scalar s
+ *   vec_02_nv, vec_03_bv  : the vector v / w (space_ndim)
+ */
+typedef enum gl_coef_mode {
+    GL_COEF_UNIFORM = 0,    /* one record for every cell and Gauss point */
+    GL_COEF_PER_MARKER = 1, /* one record per cell marker: markers[k] -> record k */
+    GL_COEF_PER_CELL = 2,   /* record (e - cell_begin) for cell e */
+    GL_COEF_PER_GAUSS = 3   /* record (e - cell_begin)*ngauss + p for Gauss point p of cell e */
+} gl_coef_mode;
+
+typedef struct gl_coef {
+    int32_t mode;           /* gl_coef_mode */
+    int32_t location;       /* gl_location of `data` (UNIFORM / PER_MARKER tables must be GL_HOST) */
+    const double *data;
+    const int32_t *markers; /* PER_MARKER: host array of nrecord marker values */
+    uint64_t nrecord;       /* PER_MARKER: number of records */
+} gl_coef;
+
+typedef struct gl_out {
+    double *ptr;      /* element e occupies ptr[off[e-cell_begin] .. +size), elements in original cell-id order */
+    int32_t location; /* gl_location */
+    int32_t reserved;
+    uint64_t capacity; /* doubles available at ptr */
+} gl_out;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+
+/* `stream` is a cudaStream_t (or NULL for the device's default stream) on which all work of this ctx is ordered. */
+GL_API int gl_ctx_create(int device, void *stream, gl_ctx **ctx);
+GL_API void gl_ctx_destroy(gl_ctx *ctx);
+GL_API int gl_ctx_set_stream(gl_ctx *ctx, void *stream);
+/* Waits for the ctx stream; returns GL_ERR_ZERO_DET (and records the smallest failing cell id) if any kernel since the
+ * last sync met |det J| <= 1e-15. */
+GL_API int gl_ctx_sync(gl_ctx *ctx);
+GL_API const char *gl_last_error(const gl_ctx *ctx);
+GL_API uint64_t gl_last_error_cell(const gl_ctx *ctx);
+GL_API const char *gl_status_string(int status);
+/* number of kernels launched by this ctx so far (bench.py's gpu_launches) */
+GL_API uint64_t gl_ctx_launch_count(const gl_ctx *ctx);
+
+/* ---- GeoKind / Gauss queries (host only; replace GeoKind::nnode, ndim, class and Gauss::new, new_sized, npoint, coords) ---- */
+GL_API int gl_kind_nnode(int kind);
+GL_API int gl_kind_geo_ndim(int kind);
+GL_API int gl_kind_class(int kind);
+GL_API int gl_kind_from_name(const char *name); /* GeoKind::from (enums.rs:217-244); -1 if unknown */
+GL_API const char *gl_kind_name(int kind);
+GL_API int gl_kind_supported(int kind);
+/* rule lookup: *npoint points, data = npoint x 4 doubles {r,s,t,w} (static storage) */
+GL_API int gl_gauss_rule(int kind, int ngauss, int *npoint, const double **data);
+/* N (nnode) and L = dN/dksi (nnode x geo_ndim, row-major) of the library's own reference-element evaluation */
+GL_API int gl_shape_eval(int kind, const double *ksi, double *nn, double *ll);
+
+/* ---- mesh (replaces Mesh/Point/Cell + Mesh::set_pad, src/mesh/mesh.rs:27-54,110-135,448-456) ------ */
+
+/* coords: AoS npoint x ndim (Mesh.points[i].coords flattened); kinds: ncell GeoKind ordinals; markers: ncell (may be
+ * NULL = all zero); conn_off: ncell+1 offsets into conn; conn: point ids (usize in the reference).  All HOST pointers.
+ * The library transposes to structure-of-arrays, narrows ids to u32 and buckets cells by GeoKind. */
+GL_API int gl_mesh_upload(gl_ctx *ctx, int ndim, uint64_t npoint, const double *coords, uint64_t ncell,
+                          const uint8_t *kinds, const int32_t *markers, const uint64_t *conn_off, const uint64_t *conn,
+                          gl_mesh **mesh);
+/* Homogeneous fast path: every cell has `kind`; conn is ncell x nnode row-major, 32-bit point ids. */
+GL_API int gl_mesh_upload_homogeneous(gl_ctx *ctx, int ndim, uint64_t npoint, const double *coords, uint64_t ncell,
+                                      int kind, const int32_t *markers, const uint32_t *conn, gl_mesh **mesh);
+/* Replace the coordinates of an uploaded mesh (e.g. updated-Lagrangian steps); coords as in gl_mesh_upload. */
+GL_API int gl_mesh_update_coords(gl_ctx *ctx, gl_mesh *mesh, const double *coords, int location);
+GL_API void gl_mesh_free(gl_ctx *ctx, gl_mesh *mesh);
+GL_API uint64_t gl_mesh_ncell(const gl_mesh *mesh);
+GL_API uint64_t gl_mesh_npoint(const gl_mesh *mesh);
+GL_API int gl_mesh_ndim(const gl_mesh *mesh);
+
+/* ---- output layout ------------------------------------------------------------------------------- */
+
+/* doubles per element block of `op` for a cell of `kind` (tight, ii0 = jj0 = 0) */
+GL_API uint64_t gl_op_out_size(int op, int kind, int ndim);
+/* doubles per coefficient record */
+GL_API uint64_t gl_op_coef_size(int op, int ndim);
+/* total doubles needed for [cell_begin, cell_end) with these args */
+GL_API int gl_out_total(const gl_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                        uint64_t *total);
+/* off[0 .. cell_end-cell_begin] (HOST): start of every element block, off[n] = total */
+GL_API int gl_out_offsets(const gl_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                          uint64_t *off);
+
+/* ---- the batched integ entry points -------------------------------------------------------------- */
+
+GL_API int gl_integ(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end,
+                    const gl_args *args, const gl_coef *coef, gl_out *out);
+
+/* replaces integ::mat_10_bdb (src/integ/mat_10_bdb.rs:121-233) */
+GL_API int gl_mat_10_bdb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+/* replaces integ::mat_01_nsn (src/integ/mat_01_nsn.rs:48-102) */
+GL_API int gl_mat_01_nsn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+/* replaces integ::mat_03_btb (src/integ/mat_03_btb.rs:50-131) */
+GL_API int gl_mat_03_btb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+/* replaces integ::vec_01_ns (src/integ/vec_01_ns.rs:83-130) */
+GL_API int gl_vec_01_ns(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                        const gl_coef *coef, gl_out *out);
+/* replaces integ::vec_02_nv (src/integ/vec_02_nv.rs:85-140) */
+GL_API int gl_vec_02_nv(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                        const gl_coef *coef, gl_out *out);
+/* replaces integ::vec_03_bv (src/integ/vec_03_bv.rs:84-141) */
+GL_API int gl_vec_03_bv(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                        const gl_coef *coef, gl_out *out);
+/* replaces integ::vec_04_bt (src/integ/vec_04_bt.rs:93-170) */
+GL_API int gl_vec_04_bt(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                        const gl_coef *coef, gl_out *out);
+/* replaces the per-cell Scratchpad::calc_jacobian loop of Mesh::check_jacobian (src/mesh/check.rs:43-60) */
+GL_API int gl_jacobian(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                       gl_out *out);
+
+/* legacy (gemlab <= 1.x) names used by BASELINE.json's north_star: G was renamed to B in v2 */
+GL_API int gl_mat_10_gdg(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out); /* = gl_mat_10_bdb */
+GL_API int gl_vec_10_gs(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                        const gl_coef *coef, gl_out *out); /* = gl_vec_03_bv */
+
+/* default-initialised CommonArgs (CommonArgs::new: clear = true, axisymmetric = false, alpha = 1, ii0 = jj0 = 0) */
+GL_API void gl_args_default(gl_args *args);
+
+/* russell_tensor::LinElasticity::new(E, nu, two_dim, plane_stress).get_modulus().matrix() as a coefficient record
+ * (ns x ns column-major; ns = 4 if two_dim else 6) -- convenience for callers without russell_tensor */
+GL_API void gl_lin_elasticity(double young, double poisson, int two_dim, int plane_stress, double *dd);
+
+/* ---- micro-benchmarks used to measure the FP64 roofline denominators on the device (bench.py) ---- */
+/* runs `iters` dependent-chain DFMA (kind 0) or DMMA m8n8k4 (kind 1) per thread on the whole device and returns the
+ * achieved TFLOP/s measured with CUDA events */
+GL_API int gl_bench_fp64_peak(gl_ctx *ctx, int kind, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMLAB_CUDA_H */

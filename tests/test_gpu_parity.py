@@ -1,0 +1,381 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's known answers.
+
+Bar (BASELINE.json north_star): per element max|K_gpu - K_ref| / max|K_ref| <= 1e-12 (f64); cell order, element-block
+offsets and the index layout ii = i + m*ndim are exact.  Run on the B200 box with `pytest -m gpu`.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import gemlab_b200 as g
+from gemlab_b200 import Block, Coef, CommonArgs, GeoKind, Mesh, integ
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.loads((Path(__file__).parent / "golden" / "known_answers.json").read_text())
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Context(0)
+    yield c
+    c.close()
+
+
+def rel_err(got, ref, sizes=None):
+    """per-element max|d| / max|ref|; elements delimited by `sizes` offsets (or one element)."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape
+    if sizes is None:
+        scale = np.max(np.abs(ref))
+        return float(np.max(np.abs(got - ref)) / (scale if scale > 0 else 1.0))
+    worst = 0.0
+    for a, b in zip(sizes[:-1], sizes[1:]):
+        a, b = int(a), int(b)
+        scale = np.max(np.abs(ref[a:b]))
+        worst = max(worst, float(np.max(np.abs(got[a:b] - ref[a:b])) / (scale if scale > 0 else 1.0)))
+    return worst
+
+
+def oracle_integ(op, mesh, coef=None, cell_stride=0, gp_stride=0, **kw):
+    return po.mesh_integ(op, mesh.ndim, mesh.coords, mesh.kinds, mesh.conn_off, mesh.conn, coef=coef,
+                         coef_cell_stride=cell_stride, coef_gp_stride=gp_stride, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 1. the reference's own known-answer tests, run through the GPU path (single-cell meshes)
+# ---------------------------------------------------------------------------------------------------------------
+
+def _golden_coef(case, mesh, ngauss):
+    op = case["op"]
+    if op == "mat_10_bdb":
+        return Coef.uniform(np.array(case["dd"]).ravel(order="F"))
+    if op in ("mat_03_btb", "vec_04_bt"):
+        return Coef.uniform(case["tt"])
+    if "s" in case:
+        return Coef.uniform([case["s"]])
+    if "v" in case:
+        return Coef.uniform(case["v"])
+    # x-dependent coefficients: evaluate at the Gauss points with the oracle's get_points_coords -> PER_GAUSS records
+    pad = po.Scratchpad.new(case["ndim"], case["kind"]).set_coords(case["xx"])
+    gauss = po.Gauss(case["kind"], ngauss)
+    x = np.array(po.get_points_coords(pad, gauss))
+    if "s_field" in case:
+        return Coef.per_gauss(x[:, int(case["s_field"][1])].copy())
+    if case.get("v_field") == "x":
+        return Coef.per_gauss(x.copy())
+    if case.get("v_field") == "x0x0":
+        return Coef.per_gauss(np.repeat(x[:, [0]], case["ndim"], axis=1).copy())
+    raise AssertionError(case["name"])
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_reference_known_answers_on_gpu(ctx, case):
+    kind = GeoKind.from_str(case["kind"])
+    xx = np.array(case["xx"])
+    mesh = Mesh.homogeneous(case["ndim"], xx, kind, np.arange(kind.nnode()).reshape(1, -1))
+    dmesh = ctx.upload(mesh)
+    expect = np.array(case["expect"])
+    tols = case["tol"] if isinstance(case["tol"], list) else [case["tol"]] * len(case["ngauss"])
+    for n, tol in zip(case["ngauss"], tols):
+        args = CommonArgs(ngauss=None if n == 0 else n, alpha=case.get("alpha", 1.0),
+                          axisymmetric=case.get("axisymmetric", False))
+        # outputs pre-filled with NOISE (src/integ/testing.rs:7): clear=True must overwrite
+        out = np.full(expect.size, GOLD["noise"])
+        fn = getattr(integ, case["op"])
+        fn(ctx, dmesh, None, args, _golden_coef(case, mesh, n), out=out)
+        got = out.reshape(expect.shape, order="F") if expect.ndim == 2 else out
+        assert np.max(np.abs(got - expect)) <= max(tol, 4e-16 * np.max(np.abs(expect))), f"{case['name']} n={n} ({case['ref']})"
+
+
+def test_jacobian_doctest_on_gpu(ctx):
+    j = GOLD["jacobian_doctest"]
+    mesh = Mesh.homogeneous(2, np.array(j["xx"]), GeoKind.Qua4, [[0, 1, 2, 3]])
+    det = integ.jacobian(ctx, ctx.upload(mesh), None, j["ksi"])
+    assert abs(det[0] - j["det"]) <= j["tol"]
+
+
+@pytest.mark.parametrize("sf", GOLD["scalar_field"], ids=[s["name"] for s in GOLD["scalar_field"]])
+def test_scalar_field_integrals_on_gpu(ctx, sf):
+    """integ::scalar_field (src/integ/scalar_field.rs:153-230): sum of vec_01_ns entries = int s dOmega."""
+    kind = GeoKind.from_str(sf["kind"])
+    mesh = Mesh.homogeneous(sf["ndim"], np.array(sf["xx"], dtype=float), kind, np.arange(kind.nnode()).reshape(1, -1))
+    dmesh = ctx.upload(mesh)
+    for n in sf["ngauss"]:
+        a = integ.vec_01_ns(ctx, dmesh, None, CommonArgs(ngauss=n), Coef.uniform([1.0]))
+        assert abs(a.sum() - sf.get("volume", sf.get("area"))) <= 1e-13
+        if "int_x2" in sf:
+            pad = po.Scratchpad.new(sf["ndim"], sf["kind"]).set_coords(sf["xx"])
+            x = np.array(po.get_points_coords(pad, po.Gauss(sf["kind"], n)))
+            a2 = integ.vec_01_ns(ctx, dmesh, None, CommonArgs(ngauss=n), Coef.per_gauss(np.sum(x**2, axis=1)))
+            a3 = integ.vec_01_ns(ctx, dmesh, None, CommonArgs(ngauss=n), Coef.per_gauss(np.sum(x**3, axis=1)))
+            assert abs(a2.sum() - sf["int_x2"]) <= 1e-13
+            assert abs(a3.sum() - sf["int_x3"]) <= 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2. distorted meshes of every hot-path kind: all ops, GPU vs oracle
+# ---------------------------------------------------------------------------------------------------------------
+
+def make_mesh(kind, n=5, seed=3):
+    if kind in ("qua4", "qua8", "qua9"):
+        m = Block.new_square(2.0).set_ndiv([n, n + 1]).subdivide(GeoKind.from_str(kind))
+        m.coords[:, 0] += 1.0  # r > 0 for axisymmetric cases
+        return g.jitter_interior_points(m, 0.05 * 2.0 / n, seed)
+    if kind in ("hex8", "hex20"):
+        m = Block.new_cube(1.5).set_ndiv([n, n - 1, n + 1]).subdivide(GeoKind.from_str(kind))
+        return g.jitter_interior_points(m, 0.05 * 1.5 / n, seed)
+    if kind == "tet10":
+        return g.jitter_interior_points(g.split_hex_cells_into_tet10(n, n, n - 1, seed=seed), 0.02 / n, seed)
+    if kind == "tet4":
+        t10 = g.split_hex_cells_into_tet10(n, n, n - 1, seed=seed)
+        conn = t10.conn_matrix()[:, :4]
+        used, inv = np.unique(conn, return_inverse=True)
+        m = Mesh.homogeneous(3, t10.coords[used.astype(np.int64)], GeoKind.Tet4, inv.reshape(-1, 4))
+        return g.jitter_interior_points(m, 0.05 / n, seed)
+    if kind in ("tri3", "tri6"):
+        q = Block.new_square(2.0).set_ndiv([n, n]).subdivide(GeoKind.Qua9 if kind == "tri6" else GeoKind.Qua4)
+        q.coords[:, 0] += 1.0
+        c = q.conn_matrix()
+        if kind == "tri3":
+            tris = np.concatenate([c[:, [0, 1, 2]], c[:, [0, 2, 3]]])
+        else:  # split a Qua9 along the 0-2 diagonal: mid nodes 4 (0-1), 5 (1-2), 8 (centre), 6 (2-3), 7 (3-0)
+            tris = np.concatenate([c[:, [0, 1, 2, 4, 5, 8]], c[:, [0, 2, 3, 8, 6, 7]]])
+        m = Mesh.homogeneous(2, q.coords, GeoKind.from_str(kind), tris)
+        return g.jitter_interior_points(m, 0.04 * 2.0 / n, seed)
+    raise AssertionError(kind)
+
+
+def random_coef(op, ndim, nrec, rng, spd=True):
+    ns = 2 * ndim
+    if op == "mat_10_bdb":
+        a = rng.standard_normal((nrec, ns, ns))
+        d = a @ np.transpose(a, (0, 2, 1)) + ns * np.eye(ns) if spd else a  # column-major flatten of a symmetric matrix
+        return np.ascontiguousarray(np.transpose(d, (0, 2, 1)).reshape(nrec, ns * ns))
+    n = integ.op_coef_size(op, ndim)
+    return rng.standard_normal((nrec, n)) + 2.0
+
+
+SOLID_KINDS = ["tri3", "tri6", "qua4", "qua8", "qua9", "tet4", "tet10", "hex8", "hex20"]
+OPS = ["mat_10_bdb", "mat_01_nsn", "mat_03_btb", "vec_01_ns", "vec_02_nv", "vec_03_bv", "vec_04_bt"]
+
+
+@pytest.mark.parametrize("kind", SOLID_KINDS)
+@pytest.mark.parametrize("op", OPS)
+def test_all_ops_uniform_coefficient(ctx, kind, op):
+    mesh = make_mesh(kind)
+    dmesh = ctx.upload(mesh)
+    rng = np.random.default_rng(11)
+    coef = random_coef(op, mesh.ndim, 1, rng)[0]
+    for axisym in ([False, True] if mesh.ndim == 2 else [False]):
+        args = CommonArgs(alpha=0.7, axisymmetric=axisym)
+        got = getattr(integ, op)(ctx, dmesh, None, args, Coef.uniform(coef))
+        ref = oracle_integ(op, mesh, coef, alpha=0.7, axisymmetric=axisym)
+        off = integ.out_offsets(dmesh, op, None, args)
+        assert off[-1] == ref.size
+        assert rel_err(got, ref, off) <= TOL, f"{kind} {op} axisym={axisym}"
+
+
+@pytest.mark.parametrize("kind", ["qua8", "hex8", "tet10"])
+def test_non_symmetric_modulus_and_rules(ctx, kind):
+    """D need not be major-symmetric (the API only requires minor symmetry); also sweeps the sized Gauss rules."""
+    mesh = make_mesh(kind, n=3)
+    dmesh = ctx.upload(mesh)
+    rng = np.random.default_rng(5)
+    coef = random_coef("mat_10_bdb", mesh.ndim, 1, rng, spd=False)[0]
+    rules = {"qua8": [4, 9, 16], "hex8": [6, 8, 14, 27, 64], "tet10": [4, 5, 8, 14, 15, 24]}[kind]
+    for n in rules:
+        got = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(ngauss=n), Coef.uniform(coef))
+        ref = oracle_integ("mat_10_bdb", mesh, coef, ngauss=n)
+        bs = integ.op_out_size("mat_10_bdb", GeoKind.from_str(kind), mesh.ndim)
+        assert rel_err(got, ref, np.arange(mesh.ncell + 1) * bs) <= TOL, f"{kind} rule {n}"
+
+
+@pytest.mark.parametrize("kind,op", [("hex8", "mat_10_bdb"), ("qua4", "mat_10_bdb"), ("tet10", "mat_01_nsn"),
+                                     ("tri3", "vec_03_bv"), ("qua8", "mat_03_btb"), ("hex20", "vec_04_bt")])
+def test_coefficient_modes(ctx, kind, op):
+    import torch
+
+    mesh = make_mesh(kind, n=4)
+    ncell = mesh.ncell
+    rng = np.random.default_rng(17)
+    mesh.markers[:] = rng.integers(0, 3, ncell) * 10 - 5  # markers -5, 5, 15
+    dmesh = ctx.upload(mesh)
+    ng = g.Gauss.new(GeoKind.from_str(kind)).npoint()
+    clen = integ.op_coef_size(op, mesh.ndim)
+    args = CommonArgs()
+    bs = integ.op_out_size(op, GeoKind.from_str(kind), mesh.ndim)
+    sizes = np.arange(ncell + 1) * bs
+    fn = getattr(integ, op)
+    # PER_MARKER
+    recs = random_coef(op, mesh.ndim, 3, rng)
+    got = fn(ctx, dmesh, None, args, Coef.per_marker([15, -5, 5], recs))
+    per_cell = recs[np.searchsorted([-5, 5, 15], mesh.markers)][:, :]
+    per_cell = recs[[{15: 0, -5: 1, 5: 2}[int(m)] for m in mesh.markers]]
+    ref = oracle_integ(op, mesh, per_cell, cell_stride=clen)
+    assert rel_err(got, ref, sizes) <= TOL
+    # PER_CELL (host) and a sub-range
+    recs = random_coef(op, mesh.ndim, ncell, rng)
+    got = fn(ctx, dmesh, None, args, Coef.per_cell(recs))
+    ref = oracle_integ(op, mesh, recs, cell_stride=clen)
+    assert rel_err(got, ref, sizes) <= TOL
+    b, e = ncell // 3, ncell - 2
+    got = fn(ctx, dmesh, (b, e), args, Coef.per_cell(recs[b:e]))
+    assert rel_err(got, ref[b * bs:e * bs], sizes[: e - b + 1]) <= TOL
+    # PER_GAUSS from a device tensor, device output
+    recs = random_coef(op, mesh.ndim, ncell * ng, rng)
+    out = torch.full((ncell * bs,), 7.0, dtype=torch.float64, device="cuda")
+    fn(ctx, dmesh, None, args, Coef.per_gauss(torch.from_numpy(recs).cuda()), out=out)
+    ctx.sync()
+    ref = oracle_integ(op, mesh, recs, cell_stride=ng * clen, gp_stride=clen)
+    assert rel_err(out.cpu().numpy(), ref, sizes) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3. layout: mixed kinds, cell ranges, offsets, accumulation, ii0/jj0
+# ---------------------------------------------------------------------------------------------------------------
+
+def mixed_mesh_2d(n=6, seed=2):
+    """Config 5 shape: alternating stripes of Qua8 cells and Qua -> 2 x Tri3 splits over x in [1, 3]."""
+    q8 = Block.new_square(2.0).set_ndiv([n, n]).subdivide(GeoKind.Qua8)
+    q8.coords[:, 0] += 1.0
+    c = q8.conn_matrix()
+    cells = []
+    for e in range(q8.ncell):
+        row = e // n
+        if row % 2 == 0:
+            cells.append((GeoKind.Qua8, c[e]))
+        else:
+            cells.append((GeoKind.Tri3, c[e, [0, 1, 2]]))
+            cells.append((GeoKind.Tri3, c[e, [0, 2, 3]]))
+    m = Mesh.from_cells(2, q8.coords, cells)
+    return g.jitter_interior_points(m, 0.01, seed)
+
+
+@pytest.mark.parametrize("op", ["mat_10_bdb", "mat_03_btb", "vec_03_bv", "vec_01_ns"])
+def test_mixed_kind_mesh_layout_and_values(ctx, op):
+    mesh = mixed_mesh_2d()
+    dmesh = ctx.upload(mesh)
+    rng = np.random.default_rng(23)
+    coef = random_coef(op, 2, 1, rng)[0]
+    args = CommonArgs(axisymmetric=True)
+    off = integ.out_offsets(dmesh, op, None, args)
+    sizes = np.array([integ.op_out_size(op, GeoKind(int(k)), 2) for k in mesh.kinds])
+    np.testing.assert_array_equal(off, np.concatenate([[0], np.cumsum(sizes)]))  # exact layout
+    got = getattr(integ, op)(ctx, dmesh, None, args, Coef.uniform(coef))
+    ref = oracle_integ(op, mesh, coef, axisymmetric=True)
+    assert rel_err(got, ref, off) <= TOL
+    # a range that starts and ends inside different stripes
+    b, e = 4, mesh.ncell - 5
+    sub = getattr(integ, op)(ctx, dmesh, (b, e), args, Coef.uniform(coef))
+    np.testing.assert_array_equal(sub, got[int(off[b]):int(off[e])])  # same arithmetic => bit-identical
+
+
+def test_partition_concatenation_is_bit_identical(ctx):
+    mesh = make_mesh("hex8", n=6)
+    dmesh = ctx.upload(mesh)
+    dd = g.mandel_matrix(g.lin_elasticity(480.0, 1 / 3, False))
+    full = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.uniform(dd))
+    for world in (2, 3, 8):
+        parts = [integ.mat_10_bdb(ctx, dmesh, g.partition(mesh.ncell, world, r), CommonArgs(), Coef.uniform(dd))
+                 for r in range(world)]
+        np.testing.assert_array_equal(np.concatenate(parts), full)
+
+
+def test_clear_false_accumulates_and_offsets(ctx):
+    mesh = make_mesh("qua4", n=3)
+    dmesh = ctx.upload(mesh)
+    dd = g.mandel_matrix(g.lin_elasticity(10_000.0, 0.2, True))
+    base = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.uniform(dd))
+    out = np.full(base.size, 1234.56)
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(clear=False), Coef.uniform(dd), out=out)
+    np.testing.assert_allclose(out, base + 1234.56, rtol=1e-15, atol=0)
+    # ii0 / jj0 inside a larger (nrow x ncol) block, as for coupled elements (CommonArgs.ii0/jj0)
+    args = CommonArgs(ii0=2, jj0=3, nrow=12, ncol=13)
+    blk = integ.mat_10_bdb(ctx, dmesh, None, args, Coef.uniform(dd)).reshape(mesh.ncell, 13, 12)  # [cell][col][row]
+    kk = base.reshape(mesh.ncell, 8, 8)
+    np.testing.assert_array_equal(blk[:, 3:11, 2:10], kk)
+    assert np.count_nonzero(blk) == np.count_nonzero(kk)
+    # empty range
+    assert integ.mat_10_bdb(ctx, dmesh, (2, 2), CommonArgs(), Coef.uniform(dd)).size == 0
+
+
+def test_host_path_chunking_matches_device_path(ctx):
+    """The host-output path pipelines 128 MiB chunks; results must equal the device path bit for bit."""
+    import torch
+
+    mesh = Block.new_cube(1.0).set_ndiv([40, 40, 30]).subdivide(GeoKind.Hex8)  # 48k cells * 4608 B = 221 MB -> 2 chunks
+    dmesh = ctx.upload(mesh)
+    dd = g.mandel_matrix(g.lin_elasticity(480.0, 1 / 3, False))
+    host = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.uniform(dd))
+    dev = torch.empty(host.size, dtype=torch.float64, device="cuda")
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.uniform(dd), out=dev)
+    ctx.sync()
+    np.testing.assert_array_equal(host, dev.cpu().numpy())
+    # every cell of an undistorted block has the same matrix; rigid translations are in the null space
+    k0 = host[:576].reshape(24, 24, order="F")
+    np.testing.assert_allclose(host.reshape(-1, 576), np.broadcast_to(host[:576], (mesh.ncell, 576)), rtol=0, atol=1e-11)
+    for i in range(3):
+        t = np.zeros(24)
+        t[i::3] = 1.0
+        assert np.max(np.abs(k0 @ t)) <= 1e-12 * np.max(np.abs(k0))
+    np.testing.assert_allclose(k0, k0.T, rtol=0, atol=1e-12 * np.max(np.abs(k0)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 4. error behaviour (the reference's strings)
+# ---------------------------------------------------------------------------------------------------------------
+
+def test_error_strings(ctx):
+    mesh = make_mesh("qua4", n=2)
+    dmesh = ctx.upload(mesh)
+    dd = Coef.uniform(g.mandel_matrix(g.lin_elasticity(1.0, 0.25, True)))
+    with pytest.raises(g.GemlabError, match=r"nrow\(K\) must be ≥ ii0 \+ nnode ⋅ space_ndim"):
+        integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(ii0=1, nrow=8, ncol=8), dd)
+    with pytest.raises(g.GemlabError, match=r"ncol\(K\) must be ≥ jj0 \+ nnode ⋅ space_ndim"):
+        integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(jj0=1, nrow=8, ncol=8), dd)
+    with pytest.raises(g.GemlabError, match=r"nrow\(K\) must be ≥ ii0 \+ nnode$"):
+        integ.mat_01_nsn(ctx, dmesh, None, CommonArgs(ii0=1, nrow=4, ncol=4), Coef.uniform([1.0]))
+    with pytest.raises(g.GemlabError, match=r"a.len\(\) must be ≥ ii0 \+ nnode"):
+        integ.vec_01_ns(ctx, dmesh, None, CommonArgs(ii0=1, nrow=4), Coef.uniform([1.0]))
+    with pytest.raises(g.GemlabError, match="not available for Qua class"):
+        integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(ngauss=5), dd)
+    with pytest.raises(g.GemlabError, match="cell range is out of bounds"):
+        integ.mat_10_bdb(ctx, dmesh, (0, mesh.ncell + 1), CommonArgs(), dd)
+    # axisymmetric needs 2D
+    m3 = make_mesh("tet4", n=2)
+    d3 = ctx.upload(m3)
+    with pytest.raises(g.GemlabError, match="axisymmetric requires space_ndim = 2"):
+        integ.mat_10_bdb(ctx, d3, None, CommonArgs(axisymmetric=True), Coef.uniform(np.eye(6).ravel()))
+    # cable cells: gradient-based cases fail, N-based cases work (src/integ/vec_01_ns.rs works on Lin2 in 2D)
+    lin = Mesh.homogeneous(2, np.array([[3.0, 4.0], [3.0 + 6 / np.sqrt(2), 4.0 + 6 / np.sqrt(2)]]), GeoKind.Lin2, [[0, 1]])
+    dl = ctx.upload(lin)
+    with pytest.raises(g.GemlabError, match="calc_gradient requires that geo_ndim = space_ndim"):
+        integ.mat_01_nsn(ctx, dl, None, CommonArgs(), Coef.uniform([1.0]))
+    a = integ.vec_01_ns(ctx, dl, None, CommonArgs(), Coef.uniform([2.0]))
+    np.testing.assert_allclose(a, [6.0, 6.0], rtol=1e-15)
+    # zero determinant: reports the smallest failing cell id
+    bad = make_mesh("qua4", n=3)
+    c = bad.conn_matrix()
+    bad.coords[c[4]] = bad.coords[c[4, 0]]  # collapse cell 4 (also damages its neighbours' geometry, not their det)
+    db = ctx.upload(bad)
+    with pytest.raises(g.GemlabError, match="cannot compute inverse due to zero determinant") as ei:
+        integ.mat_10_bdb(ctx, db, None, CommonArgs(), dd)
+    assert ei.value.cell == 4
+    # the context stays usable afterwards
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), dd)
+
+
+def test_check_jacobian_loop(ctx):
+    """Mesh::check_jacobian (src/mesh/check.rs:43-60): det J at ksi = [1/3, 1/3, 1/3] for every cell."""
+    mesh = make_mesh("tet10", n=3)
+    dmesh = ctx.upload(mesh)
+    ksi = [1 / 3, 1 / 3, 1 / 3]
+    got = integ.jacobian(ctx, dmesh, None, ksi)
+    ref = oracle_integ("jacobian", mesh, ksi=ksi)
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=0)
+    assert np.all(got > 0)
