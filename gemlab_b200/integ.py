@@ -188,9 +188,9 @@ class Context:
         return DeviceMesh(self, h, mesh.ndim, mesh.ncell, mesh.npoint, mesh.kinds.copy())
 
     def fp64_peak(self, kind="dfma", iters=4096):
-        """Measured FP64 peak of this device in TFLOP/s (kind: 'dfma' or 'dmma')."""
+        """Measured FP64 peak of this device in TFLOP/s (kind: 'dfma', 'dmma' or 'mixed' = both interleaved)."""
         t = C.c_double()
-        st = lib().gl_bench_fp64_peak(self._h, 0 if kind == "dfma" else 1, int(iters), C.byref(t))
+        st = lib().gl_bench_fp64_peak(self._h, {"dfma": 0, "dmma": 1, "mixed": 2}[kind], int(iters), C.byref(t))
         if st:
             self._raise(st)
         return t.value

@@ -128,6 +128,7 @@ class Block:
             raise ValueError("ndim must be 2 or 3")
         ref = (_QUA_REF[:8] if ndim == 2 else _HEX_REF).astype(np.float64)
         ncorner, nfull = (4, 8) if ndim == 2 else (8, 20)
+        self._corners = coords.copy() if coords.shape[0] == ncorner else None
         if coords.shape[0] == ncorner:
             # Block::new accepts corners only and generates the mid nodes on straight edges (block.rs:225-262)
             lin = np.ones((nfull, ncorner))
@@ -214,7 +215,16 @@ class Block:
         coords = np.empty((lp.shape[0], ndim))
         step = 1 << 20
         for s in range(0, lp.shape[0], step):
-            coords[s:s + step] = _serendipity_interp(bref, ksi[s:s + step]) @ self.coords
+            k = ksi[s:s + step]
+            if self._corners is not None:
+                # straight-edged block: the Qua8/Hex20 serendipity map reduces to the bi/tri-linear map of the corners
+                ncorner = self._corners.shape[0]
+                lin = np.full((k.shape[0], ncorner), 0.25 if ndim == 2 else 0.125)
+                for d in range(ndim):
+                    lin *= 1.0 + k[:, [d]] * bref[None, :ncorner, d]
+                coords[s:s + step] = lin @ self._corners
+            else:
+                coords[s:s + step] = _serendipity_interp(bref, k) @ self.coords
         markers = np.full(ncell, self.cell_marker, dtype=np.int32)
         return Mesh.homogeneous(ndim, coords, target, conn.astype(np.uint64), markers)
 

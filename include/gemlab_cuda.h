@@ -235,7 +235,7 @@ GL_API void gl_lin_elasticity(double young, double poisson, int two_dim, int pla
 
 /* ---- micro-benchmarks used to measure the FP64 roofline denominators on the device (bench.py) ---- */
 /* runs `iters` dependent-chain DFMA (kind 0) or DMMA m8n8k4 (kind 1) per thread on the whole device and returns the
- * achieved TFLOP/s measured with CUDA events */
+ * achieved TFLOP/s measured with CUDA events; kind 2 interleaves both */
 GL_API int gl_bench_fp64_peak(gl_ctx *ctx, int kind, int iters, double *tflops);
 
 #ifdef __cplusplus
