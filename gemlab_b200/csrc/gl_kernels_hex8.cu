@@ -16,6 +16,8 @@
 // hits 16 distinct bank pairs in phases 1 and 2.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "gl_internal.hpp"
 
 namespace gl {
@@ -36,8 +38,21 @@ struct Hex8Consts {
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <bool SYM>
+// structure of the (Mandel-scaled) modulus d', decided on the host from the coefficient record:
+//   PAT 0  general (minor-symmetric only): all 8 row blocks per lane
+//   PAT 1  major-symmetric d' = d'^T      : K is symmetric -> circulant half + mirror
+//   PAT 2  PAT 1 and d' = [A 0; 0 diag]   : normal/shear uncoupled with a diagonal shear block (isotropic and
+//          axis-aligned orthotropic elasticity): the structural zeros of T = d'.M are skipped, which is exact
+//          (the skipped terms are products with an exact 0)
+__host__ __device__ constexpr bool d_nz(int pat, int a, int b) { return pat < 2 ? true : ((a < 3 && b < 3) || a == b); }
+// rows of the strain-displacement column (n, j) that are non-zero, and which gradient component sits there
+__host__ __device__ constexpr int col_row(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 3 : 5)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 3 : 4)) : (t == 0 ? 2 : (t == 1 ? 4 : 5))); }
+__host__ __device__ constexpr int col_comp(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 1 : 2)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 0 : 2)) : (t == 0 ? 2 : (t == 1 ? 1 : 0))); }
+__host__ __device__ constexpr bool t_nz(int pat, int a, int j) { return d_nz(pat, a, col_row(j, 0)) || d_nz(pat, a, col_row(j, 1)) || d_nz(pat, a, col_row(j, 2)); }
+
+template <int PAT, int GP_UNROLL_N>
 __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegParams p, const Hex8Consts cst) {
+    constexpr bool SYM = PAT >= 1;
     constexpr int ND = SYM ? 5 : 8; // node-pair blocks per lane
     extern __shared__ __align__(16) double smem[];
     double *s_L = smem;                         // [8][L_STRIDE]  L[gp][m*3+j]
@@ -143,32 +158,49 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
 #pragma unroll
             for (int q = 0; q < 9; q++) acc[b][q] = 0.0;
 
-#pragma unroll 1
+#pragma unroll GP_UNROLL_N
         for (int gp = 0; gp < 8; gp++) {
             const double *Bg = Bc + gp * GP_STRIDE;
             const double c = Bg[24];
-            const double b0 = Bg[g * 3 + 0] * c, b1 = Bg[g * 3 + 1] * c, b2 = Bg[g * 3 + 2] * c;
-            // T[a][j] = sum_b d'[a][b] M'(n)[b][j] with M' columns: j=0 -> rows (0,3,5) = (b0,b1,b2);
-            //                                                      j=1 -> rows (1,3,4) = (b1,b0,b2);
-            //                                                      j=2 -> rows (2,4,5) = (b2,b1,b0)
+            const double bn[3] = {Bg[g * 3 + 0] * c, Bg[g * 3 + 1] * c, Bg[g * 3 + 2] * c};
+            // T[a][j] = sum_t d'[a][row(j,t)] * bn[comp(j,t)]: column (n,j) of M' has the gradient components
+            // j=0 -> rows (0,3,5) = (b0,b1,b2); j=1 -> rows (1,3,4) = (b1,b0,b2); j=2 -> rows (2,4,5) = (b2,b1,b0)
             double T[6][3];
 #pragma unroll
-            for (int a = 0; a < 6; a++) {
-                T[a][0] = fma(cst.d[a * 6 + 5], b2, fma(cst.d[a * 6 + 3], b1, cst.d[a * 6 + 0] * b0));
-                T[a][1] = fma(cst.d[a * 6 + 4], b2, fma(cst.d[a * 6 + 3], b0, cst.d[a * 6 + 1] * b1));
-                T[a][2] = fma(cst.d[a * 6 + 5], b0, fma(cst.d[a * 6 + 4], b1, cst.d[a * 6 + 2] * b2));
-            }
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double t = 0.0;
+                    bool have = false;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        if (d_nz(PAT, a, col_row(j, q))) {
+                            const double dv = cst.d[a * 6 + col_row(j, q)], bv = bn[col_comp(j, q)];
+                            t = have ? fma(dv, bv, t) : dv * bv;
+                            have = true;
+                        }
+                    }
+                    T[a][j] = t;
+                }
 #pragma unroll
             for (int b = 0; b < ND; b++) {
                 const int m = (g + b) & 7;
-                const double m0 = Bg[m * 3 + 0], m1 = Bg[m * 3 + 1], m2 = Bg[m * 3 + 2];
+                const double bm[3] = {Bg[m * 3 + 0], Bg[m * 3 + 1], Bg[m * 3 + 2]};
+                // In the symmetric variants the diagonal block (b = 0) is itself symmetric, and the block at distance 4 is
+                // held as a transposed duplicate by lane g+4: both need only their upper triangles (i <= j).
+                const bool tri = SYM && (b == 0 || b == 4);
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    // rows of M'(m): i=0 -> (0:m0, 3:m1, 5:m2); i=1 -> (1:m1, 3:m0, 4:m2); i=2 -> (2:m2, 4:m1, 5:m0)
-                    acc[b][0 + 3 * j] = fma(m0, T[0][j], fma(m1, T[3][j], fma(m2, T[5][j], acc[b][0 + 3 * j])));
-                    acc[b][1 + 3 * j] = fma(m1, T[1][j], fma(m0, T[3][j], fma(m2, T[4][j], acc[b][1 + 3 * j])));
-                    acc[b][2 + 3 * j] = fma(m2, T[2][j], fma(m1, T[4][j], fma(m0, T[5][j], acc[b][2 + 3 * j])));
-                }
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        if (tri && i > j) continue;
+                        // K(3m+i, 3n+j) += sum_t M'(m)[row(i,t)][i] * T[row(i,t)][j]
+                        double v = acc[b][i + 3 * j];
+#pragma unroll
+                        for (int q = 2; q >= 0; q--)
+                            if (t_nz(PAT, col_row(i, q), j)) v = fma(bm[col_comp(i, q)], T[col_row(i, q)][j], v);
+                        acc[b][i + 3 * j] = v;
+                    }
             }
         }
 
@@ -179,13 +211,16 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
 #pragma unroll
         for (int b = 0; b < ND; b++) {
             const int m = (g + b) & 7;
+            const bool tri = SYM && (b == 0 || b == 4);
 #pragma unroll
             for (int j = 0; j < 3; j++)
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
+                    if (tri && i > j) continue; // lower triangle comes from the mirror (b = 0) or from lane g+4 (b = 4)
                     const double v = acc[b][i + 3 * j];
                     Kc[(3 * m + i) + 24 * (3 * g + j)] = v;
-                    if (SYM && b >= 1 && b <= 3) Kc[(3 * g + j) + 24 * (3 * m + i)] = v; // mirrored block K(n,m) = K(m,n)^T
+                    // mirrored entry K(n,m)^T: whole blocks at distance 1..3, strict upper triangles of the b = 0 / b = 4 blocks
+                    if (SYM && ((b >= 1 && b <= 3) || (tri && i < j))) Kc[(3 * g + j) + 24 * (3 * m + i)] = v;
                 }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -230,12 +265,29 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
             cst.d[a * 6 + b] = p.coef_uniform[a + b * 6] * fa * fb; // ABI record is column-major
             if (p.coef_uniform[a + b * 6] != p.coef_uniform[b + a * 6]) sym = false;
         }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(hex8_bdb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8_SMEM) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(hex8_bdb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8_SMEM) != cudaSuccess) return -1;
-        attr_set = true;
+    // unroll factor of the Gauss-point loop (tuning knob; GL_HEX8_UNROLL overrides the default)
+    static int unroll = -1;
+    if (unroll < 0) {
+        const char *e = getenv("GL_HEX8_UNROLL");
+        unroll = e ? atoi(e) : 1;
+        if (unroll != 1 && unroll != 2) unroll = 1;
     }
+    int pat = 0;
+    if (sym) {
+        pat = 2;
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++)
+                if (!d_nz(2, a, b) && cst.d[a * 6 + b] != 0.0) pat = 1;
+    }
+    {
+        const char *e = getenv("GL_HEX8_PATTERN"); // tuning/testing knob: cap the specialisation level
+        if (e && atoi(e) < pat) pat = atoi(e) < 0 ? 0 : atoi(e);
+    }
+    typedef void (*kern_t)(const IntegParams, const Hex8Consts);
+    kern_t kern;
+    if (unroll == 2) kern = pat == 2 ? hex8_bdb_kernel<2, 2> : (pat == 1 ? hex8_bdb_kernel<1, 2> : hex8_bdb_kernel<0, 2>);
+    else kern = pat == 2 ? hex8_bdb_kernel<2, 1> : (pat == 1 ? hex8_bdb_kernel<1, 1> : hex8_bdb_kernel<0, 1>);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8_SMEM) != cudaSuccess) return -1;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -243,8 +295,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     unsigned long long grid = (unsigned long long)nsm * 2; // persistent: two resident CTAs per SM
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
-    if (sym) hex8_bdb_kernel<true><<<(unsigned)grid, H8_THREADS, H8_SMEM, (cudaStream_t)stream>>>(p, cst);
-    else hex8_bdb_kernel<false><<<(unsigned)grid, H8_THREADS, H8_SMEM, (cudaStream_t)stream>>>(p, cst);
+    kern<<<(unsigned)grid, H8_THREADS, H8_SMEM, (cudaStream_t)stream>>>(p, cst);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
