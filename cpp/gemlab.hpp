@@ -1,0 +1,198 @@
+// gemlab.hpp -- header-only C++ host mirror of gemlab's integration interface over the C ABI (include/gemlab_cuda.h).
+//
+// The reference is compiled Rust and its toolchain is not in the authoring image, so the compiled-language host side is
+// written in C++ with the reference's names and argument meaning:
+//   gemlab::GeoKind                         src/shapes/enums.rs:116-176 (VALUES order)
+//   gemlab::Point / Cell / Mesh             src/mesh/mesh.rs:27-54, 110-135 (array-of-structures, exactly as the reference)
+//   gemlab::integ::CommonArgs               src/integ/common_args.rs:5-43 (pad and gauss are implied by the mesh / ngauss)
+//   gemlab::integ::batch::mat_10_bdb(...)   src/integ/mat_10_bdb.rs:121  -- and the siblings mat_01_nsn, mat_03_btb,
+//                                           vec_01_ns, vec_02_nv, vec_03_bv, vec_04_bt
+// Errors are thrown as gemlab::StrError carrying the reference's strings.
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../include/gemlab_cuda.h"
+
+namespace gemlab {
+
+enum class GeoKind : uint8_t {
+    Lin2, Lin3, Lin4, Lin5, Tri3, Tri6, Tri10, Tri15, Qua4, Qua8, Qua9, Qua12, Qua16, Qua17, Tet4, Tet10, Tet20, Hex8, Hex20, Hex32
+};
+
+struct StrError : std::runtime_error {
+    int status;
+    uint64_t cell;
+    StrError(int st, const std::string &msg, uint64_t c = ~0ull) : std::runtime_error(msg), status(st), cell(c) {}
+};
+
+struct Point {
+    size_t id;
+    int marker;
+    std::vector<double> coords;
+};
+
+struct Cell {
+    size_t id;
+    int marker;
+    GeoKind kind;
+    std::vector<size_t> points;
+};
+
+struct Mesh {
+    size_t ndim = 0;
+    std::vector<Point> points;
+    std::vector<Cell> cells;
+};
+
+class Context;
+
+class DeviceMesh {
+  public:
+    DeviceMesh(const DeviceMesh &) = delete;
+    DeviceMesh(DeviceMesh &&o) noexcept : ctx_(o.ctx_), mesh_(o.mesh_) { o.mesh_ = nullptr; }
+    ~DeviceMesh() {
+        if (mesh_) gl_mesh_free(ctx_, mesh_);
+    }
+    size_t ncell() const { return (size_t)gl_mesh_ncell(mesh_); }
+    const gl_mesh *handle() const { return mesh_; }
+
+  private:
+    friend class Context;
+    DeviceMesh(gl_ctx *ctx, gl_mesh *mesh) : ctx_(ctx), mesh_(mesh) {}
+    gl_ctx *ctx_;
+    gl_mesh *mesh_;
+};
+
+class Context {
+  public:
+    explicit Context(int device = 0, void *stream = nullptr) {
+        int st = gl_ctx_create(device, stream, &ctx_);
+        if (st) throw StrError(st, gl_status_string(st));
+    }
+    Context(const Context &) = delete;
+    ~Context() { gl_ctx_destroy(ctx_); }
+
+    // flattens the AoS Mesh and uploads it (replaces the per-cell Mesh::set_pad, src/mesh/mesh.rs:448-456)
+    DeviceMesh upload(const Mesh &mesh) {
+        std::vector<double> coords;
+        coords.reserve(mesh.points.size() * mesh.ndim);
+        for (const auto &p : mesh.points) coords.insert(coords.end(), p.coords.begin(), p.coords.begin() + mesh.ndim);
+        std::vector<uint8_t> kinds;
+        std::vector<int32_t> markers;
+        std::vector<uint64_t> off{0}, conn;
+        for (const auto &c : mesh.cells) {
+            kinds.push_back((uint8_t)c.kind);
+            markers.push_back(c.marker);
+            for (size_t p : c.points) conn.push_back((uint64_t)p);
+            off.push_back(conn.size());
+        }
+        gl_mesh *h = nullptr;
+        int st = gl_mesh_upload(ctx_, (int)mesh.ndim, mesh.points.size(), coords.data(), mesh.cells.size(), kinds.data(),
+                                markers.data(), off.data(), conn.data(), &h);
+        check(st);
+        return DeviceMesh(ctx_, h);
+    }
+    void sync() { check(gl_ctx_sync(ctx_)); }
+    gl_ctx *handle() const { return ctx_; }
+    void check(int st) const {
+        if (st) throw StrError(st, gl_last_error(ctx_), gl_last_error_cell(ctx_));
+    }
+
+  private:
+    gl_ctx *ctx_ = nullptr;
+};
+
+namespace integ {
+
+// CommonArgs::new defaults: clear = true, axisymmetric = false, alpha = 1, ii0 = jj0 = 0
+struct CommonArgs {
+    int ngauss = 0; // 0 = Gauss::new(kind)
+    bool clear = true;
+    bool axisymmetric = false;
+    double alpha = 1.0;
+    unsigned ii0 = 0, jj0 = 0, nrow = 0, ncol = 0;
+    gl_args c() const {
+        gl_args a;
+        gl_args_default(&a);
+        a.ngauss = ngauss;
+        a.clear = clear;
+        a.axisymmetric = axisymmetric;
+        a.alpha = alpha;
+        a.ii0 = ii0;
+        a.jj0 = jj0;
+        a.nrow = nrow;
+        a.ncol = ncol;
+        return a;
+    }
+};
+
+// coefficient data replacing the reference's closures
+struct Coef {
+    gl_coef_mode mode = GL_COEF_UNIFORM;
+    std::vector<double> data;
+    std::vector<int32_t> markers;
+    static Coef uniform(std::vector<double> record) { return Coef{GL_COEF_UNIFORM, std::move(record), {}}; }
+    static Coef per_marker(std::vector<int32_t> m, std::vector<double> records) { return Coef{GL_COEF_PER_MARKER, std::move(records), std::move(m)}; }
+    static Coef per_cell(std::vector<double> records) { return Coef{GL_COEF_PER_CELL, std::move(records), {}}; }
+    static Coef per_gauss(std::vector<double> records) { return Coef{GL_COEF_PER_GAUSS, std::move(records), {}}; }
+};
+
+// LinElasticity::new(E, nu, two_dim, plane_stress).get_modulus().matrix(), column-major
+inline std::vector<double> lin_elasticity(double young, double poisson, bool two_dim, bool plane_stress = false) {
+    std::vector<double> dd(two_dim ? 16 : 36);
+    gl_lin_elasticity(young, poisson, two_dim, plane_stress, dd.data());
+    return dd;
+}
+
+namespace batch {
+
+inline std::vector<double> run(int op, Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args,
+                               const Coef *coef) {
+    gl_args a = args.c();
+    uint64_t total = 0;
+    if (int st = gl_out_total(mesh.handle(), op, cells.first, cells.second, &a, &total)) throw StrError(st, gl_status_string(st));
+    std::vector<double> out(total);
+    gl_out o{out.data(), GL_HOST, 0, total};
+    gl_coef c{};
+    if (coef) {
+        c.mode = coef->mode;
+        c.location = GL_HOST;
+        c.data = coef->data.data();
+        c.markers = coef->markers.empty() ? nullptr : coef->markers.data();
+        c.nrecord = coef->markers.size();
+    }
+    ctx.check(gl_integ(ctx.handle(), mesh.handle(), op, cells.first, cells.second, &a, coef ? &c : nullptr, &o));
+    return out;
+}
+
+// element e of the range occupies out[e*size .. (e+1)*size) (homogeneous mesh), column-major, ii = i + m*ndim
+inline std::vector<double> mat_10_bdb(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &dd) {
+    return run(GL_OP_MAT_10_BDB, ctx, mesh, cells, args, &dd);
+}
+inline std::vector<double> mat_01_nsn(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &s) {
+    return run(GL_OP_MAT_01_NSN, ctx, mesh, cells, args, &s);
+}
+inline std::vector<double> mat_03_btb(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &tt) {
+    return run(GL_OP_MAT_03_BTB, ctx, mesh, cells, args, &tt);
+}
+inline std::vector<double> vec_01_ns(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &s) {
+    return run(GL_OP_VEC_01_NS, ctx, mesh, cells, args, &s);
+}
+inline std::vector<double> vec_02_nv(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &v) {
+    return run(GL_OP_VEC_02_NV, ctx, mesh, cells, args, &v);
+}
+inline std::vector<double> vec_03_bv(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &w) {
+    return run(GL_OP_VEC_03_BV, ctx, mesh, cells, args, &w);
+}
+inline std::vector<double> vec_04_bt(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &sig) {
+    return run(GL_OP_VEC_04_BT, ctx, mesh, cells, args, &sig);
+}
+
+} // namespace batch
+} // namespace integ
+} // namespace gemlab

@@ -1,0 +1,145 @@
+//! Raw bindings to the C ABI declared in `include/gemlab_cuda.h` (one `extern "C"` item per `GL_API` symbol).
+#![allow(non_camel_case_types)]
+
+use std::os::raw::{c_char, c_double, c_int, c_void};
+
+#[repr(C)]
+pub struct gl_ctx {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct gl_mesh {
+    _private: [u8; 0],
+}
+
+pub const GL_OK: c_int = 0;
+pub const GL_ERR_ZERO_DET: c_int = 2;
+
+pub const GL_OP_MAT_10_BDB: c_int = 0;
+pub const GL_OP_MAT_01_NSN: c_int = 1;
+pub const GL_OP_MAT_03_BTB: c_int = 2;
+pub const GL_OP_VEC_01_NS: c_int = 3;
+pub const GL_OP_VEC_03_BV: c_int = 4;
+pub const GL_OP_VEC_02_NV: c_int = 5;
+pub const GL_OP_VEC_04_BT: c_int = 6;
+pub const GL_OP_JACOBIAN: c_int = 8;
+
+pub const GL_HOST: i32 = 0;
+pub const GL_DEVICE: i32 = 1;
+
+pub const GL_COEF_UNIFORM: i32 = 0;
+pub const GL_COEF_PER_MARKER: i32 = 1;
+pub const GL_COEF_PER_CELL: i32 = 2;
+pub const GL_COEF_PER_GAUSS: i32 = 3;
+
+/// `struct gl_args` -- mirrors `gemlab::integ::CommonArgs` (src/integ/common_args.rs:5-43)
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct gl_args {
+    pub ngauss: i32,
+    pub axisymmetric: i32,
+    pub clear: i32,
+    pub reserved: i32,
+    pub alpha: c_double,
+    pub ii0: u32,
+    pub jj0: u32,
+    pub nrow: u32,
+    pub ncol: u32,
+    pub ksi: [c_double; 3],
+}
+
+#[repr(C)]
+pub struct gl_coef {
+    pub mode: i32,
+    pub location: i32,
+    pub data: *const c_double,
+    pub markers: *const i32,
+    pub nrecord: u64,
+}
+
+#[repr(C)]
+pub struct gl_out {
+    pub ptr: *mut c_double,
+    pub location: i32,
+    pub reserved: i32,
+    pub capacity: u64,
+}
+
+extern "C" {
+    pub fn gl_ctx_create(device: c_int, stream: *mut c_void, ctx: *mut *mut gl_ctx) -> c_int;
+    pub fn gl_ctx_destroy(ctx: *mut gl_ctx);
+    pub fn gl_ctx_set_stream(ctx: *mut gl_ctx, stream: *mut c_void) -> c_int;
+    pub fn gl_ctx_sync(ctx: *mut gl_ctx) -> c_int;
+    pub fn gl_last_error(ctx: *const gl_ctx) -> *const c_char;
+    pub fn gl_last_error_cell(ctx: *const gl_ctx) -> u64;
+    pub fn gl_status_string(status: c_int) -> *const c_char;
+    pub fn gl_ctx_launch_count(ctx: *const gl_ctx) -> u64;
+
+    pub fn gl_kind_nnode(kind: c_int) -> c_int;
+    pub fn gl_kind_geo_ndim(kind: c_int) -> c_int;
+    pub fn gl_kind_class(kind: c_int) -> c_int;
+    pub fn gl_kind_from_name(name: *const c_char) -> c_int;
+    pub fn gl_kind_name(kind: c_int) -> *const c_char;
+    pub fn gl_kind_supported(kind: c_int) -> c_int;
+    pub fn gl_gauss_rule(kind: c_int, ngauss: c_int, npoint: *mut c_int, data: *mut *const c_double) -> c_int;
+    pub fn gl_shape_eval(kind: c_int, ksi: *const c_double, nn: *mut c_double, ll: *mut c_double) -> c_int;
+
+    pub fn gl_mesh_upload(
+        ctx: *mut gl_ctx,
+        ndim: c_int,
+        npoint: u64,
+        coords: *const c_double,
+        ncell: u64,
+        kinds: *const u8,
+        markers: *const i32,
+        conn_off: *const u64,
+        conn: *const u64,
+        mesh: *mut *mut gl_mesh,
+    ) -> c_int;
+    pub fn gl_mesh_upload_homogeneous(
+        ctx: *mut gl_ctx,
+        ndim: c_int,
+        npoint: u64,
+        coords: *const c_double,
+        ncell: u64,
+        kind: c_int,
+        markers: *const i32,
+        conn: *const u32,
+        mesh: *mut *mut gl_mesh,
+    ) -> c_int;
+    pub fn gl_mesh_update_coords(ctx: *mut gl_ctx, mesh: *mut gl_mesh, coords: *const c_double, location: c_int) -> c_int;
+    pub fn gl_mesh_free(ctx: *mut gl_ctx, mesh: *mut gl_mesh);
+    pub fn gl_mesh_ncell(mesh: *const gl_mesh) -> u64;
+    pub fn gl_mesh_npoint(mesh: *const gl_mesh) -> u64;
+    pub fn gl_mesh_ndim(mesh: *const gl_mesh) -> c_int;
+
+    pub fn gl_op_out_size(op: c_int, kind: c_int, ndim: c_int) -> u64;
+    pub fn gl_op_coef_size(op: c_int, ndim: c_int) -> u64;
+    pub fn gl_out_total(mesh: *const gl_mesh, op: c_int, cell_begin: u64, cell_end: u64, args: *const gl_args, total: *mut u64) -> c_int;
+    pub fn gl_out_offsets(mesh: *const gl_mesh, op: c_int, cell_begin: u64, cell_end: u64, args: *const gl_args, off: *mut u64) -> c_int;
+
+    pub fn gl_integ(
+        ctx: *mut gl_ctx,
+        mesh: *const gl_mesh,
+        op: c_int,
+        cell_begin: u64,
+        cell_end: u64,
+        args: *const gl_args,
+        coef: *const gl_coef,
+        out: *mut gl_out,
+    ) -> c_int;
+    pub fn gl_mat_10_bdb(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_01_nsn(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_03_btb(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_vec_01_ns(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_vec_02_nv(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_vec_03_bv(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_vec_04_bt(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_jacobian(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_10_gdg(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_vec_10_gs(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+
+    pub fn gl_args_default(args: *mut gl_args);
+    pub fn gl_lin_elasticity(young: c_double, poisson: c_double, two_dim: c_int, plane_stress: c_int, dd: *mut c_double);
+    pub fn gl_bench_fp64_peak(ctx: *mut gl_ctx, kind: c_int, iters: c_int, tflops: *mut c_double) -> c_int;
+}

@@ -379,3 +379,16 @@ def test_check_jacobian_loop(ctx):
     ref = oracle_integ("jacobian", mesh, ksi=ksi)
     np.testing.assert_allclose(got, ref, rtol=1e-13, atol=0)
     assert np.all(got > 0)
+
+
+def test_cpp_host_mirror(tmp_path):
+    """cpp/gemlab.hpp (the compiled-language host mirror) drives the same C ABI: the reference's mat_10_bdb doc-test."""
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "test_batch"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-o", str(exe), str(root / "tests" / "cpp" / "test_batch.cpp"),
+                    "-L", str(root / "gemlab_b200"), "-lgemlab_cuda", f"-Wl,-rpath,{root / 'gemlab_b200'}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
