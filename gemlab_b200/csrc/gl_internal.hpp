@@ -88,6 +88,7 @@ int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op);
 
 // tuned kernels; return 0 if the configuration is not covered (caller falls back to the generic kernel)
 int launch_hex8_bdb(const IntegParams &p, void *stream);
+int launch_bdb(const IntegParams &p, int sd, void *stream);
 
 // micro-benchmarks
 int bench_fp64(int kind, int iters, void *stream, double *tflops);

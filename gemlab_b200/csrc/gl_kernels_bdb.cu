@@ -1,0 +1,377 @@
+// gl_kernels_bdb.cu -- register-blocked stiffness kernel for every solid GeoKind: integ::mat_10_bdb
+// (src/integ/mat_10_bdb.rs:121-233, incl. the axisymmetric branch :213-233) with a uniform modulus D, tight element
+// blocks and clear = true.  It generalises the Hex8 kernel (gl_kernels_hex8.cu) to NN nodes in SD dimensions:
+//
+//   phase A  gather: Mesh::set_pad (src/mesh/mesh.rs:448-456), coalesced node-major connectivity;
+//   phase B  one thread per (cell, Gauss point): J = Xt.L, closed-form inverse, det, B = L.inv(J), axisymmetric radius
+//            (scratchpad_calc_jacobian.rs:101-131, scratchpad_calc_gradient.rs:78-91); B, c = det*w*alpha[*r] and N/r -> smem;
+//   phase C  LPN lanes per COLUMN NODE n: per Gauss point T = c.D'.M(n) (D' in uniform registers), then the SD x SD
+//            node-pair blocks K(m,n) += M(m)^T.T accumulated in registers over all Gauss points.  For a major-symmetric
+//            D only the circulant half m = n, n+1, .., n+NN/2 (mod NN) is computed and mirrored; the diagonal and the
+//            half-distance blocks need their upper triangles only;
+//   phase D  blocks are staged in smem in the final column-major layout and the CTA's cells leave with ONE bulk async
+//            copy (homogeneous meshes) or a cooperative vector copy (mixed-kind meshes).
+// M(n) is the Mandel strain-displacement column block of calc_bb_matrix (mat_10_bdb.rs:238-278) with the 1/sqrt(2)
+// factors folded into D' on the host; in the axisymmetric case row 2 carries N/r and the coefficient is c*r.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "gl_internal.hpp"
+
+namespace gl {
+
+namespace {
+
+// ---- structure of the strain-displacement column (node, j): entries q = 0 .. col_n-1 -> (row, component) -----------
+// component index < SD selects a gradient component, component == SD selects the hoop value N/r (2D axisymmetric)
+__host__ __device__ constexpr int col_n(int sd, bool axi, int j) { return sd == 3 ? 3 : (j == 0 ? (axi ? 3 : 2) : 2); }
+__host__ __device__ constexpr int col_row(int sd, int j, int q) {
+    return sd == 3 ? (j == 0 ? (q == 0 ? 0 : (q == 1 ? 3 : 5)) : (j == 1 ? (q == 0 ? 1 : (q == 1 ? 3 : 4)) : (q == 0 ? 2 : (q == 1 ? 4 : 5))))
+                   : (j == 0 ? (q == 0 ? 0 : (q == 1 ? 3 : 2)) : (q == 0 ? 1 : 3));
+}
+__host__ __device__ constexpr int col_comp(int sd, int j, int q) {
+    return sd == 3 ? (j == 0 ? (q == 0 ? 0 : (q == 1 ? 1 : 2)) : (j == 1 ? (q == 0 ? 1 : (q == 1 ? 0 : 2)) : (q == 0 ? 2 : (q == 1 ? 1 : 0))))
+                   : (j == 0 ? (q == 0 ? 0 : (q == 1 ? 1 : 2)) : (q == 0 ? 1 : 0));
+}
+// PAT 0 general, PAT 1 major-symmetric, PAT 2 symmetric with uncoupled normal / diagonal shear blocks (exact zeros)
+__host__ __device__ constexpr bool d_nz(int pat, int sd, int a, int b) {
+    return pat < 2 ? true : ((a < 3 && b < 3) || a == b);
+}
+__host__ __device__ constexpr bool t_nz(int pat, int sd, bool axi, int a, int j) {
+    bool nz = false;
+    for (int q = 0; q < col_n(sd, axi, j); q++) nz = nz || d_nz(pat, sd, a, col_row(sd, j, q));
+    return nz;
+}
+
+struct BdbConsts {
+    double d[36]; // d'[a][b] = f_a f_b d[a][b] (row-major, ns x ns), f = 1 for normal rows, 1/sqrt(2) for shear rows
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int NN, int SD, int LPN, bool AXI, int PAT>
+__global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const BdbConsts cst, const int CPC, const int nthreads_used) {
+    constexpr bool SYM = PAT >= 1;
+    constexpr int NS = 2 * SD;
+    constexpr int NDOF = NN * SD;
+    constexpr int ND = SYM ? (NN / 2 + 1) : NN;       // circulant distances 0 .. ND-1 (NN odd: (NN+1)/2 = NN/2+1 too)
+    constexpr int NSLOT = (ND + LPN - 1) / LPN;        // blocks per lane
+    constexpr int GS = (1 + NN * SD + (AXI ? NN : 0)) | 1; // record per (cell, gauss point): c | B | N/r ; odd stride
+    constexpr int XS = (NN * SD) | 1;
+
+    extern __shared__ __align__(16) double smem[];
+    const int ng = p.ng;
+    double *s_K = smem;                               // [CPC][NDOF*NDOF]   (first: 16-byte aligned for the bulk copy)
+    double *s_w = s_K + CPC * NDOF * NDOF;            // [ng]
+    double *s_N = s_w + ng;                           // [ng][NN]
+    double *s_L = s_N + ng * NN;                      // [ng][NN][SD]
+    double *s_X = s_L + ng * NN * SD;                 // [CPC][XS]
+    double *s_G = s_X + CPC * XS;                     // [CPC][ng][GS]
+
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < ng * (1 + NN + NN * SD); i += nt) s_w[i] = p.rule[i];
+
+    // lane roles in phase C: part h (warp-friendly: parts occupy consecutive thread ranges), cell slot cs, node n
+    const int per_part = CPC * NN;
+    const bool worker = tid < nthreads_used;
+    const int h = worker ? tid / per_part : 0;
+    const int cs = worker ? (tid - h * per_part) / NN : 0;
+    const int n = worker ? (tid - h * per_part) % NN : 0;
+
+    const unsigned long long ntile = (p.hi - p.lo + CPC - 1) / CPC;
+    for (unsigned long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const unsigned long long cell0 = p.lo + tile * CPC;
+        const int ncell_tile = (int)min((unsigned long long)CPC, p.hi - cell0);
+        __syncthreads(); // previous tile consumed; tables staged
+
+        // ---- phase A: gather ---------------------------------------------------------------------------------------
+        for (int idx = tid; idx < ncell_tile * NN; idx += nt) {
+            const int m = idx / ncell_tile, c = idx - m * ncell_tile;
+            const unsigned int pid = p.conn[(unsigned long long)m * p.ncell_k + cell0 + c];
+#pragma unroll
+            for (int j = 0; j < SD; j++) s_X[c * XS + m * SD + j] = p.coords[(unsigned long long)j * p.npoint + pid];
+        }
+        __syncthreads();
+
+        // ---- phase B: geometry per (cell, gauss point) -------------------------------------------------------------
+        for (int task = tid; task < ncell_tile * ng; task += nt) {
+            const int gp = task / ncell_tile, c = task - gp * ncell_tile;
+            const double *X = s_X + c * XS;
+            const double *L = s_L + gp * NN * SD;
+            double J[SD][SD];
+#pragma unroll
+            for (int i = 0; i < SD; i++)
+#pragma unroll
+                for (int j = 0; j < SD; j++) J[i][j] = 0.0;
+#pragma unroll 4
+            for (int m = 0; m < NN; m++) {
+#pragma unroll
+                for (int i = 0; i < SD; i++)
+#pragma unroll
+                    for (int j = 0; j < SD; j++) J[i][j] = fma(X[m * SD + i], L[m * SD + j], J[i][j]);
+            }
+            double det, Ji[SD][SD];
+            if constexpr (SD == 2) {
+                det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+                const double rdet = 1.0 / det;
+                Ji[0][0] = J[1][1] * rdet;
+                Ji[0][1] = -J[0][1] * rdet;
+                Ji[1][0] = -J[1][0] * rdet;
+                Ji[1][1] = J[0][0] * rdet;
+            } else {
+                const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+                const double c01 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
+                const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+                det = J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02;
+                const double rdet = 1.0 / det;
+                Ji[0][0] = c00 * rdet;
+                Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * rdet;
+                Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rdet;
+                Ji[1][0] = -c01 * rdet;
+                Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * rdet;
+                Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * rdet;
+                Ji[2][0] = c02 * rdet;
+                Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * rdet;
+                Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * rdet;
+            }
+            if (fabs(det) <= ZERO_DETERMINANT) {
+                const unsigned long long cell = cell0 + c;
+                atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
+            }
+            double *G = s_G + (c * ng + gp) * GS;
+#pragma unroll 4
+            for (int m = 0; m < NN; m++) {
+#pragma unroll
+                for (int j = 0; j < SD; j++) {
+                    double sum = L[m * SD] * Ji[0][j];
+#pragma unroll
+                    for (int k = 1; k < SD; k++) sum = fma(L[m * SD + k], Ji[k][j], sum);
+                    G[1 + m * SD + j] = sum;
+                }
+            }
+            double coef = det * s_w[gp] * p.alpha;
+            if constexpr (AXI) {
+                const double *N = s_N + gp * NN;
+                double r = 0.0;
+                for (int m = 0; m < NN; m++) r = fma(N[m], X[m * SD], r);
+                const double rinv = 1.0 / r;
+                for (int m = 0; m < NN; m++) G[1 + NN * SD + m] = N[m] * rinv;
+                coef *= r;
+            }
+            G[0] = coef;
+        }
+        __syncthreads();
+
+        // ---- phase C: node-pair blocks ------------------------------------------------------------------------------
+        double acc[NSLOT][SD * SD];
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++)
+#pragma unroll
+            for (int q = 0; q < SD * SD; q++) acc[s][q] = 0.0;
+
+        if (worker && cs < ncell_tile) {
+#pragma unroll 1
+            for (int gp = 0; gp < ng; gp++) {
+                const double *G = s_G + (cs * ng + gp) * GS;
+                const double c = G[0];
+                double vn[SD + 1];
+#pragma unroll
+                for (int k = 0; k < SD; k++) vn[k] = G[1 + n * SD + k] * c;
+                vn[SD] = AXI ? G[1 + NN * SD + n] * c : 0.0;
+                double T[NS][SD];
+#pragma unroll
+                for (int a = 0; a < NS; a++)
+#pragma unroll
+                    for (int j = 0; j < SD; j++) {
+                        double t = 0.0;
+                        bool have = false;
+#pragma unroll
+                        for (int q = 0; q < col_n(SD, AXI, j); q++) {
+                            if (d_nz(PAT, SD, a, col_row(SD, j, q))) {
+                                const double dv = cst.d[a * NS + col_row(SD, j, q)], bv = vn[col_comp(SD, j, q)];
+                                t = have ? fma(dv, bv, t) : dv * bv;
+                                have = true;
+                            }
+                        }
+                        T[a][j] = t;
+                    }
+#pragma unroll
+                for (int s = 0; s < NSLOT; s++) {
+                    const int b = LPN == 1 ? s : s * LPN + h;
+                    if (b >= ND) continue;
+                    int m = n + b;
+                    if (m >= NN) m -= NN;
+                    double vm[SD + 1];
+#pragma unroll
+                    for (int k = 0; k < SD; k++) vm[k] = G[1 + m * SD + k];
+                    vm[SD] = AXI ? G[1 + NN * SD + m] : 0.0;
+                    const bool tri = SYM && (b == 0 || (NN % 2 == 0 && b == NN / 2));
+#pragma unroll
+                    for (int j = 0; j < SD; j++)
+#pragma unroll
+                        for (int i = 0; i < SD; i++) {
+                            if (tri && i > j) continue;
+                            double v = acc[s][i + SD * j];
+#pragma unroll
+                            for (int q = col_n(SD, AXI, i) - 1; q >= 0; q--)
+                                if (t_nz(PAT, SD, AXI, col_row(SD, i, q), j)) v = fma(vm[col_comp(SD, i, q)], T[col_row(SD, i, q)][j], v);
+                            acc[s][i + SD * j] = v;
+                        }
+                }
+            }
+        }
+
+        // ---- phase D: stage and ship -----------------------------------------------------------------------------------
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // previous bulk copy has left s_K
+        __syncthreads();
+        if (worker && cs < ncell_tile) {
+            double *Kc = s_K + cs * NDOF * NDOF;
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++) {
+                const int b = LPN == 1 ? s : s * LPN + h;
+                if (b >= ND) continue;
+                int m = n + b;
+                if (m >= NN) m -= NN;
+                const bool tri = SYM && (b == 0 || (NN % 2 == 0 && b == NN / 2));
+                const bool mirror_all = SYM && !tri;
+#pragma unroll
+                for (int j = 0; j < SD; j++)
+#pragma unroll
+                    for (int i = 0; i < SD; i++) {
+                        if (tri && i > j) continue;
+                        const double v = acc[s][i + SD * j];
+                        Kc[(SD * m + i) + NDOF * (SD * n + j)] = v;
+                        if (mirror_all || (tri && i < j)) Kc[(SD * n + j) + NDOF * (SD * m + i)] = v;
+                    }
+            }
+        }
+        if (p.cell_ids == nullptr) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned int nbytes = (unsigned int)ncell_tile * (unsigned int)(NDOF * NDOF * sizeof(double));
+                double *dst = p.out + (cell0 - p.cell_begin) * (unsigned long long)(NDOF * NDOF);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(s_K)), "r"(nbytes)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            // mixed-kind mesh: every cell has its own destination (prefix of block sizes); cooperative 16-byte copy
+            __syncthreads();
+            constexpr int V = NDOF * NDOF / 2; // double2 per cell (NDOF*NDOF is even for every supported kind)
+            for (int idx = tid; idx < ncell_tile * V; idx += nt) {
+                const int c = idx / V, q = idx - c * V;
+                const unsigned long long cell = cell0 + c;
+                double *dst = p.out + (p.out_off ? (p.out_off[cell] - p.out_base)
+                                                 : ((unsigned long long)p.cell_ids[cell] - p.cell_begin) * (unsigned long long)(NDOF * NDOF));
+                reinterpret_cast<double2 *>(dst)[q] = reinterpret_cast<const double2 *>(s_K + c * NDOF * NDOF)[q];
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int NN, int SD, int LPN>
+size_t bdb_smem(int ng, int cpc, bool axi) {
+    const int gs = (1 + NN * SD + (axi ? NN : 0)) | 1;
+    const int xs = (NN * SD) | 1;
+    return sizeof(double) * ((size_t)cpc * NN * SD * NN * SD + (size_t)ng * (1 + NN + NN * SD) + (size_t)cpc * xs + (size_t)cpc * ng * gs);
+}
+
+template <int NN, int SD, int LPN>
+int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *stream) {
+    const bool axi = p.axisym != 0;
+    // cells per CTA: fill ~256 threads, at most ~110 KB of shared memory (two CTAs per SM)
+    int cpc = 256 / (NN * LPN);
+    if (cpc < 1) cpc = 1;
+    while (cpc > 1 && bdb_smem<NN, SD, LPN>(p.ng, cpc, axi) > 110 * 1024) cpc--;
+    const size_t smem = bdb_smem<NN, SD, LPN>(p.ng, cpc, axi);
+    if (smem > 200 * 1024) return 0;
+    const int used = cpc * NN * LPN;
+    const int threads = (used + 31) / 32 * 32;
+    typedef void (*kern_t)(const IntegParams, const BdbConsts, const int, const int);
+    kern_t kern = nullptr;
+    if constexpr (SD == 2) {
+        if (axi) kern = pat == 2 ? bdb_kernel<NN, SD, LPN, true, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, true, 1> : bdb_kernel<NN, SD, LPN, true, 0>);
+        else kern = pat == 2 ? bdb_kernel<NN, SD, LPN, false, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, false, 1> : bdb_kernel<NN, SD, LPN, false, 0>);
+    } else {
+        kern = pat == 2 ? bdb_kernel<NN, SD, LPN, false, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, false, 1> : bdb_kernel<NN, SD, LPN, false, 0>);
+    }
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (ctas_per_sm > 2048 / threads) ctas_per_sm = 2048 / threads;
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const unsigned long long ntile = (p.hi - p.lo + cpc - 1) / cpc;
+    unsigned long long grid = (unsigned long long)nsm * ctas_per_sm;
+    if (grid > ntile) grid = ntile;
+    if (grid == 0) return 0;
+    kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, cst, cpc, used);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+} // namespace
+
+int launch_bdb(const IntegParams &p, int sd, void *stream) {
+    // covered: uniform D, tight blocks, overwrite; homogeneous or mixed layout; 16-byte aligned output
+    if (p.op != GL_OP_MAT_10_BDB || p.coef != nullptr || !p.clear) return 0;
+    const unsigned ndof = (unsigned)p.nnode * (unsigned)sd;
+    if (p.nrow != ndof || p.ncol != ndof || p.ii0 != 0 || p.jj0 != 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
+    if (getenv("GL_DISABLE_BDB")) return 0; // testing knob: force the generic kernel
+
+    const int ns = 2 * sd;
+    BdbConsts cst;
+    const double hs = 0.70710678118654752440084436210484903928;
+    bool sym = true;
+    for (int a = 0; a < ns; a++)
+        for (int b = 0; b < ns; b++) {
+            const double fa = a < 3 ? 1.0 : hs, fb = b < 3 ? 1.0 : hs;
+            cst.d[a * ns + b] = p.coef_uniform[a + b * ns] * fa * fb;
+            if (p.coef_uniform[a + b * ns] != p.coef_uniform[b + a * ns]) sym = false;
+        }
+    int pat = 0;
+    if (sym) {
+        pat = 2;
+        for (int a = 0; a < ns; a++)
+            for (int b = 0; b < ns; b++)
+                if (!d_nz(2, sd, a, b) && cst.d[a * ns + b] != 0.0) pat = 1;
+    }
+    if (const char *e = getenv("GL_BDB_PATTERN")) {
+        const int cap = atoi(e);
+        if (cap < pat) pat = cap < 0 ? 0 : cap;
+    }
+    if (sd == 2) {
+        switch (p.nnode) {
+        case 3: return launch_kind<3, 2, 1>(p, cst, pat, stream);
+        case 4: return launch_kind<4, 2, 1>(p, cst, pat, stream);
+        case 6: return launch_kind<6, 2, 1>(p, cst, pat, stream);
+        case 8: return launch_kind<8, 2, 1>(p, cst, pat, stream);
+        case 9: return launch_kind<9, 2, 1>(p, cst, pat, stream);
+        default: return 0;
+        }
+    }
+    switch (p.nnode) {
+    case 4: return launch_kind<4, 3, 1>(p, cst, pat, stream);
+    case 8: return launch_kind<8, 3, 1>(p, cst, pat, stream);
+    case 10: return launch_kind<10, 3, 1>(p, cst, pat, stream);
+    case 20: {
+        // Hex20: 11 circulant blocks per column node are split over LPN lanes (tuning knob GL_HEX20_LPN = 2, 3 or 4)
+        static int lpn = -1;
+        if (lpn < 0) {
+            const char *e = getenv("GL_HEX20_LPN");
+            lpn = e ? atoi(e) : 3;
+        }
+        if (lpn == 2) return launch_kind<20, 3, 2>(p, cst, pat, stream);
+        if (lpn == 4) return launch_kind<20, 3, 4>(p, cst, pat, stream);
+        return launch_kind<20, 3, 3>(p, cst, pat, stream);
+    }
+    default: return 0;
+    }
+}
+
+} // namespace gl
