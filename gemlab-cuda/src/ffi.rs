@@ -65,7 +65,16 @@ pub struct gl_out {
     pub capacity: u64,
 }
 
+#[repr(C)]
+pub struct gl_fused_item {
+    pub op: i32,
+    pub reserved: i32,
+    pub coef: *const gl_coef,
+    pub out: *mut gl_out,
+}
+
 extern "C" {
+    pub fn gl_integ_fused(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, items: *const gl_fused_item, nitems: c_int) -> c_int;
     pub fn gl_ctx_create(device: c_int, stream: *mut c_void, ctx: *mut *mut gl_ctx) -> c_int;
     pub fn gl_ctx_destroy(ctx: *mut gl_ctx);
     pub fn gl_ctx_set_stream(ctx: *mut gl_ctx, stream: *mut c_void) -> c_int;

@@ -29,6 +29,10 @@ class GlOut(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("location", C.c_int32), ("reserved", C.c_int32), ("capacity", C.c_uint64)]
 
 
+class GlFusedItem(C.Structure):
+    _fields_ = [("op", C.c_int32), ("reserved", C.c_int32), ("coef", C.POINTER(GlCoef)), ("out", C.POINTER(GlOut))]
+
+
 # every symbol include/gemlab_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -61,6 +65,7 @@ SYMBOLS = {
     "gl_out_offsets": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), _P]),
     "gl_integ": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlOut)]),
     "gl_jacobian": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlOut)]),
+    "gl_integ_fused": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlFusedItem), C.c_int]),
     "gl_args_default": (None, [C.POINTER(GlArgs)]),
     "gl_lin_elasticity": (None, [C.c_double, C.c_double, C.c_int, C.c_int, _P]),
     "gl_bench_fp64_peak": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),

@@ -656,6 +656,19 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         int nl = 0;
         if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb(p, mesh->ndim, ctx->stream);
+        if (nl == 0 && gd == mesh->ndim && cr.dev == nullptr && a->clear && a->ii0 == 0 && (a->jj0 == 0 || !op_is_matrix(op)) &&
+            a->nrow == 0 && a->ncol == 0 &&
+            (op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_01_NS || op == GL_OP_VEC_03_BV)) {
+            ScalarFused f;
+            std::memset(&f, 0, sizeof(f));
+            if (op == GL_OP_MAT_01_NSN) { f.mask = 1; f.s_mat = cr.uniform[0]; f.out_m01 = d_out; }
+            if (op == GL_OP_MAT_03_BTB) { f.mask = 2; std::memcpy(f.t, cr.uniform, sizeof(double) * 2 * mesh->ndim); f.out_m03 = d_out; }
+            if (op == GL_OP_VEC_01_NS) { f.mask = 4; f.s_vec = cr.uniform[0]; f.out_v01 = d_out; }
+            if (op == GL_OP_VEC_03_BV) { f.mask = 8; std::memcpy(f.w, cr.uniform, sizeof(double) * mesh->ndim); f.out_v03 = d_out; }
+            if (op_is_matrix(op)) { f.moff = p.out_off; f.mbase = p.out_base; }
+            else { f.voff = p.out_off; f.vbase = p.out_base; }
+            nl = launch_scalar_fused(p, f, mesh->ndim, ctx->stream);
+        }
         if (nl == 0) {
             p.cells_per_cta = generic_pick_cells_per_cta(mesh->ndim, gd, p.nnode, p.ng, op);
             nl = launch_generic(p, mesh->ndim, gd, ctx->stream);
@@ -819,6 +832,123 @@ int gl_integ(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, 
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(s_copy));
     return gl_ctx_sync(ctx);
+}
+
+// ---- fused entry point ---------------------------------------------------------------------------------------------------
+static bool scalar_family(int op) {
+    return op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_01_NS || op == GL_OP_VEC_03_BV;
+}
+
+int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, const gl_args *a, const gl_fused_item *items, int nitems) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
+    if (!mesh || !a || !items || nitems <= 0) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    if (b > e || e > mesh->ncell) return fail(ctx, GL_ERR_CELL_RANGE);
+    // can the items share one kernel?
+    bool fusable = nitems <= 4 && a->clear && a->ii0 == 0 && a->jj0 == 0 && a->nrow == 0 && a->ncol == 0 && e > b;
+    int mask = 0;
+    for (int i = 0; i < nitems && fusable; i++) {
+        const gl_fused_item &it = items[i];
+        if (!scalar_family(it.op) || !it.coef || !it.out || it.coef->mode != GL_COEF_UNIFORM || it.coef->location != GL_HOST ||
+            !it.coef->data || it.out->location != GL_DEVICE || !it.out->ptr)
+            fusable = false;
+        const int bit = it.op == GL_OP_MAT_01_NSN ? 1 : (it.op == GL_OP_MAT_03_BTB ? 2 : (it.op == GL_OP_VEC_01_NS ? 4 : 8));
+        if (mask & bit) fusable = false; // the same case twice
+        mask |= bit;
+    }
+    for (auto &bk : mesh->buckets)
+        if (kind_geo_ndim(bk.kind) != mesh->ndim) fusable = false;
+    if (!fusable) {
+        for (int i = 0; i < nitems; i++) {
+            int st = gl_integ(ctx, cmesh, items[i].op, b, e, a, items[i].coef, items[i].out);
+            if (st) return st;
+        }
+        return GL_OK;
+    }
+    cudaSetDevice(ctx->device);
+    ScalarFused f;
+    std::memset(&f, 0, sizeof(f));
+    f.mask = mask;
+    int mat_op = -1, vec_op = -1;
+    for (int i = 0; i < nitems; i++) {
+        const gl_fused_item &it = items[i];
+        uint64_t total = 0;
+        int st = range_layout(mesh, it.op, b, e, a, &total, nullptr);
+        if (st) return fail(ctx, st);
+        if (it.out->capacity < total) return fail(ctx, GL_ERR_OUT_CAPACITY);
+        switch (it.op) {
+        case GL_OP_MAT_01_NSN: f.s_mat = it.coef->data[0]; f.out_m01 = it.out->ptr; mat_op = it.op; break;
+        case GL_OP_MAT_03_BTB: std::memcpy(f.t, it.coef->data, sizeof(double) * 2 * mesh->ndim); f.out_m03 = it.out->ptr; mat_op = it.op; break;
+        case GL_OP_VEC_01_NS: f.s_vec = it.coef->data[0]; f.out_v01 = it.out->ptr; vec_op = it.op; break;
+        default: std::memcpy(f.w, it.coef->data, sizeof(double) * mesh->ndim); f.out_v03 = it.out->ptr; vec_op = it.op; break;
+        }
+    }
+    const std::vector<uint64_t> *mpre = nullptr, *vpre = nullptr;
+    int mkey = 0, vkey = 0, st = GL_OK;
+    if (!mesh->homogeneous) {
+        if (mat_op >= 0) mpre = mesh_prefix(mesh, mat_op, a, &mkey, &st);
+        if (vec_op >= 0) vpre = mesh_prefix(mesh, vec_op, a, &vkey, &st);
+    }
+    auto device_offsets = [&](gl_mesh_bucket &bk, const std::vector<uint64_t> *pre, int key, const unsigned long long **out) -> int {
+        auto it = bk.d_out_off.find(key);
+        if (it == bk.d_out_off.end()) {
+            std::vector<unsigned long long> offs(bk.ncell);
+            for (uint64_t c = 0; c < bk.ncell; c++) offs[c] = (*pre)[bk.h_cell_ids[c]];
+            unsigned long long *d = nullptr;
+            CUDA_TRY(ctx, cudaMalloc(&d, offs.size() * sizeof(unsigned long long)));
+            CUDA_TRY(ctx, cudaMemcpy(d, offs.data(), offs.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+            it = bk.d_out_off.emplace(key, d).first;
+        }
+        *out = it->second;
+        return GL_OK;
+    };
+    for (auto &bk : mesh->buckets) {
+        uint64_t lo, hi;
+        bucket_range(mesh, bk, b, e, lo, hi);
+        if (lo >= hi) continue;
+        IntegParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.coords = mesh->d_coords;
+        p.npoint = mesh->npoint;
+        p.conn = bk.d_conn;
+        p.ncell_k = bk.ncell;
+        p.cell_ids = bk.d_cell_ids;
+        p.lo = lo;
+        p.hi = hi;
+        p.cell_begin = b;
+        p.coef_begin = b;
+        p.axisym = a->axisymmetric ? 1 : 0;
+        p.clear = 1;
+        p.alpha = a->alpha;
+        p.nnode = bk.nnode;
+        RuleTable *rt = get_rule(ctx, bk.kind, a->ngauss, &st);
+        if (!rt) return fail(ctx, st);
+        p.rule = rt->dev;
+        p.ng = rt->ng;
+        p.err_cell = ctx->d_err_cell;
+        ScalarFused fb = f;
+        if (mpre) {
+            st = device_offsets(bk, mpre, mkey, &fb.moff);
+            if (st) return st;
+            fb.mbase = (*mpre)[b];
+        }
+        if (vpre) {
+            st = device_offsets(bk, vpre, vkey, &fb.voff);
+            if (st) return st;
+            fb.vbase = (*vpre)[b];
+        }
+        int nl = launch_scalar_fused(p, fb, mesh->ndim, ctx->stream);
+        if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
+        if (nl == 0) { // kind not covered by the fused kernel: run the items one after the other for the whole range
+            for (int i = 0; i < nitems; i++) {
+                int st2 = gl_integ(ctx, cmesh, items[i].op, b, e, a, items[i].coef, items[i].out);
+                if (st2) return st2;
+            }
+            return GL_OK;
+        }
+        ctx->launches += (uint64_t)nl;
+    }
+    return GL_OK;
 }
 
 int gl_mat_10_bdb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {

@@ -90,6 +90,21 @@ int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op);
 int launch_hex8_bdb(const IntegParams &p, void *stream);
 int launch_bdb(const IntegParams &p, int sd, void *stream);
 
+// fused scalar-dof cases (gl_kernels_scalar.cu): any subset of mat_01_nsn (bit 0), mat_03_btb (bit 1), vec_01_ns (bit 2),
+// vec_03_bv (bit 3) from one geometry pass; uniform coefficients
+struct ScalarFused {
+    int mask;
+    double s_mat, s_vec; // mat_01_nsn / vec_01_ns scalars
+    double t[6];         // mat_03_btb Mandel vector
+    double w[3];         // vec_03_bv vector
+    double *out_m01, *out_m03, *out_v01, *out_v03;
+    const unsigned long long *moff; // mixed meshes: bucket-local cell -> absolute offset of its nnode x nnode block
+    unsigned long long mbase;
+    const unsigned long long *voff; // ... of its nnode vector
+    unsigned long long vbase;
+};
+int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
+
 // micro-benchmarks
 int bench_fp64(int kind, int iters, void *stream, double *tflops);
 

@@ -19,7 +19,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import GlArgs, GlCoef, GlOut, lib
+from ._lib import GlArgs, GlCoef, GlFusedItem, GlOut, lib
 from .geo import GemlabError, GeoKind
 from .mesh import Mesh
 
@@ -228,39 +228,30 @@ def _range(dmesh, cell_range):
     return int(b), int(e)
 
 
-def _integ(op, ctx, dmesh, cell_range, args, coef, out):
-    b, e = _range(dmesh, cell_range)
-    a = args._c()
-    total = C.c_uint64()
-    st = lib().gl_out_total(dmesh._h, OPS[op], b, e, C.byref(a), C.byref(total))
-    if st:
-        raise GemlabError(st)
-    total = total.value
-    keep = []
-    # coefficient
+def _marshal_coef(coef, keep):
     c = GlCoef()
-    cptr = None
-    if coef is not None:
-        c.mode = coef.mode
-        if _is_torch_tensor(coef.data):
-            if not coef.data.is_cuda:
-                raise ValueError("coefficient tensor must be a CUDA tensor or a numpy array")
-            t = coef.data.contiguous()
-            keep.append(t)
-            c.location, c.data = GL_DEVICE, t.data_ptr()
-        else:
-            arr = np.ascontiguousarray(coef.data, dtype=np.float64)
-            keep.append(arr)
-            c.location, c.data = GL_HOST, arr.ctypes.data
-        if coef.markers is not None:
-            c.markers = coef.markers.ctypes.data
-            c.nrecord = coef.markers.shape[0]
-        cptr = C.byref(c)
-    # output
+    c.mode = coef.mode
+    if _is_torch_tensor(coef.data):
+        if not coef.data.is_cuda:
+            raise ValueError("coefficient tensor must be a CUDA tensor or a numpy array")
+        t = coef.data.contiguous()
+        keep.append(t)
+        c.location, c.data = GL_DEVICE, t.data_ptr()
+    else:
+        arr = np.ascontiguousarray(coef.data, dtype=np.float64)
+        keep.append(arr)
+        c.location, c.data = GL_HOST, arr.ctypes.data
+    if coef.markers is not None:
+        c.markers = coef.markers.ctypes.data
+        c.nrecord = coef.markers.shape[0]
+    return c
+
+
+def _marshal_out(out, total, clear):
     o = GlOut()
     result = out
     if out is None:
-        result = np.empty(total, dtype=np.float64) if args.clear else np.zeros(total, dtype=np.float64)
+        result = np.empty(total, dtype=np.float64) if clear else np.zeros(total, dtype=np.float64)
         o.ptr, o.location, o.capacity = result.ctypes.data, GL_HOST, total
     elif _is_torch_tensor(out):
         if not out.is_contiguous():
@@ -271,10 +262,51 @@ def _integ(op, ctx, dmesh, cell_range, args, coef, out):
         if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
             raise ValueError("output must be a contiguous float64 numpy array")
         o.ptr, o.location, o.capacity = out.ctypes.data, GL_HOST, out.size
-    st = lib().gl_integ(ctx._h, dmesh._h, OPS[op], b, e, C.byref(a), cptr, C.byref(o))
+    return o, result
+
+
+def _total(dmesh, op, b, e, a):
+    total = C.c_uint64()
+    st = lib().gl_out_total(dmesh._h, OPS[op], b, e, C.byref(a), C.byref(total))
+    if st:
+        raise GemlabError(st)
+    return total.value
+
+
+def _integ(op, ctx, dmesh, cell_range, args, coef, out):
+    b, e = _range(dmesh, cell_range)
+    a = args._c()
+    total = _total(dmesh, op, b, e, a)
+    keep = []
+    c = None if coef is None else _marshal_coef(coef, keep)
+    o, result = _marshal_out(out, total, args.clear)
+    st = lib().gl_integ(ctx._h, dmesh._h, OPS[op], b, e, C.byref(a), None if c is None else C.byref(c), C.byref(o))
     if st:
         ctx._raise(st)
     return result
+
+
+def fused(ctx, dmesh, cell_range, args, items):
+    """Several integration cases from ONE geometry pass (gl_integ_fused).  `items` is a list of (op name, Coef, out);
+    returns the list of outputs.  Equivalent to calling each `integ.<op>` separately; the library fuses mat_01_nsn,
+    mat_03_btb, vec_01_ns and vec_03_bv (uniform coefficients, CUDA-tensor outputs) into one kernel."""
+    b, e = _range(dmesh, cell_range)
+    a = args._c()
+    keep, results = [], []
+    arr = (GlFusedItem * len(items))()
+    for i, (op, coef, out) in enumerate(items):
+        total = _total(dmesh, op, b, e, a)
+        c = _marshal_coef(coef, keep)
+        o, result = _marshal_out(out, total, args.clear)
+        keep.extend([c, o])
+        arr[i].op = OPS[op]
+        arr[i].coef = C.pointer(c)
+        arr[i].out = C.pointer(o)
+        results.append(result)
+    st = lib().gl_integ_fused(ctx._h, dmesh._h, b, e, C.byref(a), arr, len(items))
+    if st:
+        ctx._raise(st)
+    return results
 
 
 def mat_10_bdb(ctx, dmesh, cell_range, args, coef, out=None):

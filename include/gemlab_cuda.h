@@ -220,6 +220,21 @@ GL_API int gl_vec_04_bt(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, u
 GL_API int gl_jacobian(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                        gl_out *out);
 
+/* Several integration cases over ONE geometry pass (one Jacobian / gradient evaluation per Gauss point for all of them).
+ * Semantically identical to calling gl_integ once per item with the same mesh, range and args; the library fuses the
+ * items into one kernel when it can (today: any subset of mat_01_nsn, mat_03_btb, vec_01_ns, vec_03_bv with uniform
+ * coefficients and device outputs -- e.g. the mass matrix and the body-force vector of BASELINE.json config 4) and
+ * otherwise runs them one after the other.  The reference has no counterpart: its callers invoke integ::mat_01_nsn and
+ * integ::vec_01_ns separately, each recomputing the Jacobian (src/integ/mat_01_nsn.rs:75-76, vec_01_ns.rs:106-107). */
+typedef struct gl_fused_item {
+    int32_t op; /* gl_op */
+    int32_t reserved;
+    const gl_coef *coef;
+    gl_out *out;
+} gl_fused_item;
+GL_API int gl_integ_fused(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                          const gl_fused_item *items, int nitems);
+
 /* legacy (gemlab <= 1.x) names used by BASELINE.json's north_star: G was renamed to B in v2 */
 GL_API int gl_mat_10_gdg(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                          const gl_coef *coef, gl_out *out); /* = gl_mat_10_bdb */

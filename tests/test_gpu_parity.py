@@ -395,3 +395,52 @@ def test_cpp_host_mirror(tmp_path):
                     "-L", str(root / "gemlab_b200"), "-lgemlab_cuda", f"-Wl,-rpath,{root / 'gemlab_b200'}"], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("kind", ["tri3", "qua8", "tet10", "hex8"])
+def test_fused_scalar_cases_share_one_geometry_pass(ctx, kind):
+    """gl_integ_fused: mat_01_nsn + mat_03_btb + vec_01_ns + vec_03_bv from one kernel == the four separate calls
+    (BASELINE.json config 4: fused Tet10 mass matrix + body-force vector)."""
+    import torch
+
+    mesh = make_mesh(kind, n=4)
+    dmesh = ctx.upload(mesh)
+    nd = mesh.ndim
+    k = GeoKind.from_str(kind)
+    rng = np.random.default_rng(29)
+    coefs = {"mat_01_nsn": np.array([2.7]), "mat_03_btb": random_coef("mat_03_btb", nd, 1, rng)[0],
+             "vec_01_ns": np.array([9.81 * 2.7]), "vec_03_bv": random_coef("vec_03_bv", nd, 1, rng)[0]}
+    for axisym in ([False, True] if nd == 2 else [False]):
+        args = CommonArgs(axisymmetric=axisym, alpha=1.3)
+        outs = {op: torch.full((mesh.ncell * integ.op_out_size(op, k, nd),), 5.0, dtype=torch.float64, device="cuda") for op in coefs}
+        launches = ctx.launch_count()
+        integ.fused(ctx, dmesh, None, args, [(op, Coef.uniform(c), outs[op]) for op, c in coefs.items()])
+        ctx.sync()
+        assert ctx.launch_count() - launches == 1  # one kernel for the four cases
+        for op, c in coefs.items():
+            ref = oracle_integ(op, mesh, c, alpha=1.3, axisymmetric=axisym)
+            sizes = np.arange(mesh.ncell + 1) * integ.op_out_size(op, k, nd)
+            assert rel_err(outs[op].cpu().numpy(), ref, sizes) <= TOL, (kind, op, axisym)
+    # sub-range + a non-fusable item (host output) falls back to sequential calls with identical results
+    b, e = 3, mesh.ncell - 2
+    host = integ.fused(ctx, dmesh, (b, e), CommonArgs(), [("mat_01_nsn", Coef.uniform(coefs["mat_01_nsn"]), None),
+                                                          ("vec_01_ns", Coef.uniform(coefs["vec_01_ns"]), None)])
+    np.testing.assert_array_equal(host[0], integ.mat_01_nsn(ctx, dmesh, (b, e), CommonArgs(), Coef.uniform(coefs["mat_01_nsn"])))
+    np.testing.assert_array_equal(host[1], integ.vec_01_ns(ctx, dmesh, (b, e), CommonArgs(), Coef.uniform(coefs["vec_01_ns"])))
+
+
+def test_fused_on_mixed_mesh(ctx):
+    import torch
+
+    mesh = mixed_mesh_2d()
+    dmesh = ctx.upload(mesh)
+    args = CommonArgs(axisymmetric=True)
+    tt, w = np.array([2.0, 3.0, 0.0, 0.5]), np.array([1.0, 2.0])
+    om = torch.empty(integ.out_total(dmesh, "mat_03_btb", None, args), dtype=torch.float64, device="cuda")
+    ov = torch.empty(integ.out_total(dmesh, "vec_03_bv", None, args), dtype=torch.float64, device="cuda")
+    integ.fused(ctx, dmesh, None, args, [("mat_03_btb", Coef.uniform(tt), om), ("vec_03_bv", Coef.uniform(w), ov)])
+    ctx.sync()
+    assert rel_err(om.cpu().numpy(), oracle_integ("mat_03_btb", mesh, tt, axisymmetric=True),
+                   integ.out_offsets(dmesh, "mat_03_btb", None, args)) <= TOL
+    assert rel_err(ov.cpu().numpy(), oracle_integ("vec_03_bv", mesh, w, axisymmetric=True),
+                   integ.out_offsets(dmesh, "vec_03_bv", None, args)) <= TOL

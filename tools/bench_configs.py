@@ -109,8 +109,8 @@ def main():
         out_v = torch.empty(mesh.ncell * 10, dtype=torch.float64, device="cuda")
 
         def step():
-            integ.mat_01_nsn(ctx, dm, None, CommonArgs(), Coef.uniform([2.7]), out=out_m)
-            integ.vec_01_ns(ctx, dm, None, CommonArgs(), Coef.uniform([9.81 * 2.7]), out=out_v)
+            integ.fused(ctx, dm, None, CommonArgs(), [("mat_01_nsn", Coef.uniform([2.7]), out_m),
+                                                      ("vec_01_ns", Coef.uniform([9.81 * 2.7]), out_v)])
 
         ms = timed(step)
         ctx.sync()
@@ -155,8 +155,8 @@ def main():
 
         def step():
             integ.mat_10_bdb(ctx, dm, None, a, Coef.uniform(dd), out=out_k)
-            integ.mat_03_btb(ctx, dm, None, a, Coef.uniform([2.0, 2.0, 0.0, 0.0]), out=out_h)
-            integ.vec_03_bv(ctx, dm, None, a, Coef.uniform([1.0, 2.0]), out=out_v)
+            integ.fused(ctx, dm, None, a, [("mat_03_btb", Coef.uniform([2.0, 2.0, 0.0, 0.0]), out_h),
+                                           ("vec_03_bv", Coef.uniform([1.0, 2.0]), out_v)])
 
         ms = timed(step, steps=3, warmup=1)
         ctx.sync()
