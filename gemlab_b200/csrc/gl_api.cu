@@ -336,6 +336,70 @@ uint64_t gl_op_out_size(int op, int kind, int ndim) {
 
 uint64_t gl_op_coef_size(int op, int ndim) { return coef_len(op, ndim); }
 
+} // extern "C" (reopened below)
+
+// ---- device-side structure-of-arrays transposition (upload path of homogeneous meshes) -----------------------------------
+namespace {
+
+template <typename IdT>
+__global__ void conn_to_soa_kernel(const IdT *__restrict__ raw, uint32_t *__restrict__ soa, unsigned long long ncell, int nnode,
+                                   unsigned long long npoint, int *__restrict__ bad) {
+    // raw: [ncell][nnode] (Cell.points flattened); soa: [nnode][ncell].  Reads are coalesced over the flattened array,
+    // writes are strided by nnode across a warp but stay within nnode cache lines per warp.
+    const unsigned long long total = ncell * (unsigned long long)nnode;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = i / nnode;
+        const int m = (int)(i - c * nnode);
+        const unsigned long long pid = (unsigned long long)raw[i];
+        if (pid >= npoint) *bad = 1;
+        soa[(unsigned long long)m * ncell + c] = (uint32_t)pid;
+    }
+}
+
+__global__ void coords_to_soa_kernel(const double *__restrict__ aos, double *__restrict__ soa, unsigned long long npoint, int ndim) {
+    const unsigned long long total = npoint * (unsigned long long)ndim;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long pt = i / ndim;
+        const int j = (int)(i - pt * ndim);
+        soa[(unsigned long long)j * npoint + pt] = aos[i];
+    }
+}
+
+// uploads a homogeneous mesh: raw host arrays go to the device as they are and are transposed there
+template <typename IdT>
+int upload_homogeneous_device(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, const double *coords, const IdT *conn) {
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    const size_t conn_bytes = (size_t)bk.ncell * bk.nnode * sizeof(IdT);
+    const size_t coord_bytes = (size_t)mesh->npoint * mesh->ndim * sizeof(double);
+    void *d_raw = nullptr;
+    int *d_bad = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_raw, std::max(conn_bytes, coord_bytes)));
+    CUDA_TRY(ctx, cudaMalloc(&d_bad, sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    CUDA_TRY(ctx, cudaMalloc(&mesh->d_coords, coord_bytes));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_raw, coords, coord_bytes, cudaMemcpyHostToDevice, st));
+    coords_to_soa_kernel<<<1184, 256, 0, st>>>((const double *)d_raw, mesh->d_coords, mesh->npoint, mesh->ndim);
+    if (bk.ncell) {
+        CUDA_TRY(ctx, cudaMalloc(&bk.d_conn, (size_t)bk.ncell * bk.nnode * sizeof(uint32_t)));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_raw, conn, conn_bytes, cudaMemcpyHostToDevice, st));
+        conn_to_soa_kernel<IdT><<<1184, 256, 0, st>>>((const IdT *)d_raw, bk.d_conn, bk.ncell, bk.nnode, mesh->npoint, d_bad);
+    }
+    int bad = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->launches += bk.ncell ? 2 : 1;
+    cudaFree(d_raw);
+    cudaFree(d_bad);
+    if (bad) return fail(ctx, GL_ERR_MESH, "point id out of range");
+    return GL_OK;
+}
+
+} // namespace
+
+extern "C" {
+
 // =====================================================================================================
 // mesh
 // =====================================================================================================
@@ -355,13 +419,23 @@ static void coords_to_soa(int ndim, uint64_t npoint, const double *coords, std::
 static int build_markers(gl_ctx *ctx, gl_mesh *mesh, const int32_t *markers, std::vector<uint32_t> &marker_idx) {
     (void)ctx;
     marker_idx.clear();
-    if (!markers) {
+    if (!markers || mesh->ncell == 0) {
         mesh->marker_values = {0};
         return GL_OK;
     }
-    std::vector<int32_t> uniq(markers, markers + mesh->ncell);
-    std::sort(uniq.begin(), uniq.end());
-    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    // distinct markers without sorting the whole array (meshes carry a handful of markers)
+    std::vector<int32_t> uniq;
+    {
+        int32_t last = markers[0];
+        uniq.push_back(last);
+        for (uint64_t e = 1; e < mesh->ncell; e++) {
+            const int32_t mk = markers[e];
+            if (mk == last) continue;
+            last = mk;
+            if (std::find(uniq.begin(), uniq.end(), mk) == uniq.end()) uniq.push_back(mk);
+        }
+        std::sort(uniq.begin(), uniq.end());
+    }
     mesh->marker_values = uniq;
     if (uniq.size() > 1) {
         marker_idx.resize(mesh->ncell);
@@ -398,6 +472,22 @@ int gl_mesh_upload(gl_ctx *ctx, int ndim, uint64_t npoint, const double *coords,
     mesh->homogeneous = nkinds <= 1;
     std::vector<uint32_t> marker_idx;
     build_markers(ctx, mesh.get(), markers, marker_idx);
+    if (mesh->homogeneous && ncell > 0) {
+        // one GeoKind: conn is already a dense [ncell][nnode] table -> transposed and range-checked on the device
+        gl_mesh_bucket bk;
+        bk.kind = kinds[0];
+        bk.nnode = kind_nnode(bk.kind);
+        bk.ncell = ncell;
+        int st = upload_homogeneous_device<uint64_t>(ctx, mesh.get(), bk, coords, conn + conn_off[0]);
+        if (st) return st;
+        if (!marker_idx.empty()) {
+            CUDA_TRY(ctx, cudaMalloc(&bk.d_marker_idx, marker_idx.size() * sizeof(uint32_t)));
+            CUDA_TRY(ctx, cudaMemcpy(bk.d_marker_idx, marker_idx.data(), marker_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        mesh->buckets.push_back(std::move(bk));
+        *out = mesh.release();
+        return GL_OK;
+    }
     if (!mesh->homogeneous) mesh->h_kinds.assign(kinds, kinds + ncell);
     for (int k = 0; k < GL_NKIND; k++) {
         if (!count[k]) continue;
@@ -462,27 +552,15 @@ int gl_mesh_upload_homogeneous(gl_ctx *ctx, int ndim, uint64_t npoint, const dou
     bk.kind = kind;
     bk.nnode = kind_nnode(kind);
     bk.ncell = ncell;
-    const int nn = bk.nnode;
-    std::vector<uint32_t> soa((size_t)nn * ncell);
-    for (uint64_t c = 0; c < ncell; c++)
-        for (int m = 0; m < nn; m++) {
-            const uint32_t pid = conn[c * nn + m];
-            if (pid >= npoint) return fail(ctx, GL_ERR_MESH, "point id out of range");
-            soa[(size_t)m * ncell + c] = pid;
-        }
-    if (ncell) {
-        CUDA_TRY(ctx, cudaMalloc(&bk.d_conn, soa.size() * sizeof(uint32_t)));
-        CUDA_TRY(ctx, cudaMemcpy(bk.d_conn, soa.data(), soa.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        if (!marker_idx.empty()) {
-            CUDA_TRY(ctx, cudaMalloc(&bk.d_marker_idx, marker_idx.size() * sizeof(uint32_t)));
-            CUDA_TRY(ctx, cudaMemcpy(bk.d_marker_idx, marker_idx.data(), marker_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        }
+    {
+        int st = upload_homogeneous_device<uint32_t>(ctx, mesh.get(), bk, coords, conn);
+        if (st) return st;
+    }
+    if (ncell && !marker_idx.empty()) {
+        CUDA_TRY(ctx, cudaMalloc(&bk.d_marker_idx, marker_idx.size() * sizeof(uint32_t)));
+        CUDA_TRY(ctx, cudaMemcpy(bk.d_marker_idx, marker_idx.data(), marker_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     mesh->buckets.push_back(std::move(bk));
-    std::vector<double> csoa;
-    coords_to_soa(ndim, npoint, coords, csoa);
-    int st = finish_mesh_upload(ctx, mesh.get(), csoa);
-    if (st) return st;
     *out = mesh.release();
     return GL_OK;
 }

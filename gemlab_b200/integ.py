@@ -174,15 +174,10 @@ class Context:
         if not isinstance(mesh, Mesh):
             raise TypeError("expected a gemlab_b200.Mesh")
         h = C.c_void_p()
-        if mesh.is_homogeneous() and mesh.ncell > 0 and mesh.npoint < 2**32:
-            conn32 = np.ascontiguousarray(mesh.conn, dtype=np.uint32)
-            st = lib().gl_mesh_upload_homogeneous(self._h, mesh.ndim, mesh.npoint, mesh.coords.ctypes.data, mesh.ncell,
-                                                  int(mesh.kinds[0]), mesh.markers.ctypes.data, conn32.ctypes.data,
-                                                  C.byref(h))
-        else:
-            st = lib().gl_mesh_upload(self._h, mesh.ndim, mesh.npoint, mesh.coords.ctypes.data, mesh.ncell,
-                                      mesh.kinds.ctypes.data, mesh.markers.ctypes.data, mesh.conn_off.ctypes.data,
-                                      mesh.conn.ctypes.data, C.byref(h))
+        # the library detects single-kind meshes itself and transposes those on the device (no host-side copies here)
+        st = lib().gl_mesh_upload(self._h, mesh.ndim, mesh.npoint, mesh.coords.ctypes.data, mesh.ncell,
+                                  mesh.kinds.ctypes.data, mesh.markers.ctypes.data, mesh.conn_off.ctypes.data,
+                                  mesh.conn.ctypes.data, C.byref(h))
         if st:
             self._raise(st)
         return DeviceMesh(self, h, mesh.ndim, mesh.ncell, mesh.npoint, mesh.kinds.copy())

@@ -444,3 +444,26 @@ def test_fused_on_mixed_mesh(ctx):
                    integ.out_offsets(dmesh, "mat_03_btb", None, args)) <= TOL
     assert rel_err(ov.cpu().numpy(), oracle_integ("vec_03_bv", mesh, w, axisymmetric=True),
                    integ.out_offsets(dmesh, "vec_03_bv", None, args)) <= TOL
+
+
+def test_upload_paths_agree_and_validate(ctx):
+    """gl_mesh_upload (u64 ids, device-side transposition for single-kind meshes) == gl_mesh_upload_homogeneous (u32)."""
+    import ctypes as C
+
+    from gemlab_b200._lib import lib
+
+    mesh = make_mesh("hex8", n=4)
+    dd = Coef.uniform(g.mandel_matrix(g.lin_elasticity(480.0, 1 / 3, False)))
+    a = integ.mat_10_bdb(ctx, ctx.upload(mesh), None, CommonArgs(), dd)
+    h = C.c_void_p()
+    conn32 = np.ascontiguousarray(mesh.conn, dtype=np.uint32)
+    st = lib().gl_mesh_upload_homogeneous(ctx._h, 3, mesh.npoint, mesh.coords.ctypes.data, mesh.ncell, int(GeoKind.Hex8),
+                                          mesh.markers.ctypes.data, conn32.ctypes.data, C.byref(h))
+    assert st == 0
+    dm = g.DeviceMesh(ctx, h, 3, mesh.ncell, mesh.npoint, mesh.kinds.copy())
+    b = integ.mat_10_bdb(ctx, dm, None, CommonArgs(), dd)
+    np.testing.assert_array_equal(a, b)
+    bad = Mesh(3, mesh.coords, mesh.kinds, mesh.conn_off, mesh.conn.copy(), mesh.markers)
+    bad.conn[5] = mesh.npoint  # out of range
+    with pytest.raises(g.GemlabError, match="point id out of range"):
+        ctx.upload(bad)
