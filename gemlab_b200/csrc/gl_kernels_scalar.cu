@@ -59,6 +59,26 @@ __global__ void __launch_bounds__(256) scalar_kernel(const IntegParams p, const 
             }
     }
 
+    // software-pipelined gather (Mesh::set_pad): thread (node gm, cell slot gc) keeps the coordinates of the NEXT tile in
+    // registers (loaded one tile ahead) and the point id of the tile after that (two tiles ahead), so neither the index
+    // load nor the dependent coordinate loads are exposed
+    const bool gather_lane = tid < CPC * NN;
+    const int gm = tid / CPC, gc = tid - gm * CPC;
+    const unsigned long long gstep = (unsigned long long)gridDim.x * CPC;
+    double gx[SD];
+    unsigned int gpid = 0;
+#pragma unroll
+    for (int j = 0; j < SD; j++) gx[j] = 0.0;
+    if (gather_lane) {
+        const unsigned long long cell = p.lo + (unsigned long long)blockIdx.x * CPC + gc;
+        if (cell < p.hi) {
+            const unsigned int pid = p.conn[(unsigned long long)gm * p.ncell_k + cell];
+#pragma unroll
+            for (int j = 0; j < SD; j++) gx[j] = p.coords[(unsigned long long)j * p.npoint + pid];
+        }
+        if (cell + gstep < p.hi) gpid = p.conn[(unsigned long long)gm * p.ncell_k + cell + gstep];
+    }
+
     const unsigned long long ntile = (p.hi - p.lo + CPC - 1) / CPC;
     for (unsigned long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const unsigned long long cell0 = p.lo + tile * CPC;
@@ -66,11 +86,17 @@ __global__ void __launch_bounds__(256) scalar_kernel(const IntegParams p, const 
         __syncthreads();
 
         // ---- phase A: gather (Mesh::set_pad) ---------------------------------------------------------------------------
-        for (int idx = tid; idx < ncell_tile * NN; idx += nt) {
-            const int m = idx / ncell_tile, c = idx - m * ncell_tile;
-            const unsigned int pid = p.conn[(unsigned long long)m * p.ncell_k + cell0 + c];
+        if (gather_lane) {
+            const unsigned long long cell = cell0 + gc;
+            if (gc < ncell_tile) {
 #pragma unroll
-            for (int j = 0; j < SD; j++) s_X[c * XS + m * SD + j] = p.coords[(unsigned long long)j * p.npoint + pid];
+                for (int j = 0; j < SD; j++) s_X[gc * XS + gm * SD + j] = gx[j];
+            }
+            if (cell + gstep < p.hi) {
+#pragma unroll
+                for (int j = 0; j < SD; j++) gx[j] = p.coords[(unsigned long long)j * p.npoint + gpid];
+            }
+            if (cell + 2 * gstep < p.hi) gpid = p.conn[(unsigned long long)gm * p.ncell_k + cell + 2 * gstep];
         }
         __syncthreads();
 

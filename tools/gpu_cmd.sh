@@ -1,2 +1,2 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/e2e_probe.py
+python tools/bench_configs.py --scale 0.2 2>&1 | tail -4 | cut -c1-420
