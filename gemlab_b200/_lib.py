@@ -69,6 +69,7 @@ SYMBOLS = {
     "gl_args_default": (None, [C.POINTER(GlArgs)]),
     "gl_lin_elasticity": (None, [C.c_double, C.c_double, C.c_int, C.c_int, _P]),
     "gl_bench_fp64_peak": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "gl_bench_hbm_write": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
 }
 for _name in ("gl_mat_10_bdb", "gl_mat_01_nsn", "gl_mat_03_btb", "gl_vec_01_ns", "gl_vec_02_nv", "gl_vec_03_bv",
               "gl_vec_04_bt", "gl_mat_10_gdg", "gl_vec_10_gs"):

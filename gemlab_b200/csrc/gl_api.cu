@@ -1069,4 +1069,13 @@ int gl_bench_fp64_peak(gl_ctx *ctx, int kind, int iters, double *tflops) {
     return GL_OK;
 }
 
+int gl_bench_hbm_write(gl_ctx *ctx, int kind, double *dev, uint64_t nbytes, int warps_per_sm, double *gbs) {
+    if (!ctx || !dev || !gbs || nbytes < 4608) return GL_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    int st = bench_hbm_write(kind, dev, nbytes, warps_per_sm, ctx->stream, gbs);
+    if (st < 0) return cuda_fail(ctx, cudaGetLastError(), "hbm write micro-benchmark");
+    ctx->launches += (uint64_t)st;
+    return GL_OK;
+}
+
 } // extern "C"

@@ -107,6 +107,7 @@ int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void
 
 // micro-benchmarks
 int bench_fp64(int kind, int iters, void *stream, double *tflops);
+int bench_hbm_write(int kind, double *dev, unsigned long long nbytes, int warps_per_sm, void *stream, double *gbs);
 
 } // namespace gl
 

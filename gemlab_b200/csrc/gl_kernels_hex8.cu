@@ -6,17 +6,24 @@
 //   phase 0  lane g gathers node g of its cell (Mesh::set_pad, src/mesh/mesh.rs:448-456) -- prefetched one batch ahead;
 //   phase 1  lane g owns GAUSS POINT g: J = Xt.L, closed-form inverse/det, B = L.inv(J)
 //            (scratchpad_calc_jacobian.rs:101-131, scratchpad_calc_gradient.rs:78-91); B and c = det*w*alpha go to smem;
-//   phase 2  lane n owns COLUMN NODE n: per Gauss point T = c.D'.M(n) (18 values, D' from the constant bank), then the
-//            3x3 node-pair blocks K(m,n) += M(m)^T.T with 27 DFMA each, accumulated in registers over the 8 points.
-//            For a major-symmetric D only the "circulant half" m = n..n+4 (mod 8) is computed and mirrored;
-//   phase 3  blocks are staged in smem in the final column-major layout and the 4 cells of a warp (18,432 contiguous
-//            bytes) leave the SM as ONE bulk async copy (cp.async.bulk.global.shared::cta -> UBLKCP), so HBM sees only
-//            full lines and no thread waits on a store.
-// Shared-memory strides (25 / 200 doubles) are chosen so that every 64-bit access of a half-warp (2 cells x 8 lanes)
-// hits 16 distinct bank pairs in phases 1 and 2.
+//   phase 2  lane n owns COLUMN NODE n and accumulates GEOMETRIC TENSORS  P(m,n)[k][l] = sum_p c_p B(m,k) B(n,l)
+//            (9 DFMA per node pair and Gauss point) for the "circulant half" m = n..n+4 (mod 8); P(n,m) = P(m,n)^T covers
+//            the other pairs.  D is uniform, so it is applied ONCE, after the Gauss loop:
+//            K(m,n)[i][j] = sum_kl D_ikjl P(m,n)[k][l]  (add_to_kk, mat_10_bdb.rs:179-208, with the sum over Gauss
+//            points moved inside) -- 2.5x fewer FP64 instructions than accumulating M^T.D.M per Gauss point;
+//   phase 3  the contraction with D' (from the constant bank; structural zeros of an isotropic / orthotropic D' skipped at
+//            compile time), blocks staged in smem in the final column-major layout (mirrored when D is major-symmetric);
+//            every cell (4,608 contiguous bytes) leaves the SM as one bulk async copy (cp.async.bulk.global.shared::cta ->
+//            UBLKCP, L2 evict-first), issued by one elected lane per warp, so HBM sees only full lines and no thread
+//            waits on a store.
+// The kernel is bound by the WRITE stream: with all arithmetic removed it runs as fast as with it (GL_HEX8_DEBUG=3), and
+// the 0.7 GB of gather reads cost more than their share because they interleave with 36.9 GB of writes (GL_HEX8_DEBUG=4).
+// Shared-memory strides (25 / 200 / 584 doubles) are chosen so that every 64-bit access of a half-warp (2 cells x 8
+// lanes) hits 16 distinct bank pairs in all phases.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "gl_internal.hpp"
 
@@ -29,14 +36,22 @@ constexpr int H8_CELLS = H8_THREADS / 8; // cells per CTA batch
 constexpr int GP_STRIDE = 25;            // doubles per (cell, gauss point): 24 gradient values + coefficient
 constexpr int CELL_STRIDE = 8 * GP_STRIDE; // 200 = 8 (mod 16): second cell of a half-warp lands 16 banks away
 constexpr int X_STRIDE = 25;
-constexpr int K_STRIDE = 576;            // dense: the 4 cells of a warp are one contiguous 18,432-byte run (one bulk copy)
+constexpr int K_STRIDE = 584;            // 4,608-byte element block + 64 bytes: = 8 (mod 16), so the two cells of a half-warp stage conflict-free
 constexpr int L_STRIDE = 25;
 
 struct Hex8Consts {
+    int flags;    // bit 0: blocked work distribution, bit 1: evict-first stores, bit 2: evict-last coordinate loads
     double d[36]; // d'[a][b] = f_a f_b d[a][b], f = (1,1,1,1/sqrt2,1/sqrt2,1/sqrt2): the Mandel factors folded into D
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// one lane of the (converged) warp, chosen by the hardware: lets ptxas keep the guarded code on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 
 // structure of the (Mandel-scaled) modulus d', decided on the host from the coefficient record:
 //   PAT 0  general (minor-symmetric only): all 8 row blocks per lane
@@ -48,12 +63,10 @@ __host__ __device__ constexpr bool d_nz(int pat, int a, int b) { return pat < 2 
 // rows of the strain-displacement column (n, j) that are non-zero, and which gradient component sits there
 __host__ __device__ constexpr int col_row(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 3 : 5)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 3 : 4)) : (t == 0 ? 2 : (t == 1 ? 4 : 5))); }
 __host__ __device__ constexpr int col_comp(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 1 : 2)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 0 : 2)) : (t == 0 ? 2 : (t == 1 ? 1 : 0))); }
-__host__ __device__ constexpr bool t_nz(int pat, int a, int j) { return d_nz(pat, a, col_row(j, 0)) || d_nz(pat, a, col_row(j, 1)) || d_nz(pat, a, col_row(j, 2)); }
 
-template <int PAT, int GP_UNROLL_N>
+template <int PAT, int PF, int DBG = 0>
 __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegParams p, const Hex8Consts cst) {
     constexpr bool SYM = PAT >= 1;
-    constexpr int ND = SYM ? 5 : 8; // node-pair blocks per lane
     extern __shared__ __align__(16) double smem[];
     double *s_L = smem;                         // [8][L_STRIDE]  L[gp][m*3+j]
     double *s_w = s_L + 8 * L_STRIDE;           // [8]
@@ -64,6 +77,7 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
     const int tid = threadIdx.x;
     const int g = tid & 7;   // lane within the cell group
     const int cs = tid >> 3; // cell slot in the batch
+    const int wq = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp index, known to the compiler as warp-uniform
 
     // reference-element table: w[8] | N[8][8] | L[8][8][3]
     for (int i = tid; i < 8 * 24; i += H8_THREADS) s_L[(i / 24) * L_STRIDE + (i % 24)] = p.rule[8 + 64 + i];
@@ -77,43 +91,84 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
     double *Kc = s_K + cs * K_STRIDE;
     const double *Lg = s_L + g * L_STRIDE;
 
-    // software-pipelined gather (Mesh::set_pad): coordinates are loaded one batch ahead and the point id they depend on
-    // two batches ahead, so neither the index load nor the dependent coordinate loads ever stall a warp
-    double nx = 0.0, ny = 0.0, nz = 0.0;
+    // work distribution: iteration `it` of this CTA handles batch_of(it); strided (blockIdx + it*grid) or blocked
+    // (every CTA streams through one contiguous slab of the output)
+    const unsigned long long nit = (nbatch + gridDim.x - 1) / gridDim.x;
+    const bool blocked = (cst.flags & 1) != 0;
+    auto batch_of = [&](unsigned long long it) -> unsigned long long {
+        if (it >= nit) return nbatch;
+        return blocked ? (unsigned long long)blockIdx.x * nit + it : (unsigned long long)blockIdx.x + it * gridDim.x;
+    };
+    // L2 policies: the element matrices are written once and never read here (evict-first keeps them from flushing the
+    // mesh out of L2); point coordinates are re-read by up to 8 cells, the furthest a whole z-layer later (evict-last)
+    unsigned long long pol_w, pol_r;
+    if (cst.flags & 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_w));
+    if (cst.flags & 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_r));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_r));
+    auto ldx = [&](const double *ptr) -> double {
+        if (DBG == 5) return (double)(unsigned long long)ptr; // experiment: no coordinate loads
+        double v;
+        asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(pol_r));
+        return v;
+    };
+
+    auto ldp = [&](unsigned int pid, double &x, double &y, double &z) {
+        x = ldx(p.coords + pid);
+        y = ldx(p.coords + p.npoint + pid);
+        z = ldx(p.coords + 2 * p.npoint + pid);
+    };
+
+    // software-pipelined gather (Mesh::set_pad): coordinates are loaded PF batches ahead and the point id they depend
+    // on PF+1 batches ahead.  Under a saturated write stream a read can take several microseconds -- longer than one
+    // batch -- so one batch of lookahead is not enough to keep the loads off the critical path.
+    auto cell_of = [&](unsigned long long it) -> unsigned long long { // cell of this lane in iteration it, or p.hi
+        const unsigned long long bb = batch_of(it);
+        if (DBG == 4 || bb >= nbatch) return p.hi;
+        const unsigned long long c = p.lo + bb * H8_CELLS + cs;
+        return c < p.hi ? c : p.hi;
+    };
+    auto ldpid = [&](unsigned long long c) -> unsigned int {
+        return p.conn[(unsigned long long)g * p.ncell_k + c];
+    };
+    double qx[PF], qy[PF], qz[PF];
     unsigned int pid_next = 0;
+#pragma unroll
+    for (int d = 0; d < PF; d++) {
+        qx[d] = qy[d] = qz[d] = 0.0;
+        const unsigned long long c = cell_of(d);
+        if (c < p.hi) ldp(ldpid(c), qx[d], qy[d], qz[d]);
+    }
     {
-        const unsigned long long cell = p.lo + (unsigned long long)blockIdx.x * H8_CELLS + cs;
-        if (cell < p.hi) {
-            const unsigned int pid = p.conn[(unsigned long long)g * p.ncell_k + cell];
-            nx = p.coords[pid];
-            ny = p.coords[p.npoint + pid];
-            nz = p.coords[2 * p.npoint + pid];
-        }
-        const unsigned long long cell1 = cell + (unsigned long long)gridDim.x * H8_CELLS;
-        if (cell1 < p.hi) pid_next = p.conn[(unsigned long long)g * p.ncell_k + cell1];
+        const unsigned long long c = cell_of(PF);
+        if (c < p.hi) pid_next = ldpid(c);
     }
 
-    for (unsigned long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    for (unsigned long long it = 0; it < nit; it++) {
+        const unsigned long long batch = batch_of(it);
+        if (batch >= nbatch) break;
         const unsigned long long cell = p.lo + batch * H8_CELLS + cs;
         const bool active = cell < p.hi;
 
-        // ---- phase 0: publish this batch's coordinates, prefetch the next batch's ---------------------------------
-        Xc[g * 3 + 0] = nx;
-        Xc[g * 3 + 1] = ny;
-        Xc[g * 3 + 2] = nz;
+        // ---- phase 0: publish this batch's coordinates, prefetch later batches' ------------------------------------
+        Xc[g * 3 + 0] = qx[0];
+        Xc[g * 3 + 1] = qy[0];
+        Xc[g * 3 + 2] = qz[0];
+#pragma unroll
+        for (int d = 0; d + 1 < PF; d++) {
+            qx[d] = qx[d + 1];
+            qy[d] = qy[d + 1];
+            qz[d] = qz[d + 1];
+        }
         {
-            const unsigned long long step = (unsigned long long)gridDim.x * H8_CELLS;
-            if (cell + step < p.hi) { // next batch: its point id arrived during the previous iteration
-                nx = p.coords[pid_next];
-                ny = p.coords[p.npoint + pid_next];
-                nz = p.coords[2 * p.npoint + pid_next];
-            }
-            if (cell + 2 * step < p.hi) pid_next = p.conn[(unsigned long long)g * p.ncell_k + cell + 2 * step];
+            const unsigned long long c1 = cell_of(it + PF), c2 = cell_of(it + PF + 1);
+            if (c1 < p.hi) ldp(pid_next, qx[PF - 1], qy[PF - 1], qz[PF - 1]); // its point id arrived during the previous iteration
+            if (c2 < p.hi) pid_next = ldpid(c2);
         }
         __syncwarp();
 
         // ---- phase 1: geometry at Gauss point g ------------------------------------------------------------------
-        {
+        if (DBG < 2 || DBG > 4) {
             double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
             for (int m = 0; m < 8; m++) {
@@ -151,95 +206,115 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
         }
         __syncwarp();
 
-        // ---- phase 2: lane g = column node n; accumulate its node-pair blocks over the 8 Gauss points -------------
-        double acc[ND][9];
+        // ---- phase 2: lane g = column node n; geometric tensors P(m,n)[k][l] = sum_p c_p B(m,k) B(n,l) ------------------
+        // D is the same at every Gauss point of the cell, so K(m,n)[i][j] = sum_kl D_ikjl P(m,n)[k][l]: the 9 FMA per node
+        // pair and Gauss point below replace the 27 of the T = D'.M / M^T.T form, and D enters once, in the epilogue.
+        // P(n,m) = P(m,n)^T, so the circulant half m = n .. n+4 (mod 8) covers every pair; P(n,n) is symmetric (6 values).
+        double p0[6], pb[4][9];
 #pragma unroll
-        for (int b = 0; b < ND; b++)
+        for (int q = 0; q < 6; q++) p0[q] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 9; q++) acc[b][q] = 0.0;
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int q = 0; q < 9; q++) pb[b][q] = 0.0;
 
-#pragma unroll GP_UNROLL_N
-        for (int gp = 0; gp < 8; gp++) {
+#pragma unroll 1
+        for (int gp = 0; gp < (DBG >= 1 && DBG <= 4 ? 0 : 8); gp++) {
             const double *Bg = Bc + gp * GP_STRIDE;
             const double c = Bg[24];
-            const double bn[3] = {Bg[g * 3 + 0] * c, Bg[g * 3 + 1] * c, Bg[g * 3 + 2] * c};
-            // T[a][j] = sum_t d'[a][row(j,t)] * bn[comp(j,t)]: column (n,j) of M' has the gradient components
-            // j=0 -> rows (0,3,5) = (b0,b1,b2); j=1 -> rows (1,3,4) = (b1,b0,b2); j=2 -> rows (2,4,5) = (b2,b1,b0)
-            double T[6][3];
+            const double bu[3] = {Bg[g * 3 + 0], Bg[g * 3 + 1], Bg[g * 3 + 2]};
+            const double vn[3] = {bu[0] * c, bu[1] * c, bu[2] * c};
+            p0[0] = fma(bu[0], vn[0], p0[0]);
+            p0[1] = fma(bu[0], vn[1], p0[1]);
+            p0[2] = fma(bu[0], vn[2], p0[2]);
+            p0[3] = fma(bu[1], vn[1], p0[3]);
+            p0[4] = fma(bu[1], vn[2], p0[4]);
+            p0[5] = fma(bu[2], vn[2], p0[5]);
 #pragma unroll
-            for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    double t = 0.0;
-                    bool have = false;
-#pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        if (d_nz(PAT, a, col_row(j, q))) {
-                            const double dv = cst.d[a * 6 + col_row(j, q)], bv = bn[col_comp(j, q)];
-                            t = have ? fma(dv, bv, t) : dv * bv;
-                            have = true;
-                        }
-                    }
-                    T[a][j] = t;
-                }
-#pragma unroll
-            for (int b = 0; b < ND; b++) {
+            for (int b = 1; b < 5; b++) {
                 const int m = (g + b) & 7;
                 const double bm[3] = {Bg[m * 3 + 0], Bg[m * 3 + 1], Bg[m * 3 + 2]};
-                // In the symmetric variants the diagonal block (b = 0) is itself symmetric, and the block at distance 4 is
-                // held as a transposed duplicate by lane g+4: both need only their upper triangles (i <= j).
-                const bool tri = SYM && (b == 0 || b == 4);
 #pragma unroll
-                for (int j = 0; j < 3; j++)
+                for (int l = 0; l < 3; l++)
 #pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        if (tri && i > j) continue;
-                        // K(3m+i, 3n+j) += sum_t M'(m)[row(i,t)][i] * T[row(i,t)][j]
-                        double v = acc[b][i + 3 * j];
-#pragma unroll
-                        for (int q = 2; q >= 0; q--)
-                            if (t_nz(PAT, col_row(i, q), j)) v = fma(bm[col_comp(i, q)], T[col_row(i, q)][j], v);
-                        acc[b][i + 3 * j] = v;
-                    }
+                    for (int k = 0; k < 3; k++) pb[b - 1][k + 3 * l] = fma(bm[k], vn[l], pb[b - 1][k + 3 * l]);
             }
         }
 
-        // ---- phase 3: stage the blocks column-major and ship the warp's cells with one bulk copy ------------------
-        if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // previous copy has left s_K
+        // ---- phase 3: contract with D', stage the blocks column-major, ship every cell with one bulk copy -------------
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the warp's previous copies have left s_K (no-op for lanes that issued none)
         __syncwarp();
-        // (the two cells of a half-warp are 1152 words apart: a 2-way bank conflict on these 72 stores, ~1% of the iteration)
 #pragma unroll
-        for (int b = 0; b < ND; b++) {
+        for (int b = 0; b < (DBG >= 3 && DBG <= 4 ? 0 : 5); b++) {
             const int m = (g + b) & 7;
+            // P(m,n)[k][l] of this block (compile-time indices after unrolling)
+            auto P = [&](int k, int l) -> double {
+                if (b == 0) return p0[k <= l ? (k == 0 ? l : (k == 1 ? 2 + l : 5)) : (l == 0 ? k : (l == 1 ? 2 + k : 5))];
+                return pb[b == 0 ? 0 : b - 1][k + 3 * l];
+            };
+            // In the symmetric variants the diagonal block (b = 0) is itself symmetric, and the block at distance 4 is
+            // held as a transposed duplicate by lane g+4: both need only their upper triangles (i <= j).
             const bool tri = SYM && (b == 0 || b == 4);
 #pragma unroll
             for (int j = 0; j < 3; j++)
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
-                    if (tri && i > j) continue; // lower triangle comes from the mirror (b = 0) or from lane g+4 (b = 4)
-                    const double v = acc[b][i + 3 * j];
+                    if (tri && i > j) continue;
+                    // K(3m+i, 3n+j) = sum_qr d'[row(i,q)][row(j,r)] P[comp(i,q)][comp(j,r)]
+                    double v = 0.0;
+                    bool have = false;
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+#pragma unroll
+                        for (int r = 0; r < 3; r++)
+                            if (d_nz(PAT, col_row(i, q), col_row(j, r))) {
+                                const double dv = cst.d[col_row(i, q) * 6 + col_row(j, r)], pv = P(col_comp(i, q), col_comp(j, r));
+                                v = have ? fma(dv, pv, v) : dv * pv;
+                                have = true;
+                            }
                     Kc[(3 * m + i) + 24 * (3 * g + j)] = v;
                     // mirrored entry K(n,m)^T: whole blocks at distance 1..3, strict upper triangles of the b = 0 / b = 4 blocks
                     if (SYM && ((b >= 1 && b <= 3) || (tri && i < j))) Kc[(3 * g + j) + 24 * (3 * m + i)] = v;
+                    if (!SYM && b >= 1 && b <= 3) {
+                        // general D: K(3n+j, 3m+i) = sum_qr d'[row(j,r)][row(i,q)] P(n,m)[comp(j,r)][comp(i,q)], P(n,m) = P(m,n)^T
+                        double u = 0.0;
+                        bool hv = false;
+#pragma unroll
+                        for (int q = 0; q < 3; q++)
+#pragma unroll
+                            for (int r = 0; r < 3; r++) {
+                                const double dv = cst.d[col_row(j, r) * 6 + col_row(i, q)], pv = P(col_comp(i, q), col_comp(j, r));
+                                u = hv ? fma(dv, pv, u) : dv * pv;
+                                hv = true;
+                            }
+                        Kc[(3 * g + j) + 24 * (3 * m + i)] = u;
+                    }
                 }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (p.cell_ids == nullptr) {
-            // homogeneous mesh: the warp's 4 cells are consecutive in the output
-            if ((tid & 31) == 0 && active) {
-                const unsigned long long remaining = p.hi - cell;
-                const unsigned int nb = (unsigned int)(remaining < 4 ? remaining : 4) * 4608u;
-                double *dst = p.out + (cell - p.cell_begin) * 576ull;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(Kc)), "r"(nb)
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // one elected lane issues the warp's four copies back to back; every operand is derived from warp-uniform values
+        // (wq comes from a lane-0 shuffle) so that the copies are plain UBLKCP instructions on uniform registers
+        {
+            const unsigned long long wcell = p.lo + batch * H8_CELLS + wq * 4; // first cell of this warp
+            if (wcell < p.hi) {
+                const unsigned long long remaining = p.hi - wcell;
+                const int nc = remaining < 4 ? (int)remaining : 4;
+                const unsigned src0 = smem_u32(s_K + wq * 4 * K_STRIDE);
+                if (elect_one()) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        if (c < nc) {
+                            const unsigned long long orig = p.cell_ids ? (unsigned long long)p.cell_ids[wcell + c] : wcell + c;
+                            double *dst = p.out + (orig - p.cell_begin) * 576ull;
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+                                         "r"(src0 + c * K_STRIDE * 8), "r"(4608), "l"(pol_w)
+                                         : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
-        } else if (g == 0 && active) {
-            double *dst = p.out + ((unsigned long long)p.cell_ids[cell] - p.cell_begin) * 576ull;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(Kc)), "r"(4608)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -257,6 +332,12 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
 
     Hex8Consts cst;
+    static int flags = -1;
+    if (flags < 0) {
+        const char *e = getenv("GL_HEX8_FLAGS"); // tuning knob, see Hex8Consts::flags
+        flags = e ? atoi(e) : 2;
+    }
+    cst.flags = flags;
     const double h = 0.70710678118654752440084436210484903928;
     bool sym = true;
     for (int a = 0; a < 6; a++)
@@ -265,12 +346,12 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
             cst.d[a * 6 + b] = p.coef_uniform[a + b * 6] * fa * fb; // ABI record is column-major
             if (p.coef_uniform[a + b * 6] != p.coef_uniform[b + a * 6]) sym = false;
         }
-    // unroll factor of the Gauss-point loop (tuning knob; GL_HEX8_UNROLL overrides the default)
-    static int unroll = -1;
-    if (unroll < 0) {
-        const char *e = getenv("GL_HEX8_UNROLL");
-        unroll = e ? atoi(e) : 1;
-        if (unroll != 1 && unroll != 2) unroll = 1;
+    // gather lookahead in batches (tuning knob GL_HEX8_PF = 1 or 2)
+    static int pf = -1;
+    if (pf < 0) {
+        const char *e = getenv("GL_HEX8_PF");
+        pf = e ? atoi(e) : 1;
+        if (pf < 1 || pf > 2) pf = 1;
     }
     int pat = 0;
     if (sym) {
@@ -285,14 +366,30 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     }
     typedef void (*kern_t)(const IntegParams, const Hex8Consts);
     kern_t kern;
-    if (unroll == 2) kern = pat == 2 ? hex8_bdb_kernel<2, 2> : (pat == 1 ? hex8_bdb_kernel<1, 2> : hex8_bdb_kernel<0, 2>);
-    else kern = pat == 2 ? hex8_bdb_kernel<2, 1> : (pat == 1 ? hex8_bdb_kernel<1, 1> : hex8_bdb_kernel<0, 1>);
+    auto pick = [&](auto pfc) -> kern_t {
+        constexpr int P = decltype(pfc)::value;
+        if (const char *e = getenv("GL_HEX8_DEBUG")) { // timing experiments only (1 no accumulation, 2 no geometry, 3 no staging, 4 no gather, 5 no coordinate loads)
+            switch (atoi(e)) {
+            case 1: return hex8_bdb_kernel<2, P, 1>;
+            case 2: return hex8_bdb_kernel<2, P, 2>;
+            case 3: return hex8_bdb_kernel<2, P, 3>;
+            case 4: return hex8_bdb_kernel<2, P, 4>;
+            default: return hex8_bdb_kernel<2, P, 5>;
+            }
+        }
+        return pat == 2 ? hex8_bdb_kernel<2, P> : (pat == 1 ? hex8_bdb_kernel<1, P> : hex8_bdb_kernel<0, P>);
+    };
+    kern = pf == 1 ? pick(std::integral_constant<int, 1>{}) : pick(std::integral_constant<int, 2>{});
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8_SMEM) != cudaSuccess) return -1;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const unsigned long long nbatch = (p.hi - p.lo + H8_CELLS - 1) / H8_CELLS;
-    unsigned long long grid = (unsigned long long)nsm * 2; // persistent: two resident CTAs per SM
+    // Two CTAs are resident per SM (shared memory), but the grid is 32x larger: CTAs that start and finish at different
+    // times keep the SMs out of lockstep, so gather reads and matrix writes of different SMs interleave instead of
+    // arriving at the memory system in device-wide bursts (measured: 6.5 ms with 296 persistent CTAs, 5.8 ms with 9472).
+    unsigned long long grid = (unsigned long long)nsm * 2 * 32;
+    if (const char *e = getenv("GL_HEX8_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     kern<<<(unsigned)grid, H8_THREADS, H8_SMEM, (cudaStream_t)stream>>>(p, cst);

@@ -191,6 +191,20 @@ class Context:
         return t.value
 
 
+def _hbm_write_peak(self, buf, kind="bulk", warps_per_sm=8, mode=0):
+    """Measured write bandwidth (GB/s) into the device tensor `buf` (kind: 'bulk' = cp.async.bulk shared->global in
+    4,608-byte blocks, 'stg' = 16-byte register stores, 'memset' = cudaMemsetAsync)."""
+    t = C.c_double()
+    st = lib().gl_bench_hbm_write(self._h, {"bulk": 0, "stg": 1, "memset": 2}[kind] | (int(mode) << 4), buf.data_ptr(),
+                                  buf.numel() * buf.element_size(), int(warps_per_sm), C.byref(t))
+    if st:
+        self._raise(st)
+    return t.value
+
+
+Context.hbm_write_peak = _hbm_write_peak
+
+
 def out_total(dmesh, op, cell_range, args):
     b, e = _range(dmesh, cell_range)
     a = args._c()

@@ -252,6 +252,10 @@ GL_API void gl_lin_elasticity(double young, double poisson, int two_dim, int pla
 /* runs `iters` dependent-chain DFMA (kind 0) or DMMA m8n8k4 (kind 1) per thread on the whole device and returns the
  * achieved TFLOP/s measured with CUDA events; kind 2 interleaves both */
 GL_API int gl_bench_fp64_peak(gl_ctx *ctx, int kind, int iters, double *tflops);
+/* writes `nbytes` of the DEVICE buffer `dev` once and returns the achieved write bandwidth in GB/s: kind 0 = 4,608-byte
+ * cp.async.bulk shared->global copies with `warps_per_sm` resident warps (the mechanism of the stiffness kernels),
+ * kind 1 = coalesced 16-byte stores from registers, kind 2 = cudaMemsetAsync */
+GL_API int gl_bench_hbm_write(gl_ctx *ctx, int kind, double *dev, uint64_t nbytes, int warps_per_sm, double *gbs);
 
 #ifdef __cplusplus
 }
