@@ -35,6 +35,7 @@ int kind_from_name(const char *name);
 bool kind_supported(int kind);
 int shape_eval(int kind, const double *ksi, double *nn, double *ll);
 int gauss_rule(int kind, int ngauss, int *npoint, const double **data);
+const double *shape_table(int kind, int ng); // N[ng][nnode] | L[ng][nnode][gd], exact; nullptr if not tabulated
 const char *status_string(int status);
 void lin_elasticity(double young, double poisson, int two_dim, int plane_stress, double *dd);
 

@@ -5,18 +5,20 @@
 //   phase A  gather: Mesh::set_pad (src/mesh/mesh.rs:448-456), coalesced node-major connectivity;
 //   phase B  one thread per (cell, Gauss point): J = Xt.L, closed-form inverse, det, B = L.inv(J), axisymmetric radius
 //            (scratchpad_calc_jacobian.rs:101-131, scratchpad_calc_gradient.rs:78-91); B, c = det*w*alpha[*r] and N/r -> smem;
-//   phase C  LPN lanes per COLUMN NODE n: per Gauss point T = c.D'.M(n) (D' in uniform registers), then the SD x SD
-//            node-pair blocks K(m,n) += M(m)^T.T accumulated in registers over all Gauss points.  For a major-symmetric
-//            D only the circulant half m = n, n+1, .., n+NN/2 (mod NN) is computed and mirrored; the diagonal and the
-//            half-distance blocks need their upper triangles only;
-//   phase D  blocks are staged in smem in the final column-major layout and the CTA's cells leave with ONE bulk async
-//            copy (homogeneous meshes) or a cooperative vector copy (mixed-kind meshes).
+//   phase C  LPN lanes per COLUMN NODE n accumulate the GEOMETRIC TENSORS P(m,n)[k][l] = sum_p c_p v(m)[k] v(n)[l] of the
+//            circulant half of the node pairs, m = n, n+1, .., n+NN/2 (mod NN), in registers (VD^2 DFMA per pair and Gauss
+//            point, v(m) = (B(m,.) [, N(m)/r]));  P(n,m) = P(m,n)^T gives the other half;
+//   phase D  D is the same at every Gauss point, so it is applied ONCE: K(m,n)[i][j] = sum_kl D_ikjl P(m,n)[k][l]
+//            (add_to_kk with the Gauss sum moved inside).  Blocks are staged in smem in the final column-major layout
+//            (mirrored when D is major-symmetric) and the CTA's cells leave with ONE bulk async copy (homogeneous meshes)
+//            or a cooperative vector copy (mixed-kind meshes).
 // M(n) is the Mandel strain-displacement column block of calc_bb_matrix (mat_10_bdb.rs:238-278) with the 1/sqrt(2)
 // factors folded into D' on the host; in the axisymmetric case row 2 carries N/r and the coefficient is c*r.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
 
+#include "gl_geom.cuh"
 #include "gl_internal.hpp"
 
 namespace gl {
@@ -38,12 +40,6 @@ __host__ __device__ constexpr int col_comp(int sd, int j, int q) {
 __host__ __device__ constexpr bool d_nz(int pat, int sd, int a, int b) {
     return pat < 2 ? true : ((a < 3 && b < 3) || a == b);
 }
-__host__ __device__ constexpr bool t_nz(int pat, int sd, bool axi, int a, int j) {
-    bool nz = false;
-    for (int q = 0; q < col_n(sd, axi, j); q++) nz = nz || d_nz(pat, sd, a, col_row(sd, j, q));
-    return nz;
-}
-
 struct BdbConsts {
     double d[36]; // d'[a][b] = f_a f_b d[a][b] (row-major, ns x ns), f = 1 for normal rows, 1/sqrt(2) for shear rows
 };
@@ -59,6 +55,7 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     constexpr int NSLOT = (ND + LPN - 1) / LPN;        // blocks per lane
     constexpr int GS = (1 + NN * SD + (AXI ? NN : 0)) | 1; // record per (cell, gauss point): c | B | N/r ; odd stride
     constexpr int XS = (NN * SD) | 1;
+    constexpr int VD = SD + (AXI ? 1 : 0);            // components of the per-node vector v(m) = (B(m,.) [, N(m)/r])
 
     extern __shared__ __align__(16) double smem[];
     const int ng = p.ng;
@@ -131,56 +128,21 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
 #pragma unroll
                 for (int j = 0; j < SD; j++) J[i][j] = 0.0;
 #pragma unroll 4
-            for (int m = 0; m < NN; m++) {
-#pragma unroll
-                for (int i = 0; i < SD; i++)
-#pragma unroll
-                    for (int j = 0; j < SD; j++) J[i][j] = fma(X[m * SD + i], L[m * SD + j], J[i][j]);
-            }
-            double det, Ji[SD][SD];
-            if constexpr (SD == 2) {
-                det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-                const double rdet = 1.0 / det;
-                Ji[0][0] = J[1][1] * rdet;
-                Ji[0][1] = -J[0][1] * rdet;
-                Ji[1][0] = -J[1][0] * rdet;
-                Ji[1][1] = J[0][0] * rdet;
-            } else {
-                const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-                const double c01 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
-                const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-                det = J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02;
-                const double rdet = 1.0 / det;
-                Ji[0][0] = c00 * rdet;
-                Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * rdet;
-                Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rdet;
-                Ji[1][0] = -c01 * rdet;
-                Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * rdet;
-                Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * rdet;
-                Ji[2][0] = c02 * rdet;
-                Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * rdet;
-                Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * rdet;
-            }
+            for (int m = 0; m < NN; m++) geom::jacobian_add_node<SD, SD>(J, X + m * SD, L + m * SD);
+            double Ji[SD][SD];
+            const double det = geom::invert(J, Ji);
             if (fabs(det) <= ZERO_DETERMINANT) {
                 const unsigned long long cell = cell0 + c;
                 atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
             }
             double *G = s_G + (c * ng + gp) * GS;
 #pragma unroll 4
-            for (int m = 0; m < NN; m++) {
-#pragma unroll
-                for (int j = 0; j < SD; j++) {
-                    double sum = L[m * SD] * Ji[0][j];
-#pragma unroll
-                    for (int k = 1; k < SD; k++) sum = fma(L[m * SD + k], Ji[k][j], sum);
-                    G[1 + m * SD + j] = sum;
-                }
-            }
+            for (int m = 0; m < NN; m++) geom::gradient_row<SD>(L + m * SD, Ji, G + 1 + m * SD);
             double coef = det * s_w[gp] * p.alpha;
             if constexpr (AXI) {
                 const double *N = s_N + gp * NN;
                 double r = 0.0;
-                for (int m = 0; m < NN; m++) r = fma(N[m], X[m * SD], r);
+                for (int m = 0; m < NN; m++) r = geom::add(r, geom::mul(N[m], X[m * SD])); // radius_at_ip: r = sum N.x0
                 const double rinv = 1.0 / r;
                 for (int m = 0; m < NN; m++) G[1 + NN * SD + m] = N[m] * rinv;
                 coef *= r;
@@ -189,66 +151,44 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
         }
         __syncthreads();
 
-        // ---- phase C: node-pair blocks ------------------------------------------------------------------------------
-        double acc[NSLOT][SD * SD];
+        // ---- phase C: geometric tensors of the node pairs ------------------------------------------------------------------
+        // P(m,n)[k][l] = sum_p c_p v(m)[k] v(n)[l] with v(m) = (B(m,0..SD-1) [, N(m)/r]).  D is the same at every Gauss point,
+        // so it is applied once, in phase D:  K(m,n)[i][j] = sum_qr d'[row(i,q)][row(j,r)] P(m,n)[comp(i,q)][comp(j,r)].
+        // P(n,m) = P(m,n)^T, so the circulant half of the pairs is enough even for a non-symmetric D.
+        double acc[NSLOT][VD * VD];
 #pragma unroll
         for (int s = 0; s < NSLOT; s++)
 #pragma unroll
-            for (int q = 0; q < SD * SD; q++) acc[s][q] = 0.0;
+            for (int q = 0; q < VD * VD; q++) acc[s][q] = 0.0;
 
         if (worker && cs < ncell_tile) {
 #pragma unroll 1
             for (int gp = 0; gp < ng; gp++) {
                 const double *G = s_G + (cs * ng + gp) * GS;
                 const double c = G[0];
-                double vn[SD + 1];
+                double vn[VD];
 #pragma unroll
                 for (int k = 0; k < SD; k++) vn[k] = G[1 + n * SD + k] * c;
-                vn[SD] = AXI ? G[1 + NN * SD + n] * c : 0.0;
-                double T[NS][SD];
-#pragma unroll
-                for (int a = 0; a < NS; a++)
-#pragma unroll
-                    for (int j = 0; j < SD; j++) {
-                        double t = 0.0;
-                        bool have = false;
-#pragma unroll
-                        for (int q = 0; q < col_n(SD, AXI, j); q++) {
-                            if (d_nz(PAT, SD, a, col_row(SD, j, q))) {
-                                const double dv = cst.d[a * NS + col_row(SD, j, q)], bv = vn[col_comp(SD, j, q)];
-                                t = have ? fma(dv, bv, t) : dv * bv;
-                                have = true;
-                            }
-                        }
-                        T[a][j] = t;
-                    }
+                if constexpr (AXI) vn[SD] = G[1 + NN * SD + n] * c;
 #pragma unroll
                 for (int s = 0; s < NSLOT; s++) {
                     const int b = LPN == 1 ? s : s * LPN + h;
                     if (b >= ND) continue;
                     int m = n + b;
                     if (m >= NN) m -= NN;
-                    double vm[SD + 1];
+                    double vm[VD];
 #pragma unroll
                     for (int k = 0; k < SD; k++) vm[k] = G[1 + m * SD + k];
-                    vm[SD] = AXI ? G[1 + NN * SD + m] : 0.0;
-                    const bool tri = SYM && (b == 0 || (NN % 2 == 0 && b == NN / 2));
+                    if constexpr (AXI) vm[SD] = G[1 + NN * SD + m];
 #pragma unroll
-                    for (int j = 0; j < SD; j++)
+                    for (int l = 0; l < VD; l++)
 #pragma unroll
-                        for (int i = 0; i < SD; i++) {
-                            if (tri && i > j) continue;
-                            double v = acc[s][i + SD * j];
-#pragma unroll
-                            for (int q = col_n(SD, AXI, i) - 1; q >= 0; q--)
-                                if (t_nz(PAT, SD, AXI, col_row(SD, i, q), j)) v = fma(vm[col_comp(SD, i, q)], T[col_row(SD, i, q)][j], v);
-                            acc[s][i + SD * j] = v;
-                        }
+                        for (int k = 0; k < VD; k++) acc[s][k + VD * l] = fma(vm[k], vn[l], acc[s][k + VD * l]);
                 }
             }
         }
 
-        // ---- phase D: stage and ship -----------------------------------------------------------------------------------
+        // ---- phase D: contract with D', stage and ship ------------------------------------------------------------------
         if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // previous bulk copy has left s_K
         __syncthreads();
         if (worker && cs < ncell_tile) {
@@ -259,16 +199,31 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                 if (b >= ND) continue;
                 int m = n + b;
                 if (m >= NN) m -= NN;
-                const bool tri = SYM && (b == 0 || (NN % 2 == 0 && b == NN / 2));
+                const bool half = (NN % 2 == 0) && b == NN / 2; // lane n + NN/2 holds the transposed pair itself
+                const bool tri = SYM && (b == 0 || half);
                 const bool mirror_all = SYM && !tri;
+                const bool transposed = !SYM && b != 0 && !half; // general D: K(n,m) needs its own contraction
 #pragma unroll
                 for (int j = 0; j < SD; j++)
 #pragma unroll
                     for (int i = 0; i < SD; i++) {
                         if (tri && i > j) continue;
-                        const double v = acc[s][i + SD * j];
+                        double v = 0.0, u = 0.0;
+                        bool have = false;
+#pragma unroll
+                        for (int q = 0; q < col_n(SD, AXI, i); q++)
+#pragma unroll
+                            for (int r = 0; r < col_n(SD, AXI, j); r++) {
+                                const int ra = col_row(SD, i, q), rb = col_row(SD, j, r);
+                                if (!d_nz(PAT, SD, ra, rb)) continue;
+                                const double pv = acc[s][col_comp(SD, i, q) + VD * col_comp(SD, j, r)];
+                                v = have ? fma(cst.d[ra * NS + rb], pv, v) : cst.d[ra * NS + rb] * pv;
+                                if (!SYM) u = have ? fma(cst.d[rb * NS + ra], pv, u) : cst.d[rb * NS + ra] * pv;
+                                have = true;
+                            }
                         Kc[(SD * m + i) + NDOF * (SD * n + j)] = v;
                         if (mirror_all || (tri && i < j)) Kc[(SD * n + j) + NDOF * (SD * m + i)] = v;
+                        if (transposed) Kc[(SD * n + j) + NDOF * (SD * m + i)] = u;
                     }
             }
         }
@@ -278,7 +233,10 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
             if (tid == 0) {
                 const unsigned int nbytes = (unsigned int)ncell_tile * (unsigned int)(NDOF * NDOF * sizeof(double));
                 double *dst = p.out + (cell0 - p.cell_begin) * (unsigned long long)(NDOF * NDOF);
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(s_K)), "r"(nbytes)
+                unsigned long long pol; // the element matrices are written once: keep them from flushing the mesh out of L2
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(s_K)),
+                             "r"(nbytes), "l"(pol)
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -333,7 +291,10 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     if (ctas_per_sm > 8) ctas_per_sm = 8;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const unsigned long long ntile = (p.hi - p.lo + cpc - 1) / cpc;
-    unsigned long long grid = (unsigned long long)nsm * ctas_per_sm;
+    // many more CTAs than resident slots: CTAs that start and finish at different times keep the SMs out of lockstep, so
+    // reads and writes of different SMs interleave instead of arriving in device-wide bursts (see gl_kernels_hex8.cu)
+    unsigned long long grid = (unsigned long long)nsm * ctas_per_sm * 16;
+    if (const char *e = getenv("GL_BDB_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
     kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, cst, cpc, used);

@@ -13,6 +13,7 @@
 // over the coefficient modes; hot configurations have register-blocked specialisations (gl_kernels_hex8.cu, ...).
 #include <cuda_runtime.h>
 
+#include "gl_geom.cuh"
 #include "gl_internal.hpp"
 
 namespace gl {
@@ -125,33 +126,13 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
 #pragma unroll
                 for (int i = 0; i < SD; i++)
 #pragma unroll
-                    for (int j = 0; j < GD; j++) J[i][j] += X[m * SD + i] * L[m * GD + j];
+                    for (int j = 0; j < GD; j++) J[i][j] = geom::add(J[i][j], geom::mul(X[m * SD + i], L[m * GD + j]));
             }
             double det;
             double Ji[SD][SD];
             if constexpr (GD == SD) {
                 // SOLID: closed-form inverse, as russell_lab::mat_inverse does for 2x2 / 3x3 (cofactors divided by det)
-                if constexpr (SD == 2) {
-                    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-                    Ji[0][0] = J[1][1] / det;
-                    Ji[0][1] = -J[0][1] / det;
-                    Ji[1][0] = -J[1][0] / det;
-                    Ji[1][1] = J[0][0] / det;
-                } else {
-                    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-                    const double c01 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
-                    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-                    det = J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02;
-                    Ji[0][0] = c00 / det;
-                    Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
-                    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
-                    Ji[1][0] = -c01 / det;
-                    Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
-                    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
-                    Ji[2][0] = c02 / det;
-                    Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
-                    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
-                }
+                det = geom::invert(J, Ji);
                 if (fabs(det) <= ZERO_DETERMINANT) {
                     const unsigned long long cell = cell0 + c;
                     atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
@@ -161,9 +142,9 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
                     for (int m = 0; m < nnode; m++) {
 #pragma unroll
                         for (int j = 0; j < SD; j++) {
-                            double sum = 0.0;
+                            double sum = geom::mul(L[m * GD], Ji[0][j]);
 #pragma unroll
-                            for (int k = 0; k < SD; k++) sum += L[m * GD + k] * Ji[k][j];
+                            for (int k = 1; k < SD; k++) sum = geom::add(sum, geom::mul(L[m * GD + k], Ji[k][j]));
                             Bc[m * SD + j] = sum;
                         }
                     }
@@ -171,7 +152,7 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
             } else if constexpr (GD == 1) { // CABLE: norm of the Jacobian vector
                 double n2 = 0.0;
 #pragma unroll
-                for (int i = 0; i < SD; i++) n2 += J[i][0] * J[i][0];
+                for (int i = 0; i < SD; i++) n2 = geom::add(n2, geom::mul(J[i][0], J[i][0]));
                 det = sqrt(n2);
                 (void)Ji;
             } else { // SHELL: DET_JAC_NOT_AVAILABLE
@@ -181,7 +162,7 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
             double r = 0.0;
             if (axisym) {
                 const double *N = s_N + gp * nnode;
-                for (int m = 0; m < nnode; m++) r += N[m] * X[m * SD];
+                for (int m = 0; m < nnode; m++) r = geom::add(r, geom::mul(N[m], X[m * SD]));
             }
             s_cf[c * ng + gp] = (op == GL_OP_JACOBIAN) ? det : det * s_w[gp] * p.alpha;
             s_rr[c * ng + gp] = r;

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "gl_geom.cuh"
 #include "gl_internal.hpp"
 
 namespace gl {
@@ -171,37 +172,13 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
         if (DBG < 2 || DBG > 4) {
             double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const double l0 = Lg[m * 3 + 0], l1 = Lg[m * 3 + 1], l2 = Lg[m * 3 + 2];
-                const double x0 = Xc[m * 3 + 0], x1 = Xc[m * 3 + 1], x2 = Xc[m * 3 + 2];
-                J[0][0] = fma(x0, l0, J[0][0]); J[0][1] = fma(x0, l1, J[0][1]); J[0][2] = fma(x0, l2, J[0][2]);
-                J[1][0] = fma(x1, l0, J[1][0]); J[1][1] = fma(x1, l1, J[1][1]); J[1][2] = fma(x1, l2, J[1][2]);
-                J[2][0] = fma(x2, l0, J[2][0]); J[2][1] = fma(x2, l1, J[2][1]); J[2][2] = fma(x2, l2, J[2][2]);
-            }
-            const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-            const double c01 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
-            const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-            const double det = J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02;
-            if (active && fabs(det) <= ZERO_DETERMINANT) atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
-            const double rdet = 1.0 / det;
+            for (int m = 0; m < 8; m++) geom::jacobian_add_node<3, 3>(J, Xc + m * 3, Lg + m * 3);
             double Ji[3][3];
-            Ji[0][0] = c00 * rdet;
-            Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * rdet;
-            Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rdet;
-            Ji[1][0] = -c01 * rdet;
-            Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * rdet;
-            Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * rdet;
-            Ji[2][0] = c02 * rdet;
-            Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * rdet;
-            Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * rdet;
+            const double det = geom::invert(J, Ji);
+            if (active && fabs(det) <= ZERO_DETERMINANT) atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
             double *Bg = Bc + g * GP_STRIDE;
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const double l0 = Lg[m * 3 + 0], l1 = Lg[m * 3 + 1], l2 = Lg[m * 3 + 2];
-                Bg[m * 3 + 0] = fma(l2, Ji[2][0], fma(l1, Ji[1][0], l0 * Ji[0][0]));
-                Bg[m * 3 + 1] = fma(l2, Ji[2][1], fma(l1, Ji[1][1], l0 * Ji[0][1]));
-                Bg[m * 3 + 2] = fma(l2, Ji[2][2], fma(l1, Ji[1][2], l0 * Ji[0][2]));
-            }
+            for (int m = 0; m < 8; m++) geom::gradient_row<3>(Lg + m * 3, Ji, Bg + m * 3);
             Bg[24] = det * s_w[g] * p.alpha;
         }
         __syncwarp();

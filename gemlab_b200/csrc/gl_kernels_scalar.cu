@@ -14,6 +14,7 @@
 
 #include <cstdlib>
 
+#include "gl_geom.cuh"
 #include "gl_internal.hpp"
 
 namespace gl {
@@ -110,37 +111,10 @@ __global__ void __launch_bounds__(256) scalar_kernel(const IntegParams p, const 
             for (int i = 0; i < SD; i++)
 #pragma unroll
                 for (int j = 0; j < SD; j++) J[i][j] = 0.0;
-#pragma unroll 2
-            for (int m = 0; m < NN; m++) {
-#pragma unroll
-                for (int i = 0; i < SD; i++)
-#pragma unroll
-                    for (int j = 0; j < SD; j++) J[i][j] = fma(X[m * SD + i], L[m * SD + j], J[i][j]);
-            }
-            double det, Ji[SD][SD];
-            if constexpr (SD == 2) {
-                det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-                const double rdet = 1.0 / det;
-                Ji[0][0] = J[1][1] * rdet;
-                Ji[0][1] = -J[0][1] * rdet;
-                Ji[1][0] = -J[1][0] * rdet;
-                Ji[1][1] = J[0][0] * rdet;
-            } else {
-                const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-                const double c01 = J[1][0] * J[2][2] - J[1][2] * J[2][0];
-                const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-                det = J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02;
-                const double rdet = 1.0 / det;
-                Ji[0][0] = c00 * rdet;
-                Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * rdet;
-                Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rdet;
-                Ji[1][0] = -c01 * rdet;
-                Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * rdet;
-                Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * rdet;
-                Ji[2][0] = c02 * rdet;
-                Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * rdet;
-                Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * rdet;
-            }
+#pragma unroll 4
+            for (int m = 0; m < NN; m++) geom::jacobian_add_node<SD, SD>(J, X + m * SD, L + m * SD);
+            double Ji[SD][SD];
+            const double det = geom::invert(J, Ji);
             if (fabs(det) <= ZERO_DETERMINANT) {
                 const unsigned long long cell = cell0 + c;
                 atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
@@ -162,7 +136,7 @@ __global__ void __launch_bounds__(256) scalar_kernel(const IntegParams p, const 
             if constexpr (AXI) {
                 const double *N = s_N + gp * NN;
                 double r = 0.0;
-                for (int m = 0; m < NN; m++) r = fma(N[m], X[m * SD], r);
+                for (int m = 0; m < NN; m++) r = geom::add(r, geom::mul(N[m], X[m * SD])); // radius_at_ip: r = sum N.x0
                 coef *= r;
             }
             G[0] = coef;

@@ -18,6 +18,7 @@
 namespace gl {
 
 #include "gauss_tables.inc"
+#include "shape_tables.inc"
 
 namespace {
 
@@ -163,6 +164,14 @@ void eval_hex(int nnode, const double *ksi, double *nn, double *ll) {
 }
 
 } // namespace
+
+// N | L of a (kind, rule) pair, bit-identical to the reference's expressions at its Gauss points (generated data, see
+// tools/gen_shape_tables.py); nullptr when the pair is not tabulated (the caller then evaluates shape_eval)
+const double *shape_table(int kind, int ng) {
+    for (int i = 0; i < N_SHAPE_TABLES; i++)
+        if (SHAPE_TABLES[i].kind == kind && SHAPE_TABLES[i].ng == ng) return SHAPE_TABLES[i].data;
+    return nullptr;
+}
 
 int kind_nnode(int kind) { return (kind >= 0 && kind < GL_NKIND) ? NNODE[kind] : -1; }
 int kind_geo_ndim(int kind) { return (kind >= 0 && kind < GL_NKIND) ? GNDIM[kind] : -1; }

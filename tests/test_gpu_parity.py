@@ -180,6 +180,25 @@ def test_all_ops_uniform_coefficient(ctx, kind, op):
         assert rel_err(got, ref, off) <= TOL, f"{kind} {op} axisym={axisym}"
 
 
+@pytest.mark.parametrize("kind", ["qua4", "qua8", "tri3", "hex8", "hex20", "tet10"])
+def test_parity_does_not_depend_on_mesh_conditioning(ctx, kind):
+    """Cells far from the origin (|x|/h ~ 1e5, as in a 10^7-cell mesh): J = Xt.L cancels 5 digits, so two correct
+    evaluations that sum in a different order differ by ~1e-11.  The kernels evaluate the geometry in the oracle's
+    operation order (gl_geom.cuh), so the parity bar still holds -- for every kernel family (tuned, fused, generic)."""
+    mesh = make_mesh(kind, n=4)
+    mesh.coords[:] = mesh.coords * 0.01 + 1000.0
+    dmesh = ctx.upload(mesh)
+    rng = np.random.default_rng(21)
+    for op in ["mat_10_bdb", "mat_01_nsn", "mat_03_btb", "vec_03_bv", "vec_04_bt"]:
+        coef = random_coef(op, mesh.ndim, 1, rng)[0]
+        for axisym in ([False, True] if mesh.ndim == 2 else [False]):
+            args = CommonArgs(axisymmetric=axisym)
+            got = getattr(integ, op)(ctx, dmesh, None, args, Coef.uniform(coef))
+            ref = oracle_integ(op, mesh, coef, axisymmetric=axisym)
+            off = integ.out_offsets(dmesh, op, None, args)
+            assert rel_err(got, ref, off) <= TOL, f"{kind} {op} axisym={axisym}"
+
+
 @pytest.mark.parametrize("kind", ["qua8", "hex8", "tet10"])
 def test_non_symmetric_modulus_and_rules(ctx, kind):
     """D need not be major-symmetric (the API only requires minor symmetry); also sweeps the sized Gauss rules."""
