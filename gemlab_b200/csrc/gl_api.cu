@@ -735,6 +735,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         }
         int nl = 0;
         if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
+        if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_tile(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb(p, mesh->ndim, ctx->stream);
         if (nl == 0 && gd == mesh->ndim && cr.dev == nullptr && a->clear && a->ii0 == 0 && (a->jj0 == 0 || !op_is_matrix(op)) &&
             a->nrow == 0 && a->ncol == 0 &&

@@ -40,6 +40,11 @@ __host__ __device__ constexpr int col_comp(int sd, int j, int q) {
 __host__ __device__ constexpr bool d_nz(int pat, int sd, int a, int b) {
     return pat < 2 ? true : ((a < 3 && b < 3) || a == b);
 }
+#ifndef GL_BDB_GP_UNROLL
+#define GL_BDB_GP_UNROLL 1
+#endif
+constexpr int GP_UNROLL = GL_BDB_GP_UNROLL; // unroll factor of the Gauss-point loop of phase C
+
 struct BdbConsts {
     double d[36]; // d'[a][b] = f_a f_b d[a][b] (row-major, ns x ns), f = 1 for normal rows, 1/sqrt(2) for shear rows
 };
@@ -55,6 +60,7 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     constexpr int NSLOT = (ND + LPN - 1) / LPN;        // blocks per lane
     constexpr int GS = (1 + NN * SD + (AXI ? NN : 0)) | 1; // record per (cell, gauss point): c | B | N/r ; odd stride
     constexpr int XS = (NN * SD) | 1;
+    constexpr int LS = (NN * SD + 6) / 16 * 16 + 9;   // = 9 (mod 16): the SD lanes of up to 6 Gauss points of a half-warp read L conflict-free
     constexpr int VD = SD + (AXI ? 1 : 0);            // components of the per-node vector v(m) = (B(m,.) [, N(m)/r])
 
     extern __shared__ __align__(16) double smem[];
@@ -62,12 +68,13 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     double *s_K = smem;                               // [CPC][NDOF*NDOF]   (first: 16-byte aligned for the bulk copy)
     double *s_w = s_K + CPC * NDOF * NDOF;            // [ng]
     double *s_N = s_w + ng;                           // [ng][NN]
-    double *s_L = s_N + ng * NN;                      // [ng][NN][SD]
-    double *s_X = s_L + ng * NN * SD;                 // [CPC][XS]
+    double *s_L = s_N + ng * NN;                      // [ng][LS]  L[gp][m*SD+j]; odd stride: lanes of different Gauss points hit different banks
+    double *s_X = s_L + ng * LS;                      // [CPC][XS]
     double *s_G = s_X + CPC * XS;                     // [CPC][ng][GS]
 
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < ng * (1 + NN + NN * SD); i += nt) s_w[i] = p.rule[i];
+    for (int i = tid; i < ng * (1 + NN); i += nt) s_w[i] = p.rule[i];
+    for (int i = tid; i < ng * NN * SD; i += nt) s_L[(i / (NN * SD)) * LS + i % (NN * SD)] = p.rule[ng * (1 + NN) + i];
 
     // lane roles in phase C: part h (warp-friendly: parts occupy consecutive thread ranges), cell slot cs, node n
     const int per_part = CPC * NN;
@@ -117,37 +124,93 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
         }
         __syncthreads();
 
-        // ---- phase B: geometry per (cell, gauss point) -------------------------------------------------------------
-        for (int task = tid; task < ncell_tile * ng; task += nt) {
-            const int gp = task / ncell_tile, c = task - gp * ncell_tile;
-            const double *X = s_X + c * XS;
-            const double *L = s_L + gp * NN * SD;
-            double J[SD][SD];
+        // ---- phase B: geometry per (cell, gauss point), SD lanes per pair ------------------------------------------------
+        // lane `sub` of a pair accumulates row `sub` of J = Xt.L, the rows are exchanged with shuffles, every lane inverts J
+        // (cheap, redundant) and then fills the gradient rows of the nodes m = sub, sub+SD, ..  -- SD times more lanes busy
+        // than one thread per pair, which matters for the 20-node kinds whose tiles hold few cells
+        if constexpr (NN < 10) {
+            // small kinds: one thread per (cell, gauss point) -- tiles hold many cells, every lane has a pair
+            for (int task = tid; task < ncell_tile * ng; task += nt) {
+                const int gp = task / ncell_tile, c = task - gp * ncell_tile;
+                const double *X = s_X + c * XS;
+                const double *L = s_L + gp * LS;
+                double J[SD][SD];
 #pragma unroll
-            for (int i = 0; i < SD; i++)
+                for (int i = 0; i < SD; i++)
 #pragma unroll
-                for (int j = 0; j < SD; j++) J[i][j] = 0.0;
+                    for (int j = 0; j < SD; j++) J[i][j] = 0.0;
 #pragma unroll 4
-            for (int m = 0; m < NN; m++) geom::jacobian_add_node<SD, SD>(J, X + m * SD, L + m * SD);
-            double Ji[SD][SD];
-            const double det = geom::invert(J, Ji);
-            if (fabs(det) <= ZERO_DETERMINANT) {
-                const unsigned long long cell = cell0 + c;
-                atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
-            }
-            double *G = s_G + (c * ng + gp) * GS;
+                for (int m = 0; m < NN; m++) geom::jacobian_add_node<SD, SD>(J, X + m * SD, L + m * SD);
+                double Ji[SD][SD];
+                const double det = geom::invert(J, Ji);
+                if (fabs(det) <= ZERO_DETERMINANT) {
+                    const unsigned long long cell = cell0 + c;
+                    atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
+                }
+                double *G = s_G + (c * ng + gp) * GS;
 #pragma unroll 4
-            for (int m = 0; m < NN; m++) geom::gradient_row<SD>(L + m * SD, Ji, G + 1 + m * SD);
-            double coef = det * s_w[gp] * p.alpha;
-            if constexpr (AXI) {
-                const double *N = s_N + gp * NN;
-                double r = 0.0;
-                for (int m = 0; m < NN; m++) r = geom::add(r, geom::mul(N[m], X[m * SD])); // radius_at_ip: r = sum N.x0
-                const double rinv = 1.0 / r;
-                for (int m = 0; m < NN; m++) G[1 + NN * SD + m] = N[m] * rinv;
-                coef *= r;
+                for (int m = 0; m < NN; m++) geom::gradient_row<SD>(L + m * SD, Ji, G + 1 + m * SD);
+                double coef = det * s_w[gp] * p.alpha;
+                if constexpr (AXI) {
+                    const double *N = s_N + gp * NN;
+                    double r = 0.0;
+                    for (int m = 0; m < NN; m++) r = geom::add(r, geom::mul(N[m], X[m * SD])); // radius_at_ip: r = sum N.x0
+                    const double rinv = 1.0 / r;
+                    for (int m = 0; m < NN; m++) G[1 + NN * SD + m] = N[m] * rinv;
+                    coef *= r;
+                }
+                G[0] = coef;
             }
-            G[0] = coef;
+        } else {
+            constexpr int GPW = 32 / SD; // pairs per warp pass
+            const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+            const int grp = lane / SD, sub = lane - grp * SD;
+            const int npair = ncell_tile * ng;
+            for (int base = wid * GPW; base < npair; base += nw * GPW) {
+                const int pair = base + grp;
+                const bool valid = grp < GPW && pair < npair;
+                const int pr = valid ? pair : 0;
+                const int gp = pr / ncell_tile, c = pr - gp * ncell_tile;
+                const double *X = s_X + c * XS;
+                const double *L = s_L + gp * LS;
+                double Jr[SD];
+#pragma unroll
+                for (int j = 0; j < SD; j++) Jr[j] = 0.0;
+#pragma unroll 4
+                for (int m = 0; m < NN; m++) {
+                    const double x = X[m * SD + sub];
+#pragma unroll
+                    for (int j = 0; j < SD; j++) Jr[j] = geom::add(Jr[j], geom::mul(x, L[m * SD + j]));
+                }
+                double J[SD][SD];
+#pragma unroll
+                for (int i = 0; i < SD; i++)
+#pragma unroll
+                    for (int j = 0; j < SD; j++) J[i][j] = __shfl_sync(0xffffffffu, Jr[j], (grp * SD + i) & 31);
+                double Ji[SD][SD];
+                const double det = geom::invert(J, Ji);
+                if (valid) {
+                    double *G = s_G + (c * ng + gp) * GS;
+                    for (int m = sub; m < NN; m += SD) geom::gradient_row<SD>(L + m * SD, Ji, G + 1 + m * SD);
+                    double r = 1.0;
+                    if constexpr (AXI) {
+                        const double *N = s_N + gp * NN;
+                        r = 0.0;
+                        for (int m = 0; m < NN; m++) r = geom::add(r, geom::mul(N[m], X[m * SD])); // radius_at_ip: r = sum N.x0
+                        const double rinv = 1.0 / r;
+                        for (int m = sub; m < NN; m += SD) G[1 + NN * SD + m] = N[m] * rinv;
+                    }
+                    if (sub == 0) {
+                        if (fabs(det) <= ZERO_DETERMINANT) {
+                            const unsigned long long cell = cell0 + c;
+                            atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
+                        }
+                        double coef = det * s_w[gp] * p.alpha;
+                        if constexpr (AXI) coef *= r;
+                        G[0] = coef;
+                    }
+                }
+            }
         }
         __syncthreads();
 
@@ -162,7 +225,7 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
             for (int q = 0; q < VD * VD; q++) acc[s][q] = 0.0;
 
         if (worker && cs < ncell_tile) {
-#pragma unroll 1
+#pragma unroll GP_UNROLL
             for (int gp = 0; gp < ng; gp++) {
                 const double *G = s_G + (cs * ng + gp) * GS;
                 const double c = G[0];
@@ -172,8 +235,9 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                 if constexpr (AXI) vn[SD] = G[1 + NN * SD + n] * c;
 #pragma unroll
                 for (int s = 0; s < NSLOT; s++) {
-                    const int b = LPN == 1 ? s : s * LPN + h;
-                    if (b >= ND) continue;
+                    // a slot beyond the last distance (only in the last slot of some lanes) recomputes distance 0 and is
+                    // dropped in phase D: no divergent branch inside the Gauss loop
+                    const int b = LPN == 1 ? s : ((s * LPN + h < ND) ? s * LPN + h : 0);
                     int m = n + b;
                     if (m >= NN) m -= NN;
                     double vm[VD];
@@ -260,7 +324,8 @@ template <int NN, int SD, int LPN>
 size_t bdb_smem(int ng, int cpc, bool axi) {
     const int gs = (1 + NN * SD + (axi ? NN : 0)) | 1;
     const int xs = (NN * SD) | 1;
-    return sizeof(double) * ((size_t)cpc * NN * SD * NN * SD + (size_t)ng * (1 + NN + NN * SD) + (size_t)cpc * xs + (size_t)cpc * ng * gs);
+    const int ls = (NN * SD + 6) / 16 * 16 + 9;
+    return sizeof(double) * ((size_t)cpc * NN * SD * NN * SD + (size_t)ng * (1 + NN + ls) + (size_t)cpc * xs + (size_t)cpc * ng * gs);
 }
 
 template <int NN, int SD, int LPN>
@@ -351,10 +416,11 @@ int launch_bdb(const IntegParams &p, int sd, void *stream) {
         static int lpn = -1;
         if (lpn < 0) {
             const char *e = getenv("GL_HEX20_LPN");
-            lpn = e ? atoi(e) : 3;
+            lpn = e ? atoi(e) : 4;
         }
         if (lpn == 2) return launch_kind<20, 3, 2>(p, cst, pat, stream);
         if (lpn == 4) return launch_kind<20, 3, 4>(p, cst, pat, stream);
+        if (lpn == 6) return launch_kind<20, 3, 6>(p, cst, pat, stream);
         return launch_kind<20, 3, 3>(p, cst, pat, stream);
     }
     default: return 0;
