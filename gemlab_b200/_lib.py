@@ -68,6 +68,10 @@ SYMBOLS = {
     "gl_integ_fused": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlFusedItem), C.c_int]),
     "gl_args_default": (None, [C.POINTER(GlArgs)]),
     "gl_lin_elasticity": (None, [C.c_double, C.c_double, C.c_int, C.c_int, _P]),
+    "gl_op_dofs_per_node": (C.c_int, [C.c_int, C.c_int]),
+    "gl_triplet_indices": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), _P, C.c_int, _P, _P]),
+    "gl_assemble": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), _P, C.c_int, _P, _P, _P,
+                              C.POINTER(C.c_uint64)]),
     "gl_bench_fp64_peak": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gl_bench_hbm_write": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
 }

@@ -1082,3 +1082,268 @@ int gl_bench_hbm_write(gl_ctx *ctx, int kind, double *dev, uint64_t nbytes, int 
 }
 
 } // extern "C"
+
+// =====================================================================================================
+// assembly hand-off: element blocks -> global sparse matrix / vector, on the device
+// =====================================================================================================
+// The reference stops at the element matrix; its callers (pmsim-style assemblers) map local dofs to global equations with
+// the rule of src/integ/mat_10_bdb.rs:31-46 (local row ii = i + m*ndim belongs to dof i of node m) and add every entry to
+// a sparse matrix.  With a point -> equation table that step needs no host work at all.
+namespace {
+
+struct ScatterParams {
+    const uint32_t *conn;             // [nnode][ncell_k]
+    unsigned long long ncell_k;
+    const uint32_t *cell_ids;         // bucket-local -> original id, or nullptr
+    unsigned long long lo, hi;        // bucket-local range
+    unsigned long long cell_begin;    // original id of the cell whose block starts at offset 0
+    const unsigned long long *out_off; // mixed meshes: bucket-local cell -> absolute block offset
+    unsigned long long out_base;
+    int nnode, npd;                   // dofs per node of this op (ndim or 1)
+    int nr, nc;                       // block dims (nc = 1 for vectors)
+    const int32_t *eq;                // [npoint][npd] equation numbers, negative = not assembled
+};
+
+__device__ __forceinline__ void scatter_entry(const ScatterParams &s, unsigned long long idx, unsigned long long &o, int &r, int &c) {
+    const unsigned int bs = (unsigned int)s.nr * (unsigned int)s.nc;
+    const unsigned long long cl = s.lo + idx / bs;
+    const unsigned int q = (unsigned int)(idx % bs);
+    const unsigned int jj = q / (unsigned int)s.nr, ii = q - jj * (unsigned int)s.nr;
+    const unsigned long long orig = s.cell_ids ? (unsigned long long)s.cell_ids[cl] : cl;
+    o = (s.out_off ? (s.out_off[cl] - s.out_base) : (orig - s.cell_begin) * bs) + q;
+    const unsigned int pr = s.conn[(unsigned long long)(ii / s.npd) * s.ncell_k + cl];
+    r = s.eq[(unsigned long long)pr * s.npd + ii % s.npd];
+    c = 0;
+    if (s.nc > 1) {
+        const unsigned int pc = s.conn[(unsigned long long)(jj / s.npd) * s.ncell_k + cl];
+        c = s.eq[(unsigned long long)pc * s.npd + jj % s.npd];
+    }
+}
+
+__global__ void triplet_kernel(const ScatterParams s, int32_t *rows, int32_t *cols) {
+    const unsigned long long total = (s.hi - s.lo) * (unsigned long long)(s.nr * s.nc);
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long o;
+        int r, c;
+        scatter_entry(s, idx, o, r, c);
+        rows[o] = r;
+        if (cols) cols[o] = c;
+    }
+}
+
+__global__ void csr_scatter_kernel(const ScatterParams s, const double *blocks, const long long *rowptr, const int32_t *colidx,
+                                   double *vals, unsigned long long *missing) {
+    const unsigned long long total = (s.hi - s.lo) * (unsigned long long)(s.nr * s.nc);
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long o;
+        int r, c;
+        scatter_entry(s, idx, o, r, c);
+        if (r < 0 || c < 0) continue;
+        long long a = rowptr[r], b = rowptr[r + 1];
+        while (a < b) { // lower bound of c in the (ascending) column indices of row r
+            const long long mid = (a + b) >> 1;
+            if (colidx[mid] < c) a = mid + 1;
+            else b = mid;
+        }
+        if (a < rowptr[r + 1] && colidx[a] == c) atomicAdd(vals + a, blocks[o]);
+        else atomicAdd(missing, 1ull);
+    }
+}
+
+__global__ void vec_scatter_kernel(const ScatterParams s, const double *blocks, double *rhs) {
+    const unsigned long long total = (s.hi - s.lo) * (unsigned long long)s.nr;
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long o;
+        int r, c;
+        scatter_entry(s, idx, o, r, c);
+        if (r >= 0) atomicAdd(rhs + r, blocks[o]);
+    }
+}
+
+// fills the scatter description of one bucket for original cells [b, e) whose blocks start at offset 0 with cell b
+int scatter_params(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, int op, const gl_args *a, uint64_t b, uint64_t e,
+                   const int32_t *d_eq, ScatterParams &s, bool &empty) {
+    uint64_t lo, hi;
+    bucket_range(mesh, bk, b, e, lo, hi);
+    empty = lo >= hi;
+    if (empty) return GL_OK;
+    unsigned r, c;
+    op_extent(op, bk.kind, mesh->ndim, r, c);
+    s.conn = bk.d_conn;
+    s.ncell_k = bk.ncell;
+    s.cell_ids = bk.d_cell_ids;
+    s.lo = lo;
+    s.hi = hi;
+    s.cell_begin = b;
+    s.out_off = nullptr;
+    s.out_base = 0;
+    s.nnode = bk.nnode;
+    s.npd = (int)r / bk.nnode;
+    s.nr = (int)r;
+    s.nc = op_is_matrix(op) ? (int)c : 1;
+    s.eq = d_eq;
+    if (!mesh->homogeneous) {
+        int key = 0, st = 0;
+        const std::vector<uint64_t> *pre = mesh_prefix(mesh, op, a, &key, &st);
+        if (st) return fail(ctx, st);
+        auto it = bk.d_out_off.find(key);
+        if (it == bk.d_out_off.end()) {
+            std::vector<unsigned long long> offs(bk.ncell);
+            for (uint64_t k = 0; k < bk.ncell; k++) offs[k] = (*pre)[bk.h_cell_ids[k]];
+            unsigned long long *d = nullptr;
+            CUDA_TRY(ctx, cudaMalloc(&d, offs.size() * sizeof(unsigned long long)));
+            CUDA_TRY(ctx, cudaMemcpy(d, offs.data(), offs.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+            it = bk.d_out_off.emplace(key, d).first;
+        }
+        s.out_off = it->second;
+        s.out_base = (*pre)[b];
+    }
+    return GL_OK;
+}
+
+unsigned scatter_grid(const ScatterParams &s) {
+    const unsigned long long total = (s.hi - s.lo) * (unsigned long long)(s.nr * s.nc);
+    return (unsigned)std::min<unsigned long long>((total + 255) / 256, 148ull * 32);
+}
+
+// the equation table on the device (copied if the caller passed a host pointer); *owned tells the caller to free it
+int eq_on_device(gl_ctx *ctx, const gl_mesh *mesh, int npd, const int32_t *eq, int location, const int32_t **d_eq, bool *owned) {
+    *owned = false;
+    if (location == GL_DEVICE) {
+        *d_eq = eq;
+        return GL_OK;
+    }
+    int32_t *d = nullptr;
+    const size_t bytes = (size_t)mesh->npoint * npd * sizeof(int32_t);
+    CUDA_TRY(ctx, cudaMalloc(&d, bytes));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d, eq, bytes, cudaMemcpyHostToDevice, (cudaStream_t)ctx->stream));
+    *d_eq = d;
+    *owned = true;
+    return GL_OK;
+}
+
+int assemble_checks(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a) {
+    if (!mesh || !a) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    if (op_size_class(op) < 0 || op == GL_OP_JACOBIAN) return fail(ctx, GL_ERR_INVALID_ARG, "op cannot be assembled");
+    if (mesh->device != ctx->device) return fail(ctx, GL_ERR_INVALID_ARG, "mesh belongs to another device");
+    if (b > e || e > mesh->ncell) return fail(ctx, GL_ERR_CELL_RANGE);
+    if (a->ii0 || a->jj0 || a->nrow || a->ncol) return fail(ctx, GL_ERR_INVALID_ARG, "assembly needs tight element blocks (ii0 = jj0 = 0)");
+    return GL_OK;
+}
+
+int op_dofs_per_node(int op, int ndim) { return (op == GL_OP_MAT_10_BDB || op == GL_OP_VEC_02_NV || op == GL_OP_VEC_04_BT) ? ndim : 1; }
+
+} // namespace
+
+extern "C" {
+
+int gl_op_dofs_per_node(int op, int ndim) { return op_dofs_per_node(op, ndim); }
+
+int gl_triplet_indices(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, const gl_args *a, const int32_t *eq,
+                       int eq_location, int32_t *rows, int32_t *cols) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
+    int st = assemble_checks(ctx, mesh, op, b, e, a);
+    if (st) return st;
+    if (!eq || !rows || (op_is_matrix(op) && !cols)) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    if (b == e) return GL_OK;
+    cudaSetDevice(ctx->device);
+    const int32_t *d_eq = nullptr;
+    bool owned = false;
+    st = eq_on_device(ctx, mesh, op_dofs_per_node(op, mesh->ndim), eq, eq_location, &d_eq, &owned);
+    if (st) return st;
+    for (auto &bk : mesh->buckets) {
+        ScatterParams s;
+        bool empty;
+        st = scatter_params(ctx, mesh, bk, op, a, b, e, d_eq, s, empty);
+        if (st) break;
+        if (empty) continue;
+        triplet_kernel<<<scatter_grid(s), 256, 0, (cudaStream_t)ctx->stream>>>(s, rows, op_is_matrix(op) ? cols : nullptr);
+        ctx->launches++;
+    }
+    if (owned) {
+        cudaStreamSynchronize((cudaStream_t)ctx->stream);
+        cudaFree(const_cast<int32_t *>(d_eq));
+    }
+    if (st) return st;
+    if (cudaGetLastError() != cudaSuccess) return cuda_fail(ctx, cudaGetLastError(), "triplet kernel");
+    return GL_OK;
+}
+
+int gl_assemble(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *coef,
+                const int32_t *eq, int eq_location, const int64_t *rowptr, const int32_t *colidx, double *vals, uint64_t *missing) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
+    int st = assemble_checks(ctx, mesh, op, b, e, a);
+    if (st) return st;
+    const bool is_mat = op_is_matrix(op);
+    if (!eq || !vals || (is_mat && (!rowptr || !colidx))) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    if (missing) *missing = 0;
+    if (b == e) return GL_OK;
+    cudaSetDevice(ctx->device);
+    gl_args args = *a;
+    args.clear = 1; // the element blocks are scratch; accumulation happens in the global matrix / vector
+    CoefResolved cr;
+    st = resolve_coef(ctx, mesh, op, b, e, &args, coef, cr);
+    if (st) return st;
+    const int32_t *d_eq = nullptr;
+    bool owned = false;
+    st = eq_on_device(ctx, mesh, op_dofs_per_node(op, mesh->ndim), eq, eq_location, &d_eq, &owned);
+    if (st) return st;
+    unsigned long long *d_missing = nullptr;
+    if (cudaMalloc(&d_missing, sizeof(unsigned long long)) != cudaSuccess) return cuda_fail(ctx, cudaGetLastError(), "cudaMalloc");
+    cudaMemsetAsync(d_missing, 0, sizeof(unsigned long long), (cudaStream_t)ctx->stream);
+
+    // chunks of cells through one scratch slab (<= 256 MB): integrate, then scatter
+    uint64_t total = 0;
+    st = range_layout(mesh, op, b, e, &args, &total, nullptr);
+    const size_t avg = (size_t)std::max<uint64_t>(total / (e - b), 1) * sizeof(double);
+    const uint64_t per_chunk = std::max<uint64_t>(((size_t)256 << 20) / avg, 1);
+    for (uint64_t cb = b; cb < e && !st; cb += per_chunk) {
+        const uint64_t ce = std::min(e, cb + per_chunk);
+        uint64_t t = 0;
+        st = range_layout(mesh, op, cb, ce, &args, &t, nullptr);
+        if (st) { st = fail(ctx, st); break; }
+        if (ctx->stage_bytes < t * sizeof(double)) {
+            for (int i = 0; i < 2; i++) {
+                if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+                ctx->d_stage[i] = nullptr;
+            }
+            ctx->stage_bytes = 0;
+            bool ok = true;
+            for (int i = 0; i < 2; i++) ok = ok && cudaMalloc(&ctx->d_stage[i], t * sizeof(double)) == cudaSuccess;
+            if (!ok) { st = cuda_fail(ctx, cudaGetLastError(), "cudaMalloc"); break; }
+            ctx->stage_bytes = t * sizeof(double);
+        }
+        st = launch_range(ctx, mesh, op, cb, ce, &args, cr, b, ctx->d_stage[0]);
+        if (st) break;
+        for (auto &bk : mesh->buckets) {
+            ScatterParams s;
+            bool empty;
+            st = scatter_params(ctx, mesh, bk, op, &args, cb, ce, d_eq, s, empty);
+            if (st) break;
+            if (empty) continue;
+            if (is_mat)
+                csr_scatter_kernel<<<scatter_grid(s), 256, 0, (cudaStream_t)ctx->stream>>>(s, ctx->d_stage[0], (const long long *)rowptr,
+                                                                                           colidx, vals, d_missing);
+            else
+                vec_scatter_kernel<<<scatter_grid(s), 256, 0, (cudaStream_t)ctx->stream>>>(s, ctx->d_stage[0], vals);
+            ctx->launches++;
+        }
+    }
+    unsigned long long h_missing = 0;
+    cudaMemcpyAsync(&h_missing, d_missing, sizeof(h_missing), cudaMemcpyDeviceToHost, (cudaStream_t)ctx->stream);
+    const int sync = gl_ctx_sync(ctx);
+    cudaFree(d_missing);
+    if (owned) cudaFree(const_cast<int32_t *>(d_eq));
+    if (missing) *missing = h_missing;
+    if (st) return st;
+    if (sync) return sync;
+    if (h_missing) return fail(ctx, GL_ERR_INVALID_ARG, "sparsity pattern lacks entries of the element blocks");
+    return GL_OK;
+}
+
+} // extern "C"

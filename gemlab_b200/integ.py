@@ -379,3 +379,67 @@ def op_out_size(op, kind, ndim):
 
 def op_coef_size(op, ndim):
     return int(lib().gl_op_coef_size(OPS[op], int(ndim)))
+
+
+# ---- assembly hand-off (include/gemlab_cuda.h: gl_triplet_indices, gl_assemble) ---------------------------------------
+
+def dofs_per_node(op, ndim):
+    return int(lib().gl_op_dofs_per_node(OPS[op], int(ndim)))
+
+
+def _marshal_eq(eq, keep):
+    if _is_torch_tensor(eq):
+        import torch
+
+        if eq.dtype != torch.int32 or not eq.is_contiguous():
+            raise ValueError("eq must be a contiguous int32 tensor")
+        keep.append(eq)
+        return eq.data_ptr(), (GL_DEVICE if eq.is_cuda else GL_HOST)
+    arr = np.ascontiguousarray(eq, dtype=np.int32)
+    keep.append(arr)
+    return arr.ctypes.data, GL_HOST
+
+
+def triplet_indices(ctx, dmesh, op, cell_range, args, eq):
+    """(rows, cols) CUDA int32 tensors: global row / column of every double of the batched output of `op` over the range,
+    so that (rows, cols, out) is the COO triplet list of a CooMatrix::put loop.  `eq[point*npd + i]` is the point ->
+    equation table (negative = not assembled); cols is None for vector cases."""
+    import torch
+
+    b, e = _range(dmesh, cell_range)
+    a = args._c()
+    total = _total(dmesh, op, b, e, a)
+    keep = []
+    ptr, loc = _marshal_eq(eq, keep)
+    dev = torch.device("cuda", ctx.device)
+    rows = torch.empty(total, dtype=torch.int32, device=dev)
+    cols = torch.empty(total, dtype=torch.int32, device=dev) if op.startswith("mat") else None
+    st = lib().gl_triplet_indices(ctx._h, dmesh._h, OPS[op], b, e, C.byref(a), ptr, loc, rows.data_ptr(),
+                                  None if cols is None else cols.data_ptr())
+    if st:
+        ctx._raise(st)
+    return rows, cols
+
+
+def assemble(ctx, dmesh, op, cell_range, args, coef, eq, vals, rowptr=None, colidx=None):
+    """Integrates `op` over the range and adds the element blocks into the global CSR matrix (rowptr int64, colidx int32,
+    vals float64: CUDA tensors) or, for vector cases, into the global vector `vals`.  Returns `vals`."""
+    import torch
+
+    b, e = _range(dmesh, cell_range)
+    a = args._c()
+    keep = []
+    c = None if coef is None else _marshal_coef(coef, keep)
+    ptr, loc = _marshal_eq(eq, keep)
+    if not (_is_torch_tensor(vals) and vals.is_cuda and vals.dtype == torch.float64 and vals.is_contiguous()):
+        raise ValueError("vals must be a contiguous float64 CUDA tensor")
+    if op.startswith("mat"):
+        if rowptr.dtype != torch.int64 or colidx.dtype != torch.int32 or not (rowptr.is_cuda and colidx.is_cuda):
+            raise ValueError("rowptr must be an int64 and colidx an int32 CUDA tensor")
+    missing = C.c_uint64()
+    st = lib().gl_assemble(ctx._h, dmesh._h, OPS[op], b, e, C.byref(a), None if c is None else C.byref(c), ptr, loc,
+                           None if rowptr is None else rowptr.data_ptr(), None if colidx is None else colidx.data_ptr(),
+                           vals.data_ptr(), C.byref(missing))
+    if st:
+        ctx._raise(st)
+    return vals

@@ -235,6 +235,27 @@ typedef struct gl_fused_item {
 GL_API int gl_integ_fused(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                           const gl_fused_item *items, int nitems);
 
+/* ---- assembly hand-off: element blocks -> global sparse matrix / vector on the device ----------
+ * The reference stops at the element matrix; its callers (pmsim-style assemblers) map the local dof (m, i) -- local row
+ * ii = i + m*ndim, src/integ/mat_10_bdb.rs:31-46 -- to a global equation and add every entry to a sparse matrix.
+ * `eq` is the point -> equation table those assemblers hold: eq[point*npd + i], npd = gl_op_dofs_per_node(op, ndim)
+ * (ndim for mat_10_bdb / vec_02_nv / vec_04_bt, 1 for the scalar-dof cases); a negative entry means "not assembled"
+ * (prescribed dof).  Element blocks must be tight (ii0 = jj0 = 0, nrow = ncol = 0); args->clear is ignored. */
+GL_API int gl_op_dofs_per_node(int op, int ndim);
+/* rows[k], cols[k] (DEVICE, int32) = global row / column of the k-th double of the batched output of `op` over
+ * [cell_begin, cell_end): (rows, cols, out) is then the COO triplet list a CooMatrix::put loop would build, without
+ * moving the values.  cols may be NULL for vector cases. */
+GL_API int gl_triplet_indices(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end,
+                              const gl_args *args, const int32_t *eq, int eq_location, int32_t *rows, int32_t *cols);
+/* Integrates `op` over the range and ADDS the element blocks into a global object on the device:
+ *   matrix cases: CSR values `vals` of the pattern (rowptr int64 [nrow+1], colidx int32 ascending within a row; DEVICE);
+ *                 *missing (may be NULL) receives the number of entries the pattern lacks (then GL_ERR_INVALID_ARG);
+ *   vector cases: the global vector `vals` (rowptr = colidx = NULL).
+ * The element blocks only pass through a bounded scratch slab (<= 256 MB); the sum is order-independent up to rounding. */
+GL_API int gl_assemble(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                       const gl_coef *coef, const int32_t *eq, int eq_location, const int64_t *rowptr, const int32_t *colidx,
+                       double *vals, uint64_t *missing);
+
 /* legacy (gemlab <= 1.x) names used by BASELINE.json's north_star: G was renamed to B in v2 */
 GL_API int gl_mat_10_gdg(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                          const gl_coef *coef, gl_out *out); /* = gl_mat_10_bdb */

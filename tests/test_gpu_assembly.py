@@ -1,0 +1,120 @@
+"""Device-side assembly hand-off (gl_triplet_indices, gl_assemble) against a scipy assembly of the oracle's element
+matrices with the reference's local-dof rule ii = i + m*ndim (src/integ/mat_10_bdb.rs:31-46)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import gemlab_b200 as g
+from gemlab_b200 import Block, Coef, CommonArgs, GeoKind, Mesh, integ
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Context(0)
+    yield c
+    c.close()
+
+
+def reference_triplets(mesh, op, coef, npd, eq, **kw):
+    """rows, cols, vals of the CooMatrix::put loop a pmsim-style assembler runs over the oracle's element blocks."""
+    blocks = po.mesh_integ(op, mesh.ndim, mesh.coords, mesh.kinds, mesh.conn_off, mesh.conn, coef=coef, **kw)
+    rows, cols, pos = [], [], 0
+    for e in range(mesh.ncell):
+        pts = mesh.conn[int(mesh.conn_off[e]):int(mesh.conn_off[e + 1])].astype(np.int64)
+        l2g = (eq.reshape(-1, npd)[pts]).reshape(-1)  # local dof i + m*npd -> equation
+        n = l2g.size
+        if op.startswith("mat"):
+            rows.append(np.tile(l2g, n))              # column-major block: entry q = ii + jj*n
+            cols.append(np.repeat(l2g, n))
+            pos += n * n
+        else:
+            rows.append(l2g)
+            pos += n
+    assert pos == blocks.size
+    return np.concatenate(rows), (np.concatenate(cols) if cols else None), blocks
+
+
+def mixed_mesh():
+    q = Block.new_square(2.0).set_ndiv([6, 5]).subdivide(GeoKind.Qua4)
+    q = g.jitter_interior_points(q, 0.03, 5)
+    c = q.conn_matrix().astype(np.int64)
+    kinds, conn, lens = [], [], []
+    for e in range(q.ncell):
+        if e % 3 == 0:  # split into two Tri3
+            for tri in ([0, 1, 2], [0, 2, 3]):
+                kinds.append(int(GeoKind.Tri3)); conn.append(c[e, tri]); lens.append(3)
+        else:
+            kinds.append(int(GeoKind.Qua4)); conn.append(c[e]); lens.append(4)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    return Mesh(2, q.coords, np.array(kinds, dtype=np.uint8), off, np.concatenate(conn).astype(np.uint64))
+
+
+@pytest.mark.parametrize("case", ["hex8", "tet10", "mixed2d"])
+def test_triplets_and_csr_assembly_match_scipy(ctx, case):
+    import torch
+
+    if case == "hex8":
+        mesh = g.jitter_interior_points(Block.new_cube(1.0).set_ndiv([5, 4, 6]).subdivide(GeoKind.Hex8), 0.02, 3)
+    elif case == "tet10":
+        mesh = g.split_hex_cells_into_tet10(3, 3, 2, seed=4)
+    else:
+        mesh = mixed_mesh()
+    dmesh = ctx.upload(mesh)
+    dd = g.mandel_matrix(g.lin_elasticity(480.0, 1.0 / 3.0, mesh.ndim == 2))
+    npd = integ.dofs_per_node("mat_10_bdb", mesh.ndim)
+    assert npd == mesh.ndim
+    rng = np.random.default_rng(8)
+    eq = rng.permutation(mesh.npoint * npd).astype(np.int32)
+    eq[rng.choice(eq.size, size=eq.size // 10, replace=False)] = -1  # prescribed dofs are not assembled
+    neq = mesh.npoint * npd
+    rr, cc, vv = reference_triplets(mesh, "mat_10_bdb", dd, npd, eq)
+
+    # 1. triplet indices line up with the batched output
+    rows, cols = integ.triplet_indices(ctx, dmesh, "mat_10_bdb", None, CommonArgs(), eq)
+    assert np.array_equal(rows.cpu().numpy(), rr) and np.array_equal(cols.cpu().numpy(), cc)
+
+    # 2. CSR assembly == scipy's duplicate-summing conversion of the oracle triplets
+    keep = (rr >= 0) & (cc >= 0)
+    ref = sp.coo_matrix((vv[keep], (rr[keep], cc[keep])), shape=(neq, neq)).tocsr()
+    ref.sum_duplicates()
+    ref.sort_indices()
+    rowptr = torch.tensor(ref.indptr.astype(np.int64), device="cuda")
+    colidx = torch.tensor(ref.indices.astype(np.int32), device="cuda")
+    vals = torch.zeros(ref.nnz, dtype=torch.float64, device="cuda")
+    integ.assemble(ctx, dmesh, "mat_10_bdb", None, CommonArgs(), Coef.uniform(dd), eq, vals, rowptr, colidx)
+    got = vals.cpu().numpy()
+    assert np.max(np.abs(got - ref.data)) <= 1e-12 * np.max(np.abs(ref.data))
+    # two half ranges accumulate to the same matrix (the hand-off is additive, like CooMatrix::put)
+    vals2 = torch.zeros_like(vals)
+    h = mesh.ncell // 2
+    integ.assemble(ctx, dmesh, "mat_10_bdb", (0, h), CommonArgs(), Coef.uniform(dd), eq, vals2, rowptr, colidx)
+    integ.assemble(ctx, dmesh, "mat_10_bdb", (h, mesh.ncell), CommonArgs(), Coef.uniform(dd), eq, vals2, rowptr, colidx)
+    assert np.max(np.abs(vals2.cpu().numpy() - ref.data)) <= 1e-12 * np.max(np.abs(ref.data))
+
+    # 3. a pattern that lacks an entry is reported, not silently dropped
+    bad_cols = colidx.clone()
+    bad_cols[0] = bad_cols[0] + 1 if ref.indices[0] + 1 != (ref.indices[1] if ref.nnz > 1 else -2) else bad_cols[0] + 2
+    with pytest.raises(g.GemlabError):
+        integ.assemble(ctx, dmesh, "mat_10_bdb", None, CommonArgs(), Coef.uniform(dd), eq, torch.zeros_like(vals), rowptr, bad_cols)
+
+
+def test_vector_assembly_matches_numpy(ctx):
+    import torch
+
+    mesh = g.jitter_interior_points(Block.new_cube(1.0).set_ndiv([4, 4, 3]).subdivide(GeoKind.Hex20), 0.01, 2)
+    dmesh = ctx.upload(mesh)
+    for op, coef in [("vec_01_ns", np.array([9.81])), ("vec_02_nv", np.array([0.0, 0.0, -9.81]))]:
+        npd = integ.dofs_per_node(op, 3)
+        eq = np.arange(mesh.npoint * npd, dtype=np.int32)[::-1].copy()
+        eq[::7] = -1
+        rr, _, vv = reference_triplets(mesh, op, coef, npd, eq)
+        ref = np.zeros(mesh.npoint * npd)
+        np.add.at(ref, rr[rr >= 0], vv[rr >= 0])
+        rhs = torch.zeros(ref.size, dtype=torch.float64, device="cuda")
+        integ.assemble(ctx, dmesh, op, None, CommonArgs(), Coef.uniform(coef), eq, rhs)
+        assert np.max(np.abs(rhs.cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))
+        rows, cols = integ.triplet_indices(ctx, dmesh, op, None, CommonArgs(), eq)
+        assert cols is None and np.array_equal(rows.cpu().numpy(), rr)
