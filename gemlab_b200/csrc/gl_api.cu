@@ -208,6 +208,41 @@ int ensure_buffer(gl_ctx *ctx, double **buf, size_t *have, size_t need) {
     return GL_OK;
 }
 
+// ---- caching allocator of the mesh buffers (see gl_ctx::pool) ----------------------------------------------------------
+constexpr size_t POOL_LIMIT = (size_t)6 << 30;
+
+cudaError_t pool_alloc(gl_ctx *ctx, void **ptr, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    size_t best = ctx->pool.size();
+    for (size_t i = 0; i < ctx->pool.size(); i++)
+        if (ctx->pool[i].second >= bytes && ctx->pool[i].second <= bytes + bytes / 4 + 4096 &&
+            (best == ctx->pool.size() || ctx->pool[i].second < ctx->pool[best].second))
+            best = i;
+    if (best != ctx->pool.size()) {
+        *ptr = ctx->pool[best].first;
+        ctx->pool_bytes -= ctx->pool[best].second;
+        ctx->pool.erase(ctx->pool.begin() + (long)best);
+        return cudaSuccess;
+    }
+    return cudaMalloc(ptr, bytes);
+}
+
+// `bytes` must be the size passed to pool_alloc; the caller guarantees that all work using the buffer has completed or is
+// ordered on the ctx stream before any reuse (every consumer runs on that stream)
+void pool_free(gl_ctx *ctx, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    if (bytes == 0) bytes = 16;
+    if (ctx && ctx->pool_bytes + bytes <= POOL_LIMIT && ctx->pool.size() < 64) {
+        ctx->pool.emplace_back(ptr, bytes);
+        ctx->pool_bytes += bytes;
+    } else {
+        cudaFree(ptr);
+    }
+}
+
+template <typename T>
+cudaError_t pool_alloc_t(gl_ctx *ctx, T **ptr, size_t bytes) { return pool_alloc(ctx, reinterpret_cast<void **>(ptr), bytes); }
+
 struct CoefResolved {
     const double *dev = nullptr; // nullptr => uniform record in `uniform`
     uint64_t cell_stride = 0, gp_stride = 0;
@@ -271,6 +306,7 @@ void gl_ctx_destroy(gl_ctx *ctx) {
     for (int i = 0; i < 2; i++)
         if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
     if (ctx->d_coef) cudaFree(ctx->d_coef);
+    for (auto &pb : ctx->pool) cudaFree(pb.first);
     if (ctx->copy_stream) cudaStreamDestroy((cudaStream_t)ctx->copy_stream);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy((cudaEvent_t)ctx->ev[i]);
@@ -377,14 +413,14 @@ int upload_homogeneous_device(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, co
     const size_t coord_bytes = (size_t)mesh->npoint * mesh->ndim * sizeof(double);
     void *d_raw = nullptr;
     int *d_bad = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&d_raw, std::max(conn_bytes, coord_bytes)));
-    CUDA_TRY(ctx, cudaMalloc(&d_bad, sizeof(int)));
+    CUDA_TRY(ctx, pool_alloc(ctx, &d_raw, std::max(conn_bytes, coord_bytes)));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &d_bad, sizeof(int)));
     CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), st));
-    CUDA_TRY(ctx, cudaMalloc(&mesh->d_coords, coord_bytes));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &mesh->d_coords, coord_bytes));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_raw, coords, coord_bytes, cudaMemcpyHostToDevice, st));
     coords_to_soa_kernel<<<1184, 256, 0, st>>>((const double *)d_raw, mesh->d_coords, mesh->npoint, mesh->ndim);
     if (bk.ncell) {
-        CUDA_TRY(ctx, cudaMalloc(&bk.d_conn, (size_t)bk.ncell * bk.nnode * sizeof(uint32_t)));
+        CUDA_TRY(ctx, pool_alloc_t(ctx, &bk.d_conn, (size_t)bk.ncell * bk.nnode * sizeof(uint32_t)));
         CUDA_TRY(ctx, cudaMemcpyAsync(d_raw, conn, conn_bytes, cudaMemcpyHostToDevice, st));
         conn_to_soa_kernel<IdT><<<1184, 256, 0, st>>>((const IdT *)d_raw, bk.d_conn, bk.ncell, bk.nnode, mesh->npoint, d_bad);
     }
@@ -392,8 +428,8 @@ int upload_homogeneous_device(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, co
     CUDA_TRY(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     ctx->launches += bk.ncell ? 2 : 1;
-    cudaFree(d_raw);
-    cudaFree(d_bad);
+    pool_free(ctx, d_raw, std::max(conn_bytes, coord_bytes));
+    pool_free(ctx, d_bad, sizeof(int));
     if (bad) return fail(ctx, GL_ERR_MESH, "point id out of range");
     return GL_OK;
 }
@@ -407,7 +443,7 @@ extern "C" {
 // =====================================================================================================
 
 static int finish_mesh_upload(gl_ctx *ctx, gl_mesh *mesh, const std::vector<double> &soa) {
-    CUDA_TRY(ctx, cudaMalloc(&mesh->d_coords, soa.size() * sizeof(double)));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &mesh->d_coords, soa.size() * sizeof(double)));
     CUDA_TRY(ctx, cudaMemcpy(mesh->d_coords, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
     return GL_OK;
 }
@@ -509,7 +545,7 @@ int gl_mesh_upload(gl_ctx *ctx, int ndim, uint64_t npoint, const double *coords,
                 soa[(size_t)m * bk.ncell + c] = (uint32_t)pts[m];
             }
         }
-        CUDA_TRY(ctx, cudaMalloc(&bk.d_conn, soa.size() * sizeof(uint32_t)));
+        CUDA_TRY(ctx, pool_alloc_t(ctx, &bk.d_conn, soa.size() * sizeof(uint32_t)));
         CUDA_TRY(ctx, cudaMemcpy(bk.d_conn, soa.data(), soa.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         if (!marker_idx.empty()) {
             std::vector<uint32_t> mi(bk.ncell);
@@ -584,9 +620,10 @@ void gl_mesh_free(gl_ctx *ctx, gl_mesh *mesh) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize((cudaStream_t)ctx->stream);
     }
-    if (mesh->d_coords) cudaFree(mesh->d_coords);
+    // the two large buffers go back to the ctx pool (all work on them is complete: the stream was just synchronised)
+    pool_free(ctx, mesh->d_coords, (size_t)mesh->npoint * mesh->ndim * sizeof(double));
     for (auto &bk : mesh->buckets) {
-        if (bk.d_conn) cudaFree(bk.d_conn);
+        pool_free(ctx, bk.d_conn, (size_t)bk.ncell * bk.nnode * sizeof(uint32_t));
         if (bk.d_cell_ids) cudaFree(bk.d_cell_ids);
         if (bk.d_marker_idx) cudaFree(bk.d_marker_idx);
         for (auto &kv : bk.d_out_off)

@@ -152,6 +152,10 @@ struct gl_ctx {
     double *d_coef = nullptr;
     size_t coef_bytes = 0;
     double *d_rule_tmp = nullptr; // for GL_OP_JACOBIAN tables
+    // freed mesh buffers kept for reuse: an upload -> integrate -> free cycle (one per step of a host-driven loop) then
+    // performs no cudaMalloc / cudaFree, whose implicit device synchronisations dominate small uploads
+    std::vector<std::pair<void *, size_t>> pool;
+    size_t pool_bytes = 0;
     void *copy_stream = nullptr;
     void *ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
