@@ -151,4 +151,37 @@ extern "C" {
     pub fn gl_args_default(args: *mut gl_args);
     pub fn gl_lin_elasticity(young: c_double, poisson: c_double, two_dim: c_int, plane_stress: c_int, dd: *mut c_double);
     pub fn gl_bench_fp64_peak(ctx: *mut gl_ctx, kind: c_int, iters: c_int, tflops: *mut c_double) -> c_int;
+    pub fn gl_mesh_block(ctx: *mut gl_ctx, kind: c_int, ndiv: *const u32, xmin: *const c_double, xmax: *const c_double, marker: i32, mesh: *mut *mut gl_mesh) -> c_int;
+    pub fn gl_mesh_download(ctx: *mut gl_ctx, mesh: *const gl_mesh, coords: *mut c_double, conn: *mut u32) -> c_int;
+    pub fn gl_bench_hbm_write(ctx: *mut gl_ctx, kind: c_int, dev: *mut c_double, nbytes: u64, warps_per_sm: c_int, gbs: *mut c_double) -> c_int;
+
+    // assembly hand-off (element blocks -> global sparse matrix / vector on the device)
+    pub fn gl_op_dofs_per_node(op: c_int, ndim: c_int) -> c_int;
+    pub fn gl_triplet_indices(
+        ctx: *mut gl_ctx,
+        mesh: *const gl_mesh,
+        op: c_int,
+        cell_begin: u64,
+        cell_end: u64,
+        args: *const gl_args,
+        eq: *const i32,
+        eq_location: c_int,
+        rows: *mut i32,
+        cols: *mut i32,
+    ) -> c_int;
+    pub fn gl_assemble(
+        ctx: *mut gl_ctx,
+        mesh: *const gl_mesh,
+        op: c_int,
+        cell_begin: u64,
+        cell_end: u64,
+        args: *const gl_args,
+        coef: *const gl_coef,
+        eq: *const i32,
+        eq_location: c_int,
+        rowptr: *const i64,
+        colidx: *const i32,
+        vals: *mut c_double,
+        missing: *mut u64,
+    ) -> c_int;
 }

@@ -1384,3 +1384,164 @@ int gl_assemble(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t 
 }
 
 } // extern "C"
+
+// =====================================================================================================
+// device-side lattice generator: Block::subdivide for axis-aligned boxes, built in HBM
+// =====================================================================================================
+// Ordering contract of the reference (src/mesh/block.rs:749-761, 770-812; fixtures src/mesh/samples.rs:1407, 1901): cells
+// are numbered i + nx*(j + ny*k); a point receives the next free id the first time a cell touches it, scanning cells in id
+// order and nodes in local order.  For the linear targets that numbering has a closed form: lattice point (a,b,c) is first
+// touched by its "owner" cell (max(a-1,0), max(b-1,0), max(c-1,0)); its id is the number of points owned by cells with a
+// smaller id plus its rank among the owner's new nodes in local order.  tests/test_gpu_block.py checks it against the
+// host Block (which is pinned by the reference's sample meshes).
+namespace {
+
+__device__ __constant__ int LOC_HEX8[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+__device__ __constant__ int LOC_QUA4[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
+
+__device__ __forceinline__ unsigned long long owned_before(unsigned long long n) { return n + (n > 0 ? 1ull : 0ull); }
+
+// first-touch id of lattice point (a, b, c); ndim = 2 ignores c / nz
+__device__ unsigned long long lattice_point_id(int ndim, unsigned a, unsigned b, unsigned c, unsigned nx, unsigned ny) {
+    const unsigned i = a > 0 ? a - 1 : 0, j = b > 0 ? b - 1 : 0, k = (ndim == 3 && c > 0) ? c - 1 : 0;
+    const unsigned long long ax = (unsigned long long)nx + 1, ay = (unsigned long long)ny + 1;
+    unsigned long long base = owned_before(j) * ax + (j == 0 ? 2ull : 1ull) * owned_before(i);
+    if (ndim == 3) base = owned_before(k) * ay * ax + (k == 0 ? 2ull : 1ull) * base;
+    const int dx = (int)(a - i), dy = (int)(b - j), dz = ndim == 3 ? (int)(c - k) : 0;
+    int rank = 0;
+    const int nloc = ndim == 3 ? 8 : 4;
+    for (int q = 0; q < nloc; q++) {
+        const int qx = ndim == 3 ? LOC_HEX8[q][0] : LOC_QUA4[q][0];
+        const int qy = ndim == 3 ? LOC_HEX8[q][1] : LOC_QUA4[q][1];
+        const int qz = ndim == 3 ? LOC_HEX8[q][2] : 0;
+        if (qx == dx && qy == dy && qz == dz) break;
+        const bool is_new = (qx == 1 || i == 0) && (qy == 1 || j == 0) && (ndim == 2 || qz == 1 || k == 0);
+        rank += is_new ? 1 : 0;
+    }
+    return base + (unsigned long long)rank;
+}
+
+struct BlockGen {
+    int ndim;
+    unsigned nx, ny, nz;
+    double x0[3], h[3];
+    unsigned long long ncell, npoint;
+};
+
+__global__ void block_conn_kernel(const BlockGen g, uint32_t *conn) {
+    const int nn = g.ndim == 3 ? 8 : 4;
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < g.ncell;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned i = (unsigned)(e % g.nx), j = (unsigned)((e / g.nx) % g.ny), k = (unsigned)(e / ((unsigned long long)g.nx * g.ny));
+        for (int m = 0; m < nn; m++) {
+            const unsigned a = i + (g.ndim == 3 ? LOC_HEX8[m][0] : LOC_QUA4[m][0]);
+            const unsigned b = j + (g.ndim == 3 ? LOC_HEX8[m][1] : LOC_QUA4[m][1]);
+            const unsigned c = k + (g.ndim == 3 ? LOC_HEX8[m][2] : 0);
+            conn[(unsigned long long)m * g.ncell + e] = (uint32_t)lattice_point_id(g.ndim, a, b, c, g.nx, g.ny);
+        }
+    }
+}
+
+__global__ void block_coords_kernel(const BlockGen g, double *coords) {
+    const unsigned long long ax = (unsigned long long)g.nx + 1, ay = (unsigned long long)g.ny + 1;
+    for (unsigned long long q = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; q < g.npoint;
+         q += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned a = (unsigned)(q % ax), b = (unsigned)((q / ax) % ay), c = (unsigned)(q / (ax * ay));
+        const unsigned long long id = lattice_point_id(g.ndim, a, b, c, g.nx, g.ny);
+        coords[id] = g.x0[0] + g.h[0] * (double)a;
+        coords[g.npoint + id] = g.x0[1] + g.h[1] * (double)b;
+        if (g.ndim == 3) coords[2 * g.npoint + id] = g.x0[2] + g.h[2] * (double)c;
+    }
+}
+
+__global__ void soa_to_aos_kernel(const double *soa, double *aos, unsigned long long npoint, int ndim) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < npoint * ndim;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        aos[i] = soa[(i % ndim) * npoint + i / ndim];
+}
+
+__global__ void conn_to_cell_major_kernel(const uint32_t *nm, uint32_t *cm, unsigned long long ncell, int nnode) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < ncell * nnode;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        cm[i] = nm[(i % nnode) * ncell + i / nnode];
+}
+
+} // namespace
+
+extern "C" {
+
+int gl_mesh_block(gl_ctx *ctx, int kind, const uint32_t *ndiv, const double *xmin, const double *xmax, int32_t marker, gl_mesh **out) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    if (!out || !ndiv || !xmin || !xmax) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (kind != GL_QUA4 && kind != GL_HEX8) return fail(ctx, GL_ERR_KIND_UNSUPPORTED, "the device lattice generator builds Qua4 and Hex8 meshes");
+    const int ndim = kind == GL_HEX8 ? 3 : 2;
+    BlockGen g;
+    g.ndim = ndim;
+    g.nx = ndiv[0];
+    g.ny = ndiv[1];
+    g.nz = ndim == 3 ? ndiv[2] : 1;
+    if (g.nx == 0 || g.ny == 0 || g.nz == 0) return fail(ctx, GL_ERR_INVALID_ARG, "ndiv must be >= 1");
+    g.ncell = (unsigned long long)g.nx * g.ny * g.nz;
+    g.npoint = ((unsigned long long)g.nx + 1) * ((unsigned long long)g.ny + 1) * (ndim == 3 ? (unsigned long long)g.nz + 1 : 1ull);
+    if (g.npoint > 0xffffffffull) return fail(ctx, GL_ERR_MESH, "npoint/ncell must fit in 32 bits");
+    for (int d = 0; d < 3; d++) {
+        g.x0[d] = d < ndim ? xmin[d] : 0.0;
+        const unsigned n = d == 0 ? g.nx : (d == 1 ? g.ny : g.nz);
+        g.h[d] = d < ndim ? (xmax[d] - xmin[d]) / (double)n : 0.0;
+    }
+    cudaSetDevice(ctx->device);
+    auto mesh = std::make_unique<gl_mesh>();
+    mesh->ndim = ndim;
+    mesh->npoint = g.npoint;
+    mesh->ncell = g.ncell;
+    mesh->device = ctx->device;
+    mesh->homogeneous = true;
+    mesh->marker_values.assign(1, marker);
+    gl_mesh_bucket bk;
+    bk.kind = kind;
+    bk.nnode = kind_nnode(kind);
+    bk.ncell = g.ncell;
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &mesh->d_coords, (size_t)g.npoint * ndim * sizeof(double)));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &bk.d_conn, (size_t)g.ncell * bk.nnode * sizeof(uint32_t)));
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    block_conn_kernel<<<1184, 256, 0, st>>>(g, bk.d_conn);
+    block_coords_kernel<<<1184, 256, 0, st>>>(g, mesh->d_coords);
+    ctx->launches += 2;
+    if (cudaGetLastError() != cudaSuccess) return cuda_fail(ctx, cudaGetLastError(), "lattice generator");
+    mesh->buckets.push_back(std::move(bk));
+    *out = mesh.release();
+    return GL_OK;
+}
+
+int gl_mesh_download(gl_ctx *ctx, const gl_mesh *mesh, double *coords, uint32_t *conn) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    if (!mesh) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    if (coords) {
+        double *tmp = nullptr;
+        const size_t bytes = (size_t)mesh->npoint * mesh->ndim * sizeof(double);
+        CUDA_TRY(ctx, pool_alloc_t(ctx, &tmp, bytes));
+        soa_to_aos_kernel<<<1184, 256, 0, st>>>(mesh->d_coords, tmp, mesh->npoint, mesh->ndim);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaMemcpyAsync(coords, tmp, bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        pool_free(ctx, tmp, bytes);
+    }
+    if (conn) {
+        if (!mesh->homogeneous || mesh->buckets.size() != 1) return fail(ctx, GL_ERR_MESH, "connectivity download needs a single-kind mesh");
+        const gl_mesh_bucket &bk = mesh->buckets[0];
+        uint32_t *tmp = nullptr;
+        const size_t bytes = (size_t)bk.ncell * bk.nnode * sizeof(uint32_t);
+        CUDA_TRY(ctx, pool_alloc_t(ctx, &tmp, bytes));
+        conn_to_cell_major_kernel<<<1184, 256, 0, st>>>(bk.d_conn, tmp, bk.ncell, bk.nnode);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaMemcpyAsync(conn, tmp, bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        pool_free(ctx, tmp, bytes);
+    }
+    return GL_OK;
+}
+
+} // extern "C"

@@ -182,6 +182,32 @@ class Context:
             self._raise(st)
         return DeviceMesh(self, h, mesh.ndim, mesh.ncell, mesh.npoint, mesh.kinds.copy())
 
+    def block(self, kind, ndiv, xmin=None, xmax=None, marker=1):
+        """Device-side lattice generator (gl_mesh_block): the mesh of Block::new(box).set_ndiv(ndiv).subdivide(kind) for an
+        axis-aligned box, built in HBM with the reference's cell order and first-touch point numbering."""
+        kind = GeoKind(kind)
+        ndim = kind.ndim()
+        nd = (C.c_uint32 * 3)(*[int(v) for v in list(ndiv) + [1] * (3 - len(ndiv))])
+        lo = (C.c_double * 3)(*([0.0] * 3 if xmin is None else [float(v) for v in list(xmin) + [0.0] * (3 - len(xmin))]))
+        hi = (C.c_double * 3)(*([1.0] * 3 if xmax is None else [float(v) for v in list(xmax) + [0.0] * (3 - len(xmax))]))
+        h = C.c_void_p()
+        st = lib().gl_mesh_block(self._h, int(kind), nd, lo, hi, int(marker), C.byref(h))
+        if st:
+            self._raise(st)
+        ncell = int(np.prod([int(v) for v in ndiv[:ndim]]))
+        npoint = int(np.prod([int(v) + 1 for v in ndiv[:ndim]]))
+        return DeviceMesh(self, h, ndim, ncell, npoint, np.full(ncell, int(kind), dtype=np.uint8))
+
+    def download(self, dmesh):
+        """Device mesh -> host Mesh (gl_mesh_download; single-kind meshes)."""
+        kind = GeoKind(int(dmesh.kinds[0]))
+        coords = np.empty((dmesh.npoint, dmesh.ndim))
+        conn = np.empty((dmesh.ncell, kind.nnode()), dtype=np.uint32)
+        st = lib().gl_mesh_download(self._h, dmesh._h, coords.ctypes.data, conn.ctypes.data)
+        if st:
+            self._raise(st)
+        return Mesh.homogeneous(dmesh.ndim, coords, kind, conn.astype(np.uint64))
+
     def fp64_peak(self, kind="dfma", iters=4096):
         """Measured FP64 peak of this device in TFLOP/s (kind: 'dfma', 'dmma' or 'mixed' = both interleaved)."""
         t = C.c_double()

@@ -26,6 +26,10 @@ _HEX_REF = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1
                      [-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], dtype=np.int64)
 
 
+class GemlabTextError(ValueError):
+    """A StrError of the MSH reader; str(e) is the reference's message (src/mesh/read_text_mesh.rs)."""
+
+
 class Mesh:
     """Flat-array mesh (see module docstring)."""
 
@@ -68,6 +72,163 @@ class Mesh:
         conn_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
         conn = np.concatenate([np.asarray(p, dtype=np.uint64) for _, p in cells]) if cells else np.zeros(0, np.uint64)
         return Mesh(ndim, coords, kinds, conn_off, conn, markers)
+
+    # ---- MSH text format (README.md "MSH file format"; reader: src/mesh/read_text_mesh.rs:36-256, 312-420) --------------
+
+    @staticmethod
+    def from_text(text):
+        """Parses a mesh in gemlab's MSH text format (the step BEFORE the integration path: it lets the reference's own
+        data/meshes/*.msh drive the GPU path unmodified).  Same grammar and the same error strings as Mesh::read /
+        Mesh::from_text: `#` comments, header `ndim npoint ncell [nmarked_edge nmarked_face]`, points `id marker x y [z]`
+        with id == position, cells `id marker kind p0 p1 ..` with lower-case GeoKind keys (GeoKind::from,
+        src/shapes/enums.rs:217-244), then optional marked edges `marker p1 p2` and faces `marker p1 p2 p3 [p4]`."""
+        def fields(line):
+            t = line.strip()
+            return None if (not t or t.startswith("#")) else t.split()
+
+        def num(tok, conv, msg):
+            try:
+                return conv(tok)
+            except ValueError:
+                raise GemlabTextError(msg) from None
+
+        def uint(tok, msg):
+            v = num(tok, int, msg)
+            if v < 0 or not tok.lstrip("+").isdigit():
+                raise GemlabTextError(msg)
+            return v
+
+        lines = iter(text.splitlines())
+        header = None
+        for line in lines:
+            f = fields(line)
+            if f is None:
+                continue
+            names = ["ndim", "npoint", "ncell", "nmarked_edge", "nmarked_face"]
+            header = []
+            for i, name in enumerate(names):
+                if i >= len(f):
+                    raise GemlabTextError(f"cannot read {name}")
+                header.append(uint(f[i], f"cannot parse {name}"))
+            break
+        if header is None:
+            raise GemlabTextError("file is empty or header is missing")
+        ndim, npoint, ncell, nedge, nface = header
+
+        coords, pmarkers = [], []
+        for line in lines:
+            if len(coords) == npoint:
+                break
+            f = fields(line)
+            if f is None:
+                continue
+            if uint(f[0], "cannot parse point id") != len(coords):
+                raise GemlabTextError("the id and index of points must equal each other")
+            if len(f) < 2:
+                raise GemlabTextError("cannot read point marker")
+            pmarkers.append(num(f[1], int, "cannot parse point marker"))
+            xyz = []
+            for j, axis in enumerate("xyz"[:ndim]):
+                if len(f) < 3 + j:
+                    raise GemlabTextError(f"cannot read point {axis} coordinate")
+                xyz.append(num(f[2 + j], float, f"cannot parse point {axis} coordinate"))
+            if len(f) > 2 + ndim:
+                raise GemlabTextError("point data contains extra values")
+            coords.append(xyz)
+            if len(coords) == npoint:
+                break
+        if len(coords) != npoint:
+            raise GemlabTextError("not all points have been found")
+
+        cells, cmarkers = [], []
+        for line in lines:
+            f = fields(line)
+            if f is None:
+                continue
+            if uint(f[0], "cannot parse cell id") != len(cells):
+                raise GemlabTextError("the id and index of cells must equal each other")
+            if len(f) < 2:
+                raise GemlabTextError("cannot read cell marker")
+            cmarkers.append(num(f[1], int, "cannot parse cell marker"))
+            if len(f) < 3:
+                raise GemlabTextError("cannot read cell kind")
+            try:
+                kind = GeoKind.from_str(f[2])
+            except Exception:
+                raise GemlabTextError("string representation of GeoKind is incorrect") from None
+            nn = kind.nnode()
+            if len(f) < 3 + nn:
+                raise GemlabTextError("cannot read cell point id")
+            pts = [uint(t, "cannot parse cell point id") for t in f[3:3 + nn]]
+            if len(f) > 3 + nn:
+                raise GemlabTextError("cell data contains extra values")
+            cells.append((kind, pts))
+            if len(cells) == ncell:
+                break
+        if len(cells) != ncell:
+            raise GemlabTextError("not all cells have been found")
+
+        def marked(count, what, npts_min, npts_max):
+            out = []
+            if count == 0:
+                return out
+            for line in lines:
+                f = fields(line)
+                if f is None:
+                    continue
+                marker = num(f[0], int, f"cannot parse marked {what}")
+                pts = []
+                for j in range(npts_max):
+                    if len(f) < 2 + j:
+                        if j < npts_min:
+                            raise GemlabTextError(f"cannot read p{j + 1} of marked {what}")
+                        break
+                    pts.append(uint(f[1 + j], f"cannot parse p{j + 1} of marked {what}"))
+                if len(f) > 1 + npts_max:
+                    raise GemlabTextError(f"marked {what} data contains extra values")
+                out.append((marker, *pts))
+                if len(out) == count:
+                    break
+            if len(out) != count:
+                raise GemlabTextError(f"not all marked {what}s have been found")
+            return out
+
+        edges = marked(nedge, "edge", 2, 2)
+        faces = marked(nface, "face", 3, 4)
+        mesh = Mesh.from_cells(ndim, np.array(coords, dtype=np.float64).reshape(npoint, ndim), cells, cmarkers)
+        mesh.point_markers = np.array(pmarkers, dtype=np.int32)
+        mesh.marked_edges = edges
+        mesh.marked_faces = faces
+        return mesh
+
+    @staticmethod
+    def read(path):
+        """Mesh::read (src/mesh/read_text_mesh.rs:312)."""
+        try:
+            with open(path, "r") as fh:
+                text = fh.read()
+        except OSError:
+            raise GemlabTextError("cannot open file") from None
+        return Mesh.from_text(text)
+
+    def to_text(self):
+        """The inverse of from_text (Mesh::write, src/mesh/write_text_mesh.rs): ids equal positions, lower-case kinds."""
+        pm = getattr(self, "point_markers", np.zeros(self.npoint, dtype=np.int32))
+        edges = getattr(self, "marked_edges", [])
+        faces = getattr(self, "marked_faces", [])
+        out = ["# header", "# ndim npoint ncell nmarked_edge nmarked_face",
+               f"{self.ndim} {self.npoint} {self.ncell} {len(edges)} {len(faces)}", "", "# points", "# id marker x y {z}"]
+        for i in range(self.npoint):
+            out.append(f"{i} {int(pm[i])} " + " ".join(repr(float(v)) for v in self.coords[i]))
+        out += ["", "# cells", "# id marker kind points"]
+        for e in range(self.ncell):
+            out.append(f"{e} {int(self.markers[e])} {GeoKind(int(self.kinds[e])).to_string()} "
+                       + " ".join(str(int(p)) for p in self.cell_points(e)))
+        if edges:
+            out += ["", "# marked edges", "# marker p1 p2"] + [" ".join(str(int(v)) for v in ed) for ed in edges]
+        if faces:
+            out += ["", "# marked faces", "# marker p1 p2 p3 {p4}"] + [" ".join(str(int(v)) for v in fa) for fa in faces]
+        return "\n".join(out) + "\n"
 
     def is_homogeneous(self):
         return self.ncell == 0 or bool(np.all(self.kinds == self.kinds[0]))

@@ -172,6 +172,15 @@ GL_API int gl_mesh_upload_homogeneous(gl_ctx *ctx, int ndim, uint64_t npoint, co
                                       int kind, const int32_t *markers, const uint32_t *conn, gl_mesh **mesh);
 /* Replace the coordinates of an uploaded mesh (e.g. updated-Lagrangian steps); coords as in gl_mesh_upload. */
 GL_API int gl_mesh_update_coords(gl_ctx *ctx, gl_mesh *mesh, const double *coords, int location);
+/* Device-side lattice generator: the mesh that Block::new(box).set_ndiv(ndiv).subdivide(kind) returns for an axis-aligned
+ * box [xmin, xmax] -- cell id = i + nx*(j + ny*k), first-touch point numbering (src/mesh/block.rs:749-812; fixtures
+ * src/mesh/samples.rs:1407, 1901) -- built directly in HBM from a closed form of that numbering: no host arrays, no upload.
+ * kind: Qua4 (ndiv[0..1], 2D) or Hex8 (ndiv[0..2], 3D); every cell gets `marker`. */
+GL_API int gl_mesh_block(gl_ctx *ctx, int kind, const uint32_t *ndiv, const double *xmin, const double *xmax, int32_t marker,
+                         gl_mesh **mesh);
+/* Copies a device mesh back to HOST arrays (either pointer may be NULL): coords npoint x ndim (AoS, as Mesh.points),
+ * conn ncell x nnode 32-bit point ids (single-kind meshes only). */
+GL_API int gl_mesh_download(gl_ctx *ctx, const gl_mesh *mesh, double *coords, uint32_t *conn);
 GL_API void gl_mesh_free(gl_ctx *ctx, gl_mesh *mesh);
 GL_API uint64_t gl_mesh_ncell(const gl_mesh *mesh);
 GL_API uint64_t gl_mesh_npoint(const gl_mesh *mesh);

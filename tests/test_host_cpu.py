@@ -155,3 +155,15 @@ def test_sizes_and_partition():
     dd = g.lin_elasticity(480.0, 1 / 3, False)
     np.testing.assert_array_equal(dd, po.lin_elasticity(480.0, 1 / 3, False, False))
     np.testing.assert_array_equal(g.lin_elasticity(10_000.0, 0.2, True, True), po.lin_elasticity(10_000.0, 0.2, True, True))
+
+
+def test_rust_ffi_declares_every_abi_symbol():
+    """gemlab-cuda/src/ffi.rs (source only: no cargo in this image) must declare every GL_API symbol of the header."""
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    hdr = (root / "include" / "gemlab_cuda.h").read_text()
+    names = set(re.findall(r"GL_API\s+[\w\s\*]+?\b(gl_\w+)\s*\(", hdr))
+    ffi = set(re.findall(r"pub fn (gl_\w+)", (root / "gemlab-cuda" / "src" / "ffi.rs").read_text()))
+    assert names and not (names - ffi), sorted(names - ffi)
