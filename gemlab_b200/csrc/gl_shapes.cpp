@@ -182,7 +182,12 @@ int kind_from_name(const char *name) {
         if (std::strcmp(name, NAMES[k]) == 0) return k;
     return -1;
 }
-bool kind_supported(int kind) {
+// every GeoKind integrates: the kernels read N and L from the (kind, rule) tables of shape_tables.inc
+bool kind_supported(int kind) { return kind >= 0 && kind < GL_NKIND; }
+
+// kinds whose shape functions this library can also evaluate at an ARBITRARY point (gl_shape_eval, GL_OP_JACOBIAN); the
+// cubic / quartic kinds exist as tables at the reference's Gauss points only
+bool kind_has_formulas(int kind) {
     switch (kind) {
     case GL_LIN2: case GL_LIN3: case GL_TRI3: case GL_TRI6: case GL_QUA4: case GL_QUA8: case GL_QUA9:
     case GL_TET4: case GL_TET10: case GL_HEX8: case GL_HEX20:
@@ -193,7 +198,7 @@ bool kind_supported(int kind) {
 }
 
 int shape_eval(int kind, const double *ksi, double *nn, double *ll) {
-    if (!kind_supported(kind)) return GL_ERR_KIND_UNSUPPORTED;
+    if (!kind_has_formulas(kind)) return GL_ERR_KIND_UNSUPPORTED;
     const int nnode = NNODE[kind];
     switch (KCLASS[kind]) {
     case 0: eval_lin(nnode, ksi, nn, ll); break;

@@ -63,7 +63,7 @@ typedef enum gl_status {
     GL_ERR_GAUSS_QUA = 15,
     GL_ERR_GAUSS_TET = 16,
     GL_ERR_GAUSS_HEX = 17,
-    GL_ERR_KIND_UNSUPPORTED = 18, /* GeoKind has no device tables yet */
+    GL_ERR_KIND_UNSUPPORTED = 18, /* unknown GeoKind ordinal, or shape functions at an arbitrary point requested for a table-only kind */
     GL_ERR_SPACE_NDIM = 20,       /* "space_ndim must be 2 or 3" (scratchpad.rs:153) */
     /* errors of the batched boundary itself (no reference counterpart) */
     GL_ERR_INVALID_ARG = 100,
@@ -153,10 +153,13 @@ GL_API int gl_kind_geo_ndim(int kind);
 GL_API int gl_kind_class(int kind);
 GL_API int gl_kind_from_name(const char *name); /* GeoKind::from (enums.rs:217-244); -1 if unknown */
 GL_API const char *gl_kind_name(int kind);
+/* 1 for every GeoKind (all 20 integrate: N and L come from per-(kind, rule) tables) */
 GL_API int gl_kind_supported(int kind);
 /* rule lookup: *npoint points, data = npoint x 4 doubles {r,s,t,w} (static storage) */
 GL_API int gl_gauss_rule(int kind, int ngauss, int *npoint, const double **data);
-/* N (nnode) and L = dN/dksi (nnode x geo_ndim, row-major) of the library's own reference-element evaluation */
+/* N (nnode) and L = dN/dksi (nnode x geo_ndim, row-major) at an ARBITRARY point, from the library's own formulas:
+ * available for Lin2/3, Tri3/6, Qua4/8/9, Tet4/10, Hex8/20; the cubic and quartic kinds (Lin4/5, Tri10/15, Qua12/16/17,
+ * Tet20, Hex32) exist as tables at the reference's Gauss points only -> GL_ERR_KIND_UNSUPPORTED (also for gl_jacobian) */
 GL_API int gl_shape_eval(int kind, const double *ksi, double *nn, double *ll);
 
 /* ---- mesh (replaces Mesh/Point/Cell + Mesh::set_pad, src/mesh/mesh.rs:27-54,110-135,448-456) ------ */

@@ -448,6 +448,32 @@ static void hex20_deriv(double *ll, const double *ksi) {
     L3(19, 2, -rm * sp * t / 2.0);
 }
 
+/* Lin4/5, Tri10/15, Qua12/16/17, Tet20, Hex32 are not restated node by node: their N and L at the reference's Gauss points
+ * come from shape_tables_extra.inc, evaluated from the reference's own calc_interp / calc_deriv expressions by
+ * tools/gen_shape_tables.py.  The integration loops only ever evaluate shapes at Gauss points, so a lookup by the exact
+ * point serves them; any other ksi is GO_ERR_KIND_UNSUPPORTED for these kinds. */
+#include "shape_tables_extra.inc"
+
+int go_gauss(int kind, int ngauss, const double (**data)[4], int *npoint);
+
+static const double *extra_shape_row(int kind, const double *ksi, int want_deriv) {
+    const int nn = KIND_NNODE[kind], gd = KIND_NDIM[kind];
+    for (int t = 0; t < XN_SHAPE_TABLES; t++) {
+        if (XSHAPE_TABLES[t].kind != kind) continue;
+        const double (*pts)[4];
+        int np = 0;
+        if (go_gauss(kind, XSHAPE_TABLES[t].ng, &pts, &np) != GO_OK || np != XSHAPE_TABLES[t].ng) continue;
+        for (int p = 0; p < np; p++) {
+            int same = 1;
+            for (int j = 0; j < gd; j++) same = same && (pts[p][j] == ksi[j]);
+            if (!same) continue;
+            const double *base = XSHAPE_TABLES[t].data;
+            return want_deriv ? base + (size_t)np * nn + (size_t)p * nn * gd : base + (size_t)p * nn;
+        }
+    }
+    return NULL;
+}
+
 /* GeoKind::functions (src/shapes/enums.rs:1124-1152) */
 int go_interp(int kind, const double *ksi, double *nn) {
     switch (kind) {
@@ -462,7 +488,12 @@ int go_interp(int kind, const double *ksi, double *nn) {
     case GO_TET10: tet10_interp(nn, ksi); break;
     case GO_HEX8: hex8_interp(nn, ksi); break;
     case GO_HEX20: hex20_interp(nn, ksi); break;
-    default: return GO_ERR_KIND_UNSUPPORTED;
+    default: {
+        if (kind < 0 || kind >= GO_NKIND) return GO_ERR_KIND_UNSUPPORTED;
+        const double *row = extra_shape_row(kind, ksi, 0);
+        if (!row) return GO_ERR_KIND_UNSUPPORTED;
+        memcpy(nn, row, sizeof(double) * (size_t)KIND_NNODE[kind]);
+    }
     }
     return GO_OK;
 }
@@ -479,7 +510,12 @@ int go_deriv(int kind, const double *ksi, double *ll) {
     case GO_TET10: tet10_deriv(ll, ksi); break;
     case GO_HEX8: hex8_deriv(ll, ksi); break;
     case GO_HEX20: hex20_deriv(ll, ksi); break;
-    default: return GO_ERR_KIND_UNSUPPORTED;
+    default: {
+        if (kind < 0 || kind >= GO_NKIND) return GO_ERR_KIND_UNSUPPORTED;
+        const double *row = extra_shape_row(kind, ksi, 1);
+        if (!row) return GO_ERR_KIND_UNSUPPORTED;
+        memcpy(ll, row, sizeof(double) * (size_t)KIND_NNODE[kind] * (size_t)KIND_NDIM[kind]);
+    }
     }
     return GO_OK;
 }
@@ -575,7 +611,7 @@ int go_gauss(int kind, int ngauss, const double (**data)[4], int *npoint) {
 /* Scratchpad::new (src/shapes/scratchpad.rs:152-182) */
 int go_pad_init(go_pad *pad, int space_ndim, int kind) {
     if (space_ndim < 2 || space_ndim > 3) return GO_ERR_SPACE_NDIM;
-    if (!go_kind_supported(kind)) return GO_ERR_KIND_UNSUPPORTED;
+    if (kind < 0 || kind >= GO_NKIND) return GO_ERR_KIND_UNSUPPORTED; /* table-only kinds work at Gauss points (go_interp) */
     if (KIND_NDIM[kind] > space_ndim) return GO_ERR_SPACE_NDIM;
     memset(pad, 0, sizeof(*pad));
     pad->kind = kind;

@@ -486,3 +486,57 @@ def test_upload_paths_agree_and_validate(ctx):
     bad.conn[5] = mesh.npoint  # out of range
     with pytest.raises(g.GemlabError, match="point id out of range"):
         ctx.upload(bad)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the cubic / quartic kinds (Lin4/5, Tri10/15, Qua12/16/17, Tet20, Hex32): table-driven on both sides
+# ---------------------------------------------------------------------------------------------------------------
+
+REF_COORDS = json.loads((Path(__file__).parent / "golden" / "kind_reference_coords.json").read_text())
+
+
+def mapped_reference_cells(kind, space_ndim, ncell=3, seed=9):
+    """A few cells of `kind`: the reference element pushed through a smooth non-affine map, then translated."""
+    xi = np.array(REF_COORDS[kind])                      # (nnode, geo_ndim)
+    nn, gd = xi.shape
+    rng = np.random.default_rng(seed)
+    a = np.eye(space_ndim, gd) + 0.15 * rng.standard_normal((space_ndim, gd))
+    coords, conn = [], []
+    for c in range(ncell):
+        bend = 0.04 * rng.standard_normal((space_ndim, gd))
+        x = xi @ a.T + (xi ** 2) @ bend.T + np.array([3.0 * c + 2.0] + [0.5] * (space_ndim - 1))
+        conn.append(np.arange(nn) + c * nn)
+        coords.append(x)
+    return Mesh.homogeneous(space_ndim, np.concatenate(coords), GeoKind.from_str(kind), np.array(conn))
+
+
+@pytest.mark.parametrize("kind,space_ndim", [("tri10", 2), ("tri15", 2), ("qua12", 2), ("qua16", 2), ("qua17", 2), ("tet20", 3),
+                                              ("hex32", 3), ("lin4", 2), ("lin5", 3)])
+def test_higher_order_kinds(ctx, kind, space_ndim):
+    mesh = mapped_reference_cells(kind, space_ndim)
+    dmesh = ctx.upload(mesh)
+    solid = GeoKind.from_str(kind).ndim() == space_ndim
+    ops = OPS if solid else ["vec_01_ns", "vec_02_nv"]   # the other cases call calc_gradient: geo_ndim == space_ndim only
+    rng = np.random.default_rng(13)
+    for op in ops:
+        coef = random_coef(op, space_ndim, 1, rng)[0]
+        for axisym in ([False, True] if (space_ndim == 2 and solid) else [False]):
+            args = CommonArgs(alpha=1.3, axisymmetric=axisym)
+            got = getattr(integ, op)(ctx, dmesh, None, args, Coef.uniform(coef))
+            ref = oracle_integ(op, mesh, coef, alpha=1.3, axisymmetric=axisym)
+            off = integ.out_offsets(dmesh, op, None, args)
+            assert off[-1] == ref.size
+            assert rel_err(got, ref, off) <= TOL, f"{kind} {op} axisym={axisym}"
+    # the default rules are the reference's (Gauss::new, src/integ/gauss.rs:87-121); a sized rule works as well
+    if solid:
+        n = {"tri10": 7, "tri15": 12, "qua12": 9, "qua16": 9, "qua17": 9, "tet20": 14, "hex32": 27}[kind]
+        coef = random_coef("mat_10_bdb", space_ndim, 1, rng)[0]
+        got = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(ngauss=n), Coef.uniform(coef))
+        ref = oracle_integ("mat_10_bdb", mesh, coef, ngauss=n)
+        assert rel_err(got, ref, integ.out_offsets(dmesh, "mat_10_bdb", None, CommonArgs(ngauss=n))) <= TOL
+    # volume check independent of the oracle: sum of vec_01_ns with s = 1 is the cell measure; refine the rule
+    if solid:
+        v1 = integ.vec_01_ns(ctx, dmesh, None, CommonArgs(), Coef.uniform([1.0])).sum()
+        hi = {"tri10": 16, "tri15": 16, "qua12": 16, "qua16": 16, "qua17": 16, "tet20": 24, "hex32": 64}[kind]
+        v2 = integ.vec_01_ns(ctx, dmesh, None, CommonArgs(ngauss=hi), Coef.uniform([1.0])).sum()
+        assert abs(v1 - v2) <= 1e-9 * abs(v2)
