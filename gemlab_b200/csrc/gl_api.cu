@@ -405,6 +405,14 @@ __global__ void coords_to_soa_kernel(const double *__restrict__ aos, double *__r
     }
 }
 
+__global__ void coords_to_point_major_kernel(const double *__restrict__ soa, double *__restrict__ pm, unsigned long long npoint, int ndim) {
+    const int w = ndim == 2 ? 2 : 4;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < npoint;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        for (int j = 0; j < w; j++) pm[i * w + j] = j < ndim ? soa[(unsigned long long)j * npoint + i] : 0.0;
+    }
+}
+
 // uploads a homogeneous mesh: raw host arrays go to the device as they are and are transposed there
 template <typename IdT>
 int upload_homogeneous_device(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, const double *coords, const IdT *conn) {
@@ -611,6 +619,10 @@ int gl_mesh_update_coords(gl_ctx *ctx, gl_mesh *mesh, const double *coords, int 
     coords_to_soa(mesh->ndim, mesh->npoint, coords, soa);
     CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)ctx->stream));
     CUDA_TRY(ctx, cudaMemcpy(mesh->d_coords, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (mesh->d_coords_pm) {
+        coords_to_point_major_kernel<<<1184, 256, 0, (cudaStream_t)ctx->stream>>>(mesh->d_coords, mesh->d_coords_pm, mesh->npoint, mesh->ndim);
+        ctx->launches++;
+    }
     return GL_OK;
 }
 
@@ -622,6 +634,7 @@ void gl_mesh_free(gl_ctx *ctx, gl_mesh *mesh) {
     }
     // the two large buffers go back to the ctx pool (all work on them is complete: the stream was just synchronised)
     pool_free(ctx, mesh->d_coords, (size_t)mesh->npoint * mesh->ndim * sizeof(double));
+    pool_free(ctx, mesh->d_coords_pm, (size_t)mesh->npoint * (mesh->ndim == 2 ? 2 : 4) * sizeof(double));
     for (auto &bk : mesh->buckets) {
         pool_free(ctx, bk.d_conn, (size_t)bk.ncell * bk.nnode * sizeof(uint32_t));
         if (bk.d_cell_ids) cudaFree(bk.d_cell_ids);
@@ -683,6 +696,15 @@ int gl_out_offsets(const gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl
 // integration
 // =====================================================================================================
 
+// builds the point-major coordinate copy of a mesh on first use (thread-per-cell kernels gather whole points)
+static int ensure_point_major(gl_ctx *ctx, gl_mesh *mesh) {
+    if (mesh->d_coords_pm) return GL_OK;
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &mesh->d_coords_pm, (size_t)mesh->npoint * (mesh->ndim == 2 ? 2 : 4) * sizeof(double)));
+    coords_to_point_major_kernel<<<1184, 256, 0, (cudaStream_t)ctx->stream>>>(mesh->d_coords, mesh->d_coords_pm, mesh->npoint, mesh->ndim);
+    ctx->launches++;
+    return GL_OK;
+}
+
 // launches the kernels that integrate original cells [b, e) into the DEVICE buffer d_out (block of cell b at d_out[0])
 static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a,
                         const CoefResolved &cr, uint64_t coef_begin, double *d_out) {
@@ -711,6 +733,11 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         std::memset(&p, 0, sizeof(p));
         p.coords = mesh->d_coords;
         p.npoint = mesh->npoint;
+        if (op == GL_OP_MAT_01_NSN || op == GL_OP_VEC_01_NS) {
+            st = ensure_point_major(ctx, mesh);
+            if (st) return st;
+            p.coords_pm = mesh->d_coords_pm;
+        }
         p.conn = bk.d_conn;
         p.ncell_k = bk.ncell;
         p.cell_ids = bk.d_cell_ids;
@@ -785,7 +812,8 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
             if (op == GL_OP_VEC_03_BV) { f.mask = 8; std::memcpy(f.w, cr.uniform, sizeof(double) * mesh->ndim); f.out_v03 = d_out; }
             if (op_is_matrix(op)) { f.moff = p.out_off; f.mbase = p.out_base; }
             else { f.voff = p.out_off; f.vbase = p.out_base; }
-            nl = launch_scalar_fused(p, f, mesh->ndim, ctx->stream);
+            nl = launch_mass_dmma(p, f, mesh->ndim, ctx->stream);
+            if (nl == 0) nl = launch_scalar_fused(p, f, mesh->ndim, ctx->stream);
         }
         if (nl == 0) {
             p.cells_per_cta = generic_pick_cells_per_cta(mesh->ndim, gd, p.nnode, p.ng, op);
@@ -1028,6 +1056,11 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
         std::memset(&p, 0, sizeof(p));
         p.coords = mesh->d_coords;
         p.npoint = mesh->npoint;
+        if ((mask & ~5) == 0) { // mass / source vector only: thread-per-cell kernel, gathers whole points
+            int stp = ensure_point_major(ctx, mesh);
+            if (stp) return stp;
+            p.coords_pm = mesh->d_coords_pm;
+        }
         p.conn = bk.d_conn;
         p.ncell_k = bk.ncell;
         p.cell_ids = bk.d_cell_ids;
@@ -1055,7 +1088,8 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
             if (st) return st;
             fb.vbase = (*vpre)[b];
         }
-        int nl = launch_scalar_fused(p, fb, mesh->ndim, ctx->stream);
+        int nl = launch_mass_dmma(p, fb, mesh->ndim, ctx->stream);
+        if (nl == 0) nl = launch_scalar_fused(p, fb, mesh->ndim, ctx->stream);
         if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
         if (nl == 0) { // kind not covered by the fused kernel: run the items one after the other for the whole range
             for (int i = 0; i < nitems; i++) {

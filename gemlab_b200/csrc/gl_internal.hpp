@@ -51,6 +51,8 @@ struct RuleTable {
 struct IntegParams {
     // mesh (structure of arrays)
     const double *coords;     // [sd][npoint]
+    const double *coords_pm;  // point-major copy [npoint][2] (2D) / [npoint][4] (3D, padded): one 32-byte sector per point for
+                              // kernels whose lanes gather whole points of unrelated cells; nullptr if not built
     unsigned long long npoint;
     const uint32_t *conn;     // [nnode][ncell_k]  (bucket of one GeoKind)
     unsigned long long ncell_k;
@@ -106,6 +108,8 @@ struct ScalarFused {
     unsigned long long vbase;
 };
 int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
+// mat_01_nsn and/or vec_01_ns as a (cells x ng).(ng x entries) product on the FP64 tensor cores (gl_kernels_mass.cu); 0 if not covered
+int launch_mass_dmma(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
 
 // micro-benchmarks
 int bench_fp64(int kind, int iters, void *stream, double *tflops);
@@ -128,6 +132,7 @@ struct gl_mesh {
     int ndim = 0;
     uint64_t npoint = 0, ncell = 0;
     double *d_coords = nullptr; // [ndim][npoint]
+    double *d_coords_pm = nullptr; // lazily built point-major copy (see IntegParams::coords_pm)
     bool homogeneous = true;
     std::vector<gl_mesh_bucket> buckets;
     std::vector<uint8_t> h_kinds;        // per cell (mixed meshes only)
