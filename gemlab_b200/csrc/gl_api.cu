@@ -733,7 +733,8 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         std::memset(&p, 0, sizeof(p));
         p.coords = mesh->d_coords;
         p.npoint = mesh->npoint;
-        if (op == GL_OP_MAT_01_NSN || op == GL_OP_VEC_01_NS) {
+        if (op == GL_OP_MAT_01_NSN || op == GL_OP_VEC_01_NS ||
+            (op == GL_OP_MAT_10_BDB && mesh->ndim == 2 && (bk.nnode == 3 || bk.nnode == 4))) { // thread-per-cell kernels
             st = ensure_point_major(ctx, mesh);
             if (st) return st;
             p.coords_pm = mesh->d_coords_pm;
@@ -799,6 +800,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         }
         int nl = 0;
         if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
+        if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_small2d(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_tile(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb(p, mesh->ndim, ctx->stream);
         if (nl == 0 && gd == mesh->ndim && cr.dev == nullptr && a->clear && a->ii0 == 0 && (a->jj0 == 0 || !op_is_matrix(op)) &&

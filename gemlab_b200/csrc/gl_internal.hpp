@@ -92,6 +92,7 @@ int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op);
 // tuned kernels; return 0 if the configuration is not covered (caller falls back to the generic kernel)
 int launch_hex8_bdb(const IntegParams &p, void *stream);
 int launch_bdb(const IntegParams &p, int sd, void *stream);
+int launch_bdb_small2d(const IntegParams &p, int sd, void *stream); // thread-per-cell variant for Tri3 / Qua4 (gl_kernels_small2d.cu)
 int launch_bdb_tile(const IntegParams &p, int sd, void *stream); // register-tiled variant for Hex20 / Tet10 (gl_kernels_tile.cu)
 
 // fused scalar-dof cases (gl_kernels_scalar.cu): any subset of mat_01_nsn (bit 0), mat_03_btb (bit 1), vec_01_ns (bit 2),
