@@ -244,6 +244,7 @@ template <typename T>
 cudaError_t pool_alloc_t(gl_ctx *ctx, T **ptr, size_t bytes) { return pool_alloc(ctx, reinterpret_cast<void **>(ptr), bytes); }
 
 struct CoefResolved {
+    int pat = 0; // see IntegParams::coef_pat
     const double *dev = nullptr; // nullptr => uniform record in `uniform`
     uint64_t cell_stride = 0, gp_stride = 0;
     bool per_marker = false;
@@ -770,6 +771,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         }
         // coefficient
         p.coef_len = cr.len;
+        p.coef_pat = cr.pat;
         std::memcpy(p.coef_uniform, cr.uniform, sizeof(p.coef_uniform));
         p.coef = cr.dev;
         p.coef_cell_stride = cr.cell_stride;
@@ -827,6 +829,22 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
     return GL_OK;
 }
 
+// structure shared by all ns x ns Mandel moduli of a host table (column-major records): 2 = major-symmetric with
+// uncoupled normal / diagonal shear blocks, 1 = major-symmetric, 0 = general
+static int modulus_pattern(const double *records, uint64_t nrec, int ns) {
+    int pat = 2;
+    for (uint64_t r = 0; r < nrec && pat > 0; r++) {
+        const double *d = records + r * (uint64_t)(ns * ns);
+        for (int a = 0; a < ns && pat > 0; a++)
+            for (int b = 0; b < ns; b++) {
+                if (d[a + b * ns] != d[b + a * ns]) { pat = 0; break; }
+                const bool nz = (a < 3 && b < 3) || a == b;
+                if (!nz && d[a + b * ns] != 0.0) pat = 1;
+            }
+    }
+    return pat;
+}
+
 static int resolve_coef(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *coef,
                         CoefResolved &cr) {
     const uint64_t len = coef_len(op, mesh->ndim);
@@ -858,6 +876,7 @@ static int resolve_coef(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         }
         int st = ensure_buffer(ctx, &ctx->d_coef, &ctx->coef_bytes, table.size() * sizeof(double));
         if (st) return st;
+        if (op == GL_OP_MAT_10_BDB) cr.pat = modulus_pattern(table.data(), nm, 2 * mesh->ndim);
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coef, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice,
                                       (cudaStream_t)ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)ctx->stream)); // `table` is a local
@@ -898,6 +917,7 @@ static int resolve_coef(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         } else {
             int st = ensure_buffer(ctx, &ctx->d_coef, &ctx->coef_bytes, nrec * len * sizeof(double));
             if (st) return st;
+            if (op == GL_OP_MAT_10_BDB && !per_gauss) cr.pat = modulus_pattern(coef->data, nrec, 2 * mesh->ndim);
             CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coef, coef->data, nrec * len * sizeof(double), cudaMemcpyHostToDevice,
                                           (cudaStream_t)ctx->stream));
             cr.dev = ctx->d_coef;

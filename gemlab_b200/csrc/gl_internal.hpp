@@ -71,6 +71,8 @@ struct IntegParams {
     unsigned long long coef_cell_stride, coef_gp_stride; // in doubles
     const uint32_t *coef_index; // PER_MARKER: bucket-local cell -> record index; nullptr otherwise
     int coef_len;
+    int coef_pat;             // mat_10_bdb with record data: structure common to ALL records when the host could inspect them
+                              // (2 = symmetric with uncoupled normal / diagonal shear blocks, 1 = major-symmetric, 0 = unknown / general)
     double coef_uniform[36];
     // output
     double *out;

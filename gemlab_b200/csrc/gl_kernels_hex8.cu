@@ -65,7 +65,7 @@ __host__ __device__ constexpr bool d_nz(int pat, int a, int b) { return pat < 2 
 __host__ __device__ constexpr int col_row(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 3 : 5)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 3 : 4)) : (t == 0 ? 2 : (t == 1 ? 4 : 5))); }
 __host__ __device__ constexpr int col_comp(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 1 : 2)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 0 : 2)) : (t == 0 ? 2 : (t == 1 ? 1 : 0))); }
 
-template <int PAT, int PF, int DBG = 0>
+template <int PAT, int PF, int DBG = 0, bool DREC = false>
 __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegParams p, const Hex8Consts cst) {
     constexpr bool SYM = PAT >= 1;
     extern __shared__ __align__(16) double smem[];
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
     double *s_X = s_w + 8;                      // [H8_CELLS][X_STRIDE]
     double *s_B = s_X + H8_CELLS * X_STRIDE;    // [H8_CELLS][CELL_STRIDE]
     double *s_K = s_B + H8_CELLS * CELL_STRIDE; // [H8_CELLS][K_STRIDE]  (16-byte aligned: offset is a multiple of 2 doubles)
+    double *s_D = s_K + H8_CELLS * K_STRIDE;    // [H8_CELLS][36]  per-cell d' (DREC only: PER_MARKER / PER_CELL moduli)
 
     const int tid = threadIdx.x;
     const int g = tid & 7;   // lane within the cell group
@@ -90,6 +91,11 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
     double *Xc = s_X + cs * X_STRIDE;
     double *Bc = s_B + cs * CELL_STRIDE;
     double *Kc = s_K + cs * K_STRIDE;
+    double *Dc = s_D + cs * 36;
+    // d'[a][b] of this lane's cell: the constant bank for a uniform modulus, shared memory for a modulus record per cell
+    double dl[36] = {}; // DREC: register copy of the entries the pattern uses, refreshed once per batch (the staging stores in
+                   // between would otherwise force a shared-memory load per term)
+    auto dval = [&](int a, int b) -> double { return DREC ? dl[a * 6 + b] : cst.d[a * 6 + b]; };
     const double *Lg = s_L + g * L_STRIDE;
 
     // work distribution: iteration `it` of this CTA handles batch_of(it); strided (blockIdx + it*grid) or blocked
@@ -181,6 +187,20 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
             for (int m = 0; m < 8; m++) geom::gradient_row<3>(Lg + m * 3, Ji, Bg + m * 3);
             Bg[24] = det * s_w[g] * p.alpha;
         }
+        if constexpr (DREC) {
+            // the cell's modulus record (ns x ns Mandel matrix, column-major): the record of its marker (PER_MARKER) or its own
+            // (PER_CELL); the 8 lanes of the cell fold the 1/sqrt(2) factors in and publish d' for the epilogue
+            if (active) {
+                const unsigned long long rec = p.coef_index ? (unsigned long long)p.coef_index[cell]
+                                                            : (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
+                const double *D = p.coef + rec * p.coef_cell_stride;
+                const double hs = 0.70710678118654752440084436210484903928;
+                for (int idx = g; idx < 36; idx += 8) {
+                    const int a = idx / 6, b = idx - a * 6;
+                    Dc[idx] = D[a + b * 6] * (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
+                }
+            }
+        }
         __syncwarp();
 
         // ---- phase 2: lane g = column node n; geometric tensors P(m,n)[k][l] = sum_p c_p B(m,k) B(n,l) ------------------
@@ -218,6 +238,13 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
             }
         }
 
+        if constexpr (DREC) {
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int b = 0; b < 6; b++)
+                    if (d_nz(PAT, a, b)) dl[a * 6 + b] = Dc[a * 6 + b];
+        }
         // ---- phase 3: contract with D', stage the blocks column-major, ship every cell with one bulk copy -------------
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the warp's previous copies have left s_K (no-op for lanes that issued none)
         __syncwarp();
@@ -245,7 +272,7 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
 #pragma unroll
                         for (int r = 0; r < 3; r++)
                             if (d_nz(PAT, col_row(i, q), col_row(j, r))) {
-                                const double dv = cst.d[col_row(i, q) * 6 + col_row(j, r)], pv = P(col_comp(i, q), col_comp(j, r));
+                                const double dv = dval(col_row(i, q), col_row(j, r)), pv = P(col_comp(i, q), col_comp(j, r));
                                 v = have ? fma(dv, pv, v) : dv * pv;
                                 have = true;
                             }
@@ -260,7 +287,7 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
                         for (int q = 0; q < 3; q++)
 #pragma unroll
                             for (int r = 0; r < 3; r++) {
-                                const double dv = cst.d[col_row(j, r) * 6 + col_row(i, q)], pv = P(col_comp(i, q), col_comp(j, r));
+                                const double dv = dval(col_row(j, r), col_row(i, q)), pv = P(col_comp(i, q), col_comp(j, r));
                                 u = hv ? fma(dv, pv, u) : dv * pv;
                                 hv = true;
                             }
@@ -297,14 +324,17 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-constexpr size_t H8_SMEM = sizeof(double) * (8 * L_STRIDE + 8 + H8_CELLS * X_STRIDE + H8_CELLS * CELL_STRIDE + H8_CELLS * K_STRIDE);
+constexpr size_t H8_SMEM = sizeof(double) * (8 * L_STRIDE + 8 + H8_CELLS * X_STRIDE + H8_CELLS * CELL_STRIDE + H8_CELLS * K_STRIDE + H8_CELLS * 36);
 
 } // namespace
 
 int launch_hex8_bdb(const IntegParams &p, void *stream) {
-    // covered: Hex8, 8-point rule, uniform D, tight 24x24 blocks, overwrite, homogeneous layout, 16-byte aligned output
+    // covered: Hex8, 8-point rule, D uniform or one record per marker / per cell, tight 24x24 blocks, overwrite, homogeneous
+    // layout, 16-byte aligned output
     if (p.nnode != 8 || p.ng != 8 || p.op != GL_OP_MAT_10_BDB) return 0;
-    if (p.coef != nullptr || p.axisym || !p.clear || p.out_off != nullptr) return 0;
+    const bool drec = p.coef != nullptr;
+    if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 36)) return 0; // PER_GAUSS moduli: generic kernel
+    if (p.axisym || !p.clear || p.out_off != nullptr) return 0;
     if (p.nrow != 24 || p.ncol != 24 || p.ii0 != 0 || p.jj0 != 0 || p.size_r != 24) return 0;
     if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
 
@@ -337,6 +367,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
             for (int b = 0; b < 6; b++)
                 if (!d_nz(2, a, b) && cst.d[a * 6 + b] != 0.0) pat = 1;
     }
+    if (drec) pat = p.coef_pat; // structure common to all records (0 when the records live on the device only)
     {
         const char *e = getenv("GL_HEX8_PATTERN"); // tuning/testing knob: cap the specialisation level
         if (e && atoi(e) < pat) pat = atoi(e) < 0 ? 0 : atoi(e);
@@ -354,6 +385,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
             default: return hex8_bdb_kernel<2, P, 5>;
             }
         }
+        if (drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true> : hex8_bdb_kernel<0, P, 0, true>);
         return pat == 2 ? hex8_bdb_kernel<2, P> : (pat == 1 ? hex8_bdb_kernel<1, P> : hex8_bdb_kernel<0, P>);
     };
     kern = pf == 1 ? pick(std::integral_constant<int, 1>{}) : pick(std::integral_constant<int, 2>{});

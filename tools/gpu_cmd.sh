@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/bench_configs.py --scale 0.5 --only 1 5 2>&1 | tail -2 | cut -c1-330
-GL_DISABLE_SMALL2D=1 python tools/bench_configs.py --scale 0.5 --only 1 5 2>&1 | tail -2 | cut -c1-200
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/time_hex8.py 200 10 markers

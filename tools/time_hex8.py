@@ -28,4 +28,21 @@ for _ in range(reps):
     ms = e0.elapsed_time(e1)
     best = min(best, ms)
     tot += ms
+if len(sys.argv) > 3:  # two materials selected by cell marker (PER_MARKER) and one record per cell (PER_CELL)
+    import numpy as np
+    mesh.markers[mesh.ncell // 2:] = 2
+    dm2 = ctx.upload(mesh)
+    recs = np.stack([dd, 3.0 * dd])
+    for name, coef in (("per_marker", Coef.per_marker([1, 2], recs)),
+                       ("per_cell", Coef.per_cell(torch.tensor(np.tile(dd, (mesh.ncell, 1)), device="cuda")))):
+        for _ in range(3):
+            integ.mat_10_bdb(ctx, dm2, None, CommonArgs(), coef, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            integ.mat_10_bdb(ctx, dm2, None, CommonArgs(), coef, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{name}: {e0.elapsed_time(e1) / reps:.4f} ms per pass")
 print(f"n={n} cells={mesh.ncell} avg_ms={tot / reps:.4f} best_ms={best:.4f} write_TBs={mesh.ncell * 4608 / (tot / reps * 1e-3) / 1e12:.3f}")
