@@ -139,6 +139,9 @@ extern "C" {
     ) -> c_int;
     pub fn gl_mat_10_bdb(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
     pub fn gl_mat_01_nsn(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_02_bvn(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_08_ntn(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_09_nvb(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
     pub fn gl_mat_03_btb(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
     pub fn gl_vec_01_ns(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
     pub fn gl_vec_02_nv(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;

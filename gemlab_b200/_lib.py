@@ -77,7 +77,7 @@ SYMBOLS = {
     "gl_bench_fp64_peak": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gl_bench_hbm_write": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
 }
-for _name in ("gl_mat_10_bdb", "gl_mat_01_nsn", "gl_mat_03_btb", "gl_vec_01_ns", "gl_vec_02_nv", "gl_vec_03_bv",
+for _name in ("gl_mat_10_bdb", "gl_mat_01_nsn", "gl_mat_02_bvn", "gl_mat_03_btb", "gl_mat_08_ntn", "gl_mat_09_nvb", "gl_vec_01_ns", "gl_vec_02_nv", "gl_vec_03_bv",
               "gl_vec_04_bt", "gl_mat_10_gdg", "gl_vec_10_gs"):
     SYMBOLS[_name] = (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlOut)])
 

@@ -50,8 +50,8 @@ enum { SZ_NDOF2 = 0, SZ_NNODE2 = 1, SZ_NNODE = 2, SZ_NDOF = 3, SZ_ONE = 4 };
 
 int op_size_class(int op) {
     switch (op) {
-    case GL_OP_MAT_10_BDB: return SZ_NDOF2;
-    case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: return SZ_NNODE2;
+    case GL_OP_MAT_10_BDB: case GL_OP_MAT_08_NTN: case GL_OP_MAT_09_NVB: return SZ_NDOF2;
+    case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: case GL_OP_MAT_02_BVN: return SZ_NNODE2;
     case GL_OP_VEC_01_NS: case GL_OP_VEC_03_BV: return SZ_NNODE;
     case GL_OP_VEC_02_NV: case GL_OP_VEC_04_BT: return SZ_NDOF;
     case GL_OP_JACOBIAN: return SZ_ONE;
@@ -59,12 +59,15 @@ int op_size_class(int op) {
     }
 }
 
-bool op_is_matrix(int op) { return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB; }
+bool op_is_matrix(int op) {
+    return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB || op == GL_OP_MAT_02_BVN ||
+           op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB;
+}
 
 bool op_uses_gradient(int op) {
     // the reference calls Scratchpad::calc_gradient for these (mat_01_nsn too, src/integ/mat_01_nsn.rs:76)
     return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV ||
-           op == GL_OP_VEC_04_BT;
+           op == GL_OP_VEC_04_BT || op == GL_OP_MAT_02_BVN || op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB;
 }
 
 // rows / cols actually integrated for a cell of `kind`
@@ -93,8 +96,8 @@ int block_dims(int op, int kind, int ndim, const gl_args *a, BlockDims &bd) {
     bd.ncol = mat ? (a->ncol ? a->ncol : jj0 + bd.size_c) : 1;
     if (bd.nrow < ii0 + bd.size_r) {
         switch (op) {
-        case GL_OP_MAT_10_BDB: return GL_ERR_NROW_KK_NDOF;
-        case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: return GL_ERR_NROW_KK_NNODE;
+        case GL_OP_MAT_10_BDB: case GL_OP_MAT_08_NTN: case GL_OP_MAT_09_NVB: return GL_ERR_NROW_KK_NDOF;
+        case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: case GL_OP_MAT_02_BVN: return GL_ERR_NROW_KK_NNODE;
         case GL_OP_VEC_01_NS: return GL_ERR_A_LEN;
         case GL_OP_VEC_02_NV: return GL_ERR_B_LEN;
         case GL_OP_VEC_03_BV: return GL_ERR_C_LEN;
@@ -102,7 +105,7 @@ int block_dims(int op, int kind, int ndim, const gl_args *a, BlockDims &bd) {
         default: return GL_ERR_INVALID_ARG;
         }
     }
-    if (mat && bd.ncol < jj0 + bd.size_c) return op == GL_OP_MAT_10_BDB ? GL_ERR_NCOL_KK_NDOF : GL_ERR_NCOL_KK_NNODE;
+    if (mat && bd.ncol < jj0 + bd.size_c) return op_size_class(op) == SZ_NDOF2 ? GL_ERR_NCOL_KK_NDOF : GL_ERR_NCOL_KK_NNODE;
     return GL_OK;
 }
 
@@ -111,8 +114,8 @@ uint64_t coef_len(int op, int ndim) {
     switch (op) {
     case GL_OP_MAT_10_BDB: return ns * ns;
     case GL_OP_MAT_01_NSN: case GL_OP_VEC_01_NS: return 1;
-    case GL_OP_MAT_03_BTB: case GL_OP_VEC_04_BT: return ns;
-    case GL_OP_VEC_02_NV: case GL_OP_VEC_03_BV: return (uint64_t)ndim;
+    case GL_OP_MAT_03_BTB: case GL_OP_VEC_04_BT: case GL_OP_MAT_08_NTN: return ns;
+    case GL_OP_VEC_02_NV: case GL_OP_VEC_03_BV: case GL_OP_MAT_02_BVN: case GL_OP_MAT_09_NVB: return (uint64_t)ndim;
     default: return 0;
     }
 }
@@ -1134,6 +1137,15 @@ int gl_mat_01_nsn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, cons
 int gl_mat_03_btb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
     return gl_integ(ctx, mesh, GL_OP_MAT_03_BTB, b, e, a, c, o);
 }
+int gl_mat_02_bvn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_02_BVN, b, e, a, c, o);
+}
+int gl_mat_08_ntn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_08_NTN, b, e, a, c, o);
+}
+int gl_mat_09_nvb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_09_NVB, b, e, a, c, o);
+}
 int gl_vec_01_ns(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
     return gl_integ(ctx, mesh, GL_OP_VEC_01_NS, b, e, a, c, o);
 }
@@ -1327,7 +1339,9 @@ int assemble_checks(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, 
     return GL_OK;
 }
 
-int op_dofs_per_node(int op, int ndim) { return (op == GL_OP_MAT_10_BDB || op == GL_OP_VEC_02_NV || op == GL_OP_VEC_04_BT) ? ndim : 1; }
+int op_dofs_per_node(int op, int ndim) {
+    return (op == GL_OP_MAT_10_BDB || op == GL_OP_VEC_02_NV || op == GL_OP_VEC_04_BT || op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB) ? ndim : 1;
+}
 
 } // namespace
 

@@ -24,7 +24,8 @@ constexpr int NT = 256;
 constexpr double INV_SQRT_2 = 0.70710678118654752440084436210484903928;
 
 __device__ __forceinline__ bool op_needs_gradient(int op) {
-    return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV || op == GL_OP_VEC_04_BT;
+    return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV || op == GL_OP_VEC_04_BT ||
+           op == GL_OP_MAT_02_BVN || op == GL_OP_MAT_09_NVB;
 }
 
 // column (m, i) of the Mandel strain-displacement matrix (calc_bb_matrix, src/integ/mat_10_bdb.rs:238-278):
@@ -251,6 +252,36 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
                     acc += c1 * sum;
                 }
             } break;
+            case GL_OP_MAT_02_BVN: { // K(m,n) = sum_p (B(m).v) N(n) c_p   (src/integ/mat_02_bvn.rs:96-117)
+                for (int gp = 0; gp < ng; gp++) {
+                    const double *v = coef0 + gp * gstride;
+                    const double *bm = Bc + gp * bs + ii * SD;
+                    double c1 = cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    double dot = 0.0;
+#pragma unroll
+                    for (int a = 0; a < SD; a++) dot += bm[a] * v[a];
+                    acc += c1 * dot * s_N[gp * nnode + jj];
+                }
+            } break;
+            case GL_OP_MAT_08_NTN: { // K(m i, n j) = sum_p N(m) T(i,j) N(n) c_p   (src/integ/mat_08_ntn.rs:109-131)
+                const int m = ii / SD, i = ii - m * SD, n = jj / SD, j = jj - n * SD;
+                for (int gp = 0; gp < ng; gp++) {
+                    const double *t = coef0 + gp * gstride;
+                    double c1 = cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    acc += c1 * s_N[gp * nnode + m] * mandel_comp<SD>(t, i, j) * s_N[gp * nnode + n];
+                }
+            } break;
+            case GL_OP_MAT_09_NVB: { // K(m i, n j) = sum_p N(m) v(i) B(n,j) c_p   (src/integ/mat_09_nvb.rs:101-122)
+                const int m = ii / SD, i = ii - m * SD, n = jj / SD, j = jj - n * SD;
+                for (int gp = 0; gp < ng; gp++) {
+                    const double *v = coef0 + gp * gstride;
+                    double c1 = cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    acc += c1 * s_N[gp * nnode + m] * v[i] * Bc[gp * bs + n * SD + j];
+                }
+            } break;
             case GL_OP_VEC_01_NS: {
                 for (int gp = 0; gp < ng; gp++) {
                     double c1 = coef0[gp * gstride] * cf[gp];
@@ -330,7 +361,8 @@ int launch_t(const IntegParams &p, void *stream) {
 } // namespace
 
 size_t generic_smem_bytes(int sd, int gd, int nnode, int ng, int op, int C) {
-    const bool need_b = op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV || op == GL_OP_VEC_04_BT;
+    const bool need_b = op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV || op == GL_OP_VEC_04_BT ||
+                        op == GL_OP_MAT_02_BVN || op == GL_OP_MAT_09_NVB;
     size_t n = (size_t)ng * (1 + nnode + nnode * gd);
     n += (size_t)C * ((nnode * sd) | 1);
     n += (size_t)2 * C * ng;

@@ -24,7 +24,7 @@ from .geo import GemlabError, GeoKind
 from .mesh import Mesh
 
 GL_HOST, GL_DEVICE = 0, 1
-OPS = {"mat_10_bdb": 0, "mat_01_nsn": 1, "mat_03_btb": 2, "vec_01_ns": 3, "vec_03_bv": 4, "vec_02_nv": 5,
+OPS = {"mat_02_bvn": 9, "mat_08_ntn": 10, "mat_09_nvb": 11, "mat_10_bdb": 0, "mat_01_nsn": 1, "mat_03_btb": 2, "vec_01_ns": 3, "vec_03_bv": 4, "vec_02_nv": 5,
        "vec_04_bt": 6, "jacobian": 8}
 COEF_UNIFORM, COEF_PER_MARKER, COEF_PER_CELL, COEF_PER_GAUSS = 0, 1, 2, 3
 
@@ -360,6 +360,21 @@ def mat_01_nsn(ctx, dmesh, cell_range, args, coef, out=None):
 def mat_03_btb(ctx, dmesh, cell_range, args, coef, out=None):
     """K = int B.T.B, nnode x nnode -- integ::mat_03_btb (src/integ/mat_03_btb.rs:50-131)."""
     return _integ("mat_03_btb", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_02_bvn(ctx, dmesh, cell_range, args, coef, out=None):
+    """K = int (B.v) N, nnode x nnode -- integ::mat_02_bvn (src/integ/mat_02_bvn.rs:48-120); coefficient v (space_ndim)."""
+    return _integ("mat_02_bvn", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_08_ntn(ctx, dmesh, cell_range, args, coef, out=None):
+    """K = int N T N, ndof x ndof -- integ::mat_08_ntn (src/integ/mat_08_ntn.rs:56-135); coefficient Mandel vector of T."""
+    return _integ("mat_08_ntn", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_09_nvb(ctx, dmesh, cell_range, args, coef, out=None):
+    """K = int N v B, ndof x ndof -- integ::mat_09_nvb (src/integ/mat_09_nvb.rs:54-125); coefficient v (space_ndim)."""
+    return _integ("mat_09_nvb", ctx, dmesh, cell_range, args, coef, out)
 
 
 def vec_01_ns(ctx, dmesh, cell_range, args, coef, out=None):

@@ -84,7 +84,10 @@ typedef enum gl_op {
     GL_OP_VEC_03_BV = 4,  /* integ::vec_03_bv   c = int B.w         (src/integ/vec_03_bv.rs:84)    nnode */
     GL_OP_VEC_02_NV = 5,  /* integ::vec_02_nv   b = int N v         (src/integ/vec_02_nv.rs:85)    ndof */
     GL_OP_VEC_04_BT = 6,  /* integ::vec_04_bt   d = int B.sigma     (src/integ/vec_04_bt.rs:93)    ndof */
-    GL_OP_JACOBIAN = 8    /* Scratchpad::calc_jacobian at one ksi (scratchpad_calc_jacobian.rs:101; Mesh::check_jacobian, mesh/check.rs:43-60)  1 */
+    GL_OP_JACOBIAN = 8,   /* Scratchpad::calc_jacobian at one ksi (scratchpad_calc_jacobian.rs:101; Mesh::check_jacobian, mesh/check.rs:43-60)  1 */
+    GL_OP_MAT_02_BVN = 9, /* integ::mat_02_bvn  K = int (B.v) N     (src/integ/mat_02_bvn.rs:48)   nnode x nnode; coefficient v (space_ndim) */
+    GL_OP_MAT_08_NTN = 10, /* integ::mat_08_ntn K = int N T N       (src/integ/mat_08_ntn.rs:56)   ndof x ndof;   coefficient Mandel vector (ns) */
+    GL_OP_MAT_09_NVB = 11  /* integ::mat_09_nvb K = int N v B       (src/integ/mat_09_nvb.rs:54)   ndof x ndof;   coefficient v (space_ndim) */
 } gl_op;
 
 typedef enum gl_location { GL_HOST = 0, GL_DEVICE = 1 } gl_location;
@@ -106,9 +109,9 @@ typedef struct gl_args {
  * (FnMut(&mut Tensor4, p, &N, &B), mat_10_bdb.rs:121-124, and siblings).  A device cannot call a host closure, so the
  * batched boundary takes the coefficient as DATA.  One record is:
  *   mat_10_bdb : D as the ns x ns Mandel matrix `dd.matrix()`, column-major, ns = 2*space_ndim
- *   mat_03_btb, vec_04_bt : the Mandel vector `tt.vector()` (ns)
+ *   mat_03_btb, mat_08_ntn, vec_04_bt : the Mandel vector `tt.vector()` (ns)
  *   mat_01_nsn, vec_01_ns : the scalar s
- *   vec_02_nv, vec_03_bv  : the vector v / w (space_ndim)
+ *   mat_02_bvn, mat_09_nvb, vec_02_nv, vec_03_bv : the vector v / w (space_ndim)
  */
 typedef enum gl_coef_mode {
     GL_COEF_UNIFORM = 0,    /* one record for every cell and Gauss point */
@@ -215,6 +218,13 @@ GL_API int gl_mat_01_nsn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, 
                          const gl_coef *coef, gl_out *out);
 /* replaces integ::mat_03_btb (src/integ/mat_03_btb.rs:50-131) */
 GL_API int gl_mat_03_btb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+/* replace integ::mat_02_bvn (src/integ/mat_02_bvn.rs:48-120), mat_08_ntn (mat_08_ntn.rs:56-135), mat_09_nvb (mat_09_nvb.rs:54-125) */
+GL_API int gl_mat_02_bvn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+GL_API int gl_mat_08_ntn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+GL_API int gl_mat_09_nvb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                          const gl_coef *coef, gl_out *out);
 /* replaces integ::vec_01_ns (src/integ/vec_01_ns.rs:83-130) */
 GL_API int gl_vec_01_ns(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,

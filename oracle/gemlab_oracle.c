@@ -975,6 +975,110 @@ int go_mat_03_btb(double *kk, int nrow, int ncol, go_args *args, go_fn_tt fn, vo
     return GO_OK;
 }
 
+/* shared prologue of the single-pad matrix cases: N, B, det J and the coefficient c = det J * w * alpha [* r] */
+static int matrix_case_point(go_args *args, int p, double *c) {
+    go_pad *pad = args->pad;
+    const double *iota = args->gauss[p];
+    const double weight = args->gauss[p][3];
+    go_pad_calc_interp(pad, iota);
+    double det_jac;
+    int err = go_pad_calc_gradient(pad, iota, &det_jac);
+    if (err) return err;
+    if (args->axisymmetric) {
+        double r = radius_at_ip(pad);
+        *c = det_jac * weight * args->alpha * r;
+    } else {
+        *c = det_jac * weight * args->alpha;
+    }
+    return GO_OK;
+}
+
+/* integ::mat_02_bvn (src/integ/mat_02_bvn.rs:48-120): K(m,n) = sum_p (B(m).v) N(n) c_p */
+int go_mat_02_bvn(double *kk, int nrow, int ncol, go_args *args, go_fn_v fn, void *user) {
+    go_pad *pad = args->pad;
+    const int sd = pad->space_ndim, nnode = pad->nnode;
+    const int ii0 = args->ii0, jj0 = args->jj0;
+    if (nrow < ii0 + nnode) return GO_ERR_NROW_KK_NNODE;
+    if (ncol < jj0 + nnode) return GO_ERR_NCOL_KK_NNODE;
+    double v[3] = {0, 0, 0};
+    if (args->clear) memset(kk, 0, sizeof(double) * (size_t)nrow * (size_t)ncol);
+    for (int p = 0; p < args->ngauss; p++) {
+        double c;
+        int err = matrix_case_point(args, p, &c);
+        if (err) return err;
+        const double *nn = pad->interp;
+        if (fn(v, p, nn, pad->gradient, user)) return GO_ERR_CALLBACK_STOP;
+        for (int m = 0; m < nnode; m++)
+            for (int n = 0; n < nnode; n++) {
+                if (sd == 2) KK(ii0 + m, jj0 + n) += c * (B(m, 0) * v[0] + B(m, 1) * v[1]) * nn[n];
+                else KK(ii0 + m, jj0 + n) += c * (B(m, 0) * v[0] + B(m, 1) * v[1] + B(m, 2) * v[2]) * nn[n];
+            }
+    }
+    return GO_OK;
+}
+
+/* integ::mat_08_ntn (src/integ/mat_08_ntn.rs:56-135): K(m i, n j) = sum_p N(m) T(i,j) N(n) c_p, T from its Mandel vector */
+int go_mat_08_ntn(double *kk, int nrow, int ncol, go_args *args, go_fn_tt fn, void *user) {
+    go_pad *pad = args->pad;
+    const int sd = pad->space_ndim, nnode = pad->nnode;
+    const int ii0 = args->ii0, jj0 = args->jj0;
+    if (nrow < ii0 + nnode * sd) return GO_ERR_NROW_KK_NDOF;
+    if (ncol < jj0 + nnode * sd) return GO_ERR_NCOL_KK_NDOF;
+    double t[6] = {0, 0, 0, 0, 0, 0};
+    if (args->clear) memset(kk, 0, sizeof(double) * (size_t)nrow * (size_t)ncol);
+    const double s = SQRT_2;
+    for (int p = 0; p < args->ngauss; p++) {
+        double c;
+        int err = matrix_case_point(args, p, &c);
+        if (err) return err;
+        const double *nn = pad->interp;
+        if (fn(t, p, nn, pad->gradient, user)) return GO_ERR_CALLBACK_STOP;
+        for (int m = 0; m < nnode; m++)
+            for (int n = 0; n < nnode; n++) {
+                if (sd == 2) {
+                    KK(ii0 + 0 + m * 2, jj0 + 0 + n * 2) += c * nn[m] * t[0] * nn[n];
+                    KK(ii0 + 0 + m * 2, jj0 + 1 + n * 2) += c * nn[m] * t[3] * nn[n] / s;
+                    KK(ii0 + 1 + m * 2, jj0 + 0 + n * 2) += c * nn[m] * t[3] * nn[n] / s;
+                    KK(ii0 + 1 + m * 2, jj0 + 1 + n * 2) += c * nn[m] * t[1] * nn[n];
+                } else {
+                    KK(ii0 + 0 + m * 3, jj0 + 0 + n * 3) += c * nn[m] * t[0] * nn[n];
+                    KK(ii0 + 0 + m * 3, jj0 + 1 + n * 3) += c * nn[m] * t[3] * nn[n] / s;
+                    KK(ii0 + 0 + m * 3, jj0 + 2 + n * 3) += c * nn[m] * t[5] * nn[n] / s;
+                    KK(ii0 + 1 + m * 3, jj0 + 0 + n * 3) += c * nn[m] * t[3] * nn[n] / s;
+                    KK(ii0 + 1 + m * 3, jj0 + 1 + n * 3) += c * nn[m] * t[1] * nn[n];
+                    KK(ii0 + 1 + m * 3, jj0 + 2 + n * 3) += c * nn[m] * t[4] * nn[n] / s;
+                    KK(ii0 + 2 + m * 3, jj0 + 0 + n * 3) += c * nn[m] * t[5] * nn[n] / s;
+                    KK(ii0 + 2 + m * 3, jj0 + 1 + n * 3) += c * nn[m] * t[4] * nn[n] / s;
+                    KK(ii0 + 2 + m * 3, jj0 + 2 + n * 3) += c * nn[m] * t[2] * nn[n];
+                }
+            }
+    }
+    return GO_OK;
+}
+
+/* integ::mat_09_nvb (src/integ/mat_09_nvb.rs:54-125): K(m i, n j) = sum_p N(m) v(i) B(n,j) c_p */
+int go_mat_09_nvb(double *kk, int nrow, int ncol, go_args *args, go_fn_v fn, void *user) {
+    go_pad *pad = args->pad;
+    const int sd = pad->space_ndim, nnode = pad->nnode;
+    const int ii0 = args->ii0, jj0 = args->jj0;
+    if (nrow < ii0 + nnode * sd) return GO_ERR_NROW_KK_NDOF;
+    if (ncol < jj0 + nnode * sd) return GO_ERR_NCOL_KK_NDOF;
+    double v[3] = {0, 0, 0};
+    if (args->clear) memset(kk, 0, sizeof(double) * (size_t)nrow * (size_t)ncol);
+    for (int p = 0; p < args->ngauss; p++) {
+        double c;
+        int err = matrix_case_point(args, p, &c);
+        if (err) return err;
+        const double *nn = pad->interp;
+        if (fn(v, p, nn, pad->gradient, user)) return GO_ERR_CALLBACK_STOP;
+        for (int m = 0; m < nnode; m++)
+            for (int n = 0; n < nnode; n++)
+                for (int i = 0; i < sd; i++)
+                    for (int j = 0; j < sd; j++) KK(ii0 + i + m * sd, jj0 + j + n * sd) += c * nn[m] * v[i] * B(n, j);
+    }
+    return GO_OK;
+}
+
 /* integ::vec_01_ns (src/integ/vec_01_ns.rs:83-130); works for CABLE cells too (calc_jacobian only) */
 int go_vec_01_ns(double *a, int len, go_args *args, go_fn_s fn, void *user) {
     go_pad *pad = args->pad;
@@ -1173,8 +1277,8 @@ size_t go_op_out_size(int op, int kind, int ndim) {
     const size_t nnode = (size_t)go_kind_nnode(kind);
     const size_t ndof = nnode * (size_t)ndim;
     switch (op) {
-    case GO_OP_MAT_10_BDB: case GO_OP_MAT_10_BDB_ALT: return ndof * ndof;
-    case GO_OP_MAT_01_NSN: case GO_OP_MAT_03_BTB: return nnode * nnode;
+    case GO_OP_MAT_10_BDB: case GO_OP_MAT_10_BDB_ALT: case GO_OP_MAT_08_NTN: case GO_OP_MAT_09_NVB: return ndof * ndof;
+    case GO_OP_MAT_01_NSN: case GO_OP_MAT_03_BTB: case GO_OP_MAT_02_BVN: return nnode * nnode;
     case GO_OP_VEC_01_NS: case GO_OP_VEC_03_BV: return nnode;
     case GO_OP_VEC_02_NV: case GO_OP_VEC_04_BT: return ndof;
     case GO_OP_JACOBIAN: return 1;
@@ -1187,8 +1291,8 @@ size_t go_op_coef_size(int op, int ndim) {
     switch (op) {
     case GO_OP_MAT_10_BDB: case GO_OP_MAT_10_BDB_ALT: return ns * ns;
     case GO_OP_MAT_01_NSN: case GO_OP_VEC_01_NS: return 1;
-    case GO_OP_MAT_03_BTB: case GO_OP_VEC_04_BT: return ns;
-    case GO_OP_VEC_02_NV: case GO_OP_VEC_03_BV: return (size_t)ndim;
+    case GO_OP_MAT_03_BTB: case GO_OP_VEC_04_BT: case GO_OP_MAT_08_NTN: return ns;
+    case GO_OP_VEC_02_NV: case GO_OP_VEC_03_BV: case GO_OP_MAT_02_BVN: case GO_OP_MAT_09_NVB: return (size_t)ndim;
     default: return 0;
     }
 }
@@ -1237,6 +1341,9 @@ static int integ_one_cell(int op, const go_mesh *mesh, size_t e, size_t cell_beg
     case GO_OP_MAT_10_BDB_ALT: return go_mat_10_bdb_alt(out, ndof, ndof, &args, cb_copy, &cv);
     case GO_OP_MAT_01_NSN: return go_mat_01_nsn(out, nnode, nnode, &args, cb_copy, &cv);
     case GO_OP_MAT_03_BTB: return go_mat_03_btb(out, nnode, nnode, &args, cb_copy, &cv);
+    case GO_OP_MAT_02_BVN: return go_mat_02_bvn(out, nnode, nnode, &args, cb_copy, &cv);
+    case GO_OP_MAT_08_NTN: return go_mat_08_ntn(out, ndof, ndof, &args, cb_copy, &cv);
+    case GO_OP_MAT_09_NVB: return go_mat_09_nvb(out, ndof, ndof, &args, cb_copy, &cv);
     case GO_OP_VEC_01_NS: return go_vec_01_ns(out, nnode, &args, cb_copy, &cv);
     case GO_OP_VEC_02_NV: return go_vec_02_nv(out, ndof, &args, cb_copy, &cv);
     case GO_OP_VEC_03_BV: return go_vec_03_bv(out, nnode, &args, cb_copy, &cv);

@@ -126,6 +126,9 @@ typedef int (*go_fn_v)(double *v /* space_ndim */, int p, const double *nn, cons
 int go_mat_10_bdb(double *kk, int nrow, int ncol, go_args *args, go_fn_dd fn, void *user);
 int go_mat_10_bdb_alt(double *kk, int nrow, int ncol, go_args *args, go_fn_dd fn, void *user);
 int go_mat_01_nsn(double *kk, int nrow, int ncol, go_args *args, go_fn_s fn, void *user);
+int go_mat_02_bvn(double *kk, int nrow, int ncol, go_args *args, go_fn_v fn, void *user);
+int go_mat_08_ntn(double *kk, int nrow, int ncol, go_args *args, go_fn_tt fn, void *user);
+int go_mat_09_nvb(double *kk, int nrow, int ncol, go_args *args, go_fn_v fn, void *user);
 int go_mat_03_btb(double *kk, int nrow, int ncol, go_args *args, go_fn_tt fn, void *user);
 int go_vec_01_ns(double *a, int len, go_args *args, go_fn_s fn, void *user);
 int go_vec_02_nv(double *b, int len, go_args *args, go_fn_v fn, void *user);
@@ -142,7 +145,8 @@ void go_lin_elasticity(double young, double poisson, int two_dim, int plane_stre
 enum {
     GO_OP_MAT_10_BDB = 0, GO_OP_MAT_01_NSN = 1, GO_OP_MAT_03_BTB = 2,
     GO_OP_VEC_01_NS = 3, GO_OP_VEC_03_BV = 4, GO_OP_VEC_02_NV = 5, GO_OP_VEC_04_BT = 6,
-    GO_OP_MAT_10_BDB_ALT = 7, GO_OP_JACOBIAN = 8
+    GO_OP_MAT_10_BDB_ALT = 7, GO_OP_JACOBIAN = 8,
+    GO_OP_MAT_02_BVN = 9, GO_OP_MAT_08_NTN = 10, GO_OP_MAT_09_NVB = 11
 };
 /* per-element output size in doubles for op on a cell of `kind` in `ndim` space */
 size_t go_op_out_size(int op, int kind, int ndim);

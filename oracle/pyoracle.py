@@ -24,7 +24,7 @@ CLASS_LIN, CLASS_TRI, CLASS_QUA, CLASS_TET, CLASS_HEX = range(5)
 _CLASS_KIND = {CLASS_LIN: KIND["lin2"], CLASS_TRI: KIND["tri3"], CLASS_QUA: KIND["qua4"], CLASS_TET: KIND["tet4"],
                CLASS_HEX: KIND["hex8"]}
 
-OP = {"mat_10_bdb": 0, "mat_01_nsn": 1, "mat_03_btb": 2, "vec_01_ns": 3, "vec_03_bv": 4, "vec_02_nv": 5,
+OP = {"mat_02_bvn": 9, "mat_08_ntn": 10, "mat_09_nvb": 11, "mat_10_bdb": 0, "mat_01_nsn": 1, "mat_03_btb": 2, "vec_01_ns": 3, "vec_03_bv": 4, "vec_02_nv": 5,
       "vec_04_bt": 6, "mat_10_bdb_alt": 7, "jacobian": 8}
 
 GO_MAX_NNODE = 32
@@ -345,6 +345,19 @@ def mat_01_nsn(kk, args, fn_s):
 def mat_03_btb(kk, args, fn_tt):
     """fn_tt(t, p, N, B): t is the Mandel vector (ns)."""
     return _mat("go_mat_03_btb", kk, args, fn_tt, 2 * args.pad.space_ndim)
+
+
+def mat_02_bvn(kk, args, fn_v):
+    """fn_v(v, p, N, B): v has space_ndim entries."""
+    return _mat("go_mat_02_bvn", kk, args, fn_v, args.pad.space_ndim)
+
+
+def mat_08_ntn(kk, args, fn_tt):
+    return _mat("go_mat_08_ntn", kk, args, fn_tt, 2 * args.pad.space_ndim)
+
+
+def mat_09_nvb(kk, args, fn_v):
+    return _mat("go_mat_09_nvb", kk, args, fn_v, args.pad.space_ndim)
 
 
 def vec_01_ns(a, args, fn_s):

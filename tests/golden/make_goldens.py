@@ -122,6 +122,24 @@ class AnaTri3:
         c = th * s * self.area / 12.0
         return np.array([[2 * c, c, c], [c, 2 * c, c], [c, c, 2 * c]])
 
+    def mat_02_bvn(self, v0, v1):  # :253-261
+        row = self.area * (self.bb[:, 0] * v0 + self.bb[:, 1] * v1) / 3.0
+        return np.repeat(row[:, None], 3, axis=1)
+
+    def mat_08_ntn(self, rho, th):  # :300-310
+        c = th * rho * self.area / 12.0
+        return c * np.kron(np.array([[2.0, 1.0, 1.0], [1.0, 2.0, 1.0], [1.0, 1.0, 2.0]]), np.eye(2))
+
+    def mat_09_nvb(self, v0, v1):  # :314-327: K[2m+i][2n+j] = (area/3) v_i B[n][j]
+        c = self.area / 3.0
+        k = np.zeros((6, 6))
+        for m in range(3):
+            for n in range(3):
+                for i, vi in enumerate((v0, v1)):
+                    for j in range(2):
+                        k[2 * m + i, 2 * n + j] = c * self.bb[n, j] * vi
+        return k
+
     def mat_03_btb(self, kx, ky, axisymmetric):  # :257-273
         c = self.area * sum(self.x) / 3.0 if axisymmetric else self.area
         b = self.bb
@@ -203,6 +221,24 @@ class AnaTet4:
         c = self.volume / 20.0
         k = np.full((4, 4), s * c)
         np.fill_diagonal(k, 2.0 * s * c)
+        return k
+
+    def mat_02_bvn(self, v0, v1, v2):  # :262-275
+        row = self.volume / 4.0 * (self.bb @ np.array([v0, v1, v2]))
+        return np.repeat(row[:, None], 4, axis=1)
+
+    def mat_08_ntn(self, sig):  # :378-398: K[3m+i][3n+j] = sig[i][j] * V * (1/10 if m == n else 1/20)
+        w = np.full((4, 4), 1.0 / 20.0) + np.eye(4) / 20.0
+        return self.volume * np.kron(w, np.asarray(sig))
+
+    def mat_09_nvb(self, v0, v1, v2):  # :402-425: K[3m+i][3n+j] = (V/4) v_i B[n][j]
+        c = self.volume / 4.0
+        k = np.zeros((12, 12))
+        for m in range(4):
+            for n in range(4):
+                for i, vi in enumerate((v0, v1, v2)):
+                    for j in range(3):
+                        k[3 * m + i, 3 * n + j] = c * self.bb[n, j] * vi
         return k
 
     def mat_03_btb(self, tt):  # :250-266: K[m][n] = c * sum_ab B[n][a] * T[b][a] * B[m][b] (T symmetric)
@@ -393,6 +429,21 @@ def main():
     anal = AnaTri3(lewis_xx)
     add("mat_03_btb_axisym_tri3_analytical", "tests/test_integ_heat_axis_1.rs:57-70", "mat_03_btb", "tri3", 2, lewis_xx,
         anal.mat_03_btb(2.0, 2.0, True), [1e-13], [3], tt=[2.0, 2.0, 0.0, 0.0], axisymmetric=True)
+
+    # ---- mat_02_bvn, mat_08_ntn, mat_09_nvb (single-pad cases of SURVEY.md 8(f4)) ----------------------
+    ana3 = AnaTri3(PAD_TRI3)
+    add("mat_02_bvn_tri3", "src/integ/mat_02_bvn.rs:170-191", "mat_02_bvn", "tri3", 2, PAD_TRI3, ana3.mat_02_bvn(2.0, 3.0),
+        [1e-15], [3], v=[2.0, 3.0])
+    add("mat_02_bvn_tet4", "src/integ/mat_02_bvn.rs:211-235", "mat_02_bvn", "tet4", 3, PAD_TET4, anat.mat_02_bvn(2.0, 3.0, 4.0),
+        [1e-15], [4], v=[2.0, 3.0, 4.0])
+    add("mat_08_ntn_tri3", "src/integ/mat_08_ntn.rs:185-209", "mat_08_ntn", "tri3", 2, PAD_TRI3, ana3.mat_08_ntn(2.7, 1.0),
+        [1e-15, 1e-15], [3, 6], tt=[2.7, 2.7, 0.0, 0.0])
+    add("mat_08_ntn_tet4", "src/integ/mat_08_ntn.rs:211-237", "mat_08_ntn", "tet4", 3, PAD_TET4, anat.mat_08_ntn(sig),
+        [1e-15], [4], tt=sig_mandel)
+    add("mat_09_nvb_tri3", "src/integ/mat_09_nvb.rs:170-194", "mat_09_nvb", "tri3", 2, PAD_TRI3, ana3.mat_09_nvb(2.0, 3.0),
+        [1e-15], [3], v=[2.0, 3.0])
+    add("mat_09_nvb_tet4", "src/integ/mat_09_nvb.rs:211-235", "mat_09_nvb", "tet4", 3, PAD_TET4, anat.mat_09_nvb(2.0, 3.0, 4.0),
+        [1e-15], [4], v=[2.0, 3.0, 4.0])
 
     # ---- vec_01_ns ------------------------------------------------------------------------------
     add("vec_01_ns_doctest", "src/integ/vec_01_ns.rs:58-82", "vec_01_ns", "tri3", 2, [[2.0, 3.0], [6.0, 3.0], [2.0, 6.0]],

@@ -54,7 +54,7 @@ def _golden_coef(case, mesh, ngauss):
     op = case["op"]
     if op == "mat_10_bdb":
         return Coef.uniform(np.array(case["dd"]).ravel(order="F"))
-    if op in ("mat_03_btb", "vec_04_bt"):
+    if op in ("mat_03_btb", "vec_04_bt", "mat_08_ntn"):
         return Coef.uniform(case["tt"])
     if "s" in case:
         return Coef.uniform([case["s"]])
@@ -161,7 +161,8 @@ def random_coef(op, ndim, nrec, rng, spd=True):
 
 
 SOLID_KINDS = ["tri3", "tri6", "qua4", "qua8", "qua9", "tet4", "tet10", "hex8", "hex20"]
-OPS = ["mat_10_bdb", "mat_01_nsn", "mat_03_btb", "vec_01_ns", "vec_02_nv", "vec_03_bv", "vec_04_bt"]
+OPS = ["mat_10_bdb", "mat_01_nsn", "mat_02_bvn", "mat_03_btb", "mat_08_ntn", "mat_09_nvb", "vec_01_ns", "vec_02_nv", "vec_03_bv",
+       "vec_04_bt"]
 
 
 @pytest.mark.parametrize("kind", SOLID_KINDS)

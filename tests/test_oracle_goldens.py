@@ -64,6 +64,14 @@ def run_case(case, n, alt=False):
             out[:] = case["tt"]
 
         return po.mat_03_btb(kk, args, fn)
+    if op in ("mat_02_bvn", "mat_08_ntn", "mat_09_nvb"):
+        n = nnode if op == "mat_02_bvn" else nnode * ndim
+        kk = np.full((n, n), NOISE)
+
+        def fn(out, p, nn, bb):
+            out[:] = case["tt"] if op == "mat_08_ntn" else case["v"]
+
+        return getattr(po, op)(kk, args, fn)
     if op == "vec_01_ns":
         a = np.full(nnode, NOISE)
 
