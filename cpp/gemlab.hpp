@@ -180,6 +180,15 @@ inline std::vector<double> mat_01_nsn(Context &ctx, const DeviceMesh &mesh, std:
 inline std::vector<double> mat_03_btb(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &tt) {
     return run(GL_OP_MAT_03_BTB, ctx, mesh, cells, args, &tt);
 }
+inline std::vector<double> mat_02_bvn(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &v) {
+    return run(GL_OP_MAT_02_BVN, ctx, mesh, cells, args, &v); // src/integ/mat_02_bvn.rs:48
+}
+inline std::vector<double> mat_08_ntn(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &tt) {
+    return run(GL_OP_MAT_08_NTN, ctx, mesh, cells, args, &tt); // src/integ/mat_08_ntn.rs:56
+}
+inline std::vector<double> mat_09_nvb(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &v) {
+    return run(GL_OP_MAT_09_NVB, ctx, mesh, cells, args, &v); // src/integ/mat_09_nvb.rs:54
+}
 inline std::vector<double> vec_01_ns(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &s) {
     return run(GL_OP_VEC_01_NS, ctx, mesh, cells, args, &s);
 }
@@ -191,6 +200,22 @@ inline std::vector<double> vec_03_bv(Context &ctx, const DeviceMesh &mesh, std::
 }
 inline std::vector<double> vec_04_bt(Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args, const Coef &sig) {
     return run(GL_OP_VEC_04_BT, ctx, mesh, cells, args, &sig);
+}
+
+// assembly hand-off (gl_assemble): integrates `op` over the cells and adds the element blocks into the CSR values
+// (matrix cases; DEVICE pointers rowptr / colidx / vals) or into the global vector `vals` (vector cases; rowptr = colidx =
+// nullptr).  `eq` is the HOST point -> equation table eq[point * dofs_per_node + i]; negative = prescribed dof.
+inline void assemble(int op, Context &ctx, const DeviceMesh &mesh, std::pair<size_t, size_t> cells, const CommonArgs &args,
+                     const Coef &coef, const std::vector<int32_t> &eq, const int64_t *rowptr, const int32_t *colidx, double *vals) {
+    gl_args a = args.c();
+    gl_coef c{};
+    c.mode = coef.mode;
+    c.location = GL_HOST;
+    c.data = coef.data.data();
+    c.markers = coef.markers.empty() ? nullptr : coef.markers.data();
+    c.nrecord = coef.markers.size();
+    uint64_t missing = 0;
+    ctx.check(gl_assemble(ctx.handle(), mesh.handle(), op, cells.first, cells.second, &a, &c, eq.data(), GL_HOST, rowptr, colidx, vals, &missing));
 }
 
 } // namespace batch
