@@ -76,18 +76,22 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
     for (int i = tid; i < ng; i += nt) s_w[i] = p.rule[i];
     for (int i = tid; i < ng * NN * SD; i += nt) s_L[(i / (NN * SD)) * LS + i % (NN * SD)] = p.rule[ng * (1 + NN) + i];
 
-    // phase C role: cell slot cs, tile (R, C) with R <= C
+    // phase C role: cell slot cs, tile (R, C) with R <= C.  Tiles are enumerated DIAGONAL BY DIAGONAL (d = C - R = 0, 1, ..; R
+    // ascending inside a diagonal): consecutive lanes then differ in R and C together, so the staging stores of phase D --
+    // at (6R + ..) + 60 (6C + ..) and mirrored -- and the LDS.128 row / column reads of phase C fall on different banks
+    // (with a row-major enumeration the 16 lanes of a half-warp differ only in C, and 360 C = 8 C (mod 16) leaves two banks)
     const int cs = tid / LPC;
     const int tix = tid - cs * LPC;
     const bool has_tile = tix < NT;
     int R = 0, C = 0;
     {
-        int t = has_tile ? tix : 0;
-        while (t >= NP - R) {
-            t -= NP - R;
-            R++;
+        int t = has_tile ? tix : 0, d = 0;
+        while (t >= NP - d) {
+            t -= NP - d;
+            d++;
         }
-        C = R + t;
+        R = t;
+        C = t + d;
     }
 
     // software-pipelined gather (Mesh::set_pad), as in gl_kernels_bdb.cu
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
                 const int pair = base + grp;
                 const bool valid = grp < GPW && pair < npair;
                 const int pr = valid ? pair : 0;
-                const int gp = pr / ncell_tile, c = pr - gp * ncell_tile;
+                const int c = pr / ng, gp = pr - c * ng; // Gauss point fastest: neighbouring groups write records 62 doubles apart
                 const double *X = s_X + c * XS;
                 const double *L = s_L + gp * LS;
                 double Jr[SD];
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
         const bool active = has_tile && cs < ncell_tile;
         if (active) {
             const double *Gc = s_G + cs * ng * GS;
-#pragma unroll 1
+#pragma unroll 3
             for (int gp = 0; gp < ng; gp++) {
                 const double *G = Gc + gp * GS;
                 const double2 *gr = reinterpret_cast<const double2 *>(G + 6 * R);
