@@ -66,9 +66,13 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
 
     extern __shared__ __align__(16) double smem[];
     const int ng = p.ng;
+    // The gradient records G are dead once the geometric tensors sit in registers, and the staged element blocks K are dead
+    // once the bulk copy has read them: the two share one region (G is the smaller one), which is what lets three CTAs
+    // instead of two fit on an SM.  Order per tile: wait for the previous copy's read -> G written (B) -> G read (C) ->
+    // barrier -> K written over it (D) -> bulk copy.
     double *s_K = smem;                          // [CPC][NDOF*NDOF]   (16-byte aligned for the bulk copy)
-    double *s_G = s_K + CPC * NDOF * NDOF;       // [CPC][ng][GS]       (16-byte aligned for LDS.128)
-    double *s_L = s_G + CPC * ng * GS;           // [ng][LS]
+    double *s_G = smem;                          // [CPC][ng][GS]       (aliases s_K; 16-byte aligned for LDS.128)
+    double *s_L = s_K + CPC * NDOF * NDOF;       // [ng][LS]
     double *s_X = s_L + ng * LS;                 // [CPC][XS]
     double *s_w = s_X + CPC * XS;                // [ng]
 
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
     for (unsigned long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const unsigned long long cell0 = p.lo + tile * CPC;
         const int ncell_tile = (int)min((unsigned long long)CPC, p.hi - cell0);
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // previous bulk copy has left s_K / s_G
         __syncthreads(); // previous tile consumed; tables staged
 
         // ---- phase A: gather ---------------------------------------------------------------------------------------
@@ -202,8 +207,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
         }
 
         // ---- phase D: contract with D', stage, ship -------------------------------------------------------------------
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // previous bulk copy has left s_K
-        __syncthreads();
+        __syncthreads(); // every lane has finished reading G: the region becomes the K staging
         if (active) {
             double *Kc = s_K + cs * NDOF * NDOF;
 #pragma unroll
@@ -255,7 +259,8 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
 template <int NN>
 size_t tile_smem(int ng, int cpc) {
     using T = TileDims<NN>;
-    return sizeof(double) * ((size_t)cpc * T::NDOF * T::NDOF + (size_t)cpc * ng * T::GS + (size_t)ng * T::LS + (size_t)cpc * T::XS + (size_t)ng);
+    // G aliases the K staging (ng * GS <= NDOF^2 for every instantiated kind and rule the launcher accepts)
+    return sizeof(double) * ((size_t)cpc * T::NDOF * T::NDOF + (size_t)ng * T::LS + (size_t)cpc * T::XS + (size_t)ng);
 }
 
 template <int NN>
@@ -269,7 +274,8 @@ int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, void 
     int cpc = cpc_env > 0 ? cpc_env : 256 / T::LPC;
     if (cpc < 1) cpc = 1;
     if (cpc * T::LPC > 256) cpc = 256 / T::LPC;
-    while (cpc > 1 && tile_smem<NN>(p.ng, cpc) > 110 * 1024) cpc--;
+    if ((size_t)p.ng * T::GS > (size_t)T::NDOF * T::NDOF) return 0; // G must fit inside the staging region it aliases
+    while (cpc > 1 && tile_smem<NN>(p.ng, cpc) > 74 * 1024) cpc--;   // three CTAs per SM
     const size_t smem = tile_smem<NN>(p.ng, cpc);
     if (smem > 220 * 1024) return 0;
     const int threads = cpc * T::LPC;

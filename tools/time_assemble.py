@@ -1,0 +1,43 @@
+"""Times the assembly hand-off (gl_triplet_indices + gl_assemble) on an n^3 Hex8 block generated on the device.
+The CSR pattern is built on the device with torch from the triplet indices.  usage: time_assemble.py [n]"""
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
+import torch
+
+import gemlab_b200 as g
+from gemlab_b200 import Coef, CommonArgs, Context, GeoKind, integ
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+ctx = Context(0)
+dm = ctx.block(GeoKind.Hex8, (n, n, n))
+ncell, npoint = dm.ncell, dm.npoint
+neq = npoint * 3
+eq = torch.arange(neq, dtype=torch.int32, device="cuda")
+dd = g.mandel_matrix(g.lin_elasticity(480.0, 1.0 / 3.0, False))
+t0 = time.perf_counter()
+rows, cols = integ.triplet_indices(ctx, dm, "mat_10_bdb", None, CommonArgs(), eq)
+torch.cuda.synchronize()
+t_trip = time.perf_counter() - t0
+keys = torch.unique(rows.to(torch.int64) * neq + cols.to(torch.int64))
+rowptr = torch.zeros(neq + 1, dtype=torch.int64, device="cuda")
+rowptr[1:] = torch.cumsum(torch.bincount((keys // neq), minlength=neq), 0)
+colidx = (keys % neq).to(torch.int32)
+del keys, rows, cols
+vals = torch.zeros(colidx.numel(), dtype=torch.float64, device="cuda")
+torch.cuda.synchronize()
+integ.assemble(ctx, dm, "mat_10_bdb", None, CommonArgs(), Coef.uniform(dd), eq, vals, rowptr, colidx)
+torch.cuda.synchronize()
+vals.zero_()
+t0 = time.perf_counter()
+integ.assemble(ctx, dm, "mat_10_bdb", None, CommonArgs(), Coef.uniform(dd), eq, vals, rowptr, colidx)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+# K.1 = 0 for rigid translations: row sums of the assembled matrix vanish (relative to the largest entry)
+rs = torch.zeros(neq, dtype=torch.float64, device="cuda")
+rs.index_add_(0, torch.repeat_interleave(torch.arange(neq, device="cuda"), rowptr[1:] - rowptr[:-1]), vals)
+print(f"n={n}: {ncell} cells, {neq} equations, nnz {colidx.numel()}; triplet indices {t_trip*1e3:.1f} ms; "
+      f"assemble {dt*1e3:.1f} ms = {ncell/dt/1e6:.1f} M elements/s; max |row sum| / max |K| = {float(rs.abs().max() / vals.abs().max()):.1e}")
