@@ -52,7 +52,7 @@ struct BdbConsts {
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <int NN, int SD, int LPN, bool AXI, int PAT>
-__global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const BdbConsts cst, const int CPC, const int nthreads_used) {
+__global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const BdbConsts cst, const int CPC, const int nthreads_used, const int alias_g) {
     constexpr bool SYM = PAT >= 1;
     constexpr int NS = 2 * SD;
     constexpr int NDOF = NN * SD;
@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     double *s_N = s_w + ng;                           // [ng][NN]
     double *s_L = s_N + ng * NN;                      // [ng][LS]  L[gp][m*SD+j]; odd stride: lanes of different Gauss points hit different banks
     double *s_X = s_L + ng * LS;                      // [CPC][XS]
-    double *s_G = s_X + CPC * XS;                     // [CPC][ng][GS]
+    // [CPC][ng][GS]; when a cell's records fit inside its element block they ALIAS the K staging (dead before K is staged,
+    // see gl_kernels_tile.cu) -- roughly halves the shared memory of a CTA, i.e. doubles the resident warps
+    double *s_G = alias_g ? smem : s_X + CPC * XS;
 
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < ng * (1 + NN); i += nt) s_w[i] = p.rule[i];
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     for (unsigned long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const unsigned long long cell0 = p.lo + tile * CPC;
         const int ncell_tile = (int)min((unsigned long long)CPC, p.hi - cell0);
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // previous bulk copy has left s_K (/ s_G)
         __syncthreads(); // previous tile consumed; tables staged
 
         // ---- phase A: gather ---------------------------------------------------------------------------------------
@@ -253,8 +256,7 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
         }
 
         // ---- phase D: contract with D', stage and ship ------------------------------------------------------------------
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // previous bulk copy has left s_K
-        __syncthreads();
+        __syncthreads(); // every lane has finished reading G (it may alias the staging)
         if (worker && cs < ncell_tile) {
             double *Kc = s_K + cs * NDOF * NDOF;
 #pragma unroll
@@ -321,11 +323,15 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
 }
 
 template <int NN, int SD, int LPN>
+bool bdb_alias(int ng, bool axi) { return (size_t)ng * ((1 + NN * SD + (axi ? NN : 0)) | 1) <= (size_t)NN * SD * NN * SD; }
+
+template <int NN, int SD, int LPN>
 size_t bdb_smem(int ng, int cpc, bool axi) {
     const int gs = (1 + NN * SD + (axi ? NN : 0)) | 1;
     const int xs = (NN * SD) | 1;
     const int ls = (NN * SD + 6) / 16 * 16 + 9;
-    return sizeof(double) * ((size_t)cpc * NN * SD * NN * SD + (size_t)ng * (1 + NN + ls) + (size_t)cpc * xs + (size_t)cpc * ng * gs);
+    const size_t g = bdb_alias<NN, SD, LPN>(ng, axi) ? 0 : (size_t)cpc * ng * gs;
+    return sizeof(double) * ((size_t)cpc * NN * SD * NN * SD + (size_t)ng * (1 + NN + ls) + (size_t)cpc * xs + g);
 }
 
 template <int NN, int SD, int LPN>
@@ -339,7 +345,7 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     if (smem > 200 * 1024) return 0;
     const int used = cpc * NN * LPN;
     const int threads = (used + 31) / 32 * 32;
-    typedef void (*kern_t)(const IntegParams, const BdbConsts, const int, const int);
+    typedef void (*kern_t)(const IntegParams, const BdbConsts, const int, const int, const int);
     kern_t kern = nullptr;
     if constexpr (SD == 2) {
         if (axi) kern = pat == 2 ? bdb_kernel<NN, SD, LPN, true, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, true, 1> : bdb_kernel<NN, SD, LPN, true, 0>);
@@ -362,7 +368,7 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     if (const char *e = getenv("GL_BDB_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
-    kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, cst, cpc, used);
+    kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, cst, cpc, used, bdb_alias<NN, SD, LPN>(p.ng, axi) ? 1 : 0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
