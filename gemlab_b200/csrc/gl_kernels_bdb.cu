@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     double *s_X = s_L + ng * LS;                      // [CPC][XS]
     // [CPC][ng][GS]; when a cell's records fit inside its element block they ALIAS the K staging (dead before K is staged,
     // see gl_kernels_tile.cu) -- roughly halves the shared memory of a CTA, i.e. doubles the resident warps
-    double *s_G = alias_g ? smem : s_X + CPC * XS;
+    const bool drec = p.coef != nullptr;              // one modulus record per marker / per cell instead of a uniform D
+    double *s_D = s_X + CPC * XS;                     // [CPC][NS*NS] d' of every cell of the tile (record moduli only)
+    double *s_G = alias_g ? smem : s_D + (drec ? CPC * NS * NS : 0);
 
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < ng * (1 + NN); i += nt) s_w[i] = p.rule[i];
@@ -127,6 +129,19 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
         }
         __syncthreads();
 
+        if (drec) {
+            // the cell's modulus record (ns x ns Mandel matrix, column-major): of its marker (PER_MARKER) or its own (PER_CELL);
+            // the 1/sqrt(2) factors of the shear rows are folded in here
+            const double hs = 0.70710678118654752440084436210484903928;
+            for (int t = tid; t < ncell_tile * NS * NS; t += nt) {
+                const int c = t / (NS * NS), idx = t - c * (NS * NS);
+                const int a = idx / NS, b = idx - a * NS;
+                const unsigned long long cell = cell0 + c;
+                const unsigned long long rec = p.coef_index ? (unsigned long long)p.coef_index[cell]
+                                                            : (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
+                s_D[c * NS * NS + idx] = p.coef[rec * p.coef_cell_stride + a + b * NS] * (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
+            }
+        }
         // ---- phase B: geometry per (cell, gauss point), SD lanes per pair ------------------------------------------------
         // lane `sub` of a pair accumulates row `sub` of J = Xt.L, the rows are exchanged with shuffles, every lane inverts J
         // (cheap, redundant) and then fills the gradient rows of the nodes m = sub, sub+SD, ..  -- SD times more lanes busy
@@ -259,6 +274,12 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
         __syncthreads(); // every lane has finished reading G (it may alias the staging)
         if (worker && cs < ncell_tile) {
             double *Kc = s_K + cs * NDOF * NDOF;
+            double dl[NS * NS]; // d' of this lane's cell: the constant bank (uniform D) or the tile's record table
+#pragma unroll
+            for (int a = 0; a < NS; a++)
+#pragma unroll
+                for (int b = 0; b < NS; b++)
+                    if (d_nz(PAT, SD, a, b)) dl[a * NS + b] = drec ? s_D[cs * NS * NS + a * NS + b] : cst.d[a * NS + b];
 #pragma unroll
             for (int s = 0; s < NSLOT; s++) {
                 const int b = LPN == 1 ? s : s * LPN + h;
@@ -283,8 +304,8 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                                 const int ra = col_row(SD, i, q), rb = col_row(SD, j, r);
                                 if (!d_nz(PAT, SD, ra, rb)) continue;
                                 const double pv = acc[s][col_comp(SD, i, q) + VD * col_comp(SD, j, r)];
-                                v = have ? fma(cst.d[ra * NS + rb], pv, v) : cst.d[ra * NS + rb] * pv;
-                                if (!SYM) u = have ? fma(cst.d[rb * NS + ra], pv, u) : cst.d[rb * NS + ra] * pv;
+                                v = have ? fma(dl[ra * NS + rb], pv, v) : dl[ra * NS + rb] * pv;
+                                if (!SYM) u = have ? fma(dl[rb * NS + ra], pv, u) : dl[rb * NS + ra] * pv;
                                 have = true;
                             }
                         Kc[(SD * m + i) + NDOF * (SD * n + j)] = v;
@@ -326,12 +347,13 @@ template <int NN, int SD, int LPN>
 bool bdb_alias(int ng, bool axi) { return (size_t)ng * ((1 + NN * SD + (axi ? NN : 0)) | 1) <= (size_t)NN * SD * NN * SD; }
 
 template <int NN, int SD, int LPN>
-size_t bdb_smem(int ng, int cpc, bool axi) {
+size_t bdb_smem(int ng, int cpc, bool axi, bool drec) {
     const int gs = (1 + NN * SD + (axi ? NN : 0)) | 1;
     const int xs = (NN * SD) | 1;
     const int ls = (NN * SD + 6) / 16 * 16 + 9;
     const size_t g = bdb_alias<NN, SD, LPN>(ng, axi) ? 0 : (size_t)cpc * ng * gs;
-    return sizeof(double) * ((size_t)cpc * NN * SD * NN * SD + (size_t)ng * (1 + NN + ls) + (size_t)cpc * xs + g);
+    const size_t dsz = drec ? (size_t)cpc * 4 * SD * SD : 0;
+    return sizeof(double) * ((size_t)cpc * NN * SD * NN * SD + (size_t)ng * (1 + NN + ls) + (size_t)cpc * xs + dsz + g);
 }
 
 template <int NN, int SD, int LPN>
@@ -340,8 +362,9 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     // cells per CTA: fill ~256 threads, at most ~110 KB of shared memory (two CTAs per SM)
     int cpc = 256 / (NN * LPN);
     if (cpc < 1) cpc = 1;
-    while (cpc > 1 && bdb_smem<NN, SD, LPN>(p.ng, cpc, axi) > 110 * 1024) cpc--;
-    const size_t smem = bdb_smem<NN, SD, LPN>(p.ng, cpc, axi);
+    const bool drec = p.coef != nullptr;
+    while (cpc > 1 && bdb_smem<NN, SD, LPN>(p.ng, cpc, axi, drec) > 110 * 1024) cpc--;
+    const size_t smem = bdb_smem<NN, SD, LPN>(p.ng, cpc, axi, drec);
     if (smem > 200 * 1024) return 0;
     const int used = cpc * NN * LPN;
     const int threads = (used + 31) / 32 * 32;
@@ -375,8 +398,10 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
 } // namespace
 
 int launch_bdb(const IntegParams &p, int sd, void *stream) {
-    // covered: uniform D, tight blocks, overwrite; homogeneous or mixed layout; 16-byte aligned output
-    if (p.op != GL_OP_MAT_10_BDB || p.coef != nullptr || !p.clear) return 0;
+    // covered: D uniform or one record per marker / per cell, tight blocks, overwrite; homogeneous or mixed layout; 16-byte
+    // aligned output
+    if (p.op != GL_OP_MAT_10_BDB || !p.clear) return 0;
+    if (p.coef != nullptr && (p.coef_gp_stride != 0 || p.coef_cell_stride != (unsigned long long)(4 * sd * sd))) return 0; // PER_GAUSS: generic kernel
     const unsigned ndof = (unsigned)p.nnode * (unsigned)sd;
     if (p.nrow != ndof || p.ncol != ndof || p.ii0 != 0 || p.jj0 != 0) return 0;
     if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
@@ -399,6 +424,7 @@ int launch_bdb(const IntegParams &p, int sd, void *stream) {
             for (int b = 0; b < ns; b++)
                 if (!d_nz(2, sd, a, b) && cst.d[a * ns + b] != 0.0) pat = 1;
     }
+    if (p.coef != nullptr) pat = p.coef_pat; // structure common to all records (0 when they live on the device only)
     if (const char *e = getenv("GL_BDB_PATTERN")) {
         const int cap = atoi(e);
         if (cap < pat) pat = cap < 0 ? 0 : cap;

@@ -255,6 +255,40 @@ def test_coefficient_modes(ctx, kind, op):
     assert rel_err(out.cpu().numpy(), ref, sizes) <= TOL
 
 
+@pytest.mark.parametrize("kind", ["tri3", "tri6", "qua8", "qua9", "tet4", "tet10", "hex8", "hex20"])
+@pytest.mark.parametrize("structure", ["isotropic", "symmetric", "general"])
+def test_stiffness_with_one_modulus_per_marker_and_per_cell(ctx, kind, structure):
+    """Multi-material meshes through the tuned stiffness kernels: the record structure common to all records (isotropic /
+    merely symmetric / general) selects the kernel variant; device-resident records take the general one."""
+    import torch
+
+    mesh = make_mesh(kind, n=3)
+    ncell = mesh.ncell
+    rng = np.random.default_rng(23)
+    mesh.markers[:] = rng.integers(1, 4, ncell)
+    dmesh = ctx.upload(mesh)
+    two_dim = mesh.ndim == 2
+    if structure == "isotropic":
+        recs = np.stack([g.mandel_matrix(g.lin_elasticity(100.0 * (k + 1), 0.1 * (k + 1), two_dim)) for k in range(3)])
+    else:
+        recs = random_coef("mat_10_bdb", mesh.ndim, 3, rng, spd=(structure == "symmetric"))
+    ns2 = (2 * mesh.ndim) ** 2
+    bs = integ.op_out_size("mat_10_bdb", GeoKind.from_str(kind), mesh.ndim)
+    sizes = np.arange(ncell + 1) * bs
+    per_cell = recs[mesh.markers - 1]
+    for axisym in ([False, True] if two_dim else [False]):
+        args = CommonArgs(axisymmetric=axisym)
+        ref = oracle_integ("mat_10_bdb", mesh, per_cell, cell_stride=ns2, axisymmetric=axisym)
+        got = integ.mat_10_bdb(ctx, dmesh, None, args, Coef.per_marker([1, 2, 3], recs))
+        assert rel_err(got, ref, sizes) <= TOL, f"per_marker axisym={axisym}"
+        got = integ.mat_10_bdb(ctx, dmesh, None, args, Coef.per_cell(per_cell))
+        assert rel_err(got, ref, sizes) <= TOL, f"per_cell host axisym={axisym}"
+        out = torch.empty(ncell * bs, dtype=torch.float64, device="cuda")
+        integ.mat_10_bdb(ctx, dmesh, None, args, Coef.per_cell(torch.from_numpy(np.ascontiguousarray(per_cell)).cuda()), out=out)
+        ctx.sync()
+        assert rel_err(out.cpu().numpy(), ref, sizes) <= TOL, f"per_cell device axisym={axisym}"
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # 3. layout: mixed kinds, cell ranges, offsets, accumulation, ii0/jj0
 # ---------------------------------------------------------------------------------------------------------------
