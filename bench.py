@@ -240,9 +240,11 @@ def main():
         torch.cuda.synchronize()
 
     ctx = Context(local_rank)
-    mesh = slab_mesh(args, rank)
-    ncell = mesh.ncell
-    dmesh = ctx.upload(mesh)
+    # rank r owns the r-th 200^3 slab of an N-slab-tall block; the slab is generated on the device (gl_mesh_block: the
+    # reference's Block::subdivide cell order and first-touch point numbering), so no rank builds an 8M-cell host mesh
+    nx, ny, nz = args.ndiv
+    dmesh = ctx.block(g.GeoKind.Hex8, (nx, ny, nz), xmin=[0.0, 0.0, float(rank)], xmax=[1.0, 1.0, float(rank) + 1.0])
+    ncell = dmesh.ncell
     dd = g.mandel_matrix(g.lin_elasticity(YOUNG, POISSON, False))
     coef = Coef.uniform(dd)
     cargs = CommonArgs()
@@ -287,14 +289,17 @@ def main():
     checks = {"symmetry_rel": sym, "rigid_translation_rel": rigid, "first_vs_last_cell_rel": same}
 
     # ---- e2e leg: host buffers through the public call -------------------------------------------------------
+    # host sub-slab (first `layers` z-layers of this rank's slab): the e2e inputs and the CPU-baseline sample.  The pinned
+    # result buffer is 4.6 KB per cell, so the layer count shrinks with the number of ranks sharing the host's memory.
     e2e = None
-    if not args.no_e2e:
+    sub = None
+    layers = max(1, min(max(4, args.e2e_layers // world), nz))
+    if not args.no_e2e or (world == 1 and not args.no_cpu):
         from gemlab_b200 import Block, GeoKind
 
-        nx, ny, nz = args.ndiv
-        layers = max(1, min(args.e2e_layers, nz))
         sub = Block.new_cube(1.0).set_ndiv([nx, ny, layers]).subdivide(GeoKind.Hex8)
         sub.coords[:, 2] = sub.coords[:, 2] * (layers / nz) + float(rank)
+    if not args.no_e2e:
         # the step's inputs live in PINNED host memory (the mesh arrays are re-homed into page-locked buffers)
         pinned = []
         for name in ("coords", "kinds", "markers", "conn_off", "conn"):
@@ -351,11 +356,11 @@ def main():
             from oracle import pyoracle as po
 
             threads = po.ncores()
-            rate1, n1, _ = cpu_leg(args, mesh, dd, 20000, 1)
-            sample = args.cpu_sample or int(min(mesh.ncell, max(20000, rate1 * threads * 8.0)))
-            rate, n, dt = cpu_leg(args, mesh, dd, sample, threads)
+            rate1, n1, _ = cpu_leg(args, sub, dd, 20000, 1)
+            sample = args.cpu_sample or int(min(sub.ncell, max(20000, rate1 * threads * 8.0)))
+            rate, n, dt = cpu_leg(args, sub, dd, sample, threads)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"first {n} cells of the same mesh, {dt:.1f} s, OpenMP over cells with {threads} threads "
+                   "sample": f"first {n} cells of the same mesh (its first {layers} z-layers), {dt:.1f} s, OpenMP over cells with {threads} threads "
                              f"(1 thread, the reference's own execution model: {rate1:.0f} elements/s)",
                    "single_thread_value": rate1}
         line = {
