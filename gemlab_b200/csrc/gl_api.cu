@@ -737,7 +737,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         std::memset(&p, 0, sizeof(p));
         p.coords = mesh->d_coords;
         p.npoint = mesh->npoint;
-        if (op == GL_OP_MAT_01_NSN || op == GL_OP_VEC_01_NS ||
+        if (op == GL_OP_MAT_01_NSN || op == GL_OP_VEC_01_NS || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV ||
             (op == GL_OP_MAT_10_BDB && mesh->ndim == 2 && (bk.nnode == 3 || bk.nnode == 4))) { // thread-per-cell kernels
             st = ensure_point_major(ctx, mesh);
             if (st) return st;
@@ -820,6 +820,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
             if (op_is_matrix(op)) { f.moff = p.out_off; f.mbase = p.out_base; }
             else { f.voff = p.out_off; f.vbase = p.out_base; }
             nl = launch_mass_dmma(p, f, mesh->ndim, ctx->stream);
+            if (nl == 0) nl = launch_scalar_tpc(p, f, mesh->ndim, ctx->stream);
             if (nl == 0) nl = launch_scalar_fused(p, f, mesh->ndim, ctx->stream);
         }
         if (nl == 0) {
@@ -1081,7 +1082,7 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
         std::memset(&p, 0, sizeof(p));
         p.coords = mesh->d_coords;
         p.npoint = mesh->npoint;
-        if ((mask & ~5) == 0) { // mass / source vector only: thread-per-cell kernel, gathers whole points
+        if ((mask & ~5) == 0 || (mask & ~10) == 0) { // thread-per-cell kernels gather whole points
             int stp = ensure_point_major(ctx, mesh);
             if (stp) return stp;
             p.coords_pm = mesh->d_coords_pm;
@@ -1114,6 +1115,7 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
             fb.vbase = (*vpre)[b];
         }
         int nl = launch_mass_dmma(p, fb, mesh->ndim, ctx->stream);
+        if (nl == 0) nl = launch_scalar_tpc(p, fb, mesh->ndim, ctx->stream);
         if (nl == 0) nl = launch_scalar_fused(p, fb, mesh->ndim, ctx->stream);
         if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
         if (nl == 0) { // kind not covered by the fused kernel: run the items one after the other for the whole range

@@ -112,6 +112,8 @@ struct ScalarFused {
 };
 int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
 // mat_01_nsn and/or vec_01_ns as a (cells x ng).(ng x entries) product on the FP64 tensor cores (gl_kernels_mass.cu); 0 if not covered
+// mat_03_btb and/or vec_03_bv, one thread per cell (gl_kernels_scalar_tpc.cu); 0 if not covered
+int launch_scalar_tpc(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
 int launch_mass_dmma(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
 
 // micro-benchmarks

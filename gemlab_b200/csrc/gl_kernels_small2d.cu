@@ -162,26 +162,28 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
         }
         __syncwarp();
 
-        // ---- coalesced copy-out of the warp's blocks ---------------------------------------------------------------------------
-        if (p.cell_ids == nullptr && p.out_off == nullptr) {
-            if (wcell0 < p.hi) {
-                const unsigned long long nc = p.hi - wcell0 < 32 ? p.hi - wcell0 : 32;
-                double2 *dst = reinterpret_cast<double2 *>(p.out + (wcell0 - p.cell_begin) * BS);
-                const int total2 = (int)nc * (BS / 2);
-                for (int w = lane; w < total2; w += 32) {
-                    const int c = w / (BS / 2), q = 2 * (w - c * (BS / 2));
-                    dst[w] = make_double2(Tw[q * TS + c], Tw[(q + 1) * TS + c]);
+        // ---- coalesced copy-out of the warp's blocks: a flat sweep in 16-byte pieces; every lane knows the destination of its own
+        // cell and hands it out by shuffle, so runs of cells that are consecutive in the output (always, on single-kind meshes;
+        // row by row on mixed ones) leave as full lines
+        {
+            unsigned long long mo = 0;
+            if (active) mo = p.out_off ? (p.out_off[cell] - p.out_base)
+                                       : ((p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.cell_begin) * BS;
+            const int nc = wcell0 < p.hi ? (int)(p.hi - wcell0 < 32 ? p.hi - wcell0 : 32) : 0;
+            if (p.cell_ids == nullptr && p.out_off == nullptr) { // single-kind mesh: one contiguous run
+                if (nc > 0) {
+                    double2 *dst = reinterpret_cast<double2 *>(p.out + (wcell0 - p.cell_begin) * BS);
+                    for (int w = lane; w < nc * (BS / 2); w += 32) {
+                        const int c = w / (BS / 2), q = 2 * (w - c * (BS / 2));
+                        dst[w] = make_double2(Tw[q * TS + c], Tw[(q + 1) * TS + c]);
+                    }
                 }
+                continue;
             }
-        } else {
-            // mixed-kind mesh: every cell has its own destination
-            for (int c = 0; c < 32; c++) {
-                const unsigned long long cl = wcell0 + c;
-                if (cl >= p.hi) break;
-                const unsigned long long o = p.out_off ? (p.out_off[cl] - p.out_base)
-                                                       : ((unsigned long long)p.cell_ids[cl] - p.cell_begin) * BS;
-                double2 *dst = reinterpret_cast<double2 *>(p.out + o);
-                for (int w = lane; w < BS / 2; w += 32) dst[w] = make_double2(Tw[(2 * w) * TS + c], Tw[(2 * w + 1) * TS + c]);
+            for (int w0 = 0; w0 < nc * (BS / 2); w0 += 32) {
+                const int w = w0 + lane, c = w / (BS / 2), q = 2 * (w - c * (BS / 2));
+                const unsigned long long base = __shfl_sync(0xffffffffu, mo, c & 31);
+                if (w < nc * (BS / 2)) *reinterpret_cast<double2 *>(p.out + base + q) = make_double2(Tw[q * TS + c], Tw[(q + 1) * TS + c]);
             }
         }
     }
