@@ -53,6 +53,14 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
 
     const unsigned long long ncell = p.hi - p.lo;
     const unsigned long long nbatch = (ncell + S2_THREADS - 1) / S2_THREADS;
+    // point ids of the NEXT batch are fetched while this one is integrated: one hop of the dependent gather is off the
+    // critical path
+    unsigned int pid_next[NN];
+    {
+        const unsigned long long c0 = p.lo + (unsigned long long)blockIdx.x * S2_THREADS + tid;
+#pragma unroll
+        for (int m = 0; m < NN; m++) pid_next[m] = c0 < p.hi ? p.conn[(unsigned long long)m * p.ncell_k + c0] : 0u;
+    }
     for (unsigned long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const unsigned long long wcell0 = p.lo + batch * S2_THREADS + (unsigned long long)wid * 32; // first cell of this warp
         const unsigned long long cell = wcell0 + lane;
@@ -63,11 +71,15 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
         for (int m = 0; m < NN; m++) {
             x[m][0] = x[m][1] = 0.0;
             if (active) {
-                const unsigned int pid = p.conn[(unsigned long long)m * p.ncell_k + cell];
-                const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[pid];
+                const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[pid_next[m]];
                 x[m][0] = a.x;
                 x[m][1] = a.y;
             }
+        }
+        {
+            const unsigned long long cn = cell + (unsigned long long)gridDim.x * S2_THREADS;
+#pragma unroll
+            for (int m = 0; m < NN; m++) pid_next[m] = cn < p.hi ? p.conn[(unsigned long long)m * p.ncell_k + cn] : 0u;
         }
         if (!active) { // a unit cell keeps the arithmetic finite; nothing of it is stored
             x[1 % NN][0] = 1.0;
