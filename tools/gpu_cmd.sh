@@ -1,6 +1,3 @@
-python tools/bench_configs.py --scale 0.2 --only 4 > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:mass_kernel -s 1 -c 1 -o gpurun_out/prof_mass -f python tools/bench_configs.py --scale 0.2 --only 4 > gpurun_out/ncu_mass.log 2>&1
-tail -1 gpurun_out/ncu_mass.log
-python tools/bench_configs.py --scale 1.0 --only 1 > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:small2d_kernel -s 1 -c 1 -o gpurun_out/prof_small2d -f python tools/bench_configs.py --scale 1.0 --only 1 > gpurun_out/ncu_small2d.log 2>&1
-tail -1 gpurun_out/ncu_small2d.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python tools/bench_configs.py --scale 1.0 2>gpurun_out/configs_full.err | tee gpurun_out/configs_full.jsonl | cut -c1-300
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; tail -2 gpurun_out/bench_r1_final.err; cut -c1-200 gpurun_out/bench_r1_final.json
