@@ -575,3 +575,44 @@ def test_higher_order_kinds(ctx, kind, space_ndim):
         hi = {"tri10": 16, "tri15": 16, "qua12": 16, "qua16": 16, "qua17": 16, "tet20": 24, "hex32": 64}[kind]
         v2 = integ.vec_01_ns(ctx, dmesh, None, CommonArgs(ngauss=hi), Coef.uniform([1.0])).sum()
         assert abs(v1 - v2) <= 1e-9 * abs(v2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# out-of-bounds discipline: guard bands around device outputs must survive every kernel family
+# ---------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("guard", [2048, 2049])  # 2049: the output is only 8-byte aligned -> the tuned kernels must decline
+@pytest.mark.parametrize("kind", ["tri3", "qua4", "qua8", "tet10", "hex8", "hex20"])
+def test_kernels_write_only_their_own_blocks(ctx, kind, guard):
+    """compute-sanitizer is not available on the GPU pool, so stray writes are caught the plain way: every output sits between
+    two guard bands of a sentinel value, ranges are ragged (not multiples of any tile size), and the bands must be intact."""
+    import torch
+
+    mesh = make_mesh(kind, n=5)
+    dmesh = ctx.upload(mesh)
+    rng = np.random.default_rng(31)
+    sentinel = -7.25
+    b, e = 3, mesh.ncell - 5  # ragged sub-range
+    for op in ["mat_10_bdb", "mat_01_nsn", "mat_03_btb", "vec_01_ns", "vec_03_bv", "vec_04_bt"]:
+        coef = random_coef(op, mesh.ndim, 1, rng)[0]
+        total = integ.out_total(dmesh, op, (b, e), CommonArgs())
+        buf = torch.full((total + 2 * guard,), sentinel, dtype=torch.float64, device="cuda")
+        getattr(integ, op)(ctx, dmesh, (b, e), CommonArgs(), Coef.uniform(coef), out=buf[guard:guard + total])
+        ctx.sync()
+        assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + total:] == sentinel).all()), f"{kind} {op}"
+        ref = oracle_integ(op, mesh, coef)
+        bs = integ.op_out_size(op, GeoKind.from_str(kind), mesh.ndim)
+        assert rel_err(buf[guard:guard + total].cpu().numpy(), ref[b * bs:e * bs], np.arange(e - b + 1) * bs) <= TOL, f"{kind} {op}"
+    # the fused entry point (mass + source, conductivity + flux) with guard bands as well
+    for pair in ([("mat_01_nsn", [2.7]), ("vec_01_ns", [9.81])], [("mat_03_btb", [2.0] * mesh.ndim + [0.0] * mesh.ndim), ("vec_03_bv", [1.0] * mesh.ndim)]):
+        bufs = []
+        for op, _ in pair:
+            total = integ.out_total(dmesh, op, (b, e), CommonArgs())
+            bufs.append((torch.full((total + 2 * guard,), sentinel, dtype=torch.float64, device="cuda"), total))
+        integ.fused(ctx, dmesh, (b, e), CommonArgs(), [(op, Coef.uniform(c), buf[guard:guard + total]) for (op, c), (buf, total) in zip(pair, bufs)])
+        ctx.sync()
+        for (op, c), (buf, total) in zip(pair, bufs):
+            assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + total:] == sentinel).all()), f"{kind} fused {op}"
+            ref = oracle_integ(op, mesh, np.array(c))
+            bs = integ.op_out_size(op, GeoKind.from_str(kind), mesh.ndim)
+            assert rel_err(buf[guard:guard + total].cpu().numpy(), ref[b * bs:e * bs], np.arange(e - b + 1) * bs) <= TOL, f"{kind} fused {op}"
