@@ -23,6 +23,9 @@ pub const GL_OP_VEC_03_BV: c_int = 4;
 pub const GL_OP_VEC_02_NV: c_int = 5;
 pub const GL_OP_VEC_04_BT: c_int = 6;
 pub const GL_OP_JACOBIAN: c_int = 8;
+pub const GL_OP_MAT_02_BVN: c_int = 9;
+pub const GL_OP_MAT_08_NTN: c_int = 10;
+pub const GL_OP_MAT_09_NVB: c_int = 11;
 
 pub const GL_HOST: i32 = 0;
 pub const GL_DEVICE: i32 = 1;

@@ -236,6 +236,18 @@ pub mod integ {
         pub fn mat_03_btb(ctx: &Context, mesh: &DeviceMesh, cells: Range<usize>, args: &BatchArgs, tt: &Coef) -> Result<Vec<f64>, StrError> {
             run(ffi::GL_OP_MAT_03_BTB, ctx, mesh, cells, args, Some(tt))
         }
+        /// K = ∫ (B·v) N; replaces `integ::mat_02_bvn` (src/integ/mat_02_bvn.rs:48)
+        pub fn mat_02_bvn(ctx: &Context, mesh: &DeviceMesh, cells: Range<usize>, args: &BatchArgs, v: &Coef) -> Result<Vec<f64>, StrError> {
+            run(ffi::GL_OP_MAT_02_BVN, ctx, mesh, cells, args, Some(v))
+        }
+        /// K = ∫ N T N; replaces `integ::mat_08_ntn` (src/integ/mat_08_ntn.rs:56)
+        pub fn mat_08_ntn(ctx: &Context, mesh: &DeviceMesh, cells: Range<usize>, args: &BatchArgs, tt: &Coef) -> Result<Vec<f64>, StrError> {
+            run(ffi::GL_OP_MAT_08_NTN, ctx, mesh, cells, args, Some(tt))
+        }
+        /// K = ∫ N v B; replaces `integ::mat_09_nvb` (src/integ/mat_09_nvb.rs:54)
+        pub fn mat_09_nvb(ctx: &Context, mesh: &DeviceMesh, cells: Range<usize>, args: &BatchArgs, v: &Coef) -> Result<Vec<f64>, StrError> {
+            run(ffi::GL_OP_MAT_09_NVB, ctx, mesh, cells, args, Some(v))
+        }
         /// a = ∫ N s; replaces `integ::vec_01_ns` (src/integ/vec_01_ns.rs:83)
         pub fn vec_01_ns(ctx: &Context, mesh: &DeviceMesh, cells: Range<usize>, args: &BatchArgs, s: &Coef) -> Result<Vec<f64>, StrError> {
             run(ffi::GL_OP_VEC_01_NS, ctx, mesh, cells, args, Some(s))
@@ -266,6 +278,35 @@ pub mod integ {
                 return Err(static_error(st));
             }
             Ok(out)
+        }
+        /// Assembly hand-off: integrates `op` over the cells and ADDS the element blocks into a global object that lives on
+        /// the device -- the CSR values `vals` of the pattern (`rowptr`, `colidx`: device pointers) for matrix cases, the
+        /// global vector `vals` (null `rowptr` / `colidx`) for vector cases.  `eq[point * dofs_per_node + i]` is the host
+        /// point -> equation table (negative = prescribed dof); the local-dof rule is the reference's
+        /// (src/integ/mat_10_bdb.rs:31-46).  Nothing but the matrix values ever needs to leave the GPU.
+        ///
+        /// # Safety
+        /// `rowptr`, `colidx` and `vals` must be valid device pointers of the sizes the pattern implies.
+        pub unsafe fn assemble(
+            op: i32,
+            ctx: &Context,
+            mesh: &DeviceMesh,
+            cells: Range<usize>,
+            args: &BatchArgs,
+            coef: &[f64],
+            eq: &[i32],
+            rowptr: *const i64,
+            colidx: *const i32,
+            vals: *mut f64,
+        ) -> Result<(), StrError> {
+            let a = args.to_c();
+            let c = ffi::gl_coef { mode: ffi::GL_COEF_UNIFORM, location: ffi::GL_HOST, data: coef.as_ptr(), markers: ptr::null(), nrecord: 1 };
+            let mut missing = 0u64;
+            let st = ffi::gl_assemble(ctx.ctx, mesh.mesh, op, cells.start as u64, cells.end as u64, &a, &c, eq.as_ptr(), ffi::GL_HOST, rowptr, colidx, vals, &mut missing);
+            if st != 0 {
+                return Err(static_error(st));
+            }
+            Ok(())
         }
         /// legacy (gemlab <= 1.x) names
         pub use mat_10_bdb as mat_10_gdg;
