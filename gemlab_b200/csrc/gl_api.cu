@@ -711,7 +711,8 @@ static int ensure_point_major(gl_ctx *ctx, gl_mesh *mesh) {
 
 // launches the kernels that integrate original cells [b, e) into the DEVICE buffer d_out (block of cell b at d_out[0])
 static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a,
-                        const CoefResolved &cr, uint64_t coef_begin, double *d_out) {
+                        const CoefResolved &cr, uint64_t coef_begin, double *d_out, const double *d_sigma = nullptr,
+                        double *d_force = nullptr, bool *force_done = nullptr) {
     if (b == e) return GL_OK;
     const bool explicit_block = a->nrow != 0 || (op_is_matrix(op) && a->ncol != 0);
     const std::vector<uint64_t> *pre = nullptr;
@@ -804,7 +805,10 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
             p.out_base = (*pre)[b];
         }
         int nl = 0;
+        p.sigma = d_sigma; // stiffness + internal force from one pass: only the Hex8 kernel takes them
+        p.out_d = d_force;
         if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
+        if (force_done) *force_done = nl > 0 && d_sigma != nullptr;
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_small2d(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_tile(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb(p, mesh->ndim, ctx->stream);
@@ -1016,6 +1020,42 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
     gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
     if (!mesh || !a || !items || nitems <= 0) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
     if (b > e || e > mesh->ncell) return fail(ctx, GL_ERR_CELL_RANGE);
+    // stiffness + internal-force vector (the two sides of a Newton step) from ONE geometry pass: Hex8 meshes, sigma per Gauss
+    // point; any other combination of these two cases runs them one after the other
+    if (nitems == 2 && e > b) {
+        const gl_fused_item *ik = nullptr, *id = nullptr;
+        for (int i = 0; i < 2; i++) {
+            if (items[i].op == GL_OP_MAT_10_BDB) ik = &items[i];
+            if (items[i].op == GL_OP_VEC_04_BT) id = &items[i];
+        }
+        if (ik && id && ik->coef && id->coef && ik->out && id->out && mesh->homogeneous && mesh->buckets.size() == 1 &&
+            mesh->buckets[0].kind == GL_HEX8 && a->clear && !a->axisymmetric && a->ii0 == 0 && a->jj0 == 0 && a->nrow == 0 &&
+            a->ncol == 0 && ik->coef->mode != GL_COEF_PER_GAUSS && id->coef->mode == GL_COEF_PER_GAUSS && id->coef->data &&
+            ik->out->location == GL_DEVICE && id->out->location == GL_DEVICE && ik->out->ptr && id->out->ptr) {
+            if (ik->out->capacity < (e - b) * 576 || id->out->capacity < (e - b) * 24) return fail(ctx, GL_ERR_OUT_CAPACITY);
+            cudaSetDevice(ctx->device);
+            CoefResolved crk;
+            int st = resolve_coef(ctx, mesh, GL_OP_MAT_10_BDB, b, e, a, ik->coef, crk);
+            if (st) return st;
+            const double *d_sigma = id->coef->data;
+            double *tmp = nullptr;
+            const size_t sig_bytes = (size_t)(e - b) * 8 * 6 * sizeof(double);
+            if (id->coef->location != GL_DEVICE) {
+                CUDA_TRY(ctx, pool_alloc_t(ctx, &tmp, sig_bytes));
+                CUDA_TRY(ctx, cudaMemcpyAsync(tmp, id->coef->data, sig_bytes, cudaMemcpyHostToDevice, (cudaStream_t)ctx->stream));
+                d_sigma = tmp;
+            }
+            bool done = false;
+            st = launch_range(ctx, mesh, GL_OP_MAT_10_BDB, b, e, a, crk, b, ik->out->ptr, d_sigma, id->out->ptr, &done);
+            if (tmp) {
+                cudaStreamSynchronize((cudaStream_t)ctx->stream);
+                pool_free(ctx, tmp, sig_bytes);
+            }
+            if (st) return st;
+            if (!done) return gl_integ(ctx, cmesh, GL_OP_VEC_04_BT, b, e, a, id->coef, id->out); // e.g. another rule than 2x2x2
+            return GL_OK;
+        }
+    }
     // can the items share one kernel?
     bool fusable = nitems <= 4 && a->clear && a->ii0 == 0 && a->jj0 == 0 && a->nrow == 0 && a->ncol == 0 && e > b;
     int mask = 0;

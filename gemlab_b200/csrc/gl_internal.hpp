@@ -80,6 +80,10 @@ struct IntegParams {
     unsigned long long out_base;       // subtracted from out_off (offset of cell_begin)
     unsigned int nrow, ncol, ii0, jj0; // element block (ncol = 1 for vectors)
     unsigned int size_r, size_c;       // extent actually integrated (ndof / nnode, ...)
+    // fused internal-force vector (Hex8 kernel only): stress records sigma[(e - coef_begin)*ng + p][ns] (Mandel vectors, DEVICE)
+    // and the output d[(e - cell_begin)*ndof ..]; nullptr = not requested
+    const double *sigma;
+    double *out_d;
     // failure reporting: smallest original id of a cell with |det J| <= 1e-15
     unsigned long long *err_cell;
     // tile

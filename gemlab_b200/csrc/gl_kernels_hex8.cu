@@ -65,7 +65,7 @@ __host__ __device__ constexpr bool d_nz(int pat, int a, int b) { return pat < 2 
 __host__ __device__ constexpr int col_row(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 3 : 5)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 3 : 4)) : (t == 0 ? 2 : (t == 1 ? 4 : 5))); }
 __host__ __device__ constexpr int col_comp(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 1 : 2)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 0 : 2)) : (t == 0 ? 2 : (t == 1 ? 1 : 0))); }
 
-template <int PAT, int PF, int DBG = 0, bool DREC = false>
+template <int PAT, int PF, int DBG = 0, bool DREC = false, bool FD = false>
 __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegParams p, const Hex8Consts cst) {
     constexpr bool SYM = PAT >= 1;
     extern __shared__ __align__(16) double smem[];
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
     double *s_B = s_X + H8_CELLS * X_STRIDE;    // [H8_CELLS][CELL_STRIDE]
     double *s_K = s_B + H8_CELLS * CELL_STRIDE; // [H8_CELLS][K_STRIDE]  (16-byte aligned: offset is a multiple of 2 doubles)
     double *s_D = s_K + H8_CELLS * K_STRIDE;    // [H8_CELLS][36]  per-cell d' (DREC only: PER_MARKER / PER_CELL moduli)
+    double *s_S = s_D + (DREC ? H8_CELLS * 36 : 0); // [H8_CELLS][8][6] stress tensors of the Gauss points (FD only)
 
     const int tid = threadIdx.x;
     const int g = tid & 7;   // lane within the cell group
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
     double *Bc = s_B + cs * CELL_STRIDE;
     double *Kc = s_K + cs * K_STRIDE;
     double *Dc = s_D + cs * 36;
+    double *Sc = s_S + cs * 48;
     // d'[a][b] of this lane's cell: the constant bank for a uniform modulus, shared memory for a modulus record per cell
     double dl[36] = {}; // DREC: register copy of the entries the pattern uses, refreshed once per batch (the staging stores in
                    // between would otherwise force a shared-memory load per term)
@@ -187,6 +189,17 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
             for (int m = 0; m < 8; m++) geom::gradient_row<3>(Lg + m * 3, Ji, Bg + m * 3);
             Bg[24] = det * s_w[g] * p.alpha;
         }
+        if constexpr (FD) {
+            // stress at Gauss point g of this cell (Mandel vector, vec_04_bt's PER_GAUSS record): off-diagonals become plain
+            // tensor components sigma_01, sigma_12, sigma_02
+            if (active) {
+                const unsigned long long rec = ((p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin) * 8ull + g;
+                const double *t = p.sigma + rec * 6ull;
+                const double hs = 0.70710678118654752440084436210484903928;
+#pragma unroll
+                for (int a = 0; a < 6; a++) Sc[g * 6 + a] = a < 3 ? t[a] : t[a] * hs;
+            }
+        }
         if constexpr (DREC) {
             // the cell's modulus record (ns x ns Mandel matrix, column-major): the record of its marker (PER_MARKER) or its own
             // (PER_CELL); the 8 lanes of the cell fold the 1/sqrt(2) factors in and publish d' for the epilogue
@@ -215,12 +228,19 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
 #pragma unroll
             for (int q = 0; q < 9; q++) pb[b][q] = 0.0;
 
+        double dn[3] = {0.0, 0.0, 0.0}; // FD: internal-force entries of node n, d(n,i) = sum_p c_p sum_a sigma_ia B(n,a)
 #pragma unroll 1
         for (int gp = 0; gp < (DBG >= 1 && DBG <= 4 ? 0 : 8); gp++) {
             const double *Bg = Bc + gp * GP_STRIDE;
             const double c = Bg[24];
             const double bu[3] = {Bg[g * 3 + 0], Bg[g * 3 + 1], Bg[g * 3 + 2]};
             const double vn[3] = {bu[0] * c, bu[1] * c, bu[2] * c};
+            if constexpr (FD) { // integ::vec_04_bt (src/integ/vec_04_bt.rs:93-170), 3D branch
+                const double *S = Sc + gp * 6;
+                dn[0] = fma(S[5], vn[2], fma(S[3], vn[1], fma(S[0], vn[0], dn[0])));
+                dn[1] = fma(S[4], vn[2], fma(S[1], vn[1], fma(S[3], vn[0], dn[1])));
+                dn[2] = fma(S[2], vn[2], fma(S[4], vn[1], fma(S[5], vn[0], dn[2])));
+            }
             p0[0] = fma(bu[0], vn[0], p0[0]);
             p0[1] = fma(bu[0], vn[1], p0[1]);
             p0[2] = fma(bu[0], vn[2], p0[2]);
@@ -244,6 +264,14 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
 #pragma unroll
                 for (int b = 0; b < 6; b++)
                     if (d_nz(PAT, a, b)) dl[a * 6 + b] = Dc[a * 6 + b];
+        }
+        if constexpr (FD) {
+            if (active) { // the 8 lanes of a cell write its 24 contiguous doubles
+                double *d = p.out_d + ((p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.cell_begin) * 24ull + 3 * g;
+                d[0] = dn[0];
+                d[1] = dn[1];
+                d[2] = dn[2];
+            }
         }
         // ---- phase 3: contract with D', stage the blocks column-major, ship every cell with one bulk copy -------------
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the warp's previous copies have left s_K (no-op for lanes that issued none)
@@ -324,7 +352,9 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-constexpr size_t H8_SMEM = sizeof(double) * (8 * L_STRIDE + 8 + H8_CELLS * X_STRIDE + H8_CELLS * CELL_STRIDE + H8_CELLS * K_STRIDE + H8_CELLS * 36);
+constexpr size_t H8_SMEM_BASE = sizeof(double) * (8 * L_STRIDE + 8 + H8_CELLS * X_STRIDE + H8_CELLS * CELL_STRIDE + H8_CELLS * K_STRIDE);
+constexpr size_t H8_SMEM_DREC = sizeof(double) * (H8_CELLS * 36); // per-cell moduli
+constexpr size_t H8_SMEM_FD = sizeof(double) * (H8_CELLS * 48);   // per-Gauss-point stresses
 
 } // namespace
 
@@ -333,6 +363,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     // layout, 16-byte aligned output
     if (p.nnode != 8 || p.ng != 8 || p.op != GL_OP_MAT_10_BDB) return 0;
     const bool drec = p.coef != nullptr;
+    const bool fd = p.sigma != nullptr && p.out_d != nullptr; // fused internal-force vector (gl_integ_fused)
     if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 36)) return 0; // PER_GAUSS moduli: generic kernel
     if (p.axisym || !p.clear || p.out_off != nullptr) return 0;
     if (p.nrow != 24 || p.ncol != 24 || p.ii0 != 0 || p.jj0 != 0 || p.size_r != 24) return 0;
@@ -385,10 +416,13 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
             default: return hex8_bdb_kernel<2, P, 5>;
             }
         }
+        if (fd && drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true, true> : hex8_bdb_kernel<0, P, 0, true, true>);
+        if (fd) return pat == 2 ? hex8_bdb_kernel<2, P, 0, false, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, false, true> : hex8_bdb_kernel<0, P, 0, false, true>);
         if (drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true> : hex8_bdb_kernel<0, P, 0, true>);
         return pat == 2 ? hex8_bdb_kernel<2, P> : (pat == 1 ? hex8_bdb_kernel<1, P> : hex8_bdb_kernel<0, P>);
     };
     kern = pf == 1 ? pick(std::integral_constant<int, 1>{}) : pick(std::integral_constant<int, 2>{});
+    const size_t H8_SMEM = H8_SMEM_BASE + (drec ? H8_SMEM_DREC : 0) + (fd ? H8_SMEM_FD : 0);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8_SMEM) != cudaSuccess) return -1;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);

@@ -244,9 +244,10 @@ GL_API int gl_jacobian(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, ui
 
 /* Several integration cases over ONE geometry pass (one Jacobian / gradient evaluation per Gauss point for all of them).
  * Semantically identical to calling gl_integ once per item with the same mesh, range and args; the library fuses the
- * items into one kernel when it can (today: any subset of mat_01_nsn, mat_03_btb, vec_01_ns, vec_03_bv with uniform
- * coefficients and device outputs -- e.g. the mass matrix and the body-force vector of BASELINE.json config 4) and
- * otherwise runs them one after the other.  The reference has no counterpart: its callers invoke integ::mat_01_nsn and
+ * items into one kernel when it can -- today: any subset of mat_01_nsn, mat_03_btb, vec_01_ns, vec_03_bv with uniform
+ * coefficients and device outputs (e.g. the mass matrix and the body-force vector of BASELINE.json config 4), and the pair
+ * mat_10_bdb + vec_04_bt of a Hex8 mesh with the stress given per Gauss point (stiffness and internal-force vector, the two
+ * sides of a Newton step) -- and otherwise runs them one after the other.  The reference has no counterpart: its callers invoke integ::mat_01_nsn and
  * integ::vec_01_ns separately, each recomputing the Jacobian (src/integ/mat_01_nsn.rs:75-76, vec_01_ns.rs:106-107). */
 typedef struct gl_fused_item {
     int32_t op; /* gl_op */

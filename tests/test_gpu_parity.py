@@ -616,3 +616,46 @@ def test_kernels_write_only_their_own_blocks(ctx, kind, guard):
             ref = oracle_integ(op, mesh, np.array(c))
             bs = integ.op_out_size(op, GeoKind.from_str(kind), mesh.ndim)
             assert rel_err(buf[guard:guard + total].cpu().numpy(), ref[b * bs:e * bs], np.arange(e - b + 1) * bs) <= TOL, f"{kind} fused {op}"
+
+
+def test_fused_stiffness_and_internal_force_hex8(ctx):
+    """gl_integ_fused({mat_10_bdb, vec_04_bt}) on a Hex8 mesh: K and d = int B.sigma from one geometry pass (sigma per Gauss
+    point), against the two separate oracle loops; also with one modulus per marker, on a sub-range, and with host sigma."""
+    import torch
+
+    mesh = make_mesh("hex8", n=5)
+    ncell = mesh.ncell
+    rng = np.random.default_rng(41)
+    mesh.markers[:] = rng.integers(1, 3, ncell)
+    dmesh = ctx.upload(mesh)
+    dd = g.mandel_matrix(g.lin_elasticity(480.0, 1.0 / 3.0, False))
+    sig = rng.standard_normal((ncell * 8, 6))
+    ref_k = oracle_integ("mat_10_bdb", mesh, dd)
+    ref_d = oracle_integ("vec_04_bt", mesh, sig, cell_stride=48, gp_stride=6)
+    launches0 = ctx.launch_count()
+    out_k = torch.empty(ncell * 576, dtype=torch.float64, device="cuda")
+    out_d = torch.empty(ncell * 24, dtype=torch.float64, device="cuda")
+    integ.fused(ctx, dmesh, None, CommonArgs(), [("mat_10_bdb", Coef.uniform(dd), out_k),
+                                                 ("vec_04_bt", Coef.per_gauss(torch.from_numpy(sig).cuda()), out_d)])
+    ctx.sync()
+    assert ctx.launch_count() - launches0 == 1  # one kernel produced both
+    assert rel_err(out_k.cpu().numpy(), ref_k, np.arange(ncell + 1) * 576) <= TOL
+    assert rel_err(out_d.cpu().numpy(), ref_d, np.arange(ncell + 1) * 24) <= TOL
+    # sub-range, host-resident sigma records, one modulus per marker
+    b, e = 7, ncell - 3
+    recs = np.stack([dd, 2.5 * dd])
+    per_cell = recs[mesh.markers - 1]
+    ref_k2 = oracle_integ("mat_10_bdb", mesh, per_cell, cell_stride=36)
+    out_k.fill_(0.0)
+    out_d.fill_(0.0)
+    integ.fused(ctx, dmesh, (b, e), CommonArgs(alpha=0.5), [("mat_10_bdb", Coef.per_marker([1, 2], recs), out_k[: (e - b) * 576]),
+                                                            ("vec_04_bt", Coef.per_gauss(sig[b * 8:e * 8]), out_d[: (e - b) * 24])])
+    ctx.sync()
+    assert rel_err(out_k[: (e - b) * 576].cpu().numpy(), 0.5 * ref_k2[b * 576:e * 576], np.arange(e - b + 1) * 576) <= TOL
+    assert rel_err(out_d[: (e - b) * 24].cpu().numpy(), 0.5 * ref_d[b * 24:e * 24], np.arange(e - b + 1) * 24) <= TOL
+    # a rule the tuned kernel does not cover: the pair still works (run one after the other)
+    integ.fused(ctx, dmesh, None, CommonArgs(ngauss=27), [("mat_10_bdb", Coef.uniform(dd), out_k),
+                                                           ("vec_04_bt", Coef.per_gauss(np.tile(sig[:1], (ncell * 27, 1))), out_d)])
+    ctx.sync()
+    ref_k27 = oracle_integ("mat_10_bdb", mesh, dd, ngauss=27)
+    assert rel_err(out_k.cpu().numpy(), ref_k27, np.arange(ncell + 1) * 576) <= TOL
