@@ -739,6 +739,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         p.coords = mesh->d_coords;
         p.npoint = mesh->npoint;
         if (op == GL_OP_MAT_01_NSN || op == GL_OP_VEC_01_NS || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV ||
+            ((op == GL_OP_VEC_02_NV || op == GL_OP_VEC_04_BT) && gd == mesh->ndim) ||
             (op == GL_OP_MAT_10_BDB && mesh->ndim == 2 && (bk.nnode == 3 || bk.nnode == 4))) { // thread-per-cell kernels
             st = ensure_point_major(ctx, mesh);
             if (st) return st;
@@ -827,6 +828,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
             if (nl == 0) nl = launch_scalar_tpc(p, f, mesh->ndim, ctx->stream);
             if (nl == 0) nl = launch_scalar_fused(p, f, mesh->ndim, ctx->stream);
         }
+        if (nl == 0 && gd == mesh->ndim) nl = launch_vec_tpc(p, mesh->ndim, ctx->stream);
         if (nl == 0) {
             p.cells_per_cta = generic_pick_cells_per_cta(mesh->ndim, gd, p.nnode, p.ng, op);
             nl = launch_generic(p, mesh->ndim, gd, ctx->stream);

@@ -118,6 +118,8 @@ int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void
 // mat_01_nsn and/or vec_01_ns as a (cells x ng).(ng x entries) product on the FP64 tensor cores (gl_kernels_mass.cu); 0 if not covered
 // mat_03_btb and/or vec_03_bv, one thread per cell (gl_kernels_scalar_tpc.cu); 0 if not covered
 int launch_scalar_tpc(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
+// vec_02_nv / vec_04_bt, one thread per cell, every coefficient mode (gl_kernels_vec_tpc.cu); 0 if not covered
+int launch_vec_tpc(const IntegParams &p, int sd, void *stream);
 int launch_mass_dmma(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
 
 // micro-benchmarks

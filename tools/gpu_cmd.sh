@@ -1,1 +1,2 @@
-timeout 700 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "all_ops_uniform or conditioning or modulus_per_marker or fused or mixed or higher_order" > gpurun_out/memcheck.log 2>&1; echo "exit $?"; tail -5 gpurun_out/memcheck.log; grep -c "Invalid\|ERROR SUMMARY" gpurun_out/memcheck.log; grep "ERROR SUMMARY" gpurun_out/memcheck.log | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/time_hex8.py 200 5 fused 2>&1 | tail -3
