@@ -397,7 +397,18 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
 
 } // namespace
 
-int launch_bdb(const IntegParams &p, int sd, void *stream) {
+// This file is compiled twice (gl_kernels_bdb2d.cu / gl_kernels_bdb3d.cu define GL_BDB_SD and include it): the 2D and the 3D
+// instantiations build in parallel and each translation unit stays at a tolerable compile time.
+#ifndef GL_BDB_SD
+#error "compile gl_kernels_bdb2d.cu / gl_kernels_bdb3d.cu, not this file"
+#endif
+#if GL_BDB_SD == 2
+int launch_bdb_2d(const IntegParams &p, void *stream) {
+    const int sd = 2;
+#else
+int launch_bdb_3d(const IntegParams &p, void *stream) {
+    const int sd = 3;
+#endif
     // covered: D uniform or one record per marker / per cell, tight blocks, overwrite; homogeneous or mixed layout; 16-byte
     // aligned output
     if (p.op != GL_OP_MAT_10_BDB || !p.clear) return 0;
@@ -429,34 +440,24 @@ int launch_bdb(const IntegParams &p, int sd, void *stream) {
         const int cap = atoi(e);
         if (cap < pat) pat = cap < 0 ? 0 : cap;
     }
-    if (sd == 2) {
-        switch (p.nnode) {
-        case 3: return launch_kind<3, 2, 1>(p, cst, pat, stream);
-        case 4: return launch_kind<4, 2, 1>(p, cst, pat, stream);
-        case 6: return launch_kind<6, 2, 1>(p, cst, pat, stream);
-        case 8: return launch_kind<8, 2, 1>(p, cst, pat, stream);
-        case 9: return launch_kind<9, 2, 1>(p, cst, pat, stream);
-        default: return 0;
-        }
+#if GL_BDB_SD == 2
+    switch (p.nnode) {
+    case 3: return launch_kind<3, 2, 1>(p, cst, pat, stream);
+    case 4: return launch_kind<4, 2, 1>(p, cst, pat, stream);
+    case 6: return launch_kind<6, 2, 1>(p, cst, pat, stream);
+    case 8: return launch_kind<8, 2, 1>(p, cst, pat, stream);
+    case 9: return launch_kind<9, 2, 1>(p, cst, pat, stream);
+    default: return 0;
     }
+#else
     switch (p.nnode) {
     case 4: return launch_kind<4, 3, 1>(p, cst, pat, stream);
     case 8: return launch_kind<8, 3, 1>(p, cst, pat, stream);
     case 10: return launch_kind<10, 3, 1>(p, cst, pat, stream);
-    case 20: {
-        // Hex20: 11 circulant blocks per column node are split over LPN lanes (tuning knob GL_HEX20_LPN = 2, 3 or 4)
-        static int lpn = -1;
-        if (lpn < 0) {
-            const char *e = getenv("GL_HEX20_LPN");
-            lpn = e ? atoi(e) : 4;
-        }
-        if (lpn == 2) return launch_kind<20, 3, 2>(p, cst, pat, stream);
-        if (lpn == 4) return launch_kind<20, 3, 4>(p, cst, pat, stream);
-        if (lpn == 6) return launch_kind<20, 3, 6>(p, cst, pat, stream);
-        return launch_kind<20, 3, 3>(p, cst, pat, stream);
-    }
+    case 20: return launch_kind<20, 3, 4>(p, cst, pat, stream); // 11 circulant blocks per column node split over 4 lanes
     default: return 0;
     }
+#endif
 }
 
 } // namespace gl
