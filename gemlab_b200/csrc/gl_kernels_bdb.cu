@@ -397,10 +397,11 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
 
 } // namespace
 
-// This file is compiled twice (gl_kernels_bdb2d.cu / gl_kernels_bdb3d.cu define GL_BDB_SD and include it): the 2D and the 3D
-// instantiations build in parallel and each translation unit stays at a tolerable compile time.
+// This file is compiled twice so that the 2D and the 3D instantiations build in parallel: on its own it is the 3D translation
+// unit (plus the dimension dispatch); gl_kernels_bdb2d.cu defines GL_BDB_SD = 2 and includes it.
 #ifndef GL_BDB_SD
-#error "compile gl_kernels_bdb2d.cu / gl_kernels_bdb3d.cu, not this file"
+#define GL_BDB_SD 3
+#define GL_BDB_MAIN
 #endif
 #if GL_BDB_SD == 2
 int launch_bdb_2d(const IntegParams &p, void *stream) {
@@ -459,5 +460,10 @@ int launch_bdb_3d(const IntegParams &p, void *stream) {
     }
 #endif
 }
+
+#ifdef GL_BDB_MAIN
+int launch_bdb_2d(const IntegParams &p, void *stream);
+int launch_bdb(const IntegParams &p, int sd, void *stream) { return sd == 2 ? launch_bdb_2d(p, stream) : launch_bdb_3d(p, stream); }
+#endif
 
 } // namespace gl
