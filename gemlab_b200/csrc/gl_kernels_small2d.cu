@@ -32,7 +32,7 @@ struct Small2dConsts {
     double d[16]; // d'[a][b] = f_a f_b d[a][b] (row-major 4 x 4), f = (1, 1, 1, 1/sqrt 2)
 };
 
-template <int NN, bool AXI, int PAT>
+template <int NN, bool AXI, int PAT, bool DREC>
 __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p, const Small2dConsts cst) {
     constexpr bool SYM = PAT >= 1;
     constexpr int SD = 2, NDOF = NN * SD, BS = NDOF * NDOF;
@@ -140,6 +140,24 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
         }
         if (active && bad) atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
 
+        // one modulus per marker / per cell: the lane reads the record of its cell (ns x ns Mandel matrix, column-major) and
+        // folds the 1/sqrt(2) factors of the shear row in, as the launcher does for a uniform modulus
+        double dl[16] = {};
+        if constexpr (DREC) {
+            if (active) {
+                const unsigned long long rec = p.coef_index ? (unsigned long long)p.coef_index[cell]
+                                                            : (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
+                const double *D = p.coef + rec * p.coef_cell_stride;
+                const double hs = 0.70710678118654752440084436210484903928;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+                        if (d2_nz(PAT, a, b)) dl[a * 4 + b] = D[a + b * 4] * (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
+            }
+        }
+        auto dval = [&](int a, int b) -> double { return DREC ? dl[a * 4 + b] : cst.d[a * 4 + b]; };
+
         // ---- contraction with D' into the transposition buffer: entry q of this lane's block at Tw[q*TS + lane] -------------
         __syncwarp(); // the previous batch's copy-out has finished reading Tw
         {
@@ -162,8 +180,8 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
                                     const int ra = c2_row(i, q), rb = c2_row(j, r);
                                     if (!d2_nz(PAT, ra, rb)) continue;
                                     const double pv = acc[pair][c2_comp(i, q) + VD * c2_comp(j, r)];
-                                    val = have ? fma(cst.d[ra * 4 + rb], pv, val) : cst.d[ra * 4 + rb] * pv;
-                                    if (!SYM) tr = have ? fma(cst.d[rb * 4 + ra], pv, tr) : cst.d[rb * 4 + ra] * pv;
+                                    val = have ? fma(dval(ra, rb), pv, val) : dval(ra, rb) * pv;
+                                    if (!SYM) tr = have ? fma(dval(rb, ra), pv, tr) : dval(rb, ra) * pv;
                                     have = true;
                                 }
                             Tw[((SD * m + i) + NDOF * (SD * n + j)) * TS + lane] = val;
@@ -202,11 +220,12 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
 }
 
 template <int NN, bool AXI>
-int launch_small2d_kind(const IntegParams &p, const Small2dConsts &cst, int pat, void *stream) {
+int launch_small2d_kind(const IntegParams &p, const Small2dConsts &cst, int pat, bool drec, void *stream) {
     constexpr int BS = NN * 2 * NN * 2;
     const size_t head = (size_t)p.ng * (1 + NN + NN * 2);
     const size_t smem = sizeof(double) * (head + (head & 1) + (size_t)(S2_THREADS / 32) * BS * 33);
-    auto kern = pat == 2 ? small2d_kernel<NN, AXI, 2> : (pat == 1 ? small2d_kernel<NN, AXI, 1> : small2d_kernel<NN, AXI, 0>);
+    auto kern = drec ? (pat == 2 ? small2d_kernel<NN, AXI, 2, true> : (pat == 1 ? small2d_kernel<NN, AXI, 1, true> : small2d_kernel<NN, AXI, 0, true>))
+                     : (pat == 2 ? small2d_kernel<NN, AXI, 2, false> : (pat == 1 ? small2d_kernel<NN, AXI, 1, false> : small2d_kernel<NN, AXI, 0, false>));
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
@@ -225,8 +244,11 @@ int launch_small2d_kind(const IntegParams &p, const Small2dConsts &cst, int pat,
 } // namespace
 
 int launch_bdb_small2d(const IntegParams &p, int sd, void *stream) {
-    // covered: Tri3 (plane and axisymmetric) and Qua4 (plane), uniform D, tight blocks, overwrite, point-major coordinates
-    if (sd != 2 || p.op != GL_OP_MAT_10_BDB || p.coef != nullptr || !p.clear || p.coords_pm == nullptr) return 0;
+    // covered: Tri3 (plane and axisymmetric) and Qua4 (plane), uniform D or one record per marker / cell, tight blocks,
+    // overwrite, point-major coordinates
+    if (sd != 2 || p.op != GL_OP_MAT_10_BDB || !p.clear || p.coords_pm == nullptr) return 0;
+    const bool drec = p.coef != nullptr;
+    if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 16)) return 0; // PER_GAUSS moduli: gl_kernels_bdb.cu
     if (p.nnode != 3 && !(p.nnode == 4 && !p.axisym)) return 0;
     const unsigned ndof = (unsigned)p.nnode * 2u;
     if (p.nrow != ndof || p.ncol != ndof || p.ii0 != 0 || p.jj0 != 0) return 0;
@@ -249,12 +271,14 @@ int launch_bdb_small2d(const IntegParams &p, int sd, void *stream) {
             for (int b = 0; b < 4; b++)
                 if (!d2_nz(2, a, b) && cst.d[a * 4 + b] != 0.0) pat = 1;
     }
+    if (drec) pat = p.coef_pat; // structure common to all records (0 when the records live on the device only)
     if (const char *e = getenv("GL_BDB_PATTERN")) {
         const int cap = atoi(e);
         if (cap < pat) pat = cap < 0 ? 0 : cap;
     }
-    if (p.nnode == 3) return p.axisym ? launch_small2d_kind<3, true>(p, cst, pat, stream) : launch_small2d_kind<3, false>(p, cst, pat, stream);
-    return launch_small2d_kind<4, false>(p, cst, pat, stream);
+    if (p.nnode == 3)
+        return p.axisym ? launch_small2d_kind<3, true>(p, cst, pat, drec, stream) : launch_small2d_kind<3, false>(p, cst, pat, drec, stream);
+    return launch_small2d_kind<4, false>(p, cst, pat, drec, stream);
 }
 
 } // namespace gl

@@ -1,5 +1,7 @@
-// gl_kernels_tile.cu -- stiffness kernel for the larger 3D kinds (Hex20, Tet10): integ::mat_10_bdb
-// (src/integ/mat_10_bdb.rs:121-208) with a uniform modulus D, tight element blocks, clear = true, homogeneous mesh.
+// gl_kernels_tile.cu -- stiffness kernel for 20-node hexahedra: integ::mat_10_bdb (src/integ/mat_10_bdb.rs:121-208) with a
+// uniform modulus D or one record per marker / per cell, tight element blocks, clear = true, homogeneous mesh.
+// (The template also fits Tet10, but there the register-blocked kernel of gl_kernels_bdb.cu measures faster -- 265 vs
+// 163 M el/s on 750 000 cells -- so only Hex20 is instantiated.)
 //
 // Same algebra as gl_kernels_bdb.cu -- geometric tensors P(m,n)[k][l] = sum_p c_p B(m,k) B(n,l) accumulated over the Gauss
 // points, D applied once afterwards -- but register-tiled like a symmetric rank-k update, because for 20-node cells the
@@ -58,7 +60,7 @@ struct TileDims {
     static constexpr int LS = (NN * SD + 6) / 16 * 16 + 9; // = 9 (mod 16): the SD lanes of up to 6 Gauss points of a half-warp read L conflict-free
 };
 
-template <int NN, int PAT>
+template <int NN, int PAT, bool DREC>
 __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const TileConsts cst, const int CPC) {
     using T = TileDims<NN>;
     constexpr int SD = T::SD, NP = T::NP, NT = T::NT, LPC = T::LPC, NDOF = T::NDOF, GS = T::GS, XS = T::XS, LS = T::LS;
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
     double *s_L = s_K + CPC * NDOF * NDOF;       // [ng][LS]
     double *s_X = s_L + ng * LS;                 // [CPC][XS]
     double *s_w = s_X + CPC * XS;                // [ng]
+    double *s_D = s_w + ng;                      // [CPC][36]  per-cell d' (DREC only: PER_MARKER / PER_CELL moduli)
 
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < ng; i += nt) s_w[i] = p.rule[i];
@@ -135,6 +138,18 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
                 for (int j = 0; j < SD; j++) gx[j] = p.coords[(unsigned long long)j * p.npoint + gpid];
             }
             if (cell + 2 * gstep < p.hi) gpid = p.conn[(unsigned long long)gm * p.ncell_k + cell + 2 * gstep];
+        }
+        if constexpr (DREC) {
+            // modulus record of each cell of the tile (its marker's or its own; ns x ns Mandel matrix, column-major) with the
+            // 1/sqrt(2) factors of the shear rows folded in, as the launcher does for a uniform modulus
+            const double hs = 0.70710678118654752440084436210484903928;
+            for (int t = tid; t < ncell_tile * 36; t += nt) {
+                const int c = t / 36, idx = t - c * 36;
+                const int a = idx / 6, b = idx - a * 6;
+                const unsigned long long cell = cell0 + c;
+                const unsigned long long rec = p.coef_index ? (unsigned long long)p.coef_index[cell] : cell - p.coef_begin;
+                s_D[t] = p.coef[rec * p.coef_cell_stride + a + b * 6] * (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
+            }
         }
         __syncthreads();
 
@@ -210,27 +225,39 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
         __syncthreads(); // every lane has finished reading G: the region becomes the K staging
         if (active) {
             double *Kc = s_K + cs * NDOF * NDOF;
+            const double *Dc = s_D + cs * 36;
 #pragma unroll
-            for (int rn = 0; rn < 2; rn++)
+            for (int j = 0; j < SD; j++)
 #pragma unroll
-                for (int cn = 0; cn < 2; cn++) {
-                    const int m = 2 * R + rn, n = 2 * C + cn;
+                for (int i = 0; i < SD; i++) {
+                    // K(3m+i, 3n+j) = sum_qr d'[row(i,q)][row(j,r)] P(m,n)[comp(i,q)][comp(j,r)]: the (up to) 9 modulus entries of
+                    // the component pair (i, j) -- and their transposes for a non-symmetric D -- serve all four node pairs
+                    double dr[3][3], dt[3][3];
 #pragma unroll
-                    for (int j = 0; j < SD; j++)
+                    for (int q = 0; q < 3; q++)
 #pragma unroll
-                        for (int i = 0; i < SD; i++) {
-                            // K(3m+i, 3n+j) = sum_qr d'[row(i,q)][row(j,r)] P(m,n)[comp(i,q)][comp(j,r)]
+                        for (int r = 0; r < 3; r++) {
+                            const int ra = col_row3(i, q), rb = col_row3(j, r);
+                            dr[q][r] = dt[q][r] = 0.0;
+                            if (!d_nz3(PAT, ra, rb)) continue;
+                            dr[q][r] = DREC ? Dc[ra * 6 + rb] : cst.d[ra * 6 + rb];
+                            if (!SYM) dt[q][r] = DREC ? Dc[rb * 6 + ra] : cst.d[rb * 6 + ra];
+                        }
+#pragma unroll
+                    for (int rn = 0; rn < 2; rn++)
+#pragma unroll
+                        for (int cn = 0; cn < 2; cn++) {
+                            const int m = 2 * R + rn, n = 2 * C + cn;
                             double v = 0.0, u = 0.0;
                             bool have = false;
 #pragma unroll
                             for (int q = 0; q < 3; q++)
 #pragma unroll
                                 for (int r = 0; r < 3; r++) {
-                                    const int ra = col_row3(i, q), rb = col_row3(j, r);
-                                    if (!d_nz3(PAT, ra, rb)) continue;
+                                    if (!d_nz3(PAT, col_row3(i, q), col_row3(j, r))) continue;
                                     const double pv = acc[3 * rn + col_comp3(i, q)][3 * cn + col_comp3(j, r)];
-                                    v = have ? fma(cst.d[ra * 6 + rb], pv, v) : cst.d[ra * 6 + rb] * pv;
-                                    if (!SYM) u = have ? fma(cst.d[rb * 6 + ra], pv, u) : cst.d[rb * 6 + ra] * pv;
+                                    v = have ? fma(dr[q][r], pv, v) : dr[q][r] * pv;
+                                    if (!SYM) u = have ? fma(dt[q][r], pv, u) : dt[q][r] * pv;
                                     have = true;
                                 }
                             Kc[(SD * m + i) + NDOF * (SD * n + j)] = v;
@@ -257,14 +284,14 @@ __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const Ti
 }
 
 template <int NN>
-size_t tile_smem(int ng, int cpc) {
+size_t tile_smem(int ng, int cpc, bool drec) {
     using T = TileDims<NN>;
     // G aliases the K staging (ng * GS <= NDOF^2 for every instantiated kind and rule the launcher accepts)
-    return sizeof(double) * ((size_t)cpc * T::NDOF * T::NDOF + (size_t)ng * T::LS + (size_t)cpc * T::XS + (size_t)ng);
+    return sizeof(double) * ((size_t)cpc * T::NDOF * T::NDOF + (size_t)ng * T::LS + (size_t)cpc * T::XS + (size_t)ng + (drec ? (size_t)cpc * 36 : 0));
 }
 
 template <int NN>
-int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, void *stream) {
+int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, bool drec, void *stream) {
     using T = TileDims<NN>;
     static int cpc_env = -1;
     if (cpc_env < 0) {
@@ -275,12 +302,13 @@ int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, void 
     if (cpc < 1) cpc = 1;
     if (cpc * T::LPC > 256) cpc = 256 / T::LPC;
     if ((size_t)p.ng * T::GS > (size_t)T::NDOF * T::NDOF) return 0; // G must fit inside the staging region it aliases
-    while (cpc > 1 && tile_smem<NN>(p.ng, cpc) > 74 * 1024) cpc--;   // three CTAs per SM
-    const size_t smem = tile_smem<NN>(p.ng, cpc);
+    while (cpc > 1 && tile_smem<NN>(p.ng, cpc, drec) > 74 * 1024) cpc--;   // three CTAs per SM
+    const size_t smem = tile_smem<NN>(p.ng, cpc, drec);
     if (smem > 220 * 1024) return 0;
     const int threads = cpc * T::LPC;
     typedef void (*kern_t)(const IntegParams, const TileConsts, const int);
-    kern_t kern = pat == 2 ? tile_kernel<NN, 2> : (pat == 1 ? tile_kernel<NN, 1> : tile_kernel<NN, 0>);
+    kern_t kern = drec ? (pat == 2 ? tile_kernel<NN, 2, true> : (pat == 1 ? tile_kernel<NN, 1, true> : tile_kernel<NN, 0, true>))
+                       : (pat == 2 ? tile_kernel<NN, 2, false> : (pat == 1 ? tile_kernel<NN, 1, false> : tile_kernel<NN, 0, false>));
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
@@ -300,8 +328,11 @@ int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, void 
 } // namespace
 
 int launch_bdb_tile(const IntegParams &p, int sd, void *stream) {
-    // covered: 3D, even node count, uniform D, tight blocks, overwrite, homogeneous layout, 16-byte aligned output
-    if (sd != 3 || p.op != GL_OP_MAT_10_BDB || p.coef != nullptr || !p.clear || p.axisym) return 0;
+    // covered: 3D, even node count, uniform D or one record per marker / cell, tight blocks, overwrite, homogeneous layout,
+    // 16-byte aligned output
+    if (sd != 3 || p.op != GL_OP_MAT_10_BDB || !p.clear || p.axisym) return 0;
+    const bool drec = p.coef != nullptr;
+    if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 36)) return 0; // PER_GAUSS moduli: gl_kernels_bdb.cu
     if (p.cell_ids != nullptr || p.out_off != nullptr) return 0;
     const unsigned ndof = (unsigned)p.nnode * 3u;
     if (p.nrow != ndof || p.ncol != ndof || p.ii0 != 0 || p.jj0 != 0) return 0;
@@ -324,13 +355,13 @@ int launch_bdb_tile(const IntegParams &p, int sd, void *stream) {
             for (int b = 0; b < 6; b++)
                 if (!d_nz3(2, a, b) && cst.d[a * 6 + b] != 0.0) pat = 1;
     }
+    if (drec) pat = p.coef_pat; // structure common to all records (0 when the records live on the device only)
     if (const char *e = getenv("GL_BDB_PATTERN")) {
         const int cap = atoi(e);
         if (cap < pat) pat = cap < 0 ? 0 : cap;
     }
     switch (p.nnode) {
-    case 10: return launch_tile_kind<10>(p, cst, pat, stream);
-    case 20: return launch_tile_kind<20>(p, cst, pat, stream);
+    case 20: return launch_tile_kind<20>(p, cst, pat, drec, stream);
     default: return 0;
     }
 }

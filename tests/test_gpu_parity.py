@@ -255,7 +255,7 @@ def test_coefficient_modes(ctx, kind, op):
     assert rel_err(out.cpu().numpy(), ref, sizes) <= TOL
 
 
-@pytest.mark.parametrize("kind", ["tri3", "tri6", "qua8", "qua9", "tet4", "tet10", "hex8", "hex20"])
+@pytest.mark.parametrize("kind", ["tri3", "tri6", "qua4", "qua8", "qua9", "tet4", "tet10", "hex8", "hex20"])
 @pytest.mark.parametrize("structure", ["isotropic", "symmetric", "general"])
 def test_stiffness_with_one_modulus_per_marker_and_per_cell(ctx, kind, structure):
     """Multi-material meshes through the tuned stiffness kernels: the record structure common to all records (isotropic /
