@@ -73,6 +73,8 @@ struct IntegParams {
     int coef_len;
     int coef_pat;             // mat_10_bdb with record data: structure common to ALL records when the host could inspect them
                               // (2 = symmetric with uncoupled normal / diagonal shear blocks, 1 = major-symmetric, 0 = unknown / general)
+    const int *coef_pat_dev;  // device-resident records: their common structure, found by a probe kernel earlier on the stream;
+                              // the launcher then enqueues every pattern variant and all but the matching one exit at once
     double coef_uniform[36];
     // output
     double *out;
@@ -160,6 +162,7 @@ struct gl_ctx {
     uint64_t last_error_cell = gl::NO_ERR_CELL;
     uint64_t launches = 0;
     unsigned long long *d_err_cell = nullptr;
+    int *d_coef_pat = nullptr; // result of the modulus-structure probe (device-resident PER_CELL moduli)
     unsigned long long *h_err_cell = nullptr; // pinned
     std::map<std::pair<int, int>, std::unique_ptr<gl::RuleTable>> rules; // (kind, ngauss) -> table
     // scratch for host<->device staging

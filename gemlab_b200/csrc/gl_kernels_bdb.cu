@@ -53,6 +53,7 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 
 template <int NN, int SD, int LPN, bool AXI, int PAT>
 __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const BdbConsts cst, const int CPC, const int nthreads_used, const int alias_g) {
+    if (p.coef_pat_dev != nullptr && *p.coef_pat_dev != PAT) return; // another pattern variant owns this call (see launcher)
     constexpr bool SYM = PAT >= 1;
     constexpr int NS = 2 * SD;
     constexpr int NDOF = NN * SD;
@@ -369,14 +370,12 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     const int used = cpc * NN * LPN;
     const int threads = (used + 31) / 32 * 32;
     typedef void (*kern_t)(const IntegParams, const BdbConsts, const int, const int, const int);
-    kern_t kern = nullptr;
-    if constexpr (SD == 2) {
-        if (axi) kern = pat == 2 ? bdb_kernel<NN, SD, LPN, true, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, true, 1> : bdb_kernel<NN, SD, LPN, true, 0>);
-        else kern = pat == 2 ? bdb_kernel<NN, SD, LPN, false, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, false, 1> : bdb_kernel<NN, SD, LPN, false, 0>);
-    } else {
-        kern = pat == 2 ? bdb_kernel<NN, SD, LPN, false, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, false, 1> : bdb_kernel<NN, SD, LPN, false, 0>);
-    }
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    auto pick = [&](int pat) -> kern_t {
+        if constexpr (SD == 2) {
+            if (axi) return pat == 2 ? bdb_kernel<NN, SD, LPN, true, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, true, 1> : bdb_kernel<NN, SD, LPN, true, 0>);
+        }
+        return pat == 2 ? bdb_kernel<NN, SD, LPN, false, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, false, 1> : bdb_kernel<NN, SD, LPN, false, 0>);
+    };
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -391,7 +390,15 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     if (const char *e = getenv("GL_BDB_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
-    kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, cst, cpc, used, bdb_alias<NN, SD, LPN>(p.ng, axi) ? 1 : 0);
+    // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
+    const bool probe = drec && p.coef_pat_dev != nullptr && getenv("GL_BDB_PATTERN") == nullptr;
+    IntegParams q = p;
+    if (!probe) q.coef_pat_dev = nullptr;
+    for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
+        kern_t kern = pick(pt);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(q, cst, cpc, used, bdb_alias<NN, SD, LPN>(p.ng, axi) ? 1 : 0);
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

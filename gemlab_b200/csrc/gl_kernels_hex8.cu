@@ -67,6 +67,7 @@ __host__ __device__ constexpr int col_comp(int j, int t) { return j == 0 ? (t ==
 
 template <int PAT, int PF, int DBG = 0, bool DREC = false, bool FD = false>
 __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegParams p, const Hex8Consts cst) {
+    if (DREC && p.coef_pat_dev != nullptr && *p.coef_pat_dev != PAT) return; // another pattern variant owns this call
     constexpr bool SYM = PAT >= 1;
     extern __shared__ __align__(16) double smem[];
     double *s_L = smem;                         // [8][L_STRIDE]  L[gp][m*3+j]
@@ -404,8 +405,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
         if (e && atoi(e) < pat) pat = atoi(e) < 0 ? 0 : atoi(e);
     }
     typedef void (*kern_t)(const IntegParams, const Hex8Consts);
-    kern_t kern;
-    auto pick = [&](auto pfc) -> kern_t {
+    auto pick = [&](auto pfc, int pat) -> kern_t {
         constexpr int P = decltype(pfc)::value;
         if (const char *e = getenv("GL_HEX8_DEBUG")) { // timing experiments only (1 no accumulation, 2 no geometry, 3 no staging, 4 no gather, 5 no coordinate loads)
             switch (atoi(e)) {
@@ -421,9 +421,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
         if (drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true> : hex8_bdb_kernel<0, P, 0, true>);
         return pat == 2 ? hex8_bdb_kernel<2, P> : (pat == 1 ? hex8_bdb_kernel<1, P> : hex8_bdb_kernel<0, P>);
     };
-    kern = pf == 1 ? pick(std::integral_constant<int, 1>{}) : pick(std::integral_constant<int, 2>{});
     const size_t H8_SMEM = H8_SMEM_BASE + (drec ? H8_SMEM_DREC : 0) + (fd ? H8_SMEM_FD : 0);
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8_SMEM) != cudaSuccess) return -1;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -435,7 +433,15 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     if (const char *e = getenv("GL_HEX8_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
-    kern<<<(unsigned)grid, H8_THREADS, H8_SMEM, (cudaStream_t)stream>>>(p, cst);
+    // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
+    const bool probe = drec && p.coef_pat_dev != nullptr && getenv("GL_HEX8_PATTERN") == nullptr && getenv("GL_HEX8_DEBUG") == nullptr;
+    IntegParams q = p;
+    if (!probe) q.coef_pat_dev = nullptr;
+    for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
+        kern_t kern = pf == 1 ? pick(std::integral_constant<int, 1>{}, pt) : pick(std::integral_constant<int, 2>{}, pt);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8_SMEM) != cudaSuccess) return -1;
+        kern<<<(unsigned)grid, H8_THREADS, H8_SMEM, (cudaStream_t)stream>>>(q, cst);
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -34,6 +34,7 @@ struct Small2dConsts {
 
 template <int NN, bool AXI, int PAT, bool DREC>
 __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p, const Small2dConsts cst) {
+    if (DREC && p.coef_pat_dev != nullptr && *p.coef_pat_dev != PAT) return; // another pattern variant owns this call (see launcher)
     constexpr bool SYM = PAT >= 1;
     constexpr int SD = 2, NDOF = NN * SD, BS = NDOF * NDOF;
     constexpr int VD = SD + (AXI ? 1 : 0);
@@ -224,9 +225,10 @@ int launch_small2d_kind(const IntegParams &p, const Small2dConsts &cst, int pat,
     constexpr int BS = NN * 2 * NN * 2;
     const size_t head = (size_t)p.ng * (1 + NN + NN * 2);
     const size_t smem = sizeof(double) * (head + (head & 1) + (size_t)(S2_THREADS / 32) * BS * 33);
-    auto kern = drec ? (pat == 2 ? small2d_kernel<NN, AXI, 2, true> : (pat == 1 ? small2d_kernel<NN, AXI, 1, true> : small2d_kernel<NN, AXI, 0, true>))
-                     : (pat == 2 ? small2d_kernel<NN, AXI, 2, false> : (pat == 1 ? small2d_kernel<NN, AXI, 1, false> : small2d_kernel<NN, AXI, 0, false>));
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    auto pick = [&](int pat) {
+        return drec ? (pat == 2 ? small2d_kernel<NN, AXI, 2, true> : (pat == 1 ? small2d_kernel<NN, AXI, 1, true> : small2d_kernel<NN, AXI, 0, true>))
+                    : (pat == 2 ? small2d_kernel<NN, AXI, 2, false> : (pat == 1 ? small2d_kernel<NN, AXI, 1, false> : small2d_kernel<NN, AXI, 0, false>));
+    };
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -237,7 +239,15 @@ int launch_small2d_kind(const IntegParams &p, const Small2dConsts &cst, int pat,
     unsigned long long grid = (unsigned long long)nsm * ctas_per_sm * 8;
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
-    kern<<<(unsigned)grid, S2_THREADS, smem, (cudaStream_t)stream>>>(p, cst);
+    // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
+    const bool probe = drec && p.coef_pat_dev != nullptr && getenv("GL_BDB_PATTERN") == nullptr;
+    IntegParams q = p;
+    if (!probe) q.coef_pat_dev = nullptr;
+    for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
+        auto kern = pick(pt);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        kern<<<(unsigned)grid, S2_THREADS, smem, (cudaStream_t)stream>>>(q, cst);
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

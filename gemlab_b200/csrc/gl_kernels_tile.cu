@@ -62,6 +62,7 @@ struct TileDims {
 
 template <int NN, int PAT, bool DREC>
 __global__ void __launch_bounds__(256) tile_kernel(const IntegParams p, const TileConsts cst, const int CPC) {
+    if (DREC && p.coef_pat_dev != nullptr && *p.coef_pat_dev != PAT) return; // another pattern variant owns this call (see launcher)
     using T = TileDims<NN>;
     constexpr int SD = T::SD, NP = T::NP, NT = T::NT, LPC = T::LPC, NDOF = T::NDOF, GS = T::GS, XS = T::XS, LS = T::LS;
     constexpr bool SYM = PAT >= 1;
@@ -307,9 +308,10 @@ int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, bool 
     if (smem > 220 * 1024) return 0;
     const int threads = cpc * T::LPC;
     typedef void (*kern_t)(const IntegParams, const TileConsts, const int);
-    kern_t kern = drec ? (pat == 2 ? tile_kernel<NN, 2, true> : (pat == 1 ? tile_kernel<NN, 1, true> : tile_kernel<NN, 0, true>))
-                       : (pat == 2 ? tile_kernel<NN, 2, false> : (pat == 1 ? tile_kernel<NN, 1, false> : tile_kernel<NN, 0, false>));
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    auto pick = [&](int pat) -> kern_t {
+        return drec ? (pat == 2 ? tile_kernel<NN, 2, true> : (pat == 1 ? tile_kernel<NN, 1, true> : tile_kernel<NN, 0, true>))
+                    : (pat == 2 ? tile_kernel<NN, 2, false> : (pat == 1 ? tile_kernel<NN, 1, false> : tile_kernel<NN, 0, false>));
+    };
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -321,7 +323,15 @@ int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, bool 
     unsigned long long grid = (unsigned long long)nsm * ctas_per_sm * 16; // de-synchronised CTAs, see gl_kernels_hex8.cu
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
-    kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, cst, cpc);
+    // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
+    const bool probe = drec && p.coef_pat_dev != nullptr && getenv("GL_BDB_PATTERN") == nullptr;
+    IntegParams q = p;
+    if (!probe) q.coef_pat_dev = nullptr;
+    for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
+        kern_t kern = pick(pt);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(q, cst, cpc);
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
