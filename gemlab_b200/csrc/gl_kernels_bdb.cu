@@ -365,7 +365,7 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     // measured (cells per CTA swept, `profiles/r01_bdb_cells_per_cta_sweep.txt`): small CTAs -- more of them resident, cheaper
     // barriers -- win where the element block is large against the arithmetic per lane
     if (NN == 10 && SD == 3) cpc = 4;  // Tet10: 266 -> 301 M el/s
-    if (NN == 8 && SD == 2) cpc = 16;  // Qua8: 1.87 -> 1.99 G el/s
+    if (NN >= 8 && NN <= 9 && SD == 2) cpc = 16; // Qua8: 1.87 -> 1.99 G el/s, Qua9: 1.12 -> 1.22 G el/s
     if (const char *e = getenv("GL_BDB_CPC")) cpc = atoi(e); // tuning knob: cells per CTA
     if (cpc * NN * LPN > 1024) cpc = 1024 / (NN * LPN);
     if (cpc < 1) cpc = 1;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Runs mat_10_bdb a few times on one kind (uniform modulus, device-resident output): the target of an ncu capture.
-usage: python tools/run_one_stiffness.py tet10|qua8|hex20 [n]"""
+usage: python tools/run_one_stiffness.py tet10|qua4|qua8|qua9|hex8|hex20 [n]"""
 import sys
 from pathlib import Path
 
@@ -17,8 +17,8 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 ctx = Context(0)
 if kind == "tet10":
     mesh = g.split_hex_cells_into_tet10(n, n, n, seed=12345)
-elif kind == "qua8":
-    mesh = Block.new_square(1.0).set_ndiv([20 * n, 20 * n]).subdivide(GeoKind.Qua8)
+elif kind.startswith("qua"):
+    mesh = Block.new_square(1.0).set_ndiv([20 * n, 20 * n]).subdivide(GeoKind.from_str(kind))
 else:
     mesh = Block.new_cube(1.0).set_ndiv([n, n, n]).subdivide(GeoKind.from_str(kind))
 dm = ctx.upload(mesh)
