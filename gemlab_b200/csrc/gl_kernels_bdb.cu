@@ -366,6 +366,8 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     // barriers -- win where the element block is large against the arithmetic per lane
     if (NN == 10 && SD == 3) cpc = 4;  // Tet10: 266 -> 301 M el/s
     if (NN >= 8 && NN <= 9 && SD == 2) cpc = 16; // Qua8: 1.87 -> 1.99 G el/s, Qua9: 1.12 -> 1.22 G el/s
+    // (axisymmetric Qua4 also measured faster at 16 than at the default 64 -- 4.65 vs 3.83 G el/s -- not yet adopted: the
+    // parity suite has not run on that default)
     if (const char *e = getenv("GL_BDB_CPC")) cpc = atoi(e); // tuning knob: cells per CTA
     if (cpc * NN * LPN > 1024) cpc = 1024 / (NN * LPN);
     if (cpc < 1) cpc = 1;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Runs mat_10_bdb a few times on one kind (uniform modulus, device-resident output): the target of an ncu capture.
-usage: python tools/run_one_stiffness.py tet10|qua4|qua8|qua9|hex8|hex20 [n]"""
+usage: python tools/run_one_stiffness.py tet10|qua4|qua8|qua9|hex8|hex20 [n] [axi]"""
 import sys
 from pathlib import Path
 
@@ -14,6 +14,7 @@ from gemlab_b200 import Block, Coef, CommonArgs, Context, GeoKind, integ  # noqa
 
 kind = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+axi = len(sys.argv) > 3 and sys.argv[3] == "axi"
 ctx = Context(0)
 if kind == "tet10":
     mesh = g.split_hex_cells_into_tet10(n, n, n, seed=12345)
@@ -26,13 +27,13 @@ dd = g.mandel_matrix(g.lin_elasticity(480.0, 1 / 3, mesh.ndim == 2))
 bs = integ.op_out_size("mat_10_bdb", GeoKind.from_str(kind), mesh.ndim)
 out = torch.empty(mesh.ncell * bs, dtype=torch.float64, device="cuda")
 for _ in range(4):
-    integ.mat_10_bdb(ctx, dm, None, CommonArgs(), Coef.uniform(dd), out=out)
+    integ.mat_10_bdb(ctx, dm, None, CommonArgs(axisymmetric=axi), Coef.uniform(dd), out=out)
 ctx.sync()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(5):
-    integ.mat_10_bdb(ctx, dm, None, CommonArgs(), Coef.uniform(dd), out=out)
+    integ.mat_10_bdb(ctx, dm, None, CommonArgs(axisymmetric=axi), Coef.uniform(dd), out=out)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(f"{kind}: {mesh.ncell} cells, {ms:.4f} ms, {mesh.ncell / ms / 1e3:.1f} M el/s, {mesh.ncell * bs * 8 / ms / 1e6:.0f} GB/s out")
+print(f"{kind}{' axisymmetric' if axi else ''}: {mesh.ncell} cells, {ms:.4f} ms, {mesh.ncell / ms / 1e3:.1f} M el/s, {mesh.ncell * bs * 8 / ms / 1e6:.0f} GB/s out")
