@@ -6,8 +6,12 @@ usable `Context()` raises (GL_ERR_NO_DEVICE).  Nothing here imports the oracle.
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libgemlab_cuda.so"
+# GEMLAB_CUDA_TUNING=1 selects the -DGL_TUNING build (make -C gemlab_b200/csrc TUNING=1), the only one that reads the GL_*
+# environment knobs; used by the sweep tools, never by tests or bench.py
+LIB_PATH = _HERE / ("libgemlab_cuda_tuning.so" if os.environ.get("GEMLAB_CUDA_TUNING") == "1" else "libgemlab_cuda.so")
 
 
 class GlArgs(C.Structure):
@@ -44,6 +48,7 @@ SYMBOLS = {
     "gl_last_error_cell": (C.c_uint64, [_P]),
     "gl_status_string": (C.c_char_p, [C.c_int]),
     "gl_ctx_launch_count": (C.c_uint64, [_P]),
+    "gl_ctx_last_kernel": (C.c_char_p, [_P]),
     "gl_kind_nnode": (C.c_int, [C.c_int]),
     "gl_kind_geo_ndim": (C.c_int, [C.c_int]),
     "gl_kind_class": (C.c_int, [C.c_int]),

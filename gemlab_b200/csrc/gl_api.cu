@@ -12,12 +12,28 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gl_internal.hpp"
 
 using namespace gl;
+
+namespace gl {
+static thread_local char g_noted_kernel[128] = "";
+void note_kernel(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(g_noted_kernel, sizeof(g_noted_kernel), fmt, ap);
+    va_end(ap);
+}
+const char *noted_kernel() { return g_noted_kernel; }
+#ifdef GL_TUNING
+const char *tuning_env(const char *name) { return std::getenv(name); }
+#endif
+} // namespace gl
 
 namespace {
 
@@ -134,11 +150,11 @@ void bucket_range(const gl_mesh *mesh, const gl_mesh_bucket &bk, uint64_t b, uin
 }
 
 // exclusive prefix of block sizes over the whole (mixed) mesh, cached by the args that shape the block
-const std::vector<uint64_t> *mesh_prefix(gl_mesh *mesh, int op, const gl_args *a, int *key_out, int *status) {
+const std::vector<uint64_t> *mesh_prefix(gl_mesh *mesh, int op, const gl_args *a, BlockKey *key_out, int *status) {
     *status = GL_OK;
     const int cls = op_size_class(op);
     // key: size class + offsets (explicit nrow/ncol make every block equal; handled by the caller)
-    const int key = cls | ((int)(a->ii0 & 0xfff) << 4) | ((int)(a->jj0 & 0xfff) << 16);
+    const BlockKey key(cls, a->ii0, a->jj0); // the full offsets: a truncated key would alias tight-block layouts with large ii0 / jj0
     *key_out = key;
     auto it = mesh->h_prefix.find(key);
     if (it != mesh->h_prefix.end()) return &it->second;
@@ -296,6 +312,11 @@ int gl_ctx_create(int device, void *stream, gl_ctx **out) {
         cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
         ctx->ev[i] = ev;
     }
+    {
+        cudaEvent_t ev;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        ctx->ev_coef = ev;
+    }
     *out = ctx;
     return GL_OK;
 }
@@ -317,6 +338,8 @@ void gl_ctx_destroy(gl_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamDestroy((cudaStream_t)ctx->copy_stream);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy((cudaEvent_t)ctx->ev[i]);
+    if (ctx->ev_coef) cudaEventDestroy((cudaEvent_t)ctx->ev_coef);
+    if (ctx->h_coef) cudaFreeHost(ctx->h_coef);
     delete ctx;
 }
 
@@ -345,6 +368,7 @@ const char *gl_last_error(const gl_ctx *ctx) { return ctx ? ctx->last_error.c_st
 uint64_t gl_last_error_cell(const gl_ctx *ctx) { return ctx ? ctx->last_error_cell : NO_ERR_CELL; }
 const char *gl_status_string(int status) { return status_string(status); }
 uint64_t gl_ctx_launch_count(const gl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+const char *gl_ctx_last_kernel(const gl_ctx *ctx) { return ctx ? ctx->last_kernel.c_str() : ""; }
 
 int gl_kind_nnode(int kind) { return kind_nnode(kind); }
 int gl_kind_geo_ndim(int kind) { return kind_geo_ndim(kind); }
@@ -680,7 +704,8 @@ static int range_layout(const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, co
             for (uint64_t i = 0; i <= e - b; i++) off[i] = i * blk;
         return GL_OK;
     }
-    int key, st;
+    BlockKey key;
+    int st;
     const std::vector<uint64_t> *pre = mesh_prefix(mesh, op, a, &key, &st);
     if (st) return st;
     if (total) *total = (*pre)[e] - (*pre)[b];
@@ -719,7 +744,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
     if (b == e) return GL_OK;
     const bool explicit_block = a->nrow != 0 || (op_is_matrix(op) && a->ncol != 0);
     const std::vector<uint64_t> *pre = nullptr;
-    int key = 0;
+    BlockKey key;
     if (!mesh->homogeneous && !explicit_block) {
         int st;
         pre = mesh_prefix(mesh, op, a, &key, &st);
@@ -815,6 +840,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
         if (force_done) *force_done = nl > 0 && d_sigma != nullptr;
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_small2d(p, mesh->ndim, ctx->stream);
+        if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_syrk(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_tile(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb(p, mesh->ndim, ctx->stream);
         if (nl == 0 && gd == mesh->ndim && cr.dev == nullptr && a->clear && a->ii0 == 0 && (a->jj0 == 0 || !op_is_matrix(op)) &&
@@ -839,6 +865,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         }
         if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
         ctx->launches += (uint64_t)nl;
+        ctx->last_kernel = noted_kernel();
     }
     return GL_OK;
 }
@@ -919,9 +946,24 @@ static int resolve_coef(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         int st = ensure_buffer(ctx, &ctx->d_coef, &ctx->coef_bytes, table.size() * sizeof(double));
         if (st) return st;
         if (op == GL_OP_MAT_10_BDB) cr.pat = modulus_pattern(table.data(), nm, 2 * mesh->ndim);
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coef, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice,
-                                      (cudaStream_t)ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)ctx->stream)); // `table` is a local
+        // the table goes through a pinned buffer owned by the ctx, so the call stays asynchronous (no stream synchronisation per
+        // call); the buffer is reused only after the previous copy out of it has completed
+        const size_t tbytes = table.size() * sizeof(double);
+        if (ctx->h_coef_bytes < tbytes) {
+            if (ctx->h_coef) {
+                CUDA_TRY(ctx, cudaEventSynchronize((cudaEvent_t)ctx->ev_coef));
+                cudaFreeHost(ctx->h_coef);
+                ctx->h_coef = nullptr;
+                ctx->h_coef_bytes = 0;
+            }
+            CUDA_TRY(ctx, cudaMallocHost(&ctx->h_coef, std::max<size_t>(tbytes, 4096)));
+            ctx->h_coef_bytes = std::max<size_t>(tbytes, 4096);
+        } else {
+            CUDA_TRY(ctx, cudaEventSynchronize((cudaEvent_t)ctx->ev_coef));
+        }
+        std::memcpy(ctx->h_coef, table.data(), tbytes);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coef, ctx->h_coef, tbytes, cudaMemcpyHostToDevice, (cudaStream_t)ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord((cudaEvent_t)ctx->ev_coef, (cudaStream_t)ctx->stream));
         cr.dev = ctx->d_coef;
         cr.cell_stride = len;
         cr.gp_stride = 0;
@@ -1073,7 +1115,11 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
             if (items[i].op == GL_OP_MAT_10_BDB) ik = &items[i];
             if (items[i].op == GL_OP_VEC_04_BT) id = &items[i];
         }
-        if (ik && id && ik->coef && id->coef && ik->out && id->out && mesh->homogeneous && mesh->buckets.size() == 1 &&
+        int ng_rule = 0;
+        const double *rule_data = nullptr;
+        // the fused kernel is the 8-point one: with any other rule the stress buffer has another size (ng records per cell)
+        const bool rule8 = gauss_rule(GL_HEX8, a->ngauss, &ng_rule, &rule_data) == GL_OK && ng_rule == 8;
+        if (ik && id && rule8 && ik->coef && id->coef && ik->out && id->out && mesh->homogeneous && mesh->buckets.size() == 1 &&
             mesh->buckets[0].kind == GL_HEX8 && a->clear && !a->axisymmetric && a->ii0 == 0 && a->jj0 == 0 && a->nrow == 0 &&
             a->ncol == 0 && ik->coef->mode != GL_COEF_PER_GAUSS && id->coef->mode == GL_COEF_PER_GAUSS && id->coef->data &&
             ik->out->location == GL_DEVICE && id->out->location == GL_DEVICE && ik->out->ptr && id->out->ptr) {
@@ -1141,12 +1187,13 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
         }
     }
     const std::vector<uint64_t> *mpre = nullptr, *vpre = nullptr;
-    int mkey = 0, vkey = 0, st = GL_OK;
+    BlockKey mkey, vkey;
+    int st = GL_OK;
     if (!mesh->homogeneous) {
         if (mat_op >= 0) mpre = mesh_prefix(mesh, mat_op, a, &mkey, &st);
         if (vec_op >= 0) vpre = mesh_prefix(mesh, vec_op, a, &vkey, &st);
     }
-    auto device_offsets = [&](gl_mesh_bucket &bk, const std::vector<uint64_t> *pre, int key, const unsigned long long **out) -> int {
+    auto device_offsets = [&](gl_mesh_bucket &bk, const std::vector<uint64_t> *pre, const BlockKey &key, const unsigned long long **out) -> int {
         auto it = bk.d_out_off.find(key);
         if (it == bk.d_out_off.end()) {
             std::vector<unsigned long long> offs(bk.ncell);
@@ -1203,6 +1250,7 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
         if (nl == 0) nl = launch_scalar_tpc(p, fb, mesh->ndim, ctx->stream);
         if (nl == 0) nl = launch_scalar_fused(p, fb, mesh->ndim, ctx->stream);
         if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
+        if (nl > 0) ctx->last_kernel = noted_kernel();
         if (nl == 0) { // kind not covered by the fused kernel: run the items one after the other for the whole range
             for (int i = 0; i < nitems; i++) {
                 int st2 = gl_integ(ctx, cmesh, items[i].op, b, e, a, items[i].coef, items[i].out);
@@ -1378,7 +1426,8 @@ int scatter_params(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, int op, const
     s.nc = op_is_matrix(op) ? (int)c : 1;
     s.eq = d_eq;
     if (!mesh->homogeneous) {
-        int key = 0, st = 0;
+        BlockKey key;
+        int st = 0;
         const std::vector<uint64_t> *pre = mesh_prefix(mesh, op, a, &key, &st);
         if (st) return fail(ctx, st);
         auto it = bk.d_out_off.find(key);

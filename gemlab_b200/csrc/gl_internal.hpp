@@ -6,6 +6,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/gemlab_cuda.h"
@@ -92,6 +93,19 @@ struct IntegParams {
     int cells_per_cta;
 };
 
+// Tuning / testing knobs are read from the environment ONLY in a library built with -DGL_TUNING (make TUNING=1 ->
+// libgemlab_cuda_tuning.so); the product library ignores them.
+#ifdef GL_TUNING
+const char *tuning_env(const char *name);
+#else
+inline const char *tuning_env(const char *) { return nullptr; }
+#endif
+
+// every launcher records the kernel it enqueued ("family<template parameters>"); gl_api.cu copies it into the ctx after a launch
+// (gl_ctx_last_kernel) so that tests and bench.py can assert WHICH kernel ran, not only that one did
+void note_kernel(const char *fmt, ...);
+const char *noted_kernel();
+
 // launchers (gl_kernels_generic.cu, gl_kernels_hex8.cu, ...); return the number of kernels launched or < 0 on CUDA error
 int launch_generic(const IntegParams &p, int sd, int gd, void *stream);
 size_t generic_smem_bytes(int sd, int gd, int nnode, int ng, int op, int cells_per_cta);
@@ -102,6 +116,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream);
 int launch_bdb(const IntegParams &p, int sd, void *stream);
 int launch_bdb_small2d(const IntegParams &p, int sd, void *stream); // thread-per-cell variant for Tri3 / Qua4 (gl_kernels_small2d.cu)
 int launch_bdb_tile(const IntegParams &p, int sd, void *stream); // register-tiled variant for Hex20 / Tet10 (gl_kernels_tile.cu)
+int launch_bdb_syrk(const IntegParams &p, int sd, void *stream); // FP64 tensor-core (DMMA) symmetric rank-ng update for Hex20 / Tet10 (gl_kernels_syrk.cu)
 
 // fused scalar-dof cases (gl_kernels_scalar.cu): any subset of mat_01_nsn (bit 0), mat_03_btb (bit 1), vec_01_ns (bit 2),
 // vec_03_bv (bit 3) from one geometry pass; uniform coefficients
@@ -130,6 +145,9 @@ int bench_hbm_write(int kind, double *dev, unsigned long long nbytes, int warps_
 
 } // namespace gl
 
+// cache key of a mixed-mesh block layout: (size class, ii0, jj0)
+using BlockKey = std::tuple<int, uint32_t, uint32_t>;
+
 // ---- opaque handles ---------------------------------------------------------------------------------
 struct gl_mesh_bucket {
     int kind = 0, nnode = 0;
@@ -138,7 +156,7 @@ struct gl_mesh_bucket {
     uint32_t *d_cell_ids = nullptr;
     uint32_t *d_conn = nullptr;       // [nnode][ncell]
     uint32_t *d_marker_idx = nullptr; // [ncell] index into mesh->marker_values; nullptr if the mesh has one marker
-    std::map<int, unsigned long long *> d_out_off; // size-class -> absolute block offsets (mixed meshes, lazy)
+    std::map<BlockKey, unsigned long long *> d_out_off; // size-class -> absolute block offsets (mixed meshes, lazy)
 };
 
 struct gl_mesh {
@@ -150,7 +168,7 @@ struct gl_mesh {
     std::vector<gl_mesh_bucket> buckets;
     std::vector<uint8_t> h_kinds;        // per cell (mixed meshes only)
     std::vector<int32_t> marker_values;  // sorted unique markers
-    std::map<int, std::vector<uint64_t>> h_prefix; // size-class -> exclusive prefix of block sizes (mixed meshes, lazy)
+    std::map<BlockKey, std::vector<uint64_t>> h_prefix; // size-class -> exclusive prefix of block sizes (mixed meshes, lazy)
     int device = 0;
 };
 
@@ -161,6 +179,7 @@ struct gl_ctx {
     std::string last_error;
     uint64_t last_error_cell = gl::NO_ERR_CELL;
     uint64_t launches = 0;
+    std::string last_kernel; // kernel family of the most recent integration launch (gl_ctx_last_kernel)
     unsigned long long *d_err_cell = nullptr;
     int *d_coef_pat = nullptr; // result of the modulus-structure probe (device-resident PER_CELL moduli)
     unsigned long long *h_err_cell = nullptr; // pinned
@@ -176,5 +195,8 @@ struct gl_ctx {
     std::vector<std::pair<void *, size_t>> pool;
     size_t pool_bytes = 0;
     void *copy_stream = nullptr;
+    double *h_coef = nullptr; // pinned staging of PER_MARKER tables (keeps those calls asynchronous)
+    size_t h_coef_bytes = 0;
+    void *ev_coef = nullptr;  // completion of the last copy out of h_coef
     void *ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

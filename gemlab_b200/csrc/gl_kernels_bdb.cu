@@ -57,7 +57,10 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     constexpr bool SYM = PAT >= 1;
     constexpr int NS = 2 * SD;
     constexpr int NDOF = NN * SD;
-    constexpr int ND = SYM ? (NN / 2 + 1) : NN;       // circulant distances 0 .. ND-1 (NN odd: (NN+1)/2 = NN/2+1 too)
+    // circulant distances 0 .. ND-1 (NN odd: (NN+1)/2 = NN/2+1 too).  The half is enough for EVERY pattern: P(n,m) = P(m,n)^T, and for a
+    // non-symmetric D the `transposed` store of phase D contracts that transpose itself.  (With ND = NN every off-diagonal block
+    // was written twice, by two lanes whose values round differently: a shared-memory write race.)
+    constexpr int ND = NN / 2 + 1;
     constexpr int NSLOT = (ND + LPN - 1) / LPN;        // blocks per lane
     constexpr int GS = (1 + NN * SD + (AXI ? NN : 0)) | 1; // record per (cell, gauss point): c | B | N/r ; odd stride
     constexpr int XS = (NN * SD) | 1;
@@ -368,8 +371,8 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     if (NN >= 8 && NN <= 9 && SD == 2) cpc = 16; // Qua8: 1.87 -> 1.99 G el/s, Qua9: 1.12 -> 1.22 G el/s
     // (axisymmetric Qua4 also measured faster at 16 than at the default 64 -- 4.65 vs 3.83 G el/s -- not yet adopted: the
     // parity suite has not run on that default)
-    if (const char *e = getenv("GL_BDB_CPC")) cpc = atoi(e); // tuning knob: cells per CTA
-    if (cpc * NN * LPN > 1024) cpc = 1024 / (NN * LPN);
+    if (const char *e = tuning_env("GL_BDB_CPC")) cpc = atoi(e); // tuning knob: cells per CTA
+    if (cpc * NN * LPN > 256) cpc = 256 / (NN * LPN); // __launch_bounds__(256)
     if (cpc < 1) cpc = 1;
     const bool drec = p.coef != nullptr;
     while (cpc > 1 && bdb_smem<NN, SD, LPN>(p.ng, cpc, axi, drec) > 110 * 1024) cpc--;
@@ -395,11 +398,11 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     // many more CTAs than resident slots: CTAs that start and finish at different times keep the SMs out of lockstep, so
     // reads and writes of different SMs interleave instead of arriving in device-wide bursts (see gl_kernels_hex8.cu)
     unsigned long long grid = (unsigned long long)nsm * ctas_per_sm * 16;
-    if (const char *e = getenv("GL_BDB_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
+    if (const char *e = tuning_env("GL_BDB_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
     // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
-    const bool probe = drec && p.coef_pat_dev != nullptr && getenv("GL_BDB_PATTERN") == nullptr;
+    const bool probe = drec && p.coef_pat_dev != nullptr && tuning_env("GL_BDB_PATTERN") == nullptr;
     IntegParams q = p;
     if (!probe) q.coef_pat_dev = nullptr;
     for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
@@ -407,7 +410,9 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(q, cst, cpc, used, bdb_alias<NN, SD, LPN>(p.ng, axi) ? 1 : 0);
     }
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("bdb<nn=%d,sd=%d,axi=%d,pat=%d%s>", NN, SD, axi ? 1 : 0, pat, drec ? ",rec" : "");
+    return 1;
 }
 
 } // namespace
@@ -432,7 +437,7 @@ int launch_bdb_3d(const IntegParams &p, void *stream) {
     const unsigned ndof = (unsigned)p.nnode * (unsigned)sd;
     if (p.nrow != ndof || p.ncol != ndof || p.ii0 != 0 || p.jj0 != 0) return 0;
     if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
-    if (getenv("GL_DISABLE_BDB")) return 0; // testing knob: force the generic kernel
+    if (tuning_env("GL_DISABLE_BDB")) return 0; // testing knob: force the generic kernel
 
     const int ns = 2 * sd;
     BdbConsts cst;
@@ -452,7 +457,7 @@ int launch_bdb_3d(const IntegParams &p, void *stream) {
                 if (!d_nz(2, sd, a, b) && cst.d[a * ns + b] != 0.0) pat = 1;
     }
     if (p.coef != nullptr) pat = p.coef_pat; // structure common to all records (0 when they live on the device only)
-    if (const char *e = getenv("GL_BDB_PATTERN")) {
+    if (const char *e = tuning_env("GL_BDB_PATTERN")) {
         const int cap = atoi(e);
         if (cap < pat) pat = cap < 0 ? 0 : cap;
     }

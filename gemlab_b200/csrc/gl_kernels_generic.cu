@@ -355,7 +355,9 @@ int launch_t(const IntegParams &p, void *stream) {
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
     integ_generic_kernel<SD, GD><<<(unsigned int)grid, NT, smem, (cudaStream_t)stream>>>(p);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("generic<sd=%d,gd=%d>", SD, GD);
+    return 1;
 }
 
 } // namespace

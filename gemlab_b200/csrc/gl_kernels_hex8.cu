@@ -373,7 +373,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     Hex8Consts cst;
     static int flags = -1;
     if (flags < 0) {
-        const char *e = getenv("GL_HEX8_FLAGS"); // tuning knob, see Hex8Consts::flags
+        const char *e = tuning_env("GL_HEX8_FLAGS"); // tuning knob, see Hex8Consts::flags
         flags = e ? atoi(e) : 2;
     }
     cst.flags = flags;
@@ -388,7 +388,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     // gather lookahead in batches (tuning knob GL_HEX8_PF = 1 or 2)
     static int pf = -1;
     if (pf < 0) {
-        const char *e = getenv("GL_HEX8_PF");
+        const char *e = tuning_env("GL_HEX8_PF");
         pf = e ? atoi(e) : 1;
         if (pf < 1 || pf > 2) pf = 1;
     }
@@ -401,13 +401,14 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     }
     if (drec) pat = p.coef_pat; // structure common to all records (0 when the records live on the device only)
     {
-        const char *e = getenv("GL_HEX8_PATTERN"); // tuning/testing knob: cap the specialisation level
+        const char *e = tuning_env("GL_HEX8_PATTERN"); // tuning/testing knob: cap the specialisation level
         if (e && atoi(e) < pat) pat = atoi(e) < 0 ? 0 : atoi(e);
     }
     typedef void (*kern_t)(const IntegParams, const Hex8Consts);
     auto pick = [&](auto pfc, int pat) -> kern_t {
         constexpr int P = decltype(pfc)::value;
-        if (const char *e = getenv("GL_HEX8_DEBUG")) { // timing experiments only (1 no accumulation, 2 no geometry, 3 no staging, 4 no gather, 5 no coordinate loads)
+#ifdef GL_TUNING
+        if (const char *e = tuning_env("GL_HEX8_DEBUG")) { // timing experiments only (1 no accumulation, 2 no geometry, 3 no staging, 4 no gather, 5 no coordinate loads)
             switch (atoi(e)) {
             case 1: return hex8_bdb_kernel<2, P, 1>;
             case 2: return hex8_bdb_kernel<2, P, 2>;
@@ -416,6 +417,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
             default: return hex8_bdb_kernel<2, P, 5>;
             }
         }
+#endif
         if (fd && drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true, true> : hex8_bdb_kernel<0, P, 0, true, true>);
         if (fd) return pat == 2 ? hex8_bdb_kernel<2, P, 0, false, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, false, true> : hex8_bdb_kernel<0, P, 0, false, true>);
         if (drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true> : hex8_bdb_kernel<0, P, 0, true>);
@@ -430,11 +432,11 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     // times keep the SMs out of lockstep, so gather reads and matrix writes of different SMs interleave instead of
     // arriving at the memory system in device-wide bursts (measured: 6.5 ms with 296 persistent CTAs, 5.8 ms with 9472).
     unsigned long long grid = (unsigned long long)nsm * 2 * 32;
-    if (const char *e = getenv("GL_HEX8_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
+    if (const char *e = tuning_env("GL_HEX8_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
-    const bool probe = drec && p.coef_pat_dev != nullptr && getenv("GL_HEX8_PATTERN") == nullptr && getenv("GL_HEX8_DEBUG") == nullptr;
+    const bool probe = drec && p.coef_pat_dev != nullptr && tuning_env("GL_HEX8_PATTERN") == nullptr && tuning_env("GL_HEX8_DEBUG") == nullptr;
     IntegParams q = p;
     if (!probe) q.coef_pat_dev = nullptr;
     for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
@@ -442,7 +444,9 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H8_SMEM) != cudaSuccess) return -1;
         kern<<<(unsigned)grid, H8_THREADS, H8_SMEM, (cudaStream_t)stream>>>(q, cst);
     }
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("hex8_bdb<pat=%d%s%s>", pat, drec ? ",rec" : "", fd ? ",fd" : "");
+    return 1;
 }
 
 } // namespace gl

@@ -203,7 +203,9 @@ int launch_mass_kind(const IntegParams &p, const ScalarFused &f, void *stream) {
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     kern<<<(unsigned)grid, MASS_THREADS, smem, (cudaStream_t)stream>>>(p, f, KP, EP, WS, CS);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("mass_dmma<nn=%d,sd=%d,mask=%d>", NN, SD, f.mask);
+    return 1;
 }
 
 } // namespace
@@ -211,7 +213,7 @@ int launch_mass_kind(const IntegParams &p, const ScalarFused &f, void *stream) {
 // mask bits as in launch_scalar_fused; covers masks made of mat_01_nsn (1) and vec_01_ns (4) only
 int launch_mass_dmma(const IntegParams &p, const ScalarFused &f, int sd, void *stream) {
     if ((f.mask & ~5) != 0 || f.mask == 0) return 0;
-    if (getenv("GL_DISABLE_MASS")) return 0; // testing knob: fall back to gl_kernels_scalar.cu
+    if (tuning_env("GL_DISABLE_MASS")) return 0; // testing knob: fall back to gl_kernels_scalar.cu
     if (sd == 2) {
         switch (p.nnode) {
         case 3: return launch_mass_kind<3, 2>(p, f, stream);

@@ -269,13 +269,15 @@ int launch_kind(const IntegParams &p, const ScalarFused &f, void *stream) {
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
     kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, f, cpc, used);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("scalar_fused<nn=%d,sd=%d,mask=%d>", NN, SD, f.mask);
+    return 1;
 }
 
 } // namespace
 
 int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void *stream) {
-    if (getenv("GL_DISABLE_SCALAR")) return 0; // testing knob: force the generic kernel
+    if (tuning_env("GL_DISABLE_SCALAR")) return 0; // testing knob: force the generic kernel
     if (sd == 2) {
         switch (p.nnode) {
         case 3: return launch_kind<3, 2>(p, f, stream);
@@ -286,6 +288,9 @@ int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void
         default: return 0;
         }
     }
+    // the 3D instantiations carry no radius: the reference multiplies by r = sum N.x0 whenever args.axisymmetric is set, whatever
+    // the space dimension (mat_01_nsn.rs:78-84), so such calls go to the generic kernel, which honours the flag
+    if (p.axisym) return 0;
     switch (p.nnode) {
     case 4: return launch_kind<4, 3>(p, f, stream);
     case 8: return launch_kind<8, 3>(p, f, stream);

@@ -225,7 +225,9 @@ int launch_tpc_kind(const IntegParams &p, const ScalarFused &f, void *stream) {
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     kern<<<(unsigned)grid, TPC_THREADS, smem, (cudaStream_t)stream>>>(p, f);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("scalar_tpc<nn=%d,sd=%d,mask=%d>", NN, SD, f.mask);
+    return 1;
 }
 
 } // namespace
@@ -233,7 +235,7 @@ int launch_tpc_kind(const IntegParams &p, const ScalarFused &f, void *stream) {
 // masks made of mat_03_btb (2) and vec_03_bv (8) only; needs the point-major coordinates
 int launch_scalar_tpc(const IntegParams &p, const ScalarFused &f, int sd, void *stream) {
     if ((f.mask & ~10) != 0 || f.mask == 0 || p.coords_pm == nullptr) return 0;
-    if (getenv("GL_DISABLE_TPC")) return 0; // testing knob: fall back to gl_kernels_scalar.cu
+    if (tuning_env("GL_DISABLE_TPC")) return 0; // testing knob: fall back to gl_kernels_scalar.cu
     if (sd == 2) {
         switch (p.nnode) {
         case 3: return launch_tpc_kind<3, 2>(p, f, stream);

@@ -240,7 +240,7 @@ int launch_small2d_kind(const IntegParams &p, const Small2dConsts &cst, int pat,
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
-    const bool probe = drec && p.coef_pat_dev != nullptr && getenv("GL_BDB_PATTERN") == nullptr;
+    const bool probe = drec && p.coef_pat_dev != nullptr && tuning_env("GL_BDB_PATTERN") == nullptr;
     IntegParams q = p;
     if (!probe) q.coef_pat_dev = nullptr;
     for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
@@ -248,7 +248,9 @@ int launch_small2d_kind(const IntegParams &p, const Small2dConsts &cst, int pat,
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         kern<<<(unsigned)grid, S2_THREADS, smem, (cudaStream_t)stream>>>(q, cst);
     }
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("small2d<nn=%d,axi=%d,pat=%d%s>", NN, p.axisym ? 1 : 0, pat, drec ? ",rec" : "");
+    return 1;
 }
 
 } // namespace
@@ -263,7 +265,7 @@ int launch_bdb_small2d(const IntegParams &p, int sd, void *stream) {
     const unsigned ndof = (unsigned)p.nnode * 2u;
     if (p.nrow != ndof || p.ncol != ndof || p.ii0 != 0 || p.jj0 != 0) return 0;
     if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
-    if (getenv("GL_DISABLE_SMALL2D")) return 0; // testing knob: fall back to gl_kernels_bdb.cu
+    if (tuning_env("GL_DISABLE_SMALL2D")) return 0; // testing knob: fall back to gl_kernels_bdb.cu
 
     Small2dConsts cst;
     const double hs = 0.70710678118654752440084436210484903928;
@@ -282,7 +284,7 @@ int launch_bdb_small2d(const IntegParams &p, int sd, void *stream) {
                 if (!d2_nz(2, a, b) && cst.d[a * 4 + b] != 0.0) pat = 1;
     }
     if (drec) pat = p.coef_pat; // structure common to all records (0 when the records live on the device only)
-    if (const char *e = getenv("GL_BDB_PATTERN")) {
+    if (const char *e = tuning_env("GL_BDB_PATTERN")) {
         const int cap = atoi(e);
         if (cap < pat) pat = cap < 0 ? 0 : cap;
     }

@@ -296,7 +296,7 @@ int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, bool 
     using T = TileDims<NN>;
     static int cpc_env = -1;
     if (cpc_env < 0) {
-        const char *e = getenv("GL_TILE_CPC"); // tuning knob: cells per CTA
+        const char *e = tuning_env("GL_TILE_CPC"); // tuning knob: cells per CTA
         cpc_env = e ? atoi(e) : 0;
     }
     int cpc = cpc_env > 0 ? cpc_env : 256 / T::LPC;
@@ -324,7 +324,7 @@ int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, bool 
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
     // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
-    const bool probe = drec && p.coef_pat_dev != nullptr && getenv("GL_BDB_PATTERN") == nullptr;
+    const bool probe = drec && p.coef_pat_dev != nullptr && tuning_env("GL_BDB_PATTERN") == nullptr;
     IntegParams q = p;
     if (!probe) q.coef_pat_dev = nullptr;
     for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
@@ -332,7 +332,9 @@ int launch_tile_kind(const IntegParams &p, const TileConsts &cst, int pat, bool 
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(q, cst, cpc);
     }
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("tile<nn=%d,pat=%d%s>", NN, pat, drec ? ",rec" : "");
+    return 1;
 }
 
 } // namespace
@@ -347,7 +349,7 @@ int launch_bdb_tile(const IntegParams &p, int sd, void *stream) {
     const unsigned ndof = (unsigned)p.nnode * 3u;
     if (p.nrow != ndof || p.ncol != ndof || p.ii0 != 0 || p.jj0 != 0) return 0;
     if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
-    if (getenv("GL_DISABLE_TILE")) return 0; // testing knob: fall back to gl_kernels_bdb.cu
+    if (tuning_env("GL_DISABLE_TILE")) return 0; // testing knob: fall back to gl_kernels_bdb.cu
 
     TileConsts cst;
     const double hs = 0.70710678118654752440084436210484903928;
@@ -366,7 +368,7 @@ int launch_bdb_tile(const IntegParams &p, int sd, void *stream) {
                 if (!d_nz3(2, a, b) && cst.d[a * 6 + b] != 0.0) pat = 1;
     }
     if (drec) pat = p.coef_pat; // structure common to all records (0 when the records live on the device only)
-    if (const char *e = getenv("GL_BDB_PATTERN")) {
+    if (const char *e = tuning_env("GL_BDB_PATTERN")) {
         const int cap = atoi(e);
         if (cap < pat) pat = cap < 0 ? 0 : cap;
     }

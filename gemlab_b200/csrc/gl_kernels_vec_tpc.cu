@@ -185,7 +185,9 @@ int launch_vt_kind(const IntegParams &p, void *stream) {
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     kern<<<(unsigned)grid, VT_THREADS, smem, (cudaStream_t)stream>>>(p);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("vec_tpc<nn=%d,sd=%d,op=%d>", NN, SD, p.op);
+    return 1;
 }
 
 } // namespace
@@ -198,7 +200,7 @@ int launch_vec_tpc(const IntegParams &p, int sd, void *stream) {
     if (p.nrow != ndof) return 0;
     const unsigned long long cl = p.op == GL_OP_VEC_04_BT ? 2ull * sd : (unsigned long long)sd;
     if (p.coef != nullptr && p.coef_gp_stride != 0 && p.coef_gp_stride != cl) return 0;
-    if (getenv("GL_DISABLE_VEC_TPC")) return 0; // testing knob: fall back to the generic kernel
+    if (tuning_env("GL_DISABLE_VEC_TPC")) return 0; // testing knob: fall back to the generic kernel
     if (sd == 2) {
         switch (p.nnode) {
         case 3: return launch_vt_kind<3, 2>(p, stream);

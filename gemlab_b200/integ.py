@@ -169,6 +169,10 @@ class Context:
     def launch_count(self):
         return int(lib().gl_ctx_launch_count(self._h))
 
+    def last_kernel(self):
+        """Kernel family (with its template parameters) of the most recent integration launch (gl_ctx_last_kernel)."""
+        return lib().gl_ctx_last_kernel(self._h).decode("ascii")
+
     def upload(self, mesh):
         """Mesh -> device SoA (gl_mesh_upload); replaces the per-cell Mesh::set_pad gather (src/mesh/mesh.rs:448-456)."""
         if not isinstance(mesh, Mesh):

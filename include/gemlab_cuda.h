@@ -149,6 +149,11 @@ GL_API uint64_t gl_last_error_cell(const gl_ctx *ctx);
 GL_API const char *gl_status_string(int status);
 /* number of kernels launched by this ctx so far (bench.py's gpu_launches) */
 GL_API uint64_t gl_ctx_launch_count(const gl_ctx *ctx);
+/* which kernel the most recent integration launch of this ctx used: "family<template parameters>", e.g. "hex8_bdb<pat=2>",
+ * "syrk_dmma<nn=20,pat=2>", "mass_dmma<nn=10,sd=3,mask=5>", "generic<sd=3,gd=3>".  The dispatch tries the tuned kernels in
+ * turn and ends at the generic one; tests and bench.py assert the family so that a tuned kernel that starts declining a
+ * configuration cannot go unnoticed.  (No reference counterpart.) */
+GL_API const char *gl_ctx_last_kernel(const gl_ctx *ctx);
 
 /* ---- GeoKind / Gauss queries (host only; replace GeoKind::nnode, ndim, class and Gauss::new, new_sized, npoint, coords) ---- */
 GL_API int gl_kind_nnode(int kind);

@@ -1,0 +1,184 @@
+"""Which kernel ran?  The dispatch (gl_api.cu: launch_range) tries the tuned kernels in turn and ends at the generic one, so
+a tuned kernel that starts declining a configuration would leave every parity test green at a fraction of the speed.
+These tests pin the kernel FAMILY per configuration through gl_ctx_last_kernel, and exercise the FP64 tensor-core
+stiffness kernel of the quadratic solids (gl_kernels_syrk.cu) on everything its launcher accepts."""
+import numpy as np
+import pytest
+
+import gemlab_b200 as g
+from gemlab_b200 import Block, Coef, CommonArgs, GeoKind, Mesh, integ
+from oracle import pyoracle as po
+
+from test_gpu_parity import make_mesh, oracle_integ, random_coef, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Context(0)
+    yield c
+    c.close()
+
+
+def iso(ndim):
+    return g.mandel_matrix(g.lin_elasticity(480.0, 1.0 / 3.0, ndim == 2))
+
+
+# (kind, op, CommonArgs kwargs, expected family prefix)
+FAMILIES = [
+    ("hex8", "mat_10_bdb", {}, "hex8_bdb<pat=2"),
+    ("hex8", "mat_10_bdb", {"ngauss": 27}, "bdb<nn=8,sd=3"),
+    ("hex20", "mat_10_bdb", {}, "syrk_dmma<nn=20,pat=2>"),
+    ("hex20", "mat_10_bdb", {"ngauss": 8}, "syrk_dmma<nn=20,pat=2>"),
+    ("hex20", "mat_10_bdb", {"ngauss": 64}, "bdb<nn=20,sd=3"),
+    ("hex20", "mat_10_bdb", {"clear": False}, "syrk_dmma<nn=20,pat=2,gen>"),
+    ("hex20", "mat_10_bdb", {"ii0": 1, "jj0": 2, "nrow": 64, "ncol": 63}, "syrk_dmma<nn=20,pat=2,gen>"),
+    ("tet10", "mat_10_bdb", {}, "bdb<nn=10,sd=3"),
+    ("tet4", "mat_10_bdb", {}, "bdb<nn=4,sd=3"),
+    ("qua4", "mat_10_bdb", {}, "small2d<nn=4,axi=0"),
+    ("tri3", "mat_10_bdb", {}, "small2d<nn=3,axi=0"),
+    ("qua8", "mat_10_bdb", {}, "bdb<nn=8,sd=2,axi=0"),
+    ("qua8", "mat_10_bdb", {"axisymmetric": True}, "bdb<nn=8,sd=2,axi=1"),
+    ("qua9", "mat_10_bdb", {}, "bdb<nn=9,sd=2"),
+    ("tri6", "mat_10_bdb", {}, "bdb<nn=6,sd=2"),
+    ("tet10", "mat_01_nsn", {}, "mass_dmma<nn=10,sd=3"),
+    ("tet10", "vec_01_ns", {}, "mass_dmma<nn=10,sd=3"),
+    ("hex8", "mat_01_nsn", {}, "mass_dmma<nn=8,sd=3"),
+    ("qua8", "mat_03_btb", {}, "scalar_tpc<nn=8,sd=2"),
+    ("tri3", "vec_03_bv", {"axisymmetric": True}, "scalar_tpc<nn=3,sd=2"),
+    ("hex8", "vec_04_bt", {}, "vec_tpc<nn=8,sd=3"),
+    ("qua4", "vec_02_nv", {}, "vec_tpc<nn=4,sd=2"),
+    ("hex8", "mat_08_ntn", {}, "generic<sd=3,gd=3>"),
+]
+
+
+@pytest.mark.parametrize("kind,op,kw,family", FAMILIES, ids=[f"{k}-{o}-{'-'.join(map(str, a)) or 'default'}" for k, o, a, _ in FAMILIES])
+def test_kernel_family(ctx, kind, op, kw, family):
+    mesh = make_mesh(kind, n=3)
+    dmesh = ctx.upload(mesh)
+    rng = np.random.default_rng(3)
+    coef = iso(mesh.ndim) if op == "mat_10_bdb" else random_coef(op, mesh.ndim, 1, rng)[0]
+    args = CommonArgs(**kw)
+    total = integ.out_total(dmesh, op, None, args)
+    out = np.zeros(total)
+    getattr(integ, op)(ctx, dmesh, None, args, Coef.uniform(coef), out=out)
+    assert ctx.last_kernel().startswith(family), f"{kind} {op} {kw}: ran {ctx.last_kernel()!r}, expected {family!r}"
+
+
+def bulged_hex20(n=(3, 2, 4), bulge=0.05, seed=5):
+    """SURVEY.md 8(d) config 3 variant: Hex20 Block with the mid-edge nodes pushed off their edges by `bulge` x cell size
+    (curved edges: J varies inside every cell) and the corner nodes jittered."""
+    m = Block.new_cube(1.0).set_ndiv(list(n)).subdivide(GeoKind.Hex20)
+    m = g.jitter_interior_points(m, 0.03 / max(n), seed)
+    rng = np.random.default_rng(seed)
+    conn = m.conn_matrix()
+    mid = np.unique(conn[:, 8:])
+    h = 1.0 / max(n)
+    m.coords[mid.astype(np.int64)] += bulge * h * rng.uniform(-1.0, 1.0, (mid.size, 3))
+    return m
+
+
+@pytest.mark.parametrize("rule", [6, 8, 14, 27])
+@pytest.mark.parametrize("structure", ["isotropic", "symmetric", "general"])
+def test_hex20_tensor_core_stiffness(ctx, rule, structure):
+    """mat_10_bdb on bulged Hex20 cells through the DMMA kernel vs the oracle (src/integ/mat_10_bdb.rs:179-208), every rule it
+    accepts, the three modulus patterns; cell counts that do not fill the 7 cell slots of a CTA."""
+    mesh = bulged_hex20()
+    rng = np.random.default_rng(31)
+    dd = iso(3) if structure == "isotropic" else random_coef("mat_10_bdb", 3, 1, rng, spd=(structure == "symmetric"))[0]
+    dmesh = ctx.upload(mesh)
+    ref = oracle_integ("mat_10_bdb", mesh, dd, ngauss=rule)
+    for b, e in [(0, mesh.ncell), (0, 1), (3, 9), (5, 19), (1, 15)]:
+        got = integ.mat_10_bdb(ctx, dmesh, (b, e), CommonArgs(ngauss=rule), Coef.uniform(dd))
+        assert ctx.last_kernel() == f"syrk_dmma<nn=20,pat={ {'isotropic': 2, 'symmetric': 1, 'general': 0}[structure] }>"
+        assert rel_err(got, ref[b * 3600:e * 3600], np.arange(e - b + 1) * 3600) <= TOL, f"rule {rule} range {b}:{e}"
+
+
+def test_hex20_general_blocks_and_accumulation(ctx):
+    """nrow / ncol / ii0 / jj0 and clear = false in the store epilogue of the tensor-core kernel (CommonArgs,
+    src/integ/common_args.rs:5-43; kk.fill(0.0) clears the WHOLE block, mat_10_bdb.rs:141-143)."""
+    mesh = bulged_hex20((2, 2, 3))
+    dmesh = ctx.upload(mesh)
+    dd = iso(3)
+    base = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.uniform(dd)).reshape(mesh.ncell, 60, 60)
+    out = np.full(base.size, 12.5)
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(clear=False), Coef.uniform(dd), out=out)
+    assert ctx.last_kernel() == "syrk_dmma<nn=20,pat=2,gen>"
+    np.testing.assert_allclose(out.reshape(base.shape), base + 12.5, rtol=1e-13, atol=0)
+    args = CommonArgs(ii0=3, jj0=1, nrow=65, ncol=62)
+    out = np.full(mesh.ncell * 65 * 62, 99.0)
+    integ.mat_10_bdb(ctx, dmesh, None, args, Coef.uniform(dd), out=out)
+    assert ctx.last_kernel() == "syrk_dmma<nn=20,pat=2,gen>"
+    blk = out.reshape(mesh.ncell, 62, 65)  # [cell][col][row]
+    np.testing.assert_array_equal(blk[:, 1:61, 3:63], base)  # same arithmetic, another store path
+    outside = blk.copy()
+    outside[:, 1:61, 3:63] = 0.0
+    assert np.count_nonzero(outside) == 0
+    # accumulate into an offset window: everything outside stays as it was
+    out2 = np.full(out.size, 2.0)
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(ii0=3, jj0=1, nrow=65, ncol=62, clear=False), Coef.uniform(dd), out=out2)
+    blk2 = out2.reshape(mesh.ncell, 62, 65)
+    np.testing.assert_allclose(blk2[:, 1:61, 3:63], base + 2.0, rtol=1e-13, atol=0)
+    rest = blk2.copy()
+    rest[:, 1:61, 3:63] = 2.0
+    assert np.all(rest == 2.0)
+
+
+def test_hex20_moduli_per_marker_and_per_cell(ctx):
+    import torch
+
+    mesh = bulged_hex20((3, 3, 2))
+    rng = np.random.default_rng(41)
+    mesh.markers[:] = rng.integers(1, 4, mesh.ncell)
+    dmesh = ctx.upload(mesh)
+    for structure in ("isotropic", "symmetric", "general"):
+        if structure == "isotropic":
+            recs = np.stack([g.mandel_matrix(g.lin_elasticity(100.0 * (k + 1), 0.1 * (k + 1), False)) for k in range(3)])
+        else:
+            recs = random_coef("mat_10_bdb", 3, 3, rng, spd=(structure == "symmetric"))
+        per_cell = recs[mesh.markers - 1]
+        ref = oracle_integ("mat_10_bdb", mesh, per_cell, cell_stride=36)
+        sizes = np.arange(mesh.ncell + 1) * 3600
+        got = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.per_marker([1, 2, 3], recs))
+        assert ctx.last_kernel().startswith("syrk_dmma<nn=20") and ",rec" in ctx.last_kernel()
+        assert rel_err(got, ref, sizes) <= TOL, structure
+        out = torch.empty(mesh.ncell * 3600, dtype=torch.float64, device="cuda")
+        integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.per_cell(torch.from_numpy(np.ascontiguousarray(per_cell)).cuda()), out=out)
+        ctx.sync()
+        assert rel_err(out.cpu().numpy(), ref, sizes) <= TOL, structure + " (device records)"
+
+
+def test_mixed_3d_mesh_with_hex20(ctx):
+    """A 3D mesh of Hex8 and Hex20 cells: the tensor-core kernel writes its cells at their offsets in the mixed layout."""
+    h20 = bulged_hex20((2, 2, 2))
+    c20 = h20.conn_matrix()
+    cells = []
+    for e in range(h20.ncell):
+        cells.append((GeoKind.Hex20, c20[e]) if e % 3 != 1 else (GeoKind.Hex8, c20[e, :8]))
+    mesh = Mesh.from_cells(3, h20.coords, cells)
+    dmesh = ctx.upload(mesh)
+    dd = iso(3)
+    off = integ.out_offsets(dmesh, "mat_10_bdb", None, CommonArgs())
+    got = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.uniform(dd))
+    ref = oracle_integ("mat_10_bdb", mesh, dd)
+    assert rel_err(got, ref, off) <= TOL
+    sub = integ.mat_10_bdb(ctx, dmesh, (2, 7), CommonArgs(), Coef.uniform(dd))
+    np.testing.assert_array_equal(sub, got[int(off[2]):int(off[7])])
+
+
+def test_nan_coordinates_do_not_leak_into_other_cells(ctx):
+    """A cell slot reuses one shared-memory region for the gradients, the geometric tensors and the staged block of
+    successive cells: a non-finite cell must not contaminate the cells that follow it in the slot."""
+    mesh = bulged_hex20((2, 2, 4))
+    bad = 3
+    pts = mesh.conn_matrix()[bad]
+    own = [int(q) for q in pts if np.count_nonzero(mesh.conn_matrix() == q) == 1]
+    mesh.coords[own[0], 0] = np.nan
+    dmesh = ctx.upload(mesh)
+    dd = iso(3)
+    got = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.uniform(dd)).reshape(mesh.ncell, -1)
+    assert np.all(np.isnan(got[bad]).any())
+    ok = [e for e in range(mesh.ncell) if e != bad]
+    assert np.all(np.isfinite(got[ok]))
