@@ -42,7 +42,8 @@ pub struct gl_args {
     pub ngauss: i32,
     pub axisymmetric: i32,
     pub clear: i32,
-    pub reserved: i32,
+    /// 1 = element matrices leave as packed upper triangles (batched boundary only)
+    pub packed: i32,
     pub alpha: c_double,
     pub ii0: u32,
     pub jj0: u32,
@@ -86,6 +87,7 @@ extern "C" {
     pub fn gl_last_error_cell(ctx: *const gl_ctx) -> u64;
     pub fn gl_status_string(status: c_int) -> *const c_char;
     pub fn gl_ctx_launch_count(ctx: *const gl_ctx) -> u64;
+    pub fn gl_ctx_last_kernel(ctx: *const gl_ctx) -> *const c_char;
 
     pub fn gl_kind_nnode(kind: c_int) -> c_int;
     pub fn gl_kind_geo_ndim(kind: c_int) -> c_int;

@@ -47,19 +47,21 @@ pub struct BatchArgs {
     /// per-element block dims; 0 = tight
     pub nrow: usize,
     pub ncol: usize,
+    /// element matrices leave as packed upper triangles (n(n+1)/2 doubles; K(i,j), i <= j, at j(j+1)/2 + i)
+    pub packed: bool,
 }
 
 impl BatchArgs {
     /// Same defaults as `CommonArgs::new`: clear = true, axisymmetric = false, alpha = 1, ii0 = jj0 = 0
     pub fn new() -> Self {
-        BatchArgs { ngauss: None, clear: true, axisymmetric: false, alpha: 1.0, ii0: 0, jj0: 0, nrow: 0, ncol: 0 }
+        BatchArgs { ngauss: None, clear: true, axisymmetric: false, alpha: 1.0, ii0: 0, jj0: 0, nrow: 0, ncol: 0, packed: false }
     }
     fn to_c(&self) -> ffi::gl_args {
         ffi::gl_args {
             ngauss: self.ngauss.unwrap_or(0) as i32,
             axisymmetric: self.axisymmetric as i32,
             clear: self.clear as i32,
-            reserved: 0,
+            packed: self.packed as i32,
             alpha: self.alpha,
             ii0: self.ii0 as u32,
             jj0: self.jj0 as u32,

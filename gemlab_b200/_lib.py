@@ -18,7 +18,7 @@ class GlArgs(C.Structure):
     """struct gl_args (mirrors integ::CommonArgs, src/integ/common_args.rs:5-43)."""
 
     _fields_ = [
-        ("ngauss", C.c_int32), ("axisymmetric", C.c_int32), ("clear", C.c_int32), ("reserved", C.c_int32),
+        ("ngauss", C.c_int32), ("axisymmetric", C.c_int32), ("clear", C.c_int32), ("packed", C.c_int32),
         ("alpha", C.c_double), ("ii0", C.c_uint32), ("jj0", C.c_uint32), ("nrow", C.c_uint32), ("ncol", C.c_uint32),
         ("ksi", C.c_double * 3),
     ]

@@ -334,6 +334,7 @@ void gl_ctx_destroy(gl_ctx *ctx) {
     for (int i = 0; i < 2; i++)
         if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
     if (ctx->d_coef) cudaFree(ctx->d_coef);
+    if (ctx->d_full) cudaFree(ctx->d_full);
     for (auto &pb : ctx->pool) cudaFree(pb.first);
     if (ctx->copy_stream) cudaStreamDestroy((cudaStream_t)ctx->copy_stream);
     for (int i = 0; i < 4; i++)
@@ -690,6 +691,11 @@ static int range_layout(const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, co
     if (!mesh || !a || op_size_class(op) < 0) return GL_ERR_INVALID_ARG;
     if (b > e || e > mesh->ncell) return GL_ERR_CELL_RANGE;
     const bool explicit_block = a->nrow != 0 || (op_is_matrix(op) && a->ncol != 0);
+    const bool packed = a->packed && op_is_matrix(op); // vectors have no triangle: the flag is ignored for them
+    if (packed) {
+        // upper triangles only: square tight blocks of one kind, overwritten
+        if (explicit_block || a->ii0 || a->jj0 || !a->clear || !mesh->homogeneous) return GL_ERR_INVALID_ARG;
+    }
     if (mesh->homogeneous || explicit_block) {
         // all blocks equal (for explicit dims every kind in range must fit; checked at launch)
         uint64_t blk = 0;
@@ -697,7 +703,7 @@ static int range_layout(const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, co
             BlockDims bd;
             int st = block_dims(op, mesh->buckets[0].kind, mesh->ndim, a, bd);
             if (st) return st;
-            blk = bd.block();
+            blk = packed ? (uint64_t)bd.size_r * (bd.size_r + 1) / 2 : bd.block();
         }
         if (total) *total = blk * (e - b);
         if (off)
@@ -1024,6 +1030,89 @@ static int resolve_coef(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
     }
 }
 
+} // extern "C"
+
+// upper triangles of square column-major blocks, packed column-major: dst[cell * tri + j (j + 1) / 2 + i] = src[cell * n * n + i + j n],
+// i <= j.  One warp per (cell, column): coalesced reads of the column head, contiguous writes.
+__global__ void pack_upper_kernel(const double *__restrict__ src, double *__restrict__ dst, unsigned long long ncell, unsigned int n) {
+    const unsigned long long tri = (unsigned long long)n * (n + 1) / 2;
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarp = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long t = warp; t < ncell * n; t += nwarp) {
+        const unsigned long long cell = t / n;
+        const unsigned int j = (unsigned int)(t - cell * n);
+        const double *s = src + cell * n * n + (unsigned long long)j * n;
+        double *d = dst + cell * tri + (unsigned long long)j * (j + 1) / 2;
+        for (unsigned int i = lane; i <= j; i += 32) d[i] = s[i];
+    }
+}
+
+extern "C" {
+
+// gl_args.packed: the kernels write full blocks into a bounded scratch slab, a pack pass keeps the upper triangles
+static int integ_packed(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a, const CoefResolved &cr,
+                        gl_out *out) {
+    BlockDims bd;
+    gl_args full = *a;
+    full.packed = 0;
+    int st = block_dims(op, mesh->buckets[0].kind, mesh->ndim, &full, bd);
+    if (st) return fail(ctx, st);
+    const uint64_t n = bd.size_r, sq = n * n, tri = n * (n + 1) / 2;
+    const uint64_t per_chunk = std::max<uint64_t>(((uint64_t)192 << 20) / (sq * sizeof(double)), 1);
+    const uint64_t chunk_cells = std::min<uint64_t>(per_chunk, e - b);
+    st = ensure_buffer(ctx, &ctx->d_full, &ctx->full_bytes, chunk_cells * sq * sizeof(double));
+    if (st) return st;
+    cudaStream_t s_compute = (cudaStream_t)ctx->stream, s_copy = (cudaStream_t)ctx->copy_stream;
+    auto pack = [&](uint64_t ncell, double *dst) {
+        const unsigned long long warps = ncell * n;
+        const unsigned grid = (unsigned)std::min<unsigned long long>((warps * 32 + 255) / 256, 148ull * 64);
+        pack_upper_kernel<<<grid, 256, 0, s_compute>>>(ctx->d_full, dst, ncell, (unsigned)n);
+        ctx->launches++;
+    };
+    if (out->location == GL_DEVICE) {
+        for (uint64_t cb = b; cb < e; cb += per_chunk) {
+            const uint64_t ce = std::min(e, cb + per_chunk);
+            st = launch_range(ctx, mesh, op, cb, ce, &full, cr, b, ctx->d_full);
+            if (st) return st;
+            pack(ce - cb, out->ptr + (cb - b) * tri);
+        }
+        if (cudaGetLastError() != cudaSuccess) return cuda_fail(ctx, cudaGetLastError(), "pack kernel");
+        return GL_OK;
+    }
+    const size_t stage = chunk_cells * tri * sizeof(double);
+    if (ctx->stage_bytes < stage) {
+        for (int i = 0; i < 2; i++) {
+            if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+            ctx->d_stage[i] = nullptr;
+        }
+        ctx->stage_bytes = 0;
+        for (int i = 0; i < 2; i++) CUDA_TRY(ctx, cudaMalloc(&ctx->d_stage[i], stage));
+        ctx->stage_bytes = stage;
+    }
+    cudaEvent_t ev_kernel[2] = {(cudaEvent_t)ctx->ev[0], (cudaEvent_t)ctx->ev[1]};
+    cudaEvent_t ev_copy[2] = {(cudaEvent_t)ctx->ev[2], (cudaEvent_t)ctx->ev[3]};
+    size_t k = 0;
+    for (uint64_t cb = b; cb < e; cb += per_chunk, k++) {
+        const uint64_t ce = std::min(e, cb + per_chunk);
+        const int buf = (int)(k & 1);
+        if (k >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(s_compute, ev_copy[buf], 0));
+        st = launch_range(ctx, mesh, op, cb, ce, &full, cr, b, ctx->d_full);
+        if (st) {
+            cudaStreamSynchronize(s_copy);
+            cudaStreamSynchronize(s_compute);
+            return st;
+        }
+        pack(ce - cb, ctx->d_stage[buf]);
+        CUDA_TRY(ctx, cudaEventRecord(ev_kernel[buf], s_compute));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(s_copy, ev_kernel[buf], 0));
+        CUDA_TRY(ctx, cudaMemcpyAsync(out->ptr + (cb - b) * tri, ctx->d_stage[buf], (ce - cb) * tri * sizeof(double), cudaMemcpyDeviceToHost, s_copy));
+        CUDA_TRY(ctx, cudaEventRecord(ev_copy[buf], s_copy));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(s_copy));
+    return gl_ctx_sync(ctx);
+}
+
 int gl_integ(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *coef,
              gl_out *out) {
     if (!ctx) return GL_ERR_INVALID_ARG;
@@ -1042,6 +1131,7 @@ int gl_integ(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, 
     if (st) return st;
     if (b == e) return GL_OK;
 
+    if (a->packed && op_is_matrix(op)) return integ_packed(ctx, mesh, op, b, e, a, cr, out);
     if (out->location == GL_DEVICE) return launch_range(ctx, mesh, op, b, e, a, cr, b, out->ptr);
 
     // ---- host output: pipeline chunks through two device staging buffers --------------------------------
@@ -1107,6 +1197,13 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
     gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
     if (!mesh || !a || !items || nitems <= 0) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
     if (b > e || e > mesh->ncell) return fail(ctx, GL_ERR_CELL_RANGE);
+    if (a->packed) { // packed matrices go through the pack pass of gl_integ
+        for (int i = 0; i < nitems; i++) {
+            int st = gl_integ(ctx, cmesh, items[i].op, b, e, a, items[i].coef, items[i].out);
+            if (st) return st;
+        }
+        return GL_OK;
+    }
     // stiffness + internal-force vector (the two sides of a Newton step) from ONE geometry pass: Hex8 meshes, sigma per Gauss
     // point; any other combination of these two cases runs them one after the other
     if (nitems == 2 && e > b) {
@@ -1471,7 +1568,7 @@ int assemble_checks(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, 
     if (op_size_class(op) < 0 || op == GL_OP_JACOBIAN) return fail(ctx, GL_ERR_INVALID_ARG, "op cannot be assembled");
     if (mesh->device != ctx->device) return fail(ctx, GL_ERR_INVALID_ARG, "mesh belongs to another device");
     if (b > e || e > mesh->ncell) return fail(ctx, GL_ERR_CELL_RANGE);
-    if (a->ii0 || a->jj0 || a->nrow || a->ncol) return fail(ctx, GL_ERR_INVALID_ARG, "assembly needs tight element blocks (ii0 = jj0 = 0)");
+    if (a->ii0 || a->jj0 || a->nrow || a->ncol || a->packed) return fail(ctx, GL_ERR_INVALID_ARG, "assembly needs tight, full element blocks (ii0 = jj0 = 0, packed = 0)");
     return GL_OK;
 }
 

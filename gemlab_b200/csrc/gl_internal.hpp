@@ -189,6 +189,8 @@ struct gl_ctx {
     size_t stage_bytes = 0;
     double *d_coef = nullptr;
     size_t coef_bytes = 0;
+    double *d_full = nullptr; // scratch slab of full element blocks (gl_args.packed)
+    size_t full_bytes = 0;
     double *d_rule_tmp = nullptr; // for GL_OP_JACOBIAN tables
     // freed mesh buffers kept for reuse: an upload -> integrate -> free cycle (one per step of a host-driven loop) then
     // performs no cudaMalloc / cudaFree, whose implicit device synchronisations dominate small uploads

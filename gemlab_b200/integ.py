@@ -32,7 +32,7 @@ COEF_UNIFORM, COEF_PER_MARKER, COEF_PER_CELL, COEF_PER_GAUSS = 0, 1, 2, 3
 class CommonArgs:
     """gemlab::integ::CommonArgs (src/integ/common_args.rs:5-43) without pad/gauss (implied by the mesh and `ngauss`)."""
 
-    def __init__(self, ngauss=None, clear=True, axisymmetric=False, alpha=1.0, ii0=0, jj0=0, nrow=0, ncol=0):
+    def __init__(self, ngauss=None, clear=True, axisymmetric=False, alpha=1.0, ii0=0, jj0=0, nrow=0, ncol=0, packed=False):
         self.ngauss = ngauss          # None = Gauss::new(kind), else Gauss::new_sized(kind.class(), ngauss)
         self.clear = clear
         self.axisymmetric = axisymmetric
@@ -42,12 +42,14 @@ class CommonArgs:
         self.nrow = nrow              # 0 = tight element blocks
         self.ncol = ncol
         self.ksi = (0.0, 0.0, 0.0)    # integ.jacobian only
+        self.packed = packed          # batched boundary only: matrices leave as packed upper triangles (gl_args.packed)
 
     def _c(self):
         a = GlArgs()
         a.ngauss = 0 if self.ngauss is None else int(self.ngauss)
         a.axisymmetric = int(bool(self.axisymmetric))
         a.clear = int(bool(self.clear))
+        a.packed = int(bool(self.packed))
         a.alpha = float(self.alpha)
         a.ii0, a.jj0, a.nrow, a.ncol = int(self.ii0), int(self.jj0), int(self.nrow), int(self.ncol)
         for i in range(3):
@@ -410,6 +412,19 @@ def jacobian(ctx, dmesh, cell_range, ksi, out=None):
     args = CommonArgs()
     args.ksi = tuple(ksi)
     return _integ("jacobian", ctx, dmesh, cell_range, args, None, out)
+
+
+def unpack_symmetric(packed, n):
+    """Packed upper triangles (gl_args.packed: K(i,j), i <= j, at j(j+1)/2 + i) -> full symmetric blocks [ncell][n*n] (column-major)."""
+    tri = n * (n + 1) // 2
+    packed = np.asarray(packed).reshape(-1, tri)
+    jj, ii = np.triu_indices(n)  # row-major upper of the transposed = column-major upper: pairs (j >= i) sorted by j then i
+    order = np.lexsort((jj, ii))  # sort by column (ii here is the larger index) then row
+    cols, rows = ii[order], jj[order]
+    full = np.empty((packed.shape[0], n, n))
+    full[:, cols, rows] = packed   # [cell][col][row]: column-major blocks
+    full[:, rows, cols] = packed
+    return full.reshape(packed.shape[0], n * n)
 
 
 def partition(ncell, world_size, rank):

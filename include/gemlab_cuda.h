@@ -98,7 +98,11 @@ typedef struct gl_args {
     int32_t ngauss;       /* 0 = Gauss::new(kind) default rule; else Gauss::new_sized(kind.class(), ngauss) (gauss.rs:87,189) */
     int32_t axisymmetric; /* CommonArgs.axisymmetric: integrate over 1 radian, r = sum N.x0 */
     int32_t clear;        /* CommonArgs.clear: 1 = zero-fill the element block first, 0 = accumulate into `out` */
-    int32_t reserved;
+    int32_t packed;       /* batched boundary only (no reference counterpart): 1 = every element MATRIX leaves as its upper triangle,
+                             packed column-major -- K(i,j), i <= j, at j(j+1)/2 + i; n(n+1)/2 doubles instead of n^2 -- for callers
+                             that assemble into symmetric storage (K is symmetric whenever D / T is major-symmetric).  Halves the
+                             device->host bytes of the host-output path.  Needs tight blocks (ii0 = jj0 = nrow = ncol = 0),
+                             clear = 1 and a single-kind mesh; the lower triangle is NOT checked against the upper one. */
     double alpha;         /* CommonArgs.alpha (e.g. plane-stress thickness) */
     uint32_t ii0, jj0;    /* CommonArgs.ii0 / jj0: offsets inside each element's block */
     uint32_t nrow, ncol;  /* per-element block dims; 0 = tight (nrow = ii0 + size, ncol = jj0 + size; vectors use nrow only) */

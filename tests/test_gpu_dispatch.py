@@ -182,3 +182,36 @@ def test_nan_coordinates_do_not_leak_into_other_cells(ctx):
     assert np.all(np.isnan(got[bad]).any())
     ok = [e for e in range(mesh.ncell) if e != bad]
     assert np.all(np.isfinite(got[ok]))
+
+
+@pytest.mark.parametrize("kind,op", [("hex8", "mat_10_bdb"), ("hex20", "mat_10_bdb"), ("qua4", "mat_10_bdb"), ("tet10", "mat_01_nsn"),
+                                     ("qua8", "mat_03_btb")])
+def test_packed_upper_triangles(ctx, kind, op):
+    """gl_args.packed: symmetric element matrices leave as packed upper triangles (n(n+1)/2 doubles per cell) -- same values, bit
+    for bit, as the full blocks; host (chunked, pipelined) and device outputs."""
+    import torch
+
+    mesh = make_mesh(kind, n=4)
+    dmesh = ctx.upload(mesh)
+    rng = np.random.default_rng(9)
+    coef = iso(mesh.ndim) if op == "mat_10_bdb" else random_coef(op, mesh.ndim, 1, rng)[0]
+    n = int(round(np.sqrt(integ.op_out_size(op, GeoKind.from_str(kind), mesh.ndim))))
+    tri = n * (n + 1) // 2
+    full = getattr(integ, op)(ctx, dmesh, None, CommonArgs(), Coef.uniform(coef)).reshape(mesh.ncell, n, n)  # [cell][col][row]
+    args = CommonArgs(packed=True)
+    assert integ.out_total(dmesh, op, None, args) == mesh.ncell * tri
+    np.testing.assert_array_equal(integ.out_offsets(dmesh, op, (1, 4), args), np.arange(4) * tri)
+    host = getattr(integ, op)(ctx, dmesh, None, args, Coef.uniform(coef))
+    dev = torch.full((mesh.ncell * tri,), -1.0, dtype=torch.float64, device="cuda")
+    getattr(integ, op)(ctx, dmesh, (2, mesh.ncell - 1), args, Coef.uniform(coef), out=dev)
+    ctx.sync()
+    jj, ii = np.nonzero(np.triu(np.ones((n, n))).T)  # column by column: (col jj, row ii <= jj)
+    expect = full[:, jj, ii]
+    np.testing.assert_array_equal(host.reshape(mesh.ncell, tri), expect)
+    got = dev.cpu().numpy()
+    np.testing.assert_array_equal(got[:(mesh.ncell - 3) * tri].reshape(-1, tri), expect[2:mesh.ncell - 1])
+    assert np.all(got[(mesh.ncell - 3) * tri:] == -1.0)
+    sym = integ.unpack_symmetric(host, n).reshape(mesh.ncell, n, n)
+    np.testing.assert_allclose(sym, full, rtol=0, atol=1e-12 * np.max(np.abs(full)))
+    with pytest.raises(g.GemlabError):
+        getattr(integ, op)(ctx, dmesh, None, CommonArgs(packed=True, clear=False), Coef.uniform(coef), out=np.zeros(mesh.ncell * tri))
