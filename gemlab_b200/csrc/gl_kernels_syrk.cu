@@ -49,6 +49,7 @@ __host__ __device__ constexpr bool d_nz3(int pat, int a, int b) { return pat < 2
 
 struct SyrkConsts {
     double d[36]; // d'[a][b] = f_a f_b d[a][b] (row-major 6 x 6), f = 1 for normal rows, 1/sqrt(2) for shear rows
+    int stagger_ns; // start-up delay per cell slot (see the kernel)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -59,22 +60,26 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 
 constexpr int SYRK_THREADS = 448;
 
+#include "syrk_pairs.inc"
+
 template <int NN>
 struct SyrkDims {
     static constexpr int NDOF = NN * 3;
     static constexpr int NT8 = (NDOF + 7) / 8;            // 8-dof tiles per side
-    static constexpr int VS = NT8 * 8 + 4;                // V row stride: = 4 (mod 16) -> the fragment loads of a half-warp (4 rows x 4 columns) hit 16 distinct bank pairs
     static constexpr int WPC = NN == 20 ? 2 : 1;          // warps per cell
     static constexpr int LANES = 32 * WPC;                // lanes per cell slot
     static constexpr int SLOTS = SYRK_THREADS / LANES;    // cell slots per CTA
     static constexpr int MAXNG = LANES / 2;               // two lanes per Gauss point
+    static constexpr int PS = MAXNG + 4;                  // V is stored DOF-MAJOR, Vt[c][p] at c PS + p; PS = 4 (mod 16): the fragment loads of a
+                                                          // half-warp (4 columns x 4 Gauss points) hit 16 distinct bank pairs, and the 16 Gauss
+                                                          // points of a half-warp store one dof of theirs to 16 consecutive doubles
     static constexpr int LS = NDOF | 1;                   // L row stride (odd: the Gauss points of a warp read distinct banks)
-    static constexpr int RS = NDOF * NDOF;                // region per slot: V (4.ceil(ng/4) x VS) / P / staged K
+    static constexpr int RS = NDOF * NDOF;                // region per slot: Vt (8 NT8 x PS) / P / staged K
     static constexpr int NPAIR = NN * (NN + 1) / 2;       // node pairs m <= n
     static constexpr int NPASS = (NPAIR + LANES - 1) / LANES;
     static constexpr int CTAS_PER_SM = NN == 20 ? 1 : 2;
     static_assert(NDOF % 2 == 0 && NDOF <= LANES, "gather: one lane per coordinate");
-    static_assert(MAXNG * VS <= RS, "V must fit inside the region it shares with the staged element block");
+    static_assert(NT8 * 8 * PS <= RS, "V must fit inside the region it shares with the staged element block");
 };
 
 // upper 8 x 8 dof tiles (I <= J) owned by warp W of a cell
@@ -109,7 +114,7 @@ __device__ __forceinline__ void slot_sync(int slot) {
 template <int NN, int W>
 __device__ __forceinline__ void syrk_tiles(double *R, const double *s_c, int KS, int lane, int slot) {
     using T = SyrkDims<NN>;
-    constexpr int NT8 = T::NT8, VS = T::VS, NDOF = T::NDOF;
+    constexpr int NT8 = T::NT8, PS = T::PS, NDOF = T::NDOF;
     constexpr int NTL = syrk_ntile(NN, W);
     const int ar = lane >> 2, ak = lane & 3;
     double acc[NTL > 0 ? NTL : 1][2];
@@ -119,11 +124,11 @@ __device__ __forceinline__ void syrk_tiles(double *R, const double *s_c, int KS,
     for (int ks = 0; ks < KS; ks++) {
         const int row = 4 * ks + ak;
         const double c = s_c[row];
-        const double *vr = R + row * VS + ar;
+        const double *vr = R + ar * PS + row;
         double v[NT8], vs[NT8];
 #pragma unroll
         for (int t = 0; t < NT8; t++) {
-            v[t] = vr[8 * t];
+            v[t] = vr[8 * t * PS];
             vs[t] = v[t] * c;
         }
         // C[r][q] += sum_k A[r][k] B[k][q] with A[r][k] = V[k][8J + r], B[k][q] = c_k V[k][8I + q]: C[r][q] = P(8I + q, 8J + r)
@@ -131,11 +136,19 @@ __device__ __forceinline__ void syrk_tiles(double *R, const double *s_c, int KS,
         for (int t = 0; t < NTL; t++) dmma_m8n8k4(acc[t][0], acc[t][1], v[syrk_tile(NN, W, t, 1)], vs[syrk_tile(NN, W, t, 0)]);
     }
     slot_sync<T::WPC>(slot); // every warp of the slot has finished reading V: the region becomes P
+    // the lane holds P(8I + 2ak + e, 8J + ar), e = 0, 1.  Two 8-byte stores; odd fragment rows store e = 1 first: at
+    // (8I + 2ak + e) + 60 (8J + ar) = 2ak + e + 12 ar (mod 16) the 16 lanes of a half-warp then hit 16 distinct bank pairs
+    // (one 16-byte store per lane would put rows ar and ar + 1 of a quarter-warp on the same banks)
+    const int e0 = ar & 1;
 #pragma unroll
     for (int t = 0; t < NTL; t++) {
         const int prow = 8 * syrk_tile(NN, W, t, 0) + 2 * ak; // rows prow, prow + 1
         const int pcol = 8 * syrk_tile(NN, W, t, 1) + ar;
-        if (prow < NDOF && pcol < NDOF) *reinterpret_cast<double2 *>(R + prow + NDOF * pcol) = make_double2(acc[t][0], acc[t][1]);
+        if (prow < NDOF && pcol < NDOF) {
+            double *dst = R + prow + NDOF * pcol;
+            dst[e0] = e0 ? acc[t][1] : acc[t][0];
+            dst[1 - e0] = e0 ? acc[t][0] : acc[t][1];
+        }
     }
 }
 
@@ -143,16 +156,17 @@ template <int NN, int PAT, bool DREC, bool GEN>
 __global__ void __launch_bounds__(SYRK_THREADS, SyrkDims<NN>::CTAS_PER_SM) syrk_kernel(const IntegParams p, const SyrkConsts cst) {
     if (DREC && p.coef_pat_dev != nullptr && *p.coef_pat_dev != PAT) return; // another pattern variant owns this call (see launcher)
     using T = SyrkDims<NN>;
-    constexpr int NDOF = T::NDOF, VS = T::VS, WPC = T::WPC, LANES = T::LANES, SLOTS = T::SLOTS, MAXNG = T::MAXNG, LS = T::LS,
-                  RS = T::RS, NPAIR = T::NPAIR, NPASS = T::NPASS;
+    constexpr int NDOF = T::NDOF, PS = T::PS, WPC = T::WPC, LANES = T::LANES, SLOTS = T::SLOTS, MAXNG = T::MAXNG, LS = T::LS,
+                  RS = T::RS, NPASS = T::NPASS;
     constexpr bool SYM = PAT >= 1;
 
     extern __shared__ __align__(16) double smem[];
     const int ng = p.ng;
     const int KS = (ng + 3) >> 2;
     double *s_R = smem;                        // [SLOTS][RS]      (16-byte aligned: bulk copy source, double2 stores)
-    double *s_L = s_R + SLOTS * RS;            // [ng][LS]         L[gp][3m + j]
-    double *s_w = s_L + ng * LS;               // [ng]
+    double *s_L = s_R + SLOTS * RS;            // [MAXNG][LS]      L[gp][3m + j]; rows >= ng are never initialised: the lanes without a
+                                               // Gauss point read them (their own row: no bank shared with a live row) and discard the result
+    double *s_w = s_L + MAXNG * LS;            // [ng]
     double *s_X = s_w + ng;                    // [SLOTS][NDOF]    X[3m + j]
     double *s_c = s_X + SLOTS * NDOF;          // [SLOTS][MAXNG]   c_p (0 for the padding rows of the last k-step)
     double *s_D = s_c + SLOTS * MAXNG;         // [SLOTS][36]      d' of the slot's cell (DREC only)
@@ -170,22 +184,13 @@ __global__ void __launch_bounds__(SYRK_THREADS, SyrkDims<NN>::CTAS_PER_SM) syrk_
     double *cc = s_c + slot * MAXNG;
     const double *Dc = s_D + slot * 36;
 
-    // node pairs (m <= n) of this lane in the in-place contraction, enumerated DIAGONAL BY DIAGONAL (n - m = 0, 1, ..): the
-    // lanes of a half-warp then differ in m and n together, so the direct blocks (3m + 60.3n) and the mirrored ones
-    // (3n + 60.3m) both advance by 183 = 7 (mod 16) doubles per lane -- distinct bank pairs
+    // node pairs (m <= n) of this lane in the in-place contraction: a table (tools/gen_syrk_pairs.py) that gives the 16 lanes of every
+    // half-warp pairs whose direct blocks (3m + 60.3n) and mirrored blocks (3n + 60.3m) start on 16 distinct bank pairs
     int pair_mn[NPASS];
 #pragma unroll
     for (int k = 0; k < NPASS; k++) {
-        int t = ls + k * LANES, d = 0;
-        if (t < NPAIR) {
-            while (t >= NN - d) {
-                t -= NN - d;
-                d++;
-            }
-            pair_mn[k] = t | ((t + d) << 8);
-        } else {
-            pair_mn[k] = -1;
-        }
+        const unsigned short v = NN == 20 ? SYRK_PAIRS_20[k * LANES + ls] : SYRK_PAIRS_10[k * LANES + ls];
+        pair_mn[k] = v == 0xffff ? -1 : (int)v;
     }
 
     // software-pipelined gather: lane (node gm, component gj) holds the coordinate of the NEXT cell of the slot and the point id
@@ -202,6 +207,11 @@ __global__ void __launch_bounds__(SYRK_THREADS, SyrkDims<NN>::CTAS_PER_SM) syrk_
     }
     unsigned long long pol; // the element matrices are written once: keep them from flushing the mesh out of L2
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+
+    // All slots of a CTA would otherwise run in LOCKSTEP -- geometry (FP64 + shared memory), tensor cores, epilogue (shared memory
+    // only) at the same time on every slot -- and the pipes would idle in turns.  A start-up delay proportional to the slot index
+    // spreads the phases; every cell costs the same, so the skew persists.
+    if (cst.stagger_ns > 0 && slot > 0) __nanosleep((unsigned)(cst.stagger_ns * slot));
 
     for (; cell < p.hi; cell += stride) {
         const unsigned long long orig = p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell;
@@ -223,11 +233,13 @@ __global__ void __launch_bounds__(SYRK_THREADS, SyrkDims<NN>::CTAS_PER_SM) syrk_
         slot_sync<WPC>(slot);
 
         // ---- phase B: geometry, two lanes per Gauss point ---------------------------------------------------------------
-        // lane h of a pair accumulates row 2h of J and its share of row 1 (entries (1,0) and (1,1) for h = 0, (1,2) and again
-        // (1,1) for h = 1), every entry as the oracle does: m = 0 .. NN-1, product and sum rounded separately
-        const int q = ls >> 1, h = ls & 1;
+        // The 16 Gauss points of a warp sit on lanes 0..15 (h = 0) and again on lanes 16..31 (h = 1).  Lane h of a pair
+        // accumulates row 2h of J and its share of row 1 (entries (1,0) and (1,1) for h = 0, (1,2) and again (1,1) for h = 1),
+        // every entry as the oracle does: m = 0 .. NN-1, product and sum rounded separately.  A half-warp reads one node of 16
+        // different rows of L (odd stride: 16 distinct bank pairs).
+        const int q = 16 * w + (lane & 15), h = lane >> 4;
         const bool valid = q < ng;
-        const double *L = s_L + (valid ? q : 0) * LS;
+        const double *L = s_L + q * LS;
         double Ji[3][3];
         double det;
         {
@@ -244,8 +256,8 @@ __global__ void __launch_bounds__(SYRK_THREADS, SyrkDims<NN>::CTAS_PER_SM) syrk_
             }
             double Jo[3], Jbo;
 #pragma unroll
-            for (int j = 0; j < 3; j++) Jo[j] = __shfl_xor_sync(0xffffffffu, Ja[j], 1);
-            Jbo = __shfl_xor_sync(0xffffffffu, Jb0, 1);
+            for (int j = 0; j < 3; j++) Jo[j] = __shfl_xor_sync(0xffffffffu, Ja[j], 16);
+            Jbo = __shfl_xor_sync(0xffffffffu, Jb0, 16);
             double J[3][3];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -263,15 +275,17 @@ __global__ void __launch_bounds__(SYRK_THREADS, SyrkDims<NN>::CTAS_PER_SM) syrk_
         }
         slot_sync<WPC>(slot);
         if (q < 4 * KS) {
-            // gradient rows of the nodes m = h, h + 2, ..; the padding rows of the last k-step are zero-filled (the region held
-            // the previous element block)
-            double *Vr = R + q * VS;
+            // gradient rows of the nodes m = h, h + 2, .. (B = L.inv(J) is well conditioned: fused multiply-adds); the padding
+            // Gauss points of the last k-step are zero-filled (the region held the previous element block)
+            double *Vq = R + q;
 #pragma unroll 2
             for (int m = h; m < NN; m += 2) {
-                double b[3];
-                geom::gradient_row<3>(L + 3 * m, Ji, b);
+                const double l0 = L[3 * m], l1 = L[3 * m + 1], l2 = L[3 * m + 2];
 #pragma unroll
-                for (int j = 0; j < 3; j++) Vr[3 * m + j] = valid ? b[j] : 0.0;
+                for (int j = 0; j < 3; j++) {
+                    const double b = fma(l2, Ji[2][j], fma(l1, Ji[1][j], l0 * Ji[0][j]));
+                    Vq[(3 * m + j) * PS] = valid ? b : 0.0;
+                }
             }
             if (h == 0) cc[q] = valid ? det * s_w[valid ? q : 0] * p.alpha : 0.0;
         }
@@ -365,7 +379,7 @@ __global__ void __launch_bounds__(SYRK_THREADS, SyrkDims<NN>::CTAS_PER_SM) syrk_
 template <int NN>
 size_t syrk_smem(int ng, bool drec) {
     using T = SyrkDims<NN>;
-    return sizeof(double) * ((size_t)T::SLOTS * T::RS + (size_t)ng * T::LS + (size_t)ng + (size_t)T::SLOTS * T::NDOF +
+    return sizeof(double) * ((size_t)T::SLOTS * T::RS + (size_t)T::MAXNG * T::LS + (size_t)ng + (size_t)T::SLOTS * T::NDOF +
                              (size_t)T::SLOTS * T::MAXNG + (drec ? (size_t)T::SLOTS * 36 : 0));
 }
 
@@ -419,6 +433,8 @@ int launch_bdb_syrk(const IntegParams &p, int sd, void *stream) {
     const bool gen = !(tight && p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
 
     SyrkConsts cst;
+    cst.stagger_ns = p.nnode == 20 ? 1400 : 300;
+    if (const char *e = tuning_env("GL_SYRK_STAGGER")) cst.stagger_ns = atoi(e);
     const double hs = 0.70710678118654752440084436210484903928;
     bool sym = true;
     for (int a = 0; a < 6; a++)
