@@ -293,6 +293,7 @@ int gl_ctx_create(int device, void *stream, gl_ctx **out) {
     ctx->device = device;
     ctx->stream = stream;
     if (cudaMalloc(&ctx->d_err_cell, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_work_counter, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->d_coef_pat, sizeof(int)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_err_cell, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->d_rule_tmp, sizeof(double) * GL_NKIND * (1 + MAX_NNODE + 3 * MAX_NNODE)) != cudaSuccess) {
@@ -328,6 +329,7 @@ void gl_ctx_destroy(gl_ctx *ctx) {
     for (auto &kv : ctx->rules)
         if (kv.second->dev) cudaFree(kv.second->dev);
     if (ctx->d_err_cell) cudaFree(ctx->d_err_cell);
+    if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
     if (ctx->d_coef_pat) cudaFree(ctx->d_coef_pat);
     if (ctx->h_err_cell) cudaFreeHost(ctx->h_err_cell);
     if (ctx->d_rule_tmp) cudaFree(ctx->d_rule_tmp);
@@ -827,6 +829,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         p.size_r = bd.size_r;
         p.size_c = bd.size_c;
         p.err_cell = ctx->d_err_cell;
+        p.work_counter = ctx->d_work_counter;
         if (pre) {
             auto it = bk.d_out_off.find(key);
             if (it == bk.d_out_off.end()) {

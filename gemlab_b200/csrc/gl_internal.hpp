@@ -89,6 +89,8 @@ struct IntegParams {
     double *out_d;
     // failure reporting: smallest original id of a cell with |det J| <= 1e-15
     unsigned long long *err_cell;
+    // kernels whose warps draw cells from a queue (gl_kernels_syrk.cu): a counter owned by the ctx, zeroed by the launcher
+    unsigned long long *work_counter;
     // tile
     int cells_per_cta;
 };
@@ -181,6 +183,7 @@ struct gl_ctx {
     uint64_t launches = 0;
     std::string last_kernel; // kernel family of the most recent integration launch (gl_ctx_last_kernel)
     unsigned long long *d_err_cell = nullptr;
+    unsigned long long *d_work_counter = nullptr; // see IntegParams::work_counter
     int *d_coef_pat = nullptr; // result of the modulus-structure probe (device-resident PER_CELL moduli)
     unsigned long long *h_err_cell = nullptr; // pinned
     std::map<std::pair<int, int>, std::unique_ptr<gl::RuleTable>> rules; // (kind, ngauss) -> table
