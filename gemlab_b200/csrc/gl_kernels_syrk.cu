@@ -131,16 +131,16 @@ __global__ void __launch_bounds__(SyrkDims<NN>::THREADS, SyrkDims<NN>::CTAS_PER_
     const int ng = p.ng;
     const int KS = (ng + 3) >> 2;
     double *s_R = smem;                        // [SLOTS][RS]      (16-byte aligned: bulk copy source)
-    double *s_L = s_R + SLOTS * RS;            // [MAXNG][LS]      L[gp][3m + j]; rows >= ng are never initialised: the lanes without a
-                                               // Gauss point read them (their own row: no bank shared with a live row) and discard the result
-    double *s_w = s_L + MAXNG * LS;            // [ng]
-    double *s_X = s_w + ng;                    // [SLOTS][NDOF]    X[3m + j]
+    double *s_L = s_R + SLOTS * RS;            // [MAXNG][LS]      L[gp][3m + j]; rows >= ng are zero: the lanes without a Gauss point read
+                                               // their own row (no bank shared with a live row) and produce zero gradients
+    double *s_w = s_L + MAXNG * LS;            // [MAXNG]
+    double *s_X = s_w + MAXNG;                 // [SLOTS][NDOF]    X[3m + j]  (16-byte aligned: MAXNG (LS + 1) is even)
     double *s_c = s_X + SLOTS * NDOF;          // [SLOTS][MAXNG]   c_p (0 for the padding rows of the last k-step)
     double *s_D = s_c + SLOTS * MAXNG;         // [SLOTS][36]      d' of the slot's cell (DREC only)
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < ng; i += T::THREADS) s_w[i] = p.rule[i];
-    for (int i = tid; i < ng * NDOF; i += T::THREADS) s_L[(i / NDOF) * LS + i % NDOF] = p.rule[ng * (1 + NN) + i];
+    for (int i = tid; i < MAXNG; i += T::THREADS) s_w[i] = i < ng ? p.rule[i] : 0.0;
+    for (int i = tid; i < MAXNG * NDOF; i += T::THREADS) s_L[(i / NDOF) * LS + i % NDOF] = i < ng * NDOF ? p.rule[ng * (1 + NN) + i] : 0.0;
     __syncthreads();
 
     // ONE WARP PER CELL SLOT: no barrier wider than the warp below this line
@@ -152,23 +152,23 @@ __global__ void __launch_bounds__(SyrkDims<NN>::THREADS, SyrkDims<NN>::CTAS_PER_
     const int ar = lane >> 2, ak = lane & 3;
 
     // node pairs (m <= n) of this lane in the in-place contraction: a table (tools/gen_syrk_pairs.py) that gives the 16 lanes of every
-    // half-warp pairs whose direct blocks (3m + NDOF.3n) and mirrored blocks (3n + NDOF.3m) start on 16 distinct bank pairs
-    int pair_mn[NPASS];
+    // half-warp pairs whose direct blocks (at 3m + NDOF.3n) and mirrored blocks (at 3n + NDOF.3m) start on 16 distinct bank pairs;
+    // an entry holds the two block starts
+    unsigned int pair_off[NPASS];
 #pragma unroll
-    for (int k = 0; k < NPASS; k++) {
-        const unsigned short v = NN == 20 ? SYRK_PAIRS_20[k * 32 + lane] : SYRK_PAIRS_10[k * 32 + lane];
-        pair_mn[k] = v == 0xffff ? -1 : (int)v;
-    }
+    for (int k = 0; k < NPASS; k++) pair_off[k] = NN == 20 ? SYRK_PAIRS_20[k * 32 + lane] : SYRK_PAIRS_10[k * 32 + lane];
 
     // Work distribution: the slots of all CTAs draw cells from one counter (equal shares would leave the sub-partition that holds
     // a single warp half idle).  A slot knows its next two cells: the point ids of the cell after next and the coordinates of the
     // next cell are in flight while the current cell is integrated.
     const unsigned long long ncell = p.hi - p.lo;
-    auto draw = [&]() -> unsigned long long {
+    auto draw_issue = [&]() -> unsigned long long { // lane 0 takes the next cell off the queue; the result is broadcast LATER
+        // (inline PTX: atomicAdd() would be warp-aggregated by the compiler, with a shuffle that waits for the result right here)
         unsigned long long v = 0;
-        if (lane == 0) v = atomicAdd(p.work_counter, 1ull);
-        return __shfl_sync(0xffffffffu, v, 0);
+        if (lane == 0) asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(v) : "l"(p.work_counter) : "memory");
+        return v;
     };
+    auto draw_get = [&](unsigned long long raw) -> unsigned long long { return __shfl_sync(0xffffffffu, raw, 0); };
     auto load_pid = [&](unsigned long long c, unsigned int (&pid)[NCOORD]) {
 #pragma unroll
         for (int k = 0; k < NCOORD; k++) {
@@ -183,13 +183,14 @@ __global__ void __launch_bounds__(SyrkDims<NN>::THREADS, SyrkDims<NN>::CTAS_PER_
             x[k] = (c < ncell && dof < NDOF) ? p.coords[(unsigned long long)(dof % 3) * p.npoint + pid[k]] : 0.0;
         }
     };
-    unsigned long long c_cur = draw(), c_nxt = draw(), c_nn = draw();
-    unsigned int pid_a[NCOORD], pid_b[NCOORD];
+    // c_cur: the cell being integrated (coordinates in gx); c_nxt: the next one (point ids in pid); raw_nn: the one after, taken off
+    // the queue during the previous cell and broadcast at the top of this one, so the atomic's round trip is never waited for
+    unsigned long long c_cur = draw_get(draw_issue()), c_nxt = draw_get(draw_issue()), raw_nn = draw_issue();
+    unsigned int pid[NCOORD];
     double gx[NCOORD];
-    load_pid(c_cur, pid_a);
-    load_x(c_cur, pid_a, gx);
-    load_pid(c_nxt, pid_a); // ids of the next cell
-    load_pid(c_nn, pid_b);  // ... and of the one after
+    load_pid(c_cur, pid);
+    load_x(c_cur, pid, gx);
+    load_pid(c_nxt, pid);
 
     unsigned long long pol; // the element matrices are written once: keep them from flushing the mesh out of L2
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -201,13 +202,14 @@ __global__ void __launch_bounds__(SyrkDims<NN>::THREADS, SyrkDims<NN>::CTAS_PER_
 #pragma unroll
         for (int k = 0; k < NCOORD; k++)
             if (lane + 32 * k < NDOF) X[lane + 32 * k] = gx[k];
-        load_x(c_nxt, pid_a, gx);
-#pragma unroll
-        for (int k = 0; k < NCOORD; k++) pid_a[k] = pid_b[k];
-        c_cur = c_nxt;
-        c_nxt = c_nn;
-        c_nn = draw();
-        load_pid(c_nn, pid_b);
+        {
+            const unsigned long long c_nn = draw_get(raw_nn);
+            load_x(c_nxt, pid, gx);  // coordinates of the next cell (its point ids arrived during the previous cell)
+            load_pid(c_nn, pid);     // point ids of the cell after next
+            c_cur = c_nxt;
+            c_nxt = c_nn;
+            raw_nn = draw_issue();
+        }
         if constexpr (DREC) {
             // the cell's modulus record (ns x ns Mandel matrix, column-major; its marker's or its own), shear factors folded in
             const double hs = 0.70710678118654752440084436210484903928;
@@ -230,18 +232,37 @@ __global__ void __launch_bounds__(SyrkDims<NN>::THREADS, SyrkDims<NN>::CTAS_PER_
 #pragma unroll
             for (int i = 0; i < NDOF; i++) l[i] = L[i];
             double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            // the cell's coordinates: the same 16-byte words for every lane (broadcast loads), four nodes (six words) at a time
+            static_assert(NN % 4 == 0 || NN % 2 == 0, "coordinate words are read in pairs of nodes");
+            constexpr int NB = NN % 4 == 0 ? 4 : 2; // nodes per batch
 #pragma unroll
-            for (int m = 0; m < NN; m++) {
-                const double x0 = X[3 * m], x1 = X[3 * m + 1], x2 = X[3 * m + 2];
+            for (int m0 = 0; m0 < NN; m0 += NB) {
+                double x[3 * NB];
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    J[0][j] = geom::add(J[0][j], geom::mul(x0, l[3 * m + j]));
-                    J[1][j] = geom::add(J[1][j], geom::mul(x1, l[3 * m + j]));
-                    J[2][j] = geom::add(J[2][j], geom::mul(x2, l[3 * m + j]));
+                for (int i = 0; i < 3 * NB / 2; i++) {
+                    const double2 xx = reinterpret_cast<const double2 *>(X + 3 * m0)[i];
+                    x[2 * i] = xx.x;
+                    x[2 * i + 1] = xx.y;
+                }
+#pragma unroll
+                for (int mm = 0; mm < NB; mm++) {
+                    const int m = m0 + mm;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        J[0][j] = geom::add(J[0][j], geom::mul(x[3 * mm], l[3 * m + j]));
+                        J[1][j] = geom::add(J[1][j], geom::mul(x[3 * mm + 1], l[3 * m + j]));
+                        J[2][j] = geom::add(J[2][j], geom::mul(x[3 * mm + 2], l[3 * m + j]));
+                    }
                 }
             }
             double Ji[3][3];
             const double det = geom::invert(J, Ji);
+            if (!valid) { // lanes without a Gauss point: zero gradients (their row of L is zero, so J is singular)
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) Ji[i][j] = 0.0;
+            }
             if (valid && fabs(det) <= ZERO_DETERMINANT) atomicMin(p.err_cell, orig);
             if constexpr (!GEN) {
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the previous bulk copy has left the region
@@ -255,9 +276,9 @@ __global__ void __launch_bounds__(SyrkDims<NN>::THREADS, SyrkDims<NN>::CTAS_PER_
 #pragma unroll
                     for (int j = 0; j < 3; j++) {
                         const double b = fma(l[3 * m + 2], Ji[2][j], fma(l[3 * m + 1], Ji[1][j], l[3 * m] * Ji[0][j]));
-                        Vq[(3 * m + j) * PS] = valid ? b : 0.0;
+                        Vq[(3 * m + j) * PS] = b;
                     }
-                cc[lane] = valid ? det * s_w[valid ? lane : 0] * p.alpha : 0.0;
+                cc[lane] = valid ? det * s_w[lane] * p.alpha : 0.0;
             }
         }
         __syncwarp();
@@ -303,47 +324,62 @@ __global__ void __launch_bounds__(SyrkDims<NN>::THREADS, SyrkDims<NN>::CTAS_PER_
         __syncwarp();
 
         // ---- phase D: K(m,n) = D' : P(m,n), in place, and its mirror ------------------------------------------------------
+        // Two passes at a time: the blocks of both are read before the first is written back (the pairs of different passes
+        // are disjoint, which the compiler cannot know), so the loads of one pass do not queue behind the stores of the previous.
+        {
+            // the modulus entries the pattern uses, in registers for the whole phase (the accumulators are dead by now)
+            double dl[36];
 #pragma unroll
-        for (int k = 0; k < NPASS; k++) {
-            if (pair_mn[k] < 0) continue;
-            const int m = pair_mn[k] & 0xff, n = pair_mn[k] >> 8;
-            const bool dg = m == n;
-            // P(m,n)[k][l] at (3m + k) + NDOF (3n + l); only the upper triangle of P was computed, so the diagonal pair reads
-            // its upper half and mirrors it
-            double P[3][3];
+            for (int a = 0; a < 6; a++)
 #pragma unroll
-            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 6; b++)
+                    if (d_nz3(PAT, a, b)) dl[a * 6 + b] = DREC ? Dc[a * 6 + b] : cst.d[a * 6 + b];
 #pragma unroll
-                for (int b = 0; b < 3; b++) {
-                    const bool low = dg && a > b;
-                    P[a][b] = R[(3 * m + (low ? b : a)) + NDOF * (3 * n + (low ? a : b))];
+            for (int k0 = 0; k0 < NPASS; k0 += 2) {
+                double P[2][3][3];
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+                    if (k0 + kk >= NPASS || pair_off[k0 + kk] == 0xffffffffu) continue;
+                    const unsigned int od = pair_off[k0 + kk] & 0xffffu, om = pair_off[k0 + kk] >> 16;
+                    const bool dg = od == om;
+                    // P(m,n)[a][b] at od + a + NDOF b; only the upper triangle of P was computed, so a diagonal pair reads its
+                    // upper half and mirrors it
+                    const double *Pb = R + od;
+#pragma unroll
+                    for (int a = 0; a < 3; a++)
+#pragma unroll
+                        for (int b = 0; b < 3; b++) P[kk][a][b] = a > b ? Pb[dg ? b + NDOF * a : a + NDOF * b] : Pb[a + NDOF * b];
                 }
 #pragma unroll
-            for (int j = 0; j < 3; j++)
+                for (int kk = 0; kk < 2; kk++) {
+                    if (k0 + kk >= NPASS || pair_off[k0 + kk] == 0xffffffffu) continue;
+                    const unsigned int od = pair_off[k0 + kk] & 0xffffu, om = pair_off[k0 + kk] >> 16;
+                    const bool dg = od == om;
+                    double *Kd = R + od, *Km = R + om;
 #pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    // K(3m+i, 3n+j) = sum_qr d'[row(i,q)][row(j,r)] P[comp(i,q)][comp(j,r)]; for a non-symmetric D the mirrored block
-                    // K(3n+j, 3m+i) = sum_qr d'[row(j,r)][row(i,q)] P[comp(i,q)][comp(j,r)]  (P(n,m) = P(m,n)^T)
-                    double v = 0.0, u = 0.0;
-                    bool have = false;
+                    for (int j = 0; j < 3; j++)
 #pragma unroll
-                    for (int qq = 0; qq < 3; qq++)
+                        for (int i = 0; i < 3; i++) {
+                            // K(3m+i, 3n+j) = sum_qr d'[row(i,q)][row(j,r)] P[comp(i,q)][comp(j,r)]; for a non-symmetric D the mirrored
+                            // block K(3n+j, 3m+i) = sum_qr d'[row(j,r)][row(i,q)] P[comp(i,q)][comp(j,r)]  (P(n,m) = P(m,n)^T)
+                            double v = 0.0, u = 0.0;
+                            bool have = false;
 #pragma unroll
-                        for (int r = 0; r < 3; r++) {
-                            const int ra = col_row3(i, qq), rb = col_row3(j, r);
-                            if (!d_nz3(PAT, ra, rb)) continue;
-                            const double dv = DREC ? Dc[ra * 6 + rb] : cst.d[ra * 6 + rb];
-                            const double pv = P[col_comp3(i, qq)][col_comp3(j, r)];
-                            v = have ? fma(dv, pv, v) : dv * pv;
-                            if (!SYM) {
-                                const double dt = DREC ? Dc[rb * 6 + ra] : cst.d[rb * 6 + ra];
-                                u = have ? fma(dt, pv, u) : dt * pv;
-                            }
-                            have = true;
+                            for (int qq = 0; qq < 3; qq++)
+#pragma unroll
+                                for (int r = 0; r < 3; r++) {
+                                    const int ra = col_row3(i, qq), rb = col_row3(j, r);
+                                    if (!d_nz3(PAT, ra, rb)) continue;
+                                    const double pv = P[kk][col_comp3(i, qq)][col_comp3(j, r)];
+                                    v = have ? fma(dl[ra * 6 + rb], pv, v) : dl[ra * 6 + rb] * pv;
+                                    if (!SYM) u = have ? fma(dl[rb * 6 + ra], pv, u) : dl[rb * 6 + ra] * pv;
+                                    have = true;
+                                }
+                            Kd[i + NDOF * j] = v;
+                            if (!dg) Km[j + NDOF * i] = SYM ? v : u;
                         }
-                    R[(3 * m + i) + NDOF * (3 * n + j)] = v;
-                    if (!dg) R[(3 * n + j) + NDOF * (3 * m + i)] = SYM ? v : u;
                 }
+            }
         }
 
         // ---- ship --------------------------------------------------------------------------------------------------------
@@ -381,7 +417,8 @@ __global__ void __launch_bounds__(SyrkDims<NN>::THREADS, SyrkDims<NN>::CTAS_PER_
 template <int NN>
 size_t syrk_smem(int ng, bool drec) {
     using T = SyrkDims<NN>;
-    return sizeof(double) * ((size_t)T::SLOTS * T::RS + (size_t)T::MAXNG * T::LS + (size_t)ng + (size_t)T::SLOTS * T::NDOF +
+    (void)ng;
+    return sizeof(double) * ((size_t)T::SLOTS * T::RS + (size_t)T::MAXNG * T::LS + (size_t)T::MAXNG + (size_t)T::SLOTS * T::NDOF +
                              (size_t)T::SLOTS * T::MAXNG + (drec ? (size_t)T::SLOTS * 36 : 0));
 }
 
