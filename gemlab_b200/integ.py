@@ -113,6 +113,15 @@ class DeviceMesh:
         self.npoint = npoint
         self.kinds = kinds  # host copy (uint8) -- used for sizes only
 
+    def update_coords(self, coords):
+        """Replaces the point coordinates (host array npoint x ndim, as Mesh.coords) of this device mesh (gl_mesh_update_coords)."""
+        arr = np.ascontiguousarray(coords, dtype=np.float64)
+        if arr.shape != (self.npoint, self.ndim):
+            raise ValueError("coords must be npoint x ndim")
+        st = lib().gl_mesh_update_coords(self.ctx._h, self._h, arr.ctypes.data, GL_HOST)
+        if st:
+            self.ctx._raise(st)
+
     def free(self):
         if self._h:
             lib().gl_mesh_free(self.ctx._h, self._h)
