@@ -50,6 +50,9 @@ pub struct gl_args {
     pub nrow: u32,
     pub ncol: u32,
     pub ksi: [c_double; 3],
+    /// two-pad cases (mat_04_nsb .. mat_07_bsn): GeoKind ordinal of the second Scratchpad; -1 otherwise
+    pub kind_b: i32,
+    pub reserved: i32,
 }
 
 #[repr(C)]
@@ -153,6 +156,14 @@ extern "C" {
     pub fn gl_vec_03_bv(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
     pub fn gl_vec_04_bt(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
     pub fn gl_jacobian(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_04_nsb(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_05_btn(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_06_nvn(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_07_bsn(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_mat_01_nsn_bry(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_vec_01_ns_bry(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_vec_02_nv_bry(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_normal_vectors(ctx: *mut gl_ctx, mesh: *const gl_mesh, cell_begin: u64, cell_end: u64, args: *const gl_args, out: *mut gl_out) -> c_int;
     pub fn gl_mat_10_gdg(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
     pub fn gl_vec_10_gs(ctx: *mut gl_ctx, mesh: *const gl_mesh, b: u64, e: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
 

@@ -49,12 +49,14 @@ pub struct BatchArgs {
     pub ncol: usize,
     /// element matrices leave as packed upper triangles (n(n+1)/2 doubles; K(i,j), i <= j, at j(j+1)/2 + i)
     pub packed: bool,
+    /// two-pad cases (`mat_04_nsb` .. `mat_07_bsn`): the `GeoKind` of the second `Scratchpad` (its nodes are the cell's first ones)
+    pub kind_b: Option<gemlab::shapes::GeoKind>,
 }
 
 impl BatchArgs {
     /// Same defaults as `CommonArgs::new`: clear = true, axisymmetric = false, alpha = 1, ii0 = jj0 = 0
     pub fn new() -> Self {
-        BatchArgs { ngauss: None, clear: true, axisymmetric: false, alpha: 1.0, ii0: 0, jj0: 0, nrow: 0, ncol: 0, packed: false }
+        BatchArgs { ngauss: None, clear: true, axisymmetric: false, alpha: 1.0, ii0: 0, jj0: 0, nrow: 0, ncol: 0, packed: false, kind_b: None }
     }
     fn to_c(&self) -> ffi::gl_args {
         ffi::gl_args {
@@ -68,6 +70,8 @@ impl BatchArgs {
             nrow: self.nrow as u32,
             ncol: self.ncol as u32,
             ksi: [0.0; 3],
+            kind_b: self.kind_b.map_or(-1, |k| k as i32),
+            reserved: 0,
         }
     }
 }

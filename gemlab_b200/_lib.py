@@ -20,7 +20,7 @@ class GlArgs(C.Structure):
     _fields_ = [
         ("ngauss", C.c_int32), ("axisymmetric", C.c_int32), ("clear", C.c_int32), ("packed", C.c_int32),
         ("alpha", C.c_double), ("ii0", C.c_uint32), ("jj0", C.c_uint32), ("nrow", C.c_uint32), ("ncol", C.c_uint32),
-        ("ksi", C.c_double * 3),
+        ("ksi", C.c_double * 3), ("kind_b", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -82,7 +82,9 @@ SYMBOLS = {
     "gl_bench_fp64_peak": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gl_bench_hbm_write": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
 }
-for _name in ("gl_mat_10_bdb", "gl_mat_01_nsn", "gl_mat_02_bvn", "gl_mat_03_btb", "gl_mat_08_ntn", "gl_mat_09_nvb", "gl_vec_01_ns", "gl_vec_02_nv", "gl_vec_03_bv",
+SYMBOLS["gl_normal_vectors"] = (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlOut)])
+for _name in ("gl_mat_04_nsb", "gl_mat_05_btn", "gl_mat_06_nvn", "gl_mat_07_bsn", "gl_mat_01_nsn_bry", "gl_vec_01_ns_bry", "gl_vec_02_nv_bry",
+              "gl_mat_10_bdb", "gl_mat_01_nsn", "gl_mat_02_bvn", "gl_mat_03_btb", "gl_mat_08_ntn", "gl_mat_09_nvb", "gl_vec_01_ns", "gl_vec_02_nv", "gl_vec_03_bv",
               "gl_vec_04_bt", "gl_mat_10_gdg", "gl_vec_10_gs"):
     SYMBOLS[_name] = (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlOut)])
 

@@ -62,38 +62,55 @@ int cuda_fail(gl_ctx *ctx, cudaError_t e, const char *what) {
     } while (0)
 
 // size classes of the element blocks
-enum { SZ_NDOF2 = 0, SZ_NNODE2 = 1, SZ_NNODE = 2, SZ_NDOF = 3, SZ_ONE = 4 };
+enum { SZ_NDOF2 = 0, SZ_NNODE2 = 1, SZ_NNODE = 2, SZ_NDOF = 3, SZ_ONE = 4, SZ_NB_NDOF = 5, SZ_NDOF_NB = 6, SZ_NORMAL = 7 };
 
 int op_size_class(int op) {
     switch (op) {
     case GL_OP_MAT_10_BDB: case GL_OP_MAT_08_NTN: case GL_OP_MAT_09_NVB: return SZ_NDOF2;
-    case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: case GL_OP_MAT_02_BVN: return SZ_NNODE2;
-    case GL_OP_VEC_01_NS: case GL_OP_VEC_03_BV: return SZ_NNODE;
-    case GL_OP_VEC_02_NV: case GL_OP_VEC_04_BT: return SZ_NDOF;
+    case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: case GL_OP_MAT_02_BVN: case GL_OP_MAT_01_NSN_BRY: return SZ_NNODE2;
+    case GL_OP_VEC_01_NS: case GL_OP_VEC_03_BV: case GL_OP_VEC_01_NS_BRY: return SZ_NNODE;
+    case GL_OP_VEC_02_NV: case GL_OP_VEC_04_BT: case GL_OP_VEC_02_NV_BRY: return SZ_NDOF;
     case GL_OP_JACOBIAN: return SZ_ONE;
+    case GL_OP_MAT_04_NSB: case GL_OP_MAT_05_BTN: return SZ_NB_NDOF;
+    case GL_OP_MAT_06_NVN: case GL_OP_MAT_07_BSN: return SZ_NDOF_NB;
+    case GL_OP_NORMAL: return SZ_NORMAL;
     default: return -1;
     }
 }
 
 bool op_is_matrix(int op) {
     return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB || op == GL_OP_MAT_02_BVN ||
-           op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB;
+           op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB || op == GL_OP_MAT_01_NSN_BRY ||
+           (op >= GL_OP_MAT_04_NSB && op <= GL_OP_MAT_07_BSN);
 }
+
+bool op_two_pads(int op) { return op >= GL_OP_MAT_04_NSB && op <= GL_OP_MAT_07_BSN; }
+bool op_boundary(int op) { return op >= GL_OP_MAT_01_NSN_BRY && op <= GL_OP_NORMAL; }
 
 bool op_uses_gradient(int op) {
     // the reference calls Scratchpad::calc_gradient for these (mat_01_nsn too, src/integ/mat_01_nsn.rs:76)
     return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_01_NSN || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV ||
-           op == GL_OP_VEC_04_BT || op == GL_OP_MAT_02_BVN || op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB;
+           op == GL_OP_VEC_04_BT || op == GL_OP_MAT_02_BVN || op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB || op_two_pads(op);
 }
 
-// rows / cols actually integrated for a cell of `kind`
-void op_extent(int op, int kind, int ndim, unsigned &size_r, unsigned &size_c) {
+// rows / cols actually integrated for a cell of `kind`; the two-pad cases read args->kind_b, GL_OP_NORMAL the rule size
+void op_extent(int op, int kind, int ndim, const gl_args *a, unsigned &size_r, unsigned &size_c) {
     const unsigned nnode = (unsigned)kind_nnode(kind), ndof = nnode * (unsigned)ndim;
+    const unsigned nb = (a && op_two_pads(op) && a->kind_b >= 0 && a->kind_b < GL_NKIND) ? (unsigned)kind_nnode(a->kind_b) : 0u;
     switch (op_size_class(op)) {
     case SZ_NDOF2: size_r = ndof; size_c = ndof; break;
     case SZ_NNODE2: size_r = nnode; size_c = nnode; break;
     case SZ_NNODE: size_r = nnode; size_c = 1; break;
     case SZ_NDOF: size_r = ndof; size_c = 1; break;
+    case SZ_NB_NDOF: size_r = nb; size_c = ndof; break;
+    case SZ_NDOF_NB: size_r = ndof; size_c = nb; break;
+    case SZ_NORMAL: {
+        int ng = 0;
+        const double *data = nullptr;
+        if (!a || gauss_rule(kind, a->ngauss, &ng, &data) != GL_OK) ng = 0;
+        size_r = (unsigned)ng * (unsigned)(ndim + 1);
+        size_c = 1;
+    } break;
     default: size_r = 1; size_c = 1; break;
     }
 }
@@ -105,7 +122,7 @@ struct BlockDims {
 
 // resolves the element block of (op, kind) under args; returns the reference's dimension errors
 int block_dims(int op, int kind, int ndim, const gl_args *a, BlockDims &bd) {
-    op_extent(op, kind, ndim, bd.size_r, bd.size_c);
+    op_extent(op, kind, ndim, a, bd.size_r, bd.size_c);
     const bool mat = op_is_matrix(op);
     const unsigned ii0 = a->ii0, jj0 = mat ? a->jj0 : 0;
     bd.nrow = a->nrow ? a->nrow : ii0 + bd.size_r;
@@ -113,15 +130,24 @@ int block_dims(int op, int kind, int ndim, const gl_args *a, BlockDims &bd) {
     if (bd.nrow < ii0 + bd.size_r) {
         switch (op) {
         case GL_OP_MAT_10_BDB: case GL_OP_MAT_08_NTN: case GL_OP_MAT_09_NVB: return GL_ERR_NROW_KK_NDOF;
-        case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: case GL_OP_MAT_02_BVN: return GL_ERR_NROW_KK_NNODE;
-        case GL_OP_VEC_01_NS: return GL_ERR_A_LEN;
-        case GL_OP_VEC_02_NV: return GL_ERR_B_LEN;
+        case GL_OP_MAT_01_NSN: case GL_OP_MAT_03_BTB: case GL_OP_MAT_02_BVN: case GL_OP_MAT_01_NSN_BRY: return GL_ERR_NROW_KK_NNODE;
+        case GL_OP_MAT_04_NSB: case GL_OP_MAT_05_BTN: return GL_ERR_NROW_KK_NNODE_B;
+        case GL_OP_MAT_06_NVN: case GL_OP_MAT_07_BSN: return GL_ERR_NROW_KK_NDOF_PAD;
+        case GL_OP_VEC_01_NS: case GL_OP_VEC_01_NS_BRY: return GL_ERR_A_LEN;
+        case GL_OP_VEC_02_NV: case GL_OP_VEC_02_NV_BRY: return GL_ERR_B_LEN;
         case GL_OP_VEC_03_BV: return GL_ERR_C_LEN;
         case GL_OP_VEC_04_BT: return GL_ERR_D_LEN;
         default: return GL_ERR_INVALID_ARG;
         }
     }
-    if (mat && bd.ncol < jj0 + bd.size_c) return op_size_class(op) == SZ_NDOF2 ? GL_ERR_NCOL_KK_NDOF : GL_ERR_NCOL_KK_NNODE;
+    if (mat && bd.ncol < jj0 + bd.size_c) {
+        switch (op_size_class(op)) {
+        case SZ_NDOF2: return GL_ERR_NCOL_KK_NDOF;
+        case SZ_NB_NDOF: return GL_ERR_NCOL_KK_NDOF_PAD;
+        case SZ_NDOF_NB: return GL_ERR_NCOL_KK_NNODE_B;
+        default: return GL_ERR_NCOL_KK_NNODE;
+        }
+    }
     return GL_OK;
 }
 
@@ -132,6 +158,10 @@ uint64_t coef_len(int op, int ndim) {
     case GL_OP_MAT_01_NSN: case GL_OP_VEC_01_NS: return 1;
     case GL_OP_MAT_03_BTB: case GL_OP_VEC_04_BT: case GL_OP_MAT_08_NTN: return ns;
     case GL_OP_VEC_02_NV: case GL_OP_VEC_03_BV: case GL_OP_MAT_02_BVN: case GL_OP_MAT_09_NVB: return (uint64_t)ndim;
+    case GL_OP_MAT_04_NSB: case GL_OP_MAT_07_BSN: return 1;
+    case GL_OP_MAT_05_BTN: return ns;
+    case GL_OP_MAT_06_NVN: return (uint64_t)ndim;
+    case GL_OP_MAT_01_NSN_BRY: case GL_OP_VEC_01_NS_BRY: case GL_OP_VEC_02_NV_BRY: return (uint64_t)ndim + 1;
     default: return 0;
     }
 }
@@ -154,7 +184,9 @@ const std::vector<uint64_t> *mesh_prefix(gl_mesh *mesh, int op, const gl_args *a
     *status = GL_OK;
     const int cls = op_size_class(op);
     // key: size class + offsets (explicit nrow/ncol make every block equal; handled by the caller)
-    const BlockKey key(cls, a->ii0, a->jj0); // the full offsets: a truncated key would alias tight-block layouts with large ii0 / jj0
+    // the full offsets (a truncated key would alias tight-block layouts with large ii0 / jj0); the block sizes of the two-pad cases
+    // and of GL_OP_NORMAL also depend on kind_b / the rule
+    const BlockKey key(cls | ((op_two_pads(op) ? (a->kind_b & 0xff) : 0) << 8) | ((cls == SZ_NORMAL ? (a->ngauss & 0xff) : 0) << 16), a->ii0, a->jj0);
     *key_out = key;
     auto it = mesh->h_prefix.find(key);
     if (it != mesh->h_prefix.end()) return &it->second;
@@ -214,6 +246,41 @@ RuleTable *get_rule(gl_ctx *ctx, int kind, int ngauss, int *status) {
     }
     RuleTable *raw = rt.get();
     ctx->rules[key] = std::move(rt);
+    return raw;
+}
+
+// table of the SECOND pad of a two-pad case: Nb[ng][nnode_b] | Lb[ng][nnode_b][gd] of kind_b at the Gauss points of the rule of
+// the cell's own kind (pad_b.fn_interp / pad_b.calc_gradient at args.gauss, src/integ/mat_04_nsb.rs:98, mat_05_btn.rs:106)
+RuleTable *get_rule_b(gl_ctx *ctx, int kind, int kind_b, int ngauss, int *status) {
+    auto key = std::make_tuple(kind, kind_b, ngauss);
+    auto it = ctx->rules_b.find(key);
+    if (it != ctx->rules_b.end()) {
+        *status = GL_OK;
+        return it->second.get();
+    }
+    int ng = 0;
+    const double *data = nullptr;
+    *status = gauss_rule(kind, ngauss, &ng, &data);
+    if (*status) return nullptr;
+    auto rt = std::make_unique<RuleTable>();
+    rt->kind = kind_b;
+    rt->ng = ng;
+    rt->nnode = kind_nnode(kind_b);
+    rt->gd = kind_geo_ndim(kind_b);
+    const int nn = rt->nnode, gd = rt->gd;
+    rt->host.assign((size_t)ng * (nn + nn * gd), 0.0);
+    double *N = rt->host.data(), *L = N + (size_t)ng * nn;
+    for (int p = 0; p < ng; p++) {
+        *status = shape_eval(kind_b, data + p * 4, N + (size_t)p * nn, L + (size_t)p * nn * gd);
+        if (*status) return nullptr;
+    }
+    if (cudaMalloc(&rt->dev, rt->host.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(rt->dev, rt->host.data(), rt->host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        *status = GL_ERR_CUDA;
+        return nullptr;
+    }
+    RuleTable *raw = rt.get();
+    ctx->rules_b[key] = std::move(rt);
     return raw;
 }
 
@@ -328,6 +395,8 @@ void gl_ctx_destroy(gl_ctx *ctx) {
     cudaStreamSynchronize((cudaStream_t)ctx->stream);
     for (auto &kv : ctx->rules)
         if (kv.second->dev) cudaFree(kv.second->dev);
+    for (auto &kv : ctx->rules_b)
+        if (kv.second->dev) cudaFree(kv.second->dev);
     if (ctx->d_err_cell) cudaFree(ctx->d_err_cell);
     if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
     if (ctx->d_coef_pat) cudaFree(ctx->d_coef_pat);
@@ -393,6 +462,7 @@ void gl_args_default(gl_args *a) {
     std::memset(a, 0, sizeof(*a));
     a->clear = 1;
     a->alpha = 1.0;
+    a->kind_b = -1;
 }
 
 void gl_lin_elasticity(double young, double poisson, int two_dim, int plane_stress, double *dd) {
@@ -402,7 +472,7 @@ void gl_lin_elasticity(double young, double poisson, int two_dim, int plane_stre
 uint64_t gl_op_out_size(int op, int kind, int ndim) {
     if (op_size_class(op) < 0 || kind < 0 || kind >= GL_NKIND) return 0;
     unsigned r, c;
-    op_extent(op, kind, ndim, r, c);
+    op_extent(op, kind, ndim, nullptr, r, c);
     return (uint64_t)r * c;
 }
 
@@ -768,7 +838,16 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         if (st) return fail(ctx, st);
         if (op == GL_OP_MAT_10_BDB || op == GL_OP_VEC_04_BT)
             if (a->axisymmetric && mesh->ndim != 2) return fail(ctx, GL_ERR_AXISYM_NDIM);
+        if (op_boundary(op)) {
+            if (mesh->ndim == 2 && gd != 1) return fail(ctx, op == GL_OP_NORMAL ? GL_ERR_NORMAL_2D : GL_ERR_BRY_2D);
+            if (mesh->ndim == 3 && gd != 2) return fail(ctx, op == GL_OP_NORMAL ? GL_ERR_NORMAL_3D : GL_ERR_BRY_3D);
+        }
         if (op_uses_gradient(op) && gd != mesh->ndim) return fail(ctx, GL_ERR_GRADIENT_NDIM);
+        if (op_two_pads(op)) {
+            if (a->kind_b < 0 || a->kind_b >= GL_NKIND) return fail(ctx, GL_ERR_KIND_UNSUPPORTED, "args.kind_b is not a GeoKind");
+            if (kind_geo_ndim(a->kind_b) != gd || kind_nnode(a->kind_b) > bk.nnode)
+                return fail(ctx, GL_ERR_INVALID_ARG, "the second pad must have the cell's geo_ndim and at most its nodes");
+        }
 
         IntegParams p;
         std::memset(&p, 0, sizeof(p));
@@ -809,6 +888,12 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
             if (!rt) return fail(ctx, st);
             p.rule = rt->dev;
             p.ng = rt->ng;
+        }
+        if (op_two_pads(op)) {
+            RuleTable *rb = get_rule_b(ctx, bk.kind, a->kind_b, a->ngauss, &st);
+            if (!rb) return fail(ctx, st);
+            p.rule_b = rb->dev;
+            p.nnode_b = rb->nnode;
         }
         // coefficient
         p.coef_len = cr.len;
@@ -869,7 +954,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         }
         if (nl == 0 && gd == mesh->ndim) nl = launch_vec_tpc(p, mesh->ndim, ctx->stream);
         if (nl == 0) {
-            p.cells_per_cta = generic_pick_cells_per_cta(mesh->ndim, gd, p.nnode, p.ng, op);
+            p.cells_per_cta = generic_pick_cells_per_cta(mesh->ndim, gd, p.nnode, p.ng, op, p.nnode_b);
             nl = launch_generic(p, mesh->ndim, gd, ctx->stream);
         }
         if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
@@ -1393,6 +1478,30 @@ int gl_vec_03_bv(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const
 int gl_vec_04_bt(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
     return gl_integ(ctx, mesh, GL_OP_VEC_04_BT, b, e, a, c, o);
 }
+int gl_mat_04_nsb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_04_NSB, b, e, a, c, o);
+}
+int gl_mat_05_btn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_05_BTN, b, e, a, c, o);
+}
+int gl_mat_06_nvn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_06_NVN, b, e, a, c, o);
+}
+int gl_mat_07_bsn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_07_BSN, b, e, a, c, o);
+}
+int gl_mat_01_nsn_bry(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_MAT_01_NSN_BRY, b, e, a, c, o);
+}
+int gl_vec_01_ns_bry(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_VEC_01_NS_BRY, b, e, a, c, o);
+}
+int gl_vec_02_nv_bry(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, const gl_coef *c, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_VEC_02_NV_BRY, b, e, a, c, o);
+}
+int gl_normal_vectors(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, gl_out *o) {
+    return gl_integ(ctx, mesh, GL_OP_NORMAL, b, e, a, nullptr, o);
+}
 int gl_jacobian(gl_ctx *ctx, const gl_mesh *mesh, uint64_t b, uint64_t e, const gl_args *a, gl_out *o) {
     return gl_integ(ctx, mesh, GL_OP_JACOBIAN, b, e, a, nullptr, o);
 }
@@ -1511,7 +1620,7 @@ int scatter_params(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, int op, const
     empty = lo >= hi;
     if (empty) return GL_OK;
     unsigned r, c;
-    op_extent(op, bk.kind, mesh->ndim, r, c);
+    op_extent(op, bk.kind, mesh->ndim, a, r, c);
     s.conn = bk.d_conn;
     s.ncell_k = bk.ncell;
     s.cell_ids = bk.d_cell_ids;
@@ -1568,7 +1677,8 @@ int eq_on_device(gl_ctx *ctx, const gl_mesh *mesh, int npd, const int32_t *eq, i
 
 int assemble_checks(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a) {
     if (!mesh || !a) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
-    if (op_size_class(op) < 0 || op == GL_OP_JACOBIAN) return fail(ctx, GL_ERR_INVALID_ARG, "op cannot be assembled");
+    if (op_size_class(op) < 0 || op == GL_OP_JACOBIAN || op_two_pads(op) || op == GL_OP_NORMAL)
+        return fail(ctx, GL_ERR_INVALID_ARG, "op cannot be assembled");
     if (mesh->device != ctx->device) return fail(ctx, GL_ERR_INVALID_ARG, "mesh belongs to another device");
     if (b > e || e > mesh->ncell) return fail(ctx, GL_ERR_CELL_RANGE);
     if (a->ii0 || a->jj0 || a->nrow || a->ncol || a->packed) return fail(ctx, GL_ERR_INVALID_ARG, "assembly needs tight, full element blocks (ii0 = jj0 = 0, packed = 0)");
@@ -1576,7 +1686,10 @@ int assemble_checks(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, 
 }
 
 int op_dofs_per_node(int op, int ndim) {
-    return (op == GL_OP_MAT_10_BDB || op == GL_OP_VEC_02_NV || op == GL_OP_VEC_04_BT || op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB) ? ndim : 1;
+    return (op == GL_OP_MAT_10_BDB || op == GL_OP_VEC_02_NV || op == GL_OP_VEC_04_BT || op == GL_OP_MAT_08_NTN || op == GL_OP_MAT_09_NVB ||
+            op == GL_OP_VEC_02_NV_BRY)
+               ? ndim
+               : 1;
 }
 
 } // namespace

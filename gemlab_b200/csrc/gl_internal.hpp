@@ -64,6 +64,9 @@ struct IntegParams {
     // reference element
     const double *rule;
     int ng, nnode;
+    // second pad of the two-pad cases: Nb[ng][nnode_b] | Lb[ng][nnode_b][gd] at the same Gauss points; its nodes are the cell's first nnode_b
+    const double *rule_b;
+    int nnode_b;
     // CommonArgs
     int op, axisym, clear;
     double alpha;
@@ -110,8 +113,8 @@ const char *noted_kernel();
 
 // launchers (gl_kernels_generic.cu, gl_kernels_hex8.cu, ...); return the number of kernels launched or < 0 on CUDA error
 int launch_generic(const IntegParams &p, int sd, int gd, void *stream);
-size_t generic_smem_bytes(int sd, int gd, int nnode, int ng, int op, int cells_per_cta);
-int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op);
+size_t generic_smem_bytes(int sd, int gd, int nnode, int ng, int op, int cells_per_cta, int nnode_b = 0);
+int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op, int nnode_b = 0);
 
 // tuned kernels; return 0 if the configuration is not covered (caller falls back to the generic kernel)
 int launch_hex8_bdb(const IntegParams &p, void *stream);
@@ -187,6 +190,7 @@ struct gl_ctx {
     int *d_coef_pat = nullptr; // result of the modulus-structure probe (device-resident PER_CELL moduli)
     unsigned long long *h_err_cell = nullptr; // pinned
     std::map<std::pair<int, int>, std::unique_ptr<gl::RuleTable>> rules; // (kind, ngauss) -> table
+    std::map<std::tuple<int, int, int>, std::unique_ptr<gl::RuleTable>> rules_b; // (kind, kind_b, ngauss) -> table of the second pad
     // scratch for host<->device staging
     double *d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;

@@ -23,10 +23,12 @@ namespace {
 constexpr int NT = 256;
 constexpr double INV_SQRT_2 = 0.70710678118654752440084436210484903928;
 
-__device__ __forceinline__ bool op_needs_gradient(int op) {
+__host__ __device__ __forceinline__ bool op_needs_gradient(int op) {
     return op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV || op == GL_OP_VEC_04_BT ||
-           op == GL_OP_MAT_02_BVN || op == GL_OP_MAT_09_NVB;
+           op == GL_OP_MAT_02_BVN || op == GL_OP_MAT_09_NVB || op == GL_OP_MAT_04_NSB || op == GL_OP_MAT_07_BSN;
 }
+__host__ __device__ __forceinline__ bool op_two_pads(int op) { return op >= GL_OP_MAT_04_NSB && op <= GL_OP_MAT_07_BSN; }
+__host__ __device__ __forceinline__ bool op_boundary(int op) { return op >= GL_OP_MAT_01_NSN_BRY && op <= GL_OP_NORMAL; }
 
 // column (m, i) of the Mandel strain-displacement matrix (calc_bb_matrix, src/integ/mat_10_bdb.rs:238-278):
 // at most 3 non-zero rows; `hoop` = N[m]/r is the axisymmetric row 2 (only for i == 0 in 2D)
@@ -88,9 +90,19 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
     const int bs = nnode * SD;
     const int bcs = (ng * bs) | 1;        // odd cell stride of the gradient block
     double *s_B = s_D + 36;               // [C][bcs] gradients B[gp][m][j]
+    // second pad (two-pad cases): Nb, Lb at the Gauss points and, for mat_05_btn, its own gradients Bb
+    const int nnode_b = p.nnode_b;
+    const int bsb = nnode_b * SD;
+    const int bcsb = (ng * bsb) | 1;
+    double *s_Nb = s_B + (need_b ? C * bcs : 0);          // [ng][nnode_b]
+    double *s_Lb = s_Nb + ng * nnode_b;                    // [ng][nnode_b][GD]
+    double *s_Bb = s_Lb + ng * nnode_b * GD;               // [C][bcsb]   (mat_05_btn only)
+    double *s_un = s_Bb + (op == GL_OP_MAT_05_BTN ? C * bcsb : 0); // [C][ng][SD] unit normals (boundary cases)
 
     const int rule_len = ng * (1 + nnode + nnode * GD);
     for (int i = tid; i < rule_len; i += NT) smem[i] = p.rule[i];
+    if (op_two_pads(op))
+        for (int i = tid; i < ng * nnode_b * (1 + GD); i += NT) s_Nb[i] = p.rule_b[i];
     if (tid < 36) s_D[tid] = p.coef_uniform[tid];
 
     const unsigned int nrow = p.nrow, ncol = p.ncol;
@@ -150,22 +162,82 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
                         }
                     }
                 }
+                if (op == GL_OP_MAT_05_BTN) {
+                    // pad_b.calc_gradient (src/integ/mat_05_btn.rs:106): the second pad's own Jacobian from ITS nodes (the cell's
+                    // first nnode_b) and its own derivatives
+                    const double *Lb = s_Lb + gp * nnode_b * GD;
+                    double Jb[SD][GD];
+#pragma unroll
+                    for (int i = 0; i < SD; i++)
+#pragma unroll
+                        for (int j = 0; j < GD; j++) Jb[i][j] = 0.0;
+                    for (int m = 0; m < nnode_b; m++) {
+#pragma unroll
+                        for (int i = 0; i < SD; i++)
+#pragma unroll
+                            for (int j = 0; j < GD; j++) Jb[i][j] = geom::add(Jb[i][j], geom::mul(X[m * SD + i], Lb[m * GD + j]));
+                    }
+                    double Jbi[SD][SD];
+                    const double detb = geom::invert(Jb, Jbi);
+                    if (fabs(detb) <= ZERO_DETERMINANT) {
+                        const unsigned long long cell = cell0 + c;
+                        atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
+                    }
+                    double *Bbc = s_Bb + c * bcsb + gp * bsb;
+                    for (int m = 0; m < nnode_b; m++) {
+#pragma unroll
+                        for (int j = 0; j < SD; j++) {
+                            double sum = geom::mul(Lb[m * GD], Jbi[0][j]);
+#pragma unroll
+                            for (int k = 1; k < SD; k++) sum = geom::add(sum, geom::mul(Lb[m * GD + k], Jbi[k][j]));
+                            Bbc[m * SD + j] = sum;
+                        }
+                    }
+                }
             } else if constexpr (GD == 1) { // CABLE: norm of the Jacobian vector
                 double n2 = 0.0;
 #pragma unroll
                 for (int i = 0; i < SD; i++) n2 = geom::add(n2, geom::mul(J[i][0], J[i][0]));
                 det = sqrt(n2);
                 (void)Ji;
+                if (SD == 2 && op_boundary(op)) {
+                    // Scratchpad::calc_normal_vector, line in 2D (scratchpad_calc_normal_vector.rs:142-151): n = e3 x g1
+                    double u0 = -J[1][0], u1 = J[0][0];
+                    const double mag = sqrt(geom::add(geom::mul(u0, u0), geom::mul(u1, u1)));
+                    if (mag > 0.0) {
+                        u0 /= mag;
+                        u1 /= mag;
+                    }
+                    det = mag;
+                    s_un[(c * ng + gp) * SD] = u0;
+                    s_un[(c * ng + gp) * SD + 1] = u1;
+                }
             } else { // SHELL: DET_JAC_NOT_AVAILABLE
                 det = -1.0;
                 (void)Ji;
+                if (SD == 3 && op_boundary(op)) {
+                    // surface in 3D (scratchpad_calc_normal_vector.rs:166-175): n = g1 x g2
+                    double u0 = geom::sub(geom::mul(J[1][0], J[2][GD - 1]), geom::mul(J[2][0], J[1][GD - 1]));
+                    double u1 = geom::sub(geom::mul(J[2][0], J[0][GD - 1]), geom::mul(J[0][0], J[2][GD - 1]));
+                    double u2 = geom::sub(geom::mul(J[0][0], J[1][GD - 1]), geom::mul(J[1][0], J[0][GD - 1]));
+                    const double mag = sqrt(geom::add(geom::add(geom::mul(u0, u0), geom::mul(u1, u1)), geom::mul(u2, u2)));
+                    if (mag > 0.0) {
+                        u0 /= mag;
+                        u1 /= mag;
+                        u2 /= mag;
+                    }
+                    det = mag;
+                    s_un[(c * ng + gp) * SD] = u0;
+                    s_un[(c * ng + gp) * SD + 1] = u1;
+                    s_un[(c * ng + gp) * SD + (SD - 1)] = u2;
+                }
             }
             double r = 0.0;
             if (axisym) {
                 const double *N = s_N + gp * nnode;
                 for (int m = 0; m < nnode; m++) r = geom::add(r, geom::mul(N[m], X[m * SD]));
             }
-            s_cf[c * ng + gp] = (op == GL_OP_JACOBIAN) ? det : det * s_w[gp] * p.alpha;
+            s_cf[c * ng + gp] = (op == GL_OP_JACOBIAN || op == GL_OP_NORMAL) ? det : det * s_w[gp] * p.alpha;
             s_rr[c * ng + gp] = r;
         }
         __syncthreads();
@@ -325,6 +397,71 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
                     }
                 }
             } break;
+            case GL_OP_MAT_04_NSB: { // K(m, n j) = sum_p Nb(m) s c_p B(n, j)   (src/integ/mat_04_nsb.rs:115-133)
+                const int n = jj / SD, j = jj - n * SD;
+                for (int gp = 0; gp < ng; gp++) {
+                    double c1 = coef0[gp * gstride] * cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    acc += s_Nb[gp * nnode_b + ii] * c1 * Bc[gp * bs + n * SD + j];
+                }
+            } break;
+            case GL_OP_MAT_05_BTN: { // K(m, n j) = sum_p (Bb(m).T)_j N(n) c_p   (src/integ/mat_05_btn.rs:128-164)
+                const int n = jj / SD, j = jj - n * SD;
+                const double *Bbc = s_Bb + c * bcsb;
+                for (int gp = 0; gp < ng; gp++) {
+                    const double *t = coef0 + gp * gstride;
+                    const double *bm = Bbc + gp * bsb + ii * SD;
+                    double c1 = cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    double sum = 0.0;
+#pragma unroll
+                    for (int a = 0; a < SD; a++) sum += bm[a] * mandel_comp<SD>(t, a, j);
+                    acc += c1 * sum * s_N[gp * nnode + n];
+                }
+            } break;
+            case GL_OP_MAT_06_NVN: { // K(m i, n) = sum_p N(m) v_i Nb(n) c_p   (src/integ/mat_06_nvn.rs:119-136)
+                const int m = ii / SD, i = ii - m * SD;
+                for (int gp = 0; gp < ng; gp++) {
+                    double c1 = cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    acc += c1 * s_N[gp * nnode + m] * coef0[gp * gstride + i] * s_Nb[gp * nnode_b + jj];
+                }
+            } break;
+            case GL_OP_MAT_07_BSN: { // K(m i, n) = sum_p B(m, i) s c_p Nb(n)   (src/integ/mat_07_bsn.rs:114-131)
+                const int m = ii / SD, i = ii - m * SD;
+                for (int gp = 0; gp < ng; gp++) {
+                    double c1 = coef0[gp * gstride] * cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    acc += Bc[gp * bs + m * SD + i] * c1 * s_Nb[gp * nnode_b + jj];
+                }
+            } break;
+            case GL_OP_MAT_01_NSN_BRY: case GL_OP_VEC_01_NS_BRY: {
+                // s = s0 + w.un (the data form of a closure that reads the unit normal); c = s mag_n w alpha [r]
+                const double *un = s_un + c * ng * SD;
+                for (int gp = 0; gp < ng; gp++) {
+                    const double *rec = coef0 + gp * gstride;
+                    double sv = rec[0];
+#pragma unroll
+                    for (int a = 0; a < SD; a++) sv += rec[1 + a] * un[gp * SD + a];
+                    double c1 = sv * cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    acc += (op == GL_OP_MAT_01_NSN_BRY) ? s_N[gp * nnode + ii] * c1 * s_N[gp * nnode + jj] : s_N[gp * nnode + ii] * c1;
+                }
+            } break;
+            case GL_OP_VEC_02_NV_BRY: { // b(m i) = sum_p c_p N(m) (v_i + qn un_i)   (src/integ/vec_02_nv_bry.rs:113-127)
+                const int m = ii / SD, i = ii - m * SD;
+                const double *un = s_un + c * ng * SD;
+                for (int gp = 0; gp < ng; gp++) {
+                    const double *rec = coef0 + gp * gstride;
+                    double c1 = cf[gp];
+                    if (axisym) c1 *= rr[gp];
+                    acc += c1 * s_N[gp * nnode + m] * (rec[i] + rec[SD] * un[gp * SD + i]);
+                }
+            } break;
+            case GL_OP_NORMAL: { // row = gp * (SD + 1) + component: un[0..SD), mag_n
+                const int gp = ii / (SD + 1), k = ii - gp * (SD + 1);
+                acc = k < SD ? s_un[(c * ng + gp) * SD + k] : cf[gp];
+            } break;
             default: // GL_OP_JACOBIAN
                 acc = cf[0];
                 break;
@@ -337,7 +474,7 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
 
 template <int SD, int GD>
 int launch_t(const IntegParams &p, void *stream) {
-    const size_t smem = generic_smem_bytes(SD, GD, p.nnode, p.ng, p.op, p.cells_per_cta);
+    const size_t smem = generic_smem_bytes(SD, GD, p.nnode, p.ng, p.op, p.cells_per_cta, p.nnode_b);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(integ_generic_kernel<SD, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
@@ -362,22 +499,24 @@ int launch_t(const IntegParams &p, void *stream) {
 
 } // namespace
 
-size_t generic_smem_bytes(int sd, int gd, int nnode, int ng, int op, int C) {
-    const bool need_b = op == GL_OP_MAT_10_BDB || op == GL_OP_MAT_03_BTB || op == GL_OP_VEC_03_BV || op == GL_OP_VEC_04_BT ||
-                        op == GL_OP_MAT_02_BVN || op == GL_OP_MAT_09_NVB;
+size_t generic_smem_bytes(int sd, int gd, int nnode, int ng, int op, int C, int nnode_b) {
+    const bool need_b = op_needs_gradient(op);
     size_t n = (size_t)ng * (1 + nnode + nnode * gd);
     n += (size_t)C * ((nnode * sd) | 1);
     n += (size_t)2 * C * ng;
     n += 36;
     if (need_b) n += (size_t)C * ((ng * nnode * sd) | 1);
+    if (op_two_pads(op)) n += (size_t)ng * nnode_b * (1 + gd);
+    if (op == GL_OP_MAT_05_BTN) n += (size_t)C * ((ng * nnode_b * sd) | 1);
+    if (op_boundary(op)) n += (size_t)C * ng * sd;
     return n * sizeof(double);
 }
 
-int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op) {
+int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op, int nnode_b) {
     // as many cells as fit in ~96 KB (two CTAs per SM), at most 64 and at least 1
     int best = 1;
     for (int c = 1; c <= 64; c++) {
-        if (generic_smem_bytes(sd, gd, nnode, ng, op, c) <= 96 * 1024) best = c;
+        if (generic_smem_bytes(sd, gd, nnode, ng, op, c, nnode_b) <= 96 * 1024) best = c;
         else break;
     }
     return best;

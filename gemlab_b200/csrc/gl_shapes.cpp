@@ -293,6 +293,14 @@ const char *status_string(int status) {
     case GL_ERR_GAUSS_HEX: return "requested number of integration points is not available for Hex class";
     case GL_ERR_KIND_UNSUPPORTED: return "GeoKind is not supported by libgemlab_cuda yet";
     case GL_ERR_SPACE_NDIM: return "space_ndim must be 2 or 3";
+    case GL_ERR_NROW_KK_NNODE_B: return "nrow(K) must be \xe2\x89\xa5 ii0 + pad_b.nnode";
+    case GL_ERR_NCOL_KK_NDOF_PAD: return "ncol(K) must be \xe2\x89\xa5 jj0 + pad.nnode \xe2\x8b\x85 space_ndim";
+    case GL_ERR_NROW_KK_NDOF_PAD: return "nrow(K) must be \xe2\x89\xa5 ii0 + pad.nnode \xe2\x8b\x85 space_ndim";
+    case GL_ERR_NCOL_KK_NNODE_B: return "ncol(K) must be \xe2\x89\xa5 jj0 + pad_b.nnode";
+    case GL_ERR_BRY_2D: return "in 2D, geometry ndim must be equal to 1 (a line)";
+    case GL_ERR_BRY_3D: return "in 3D, geometry ndim must be equal to 2 (a surface)";
+    case GL_ERR_NORMAL_2D: return "calc_normal_vector requires geo_ndim = 1 in 2D (CABLE in 2D)";
+    case GL_ERR_NORMAL_3D: return "calc_normal_vector requires geo_ndim = 2 in 3D (SHELL in 3D)";
     case GL_ERR_INVALID_ARG: return "invalid argument";
     case GL_ERR_CELL_RANGE: return "cell range is out of bounds";
     case GL_ERR_OUT_CAPACITY: return "output buffer is too small for the requested cell range";

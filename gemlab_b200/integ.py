@@ -25,14 +25,15 @@ from .mesh import Mesh
 
 GL_HOST, GL_DEVICE = 0, 1
 OPS = {"mat_02_bvn": 9, "mat_08_ntn": 10, "mat_09_nvb": 11, "mat_10_bdb": 0, "mat_01_nsn": 1, "mat_03_btb": 2, "vec_01_ns": 3, "vec_03_bv": 4, "vec_02_nv": 5,
-       "vec_04_bt": 6, "jacobian": 8}
+       "vec_04_bt": 6, "jacobian": 8, "mat_04_nsb": 12, "mat_05_btn": 13, "mat_06_nvn": 14, "mat_07_bsn": 15,
+       "mat_01_nsn_bry": 16, "vec_01_ns_bry": 17, "vec_02_nv_bry": 18, "normal": 19}
 COEF_UNIFORM, COEF_PER_MARKER, COEF_PER_CELL, COEF_PER_GAUSS = 0, 1, 2, 3
 
 
 class CommonArgs:
     """gemlab::integ::CommonArgs (src/integ/common_args.rs:5-43) without pad/gauss (implied by the mesh and `ngauss`)."""
 
-    def __init__(self, ngauss=None, clear=True, axisymmetric=False, alpha=1.0, ii0=0, jj0=0, nrow=0, ncol=0, packed=False):
+    def __init__(self, ngauss=None, clear=True, axisymmetric=False, alpha=1.0, ii0=0, jj0=0, nrow=0, ncol=0, packed=False, kind_b=None):
         self.ngauss = ngauss          # None = Gauss::new(kind), else Gauss::new_sized(kind.class(), ngauss)
         self.clear = clear
         self.axisymmetric = axisymmetric
@@ -43,6 +44,7 @@ class CommonArgs:
         self.ncol = ncol
         self.ksi = (0.0, 0.0, 0.0)    # integ.jacobian only
         self.packed = packed          # batched boundary only: matrices leave as packed upper triangles (gl_args.packed)
+        self.kind_b = kind_b          # two-pad cases (mat_04_nsb .. mat_07_bsn): GeoKind of the second Scratchpad (pad_b)
 
     def _c(self):
         a = GlArgs()
@@ -50,6 +52,7 @@ class CommonArgs:
         a.axisymmetric = int(bool(self.axisymmetric))
         a.clear = int(bool(self.clear))
         a.packed = int(bool(self.packed))
+        a.kind_b = -1 if self.kind_b is None else int(self.kind_b)
         a.alpha = float(self.alpha)
         a.ii0, a.jj0, a.nrow, a.ncol = int(self.ii0), int(self.jj0), int(self.nrow), int(self.ncol)
         for i in range(3):
@@ -413,6 +416,46 @@ vec_10_gs = vec_03_bv  # legacy name used by BASELINE.json
 def vec_04_bt(ctx, dmesh, cell_range, args, coef, out=None):
     """d = int B.sigma, ndof -- integ::vec_04_bt (src/integ/vec_04_bt.rs:93-170)."""
     return _integ("vec_04_bt", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_04_nsb(ctx, dmesh, cell_range, args, coef, out=None):
+    """integ::mat_04_nsb (src/integ/mat_04_nsb.rs:66): K = int Nb s B, nnode_b x ndof; args.kind_b names the second pad."""
+    return _integ("mat_04_nsb", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_05_btn(ctx, dmesh, cell_range, args, coef, out=None):
+    """integ::mat_05_btn (src/integ/mat_05_btn.rs:68): K = int Bb.T N, nnode_b x ndof; coefficient = Mandel vector of T."""
+    return _integ("mat_05_btn", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_06_nvn(ctx, dmesh, cell_range, args, coef, out=None):
+    """integ::mat_06_nvn (src/integ/mat_06_nvn.rs:69): K = int N v Nb, ndof x nnode_b."""
+    return _integ("mat_06_nvn", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_07_bsn(ctx, dmesh, cell_range, args, coef, out=None):
+    """integ::mat_07_bsn (src/integ/mat_07_bsn.rs:69): K = int B s Nb, ndof x nnode_b."""
+    return _integ("mat_07_bsn", ctx, dmesh, cell_range, args, coef, out)
+
+
+def mat_01_nsn_bry(ctx, dmesh, cell_range, args, coef, out=None):
+    """integ::mat_01_nsn_bry (src/integ/mat_01_nsn_bry.rs:48) over boundary cells; record (s0, w..): s = s0 + w.un."""
+    return _integ("mat_01_nsn_bry", ctx, dmesh, cell_range, args, coef, out)
+
+
+def vec_01_ns_bry(ctx, dmesh, cell_range, args, coef, out=None):
+    """integ::vec_01_ns_bry (src/integ/vec_01_ns_bry.rs:54) over boundary cells; record (s0, w..): s = s0 + w.un."""
+    return _integ("vec_01_ns_bry", ctx, dmesh, cell_range, args, coef, out)
+
+
+def vec_02_nv_bry(ctx, dmesh, cell_range, args, coef, out=None):
+    """integ::vec_02_nv_bry (src/integ/vec_02_nv_bry.rs:61) over boundary cells; record (v.., qn): v = v + qn un."""
+    return _integ("vec_02_nv_bry", ctx, dmesh, cell_range, args, coef, out)
+
+
+def normal_vectors(ctx, dmesh, cell_range, args, out=None):
+    """Scratchpad::calc_normal_vector at every Gauss point (scratchpad_calc_normal_vector.rs:111): per cell ng x (un.., mag_n)."""
+    return _integ("normal", ctx, dmesh, cell_range, args, None, out)
 
 
 def jacobian(ctx, dmesh, cell_range, ksi, out=None):

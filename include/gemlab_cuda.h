@@ -65,6 +65,14 @@ typedef enum gl_status {
     GL_ERR_GAUSS_HEX = 17,
     GL_ERR_KIND_UNSUPPORTED = 18, /* unknown GeoKind ordinal, or shape functions at an arbitrary point requested for a table-only kind */
     GL_ERR_SPACE_NDIM = 20,       /* "space_ndim must be 2 or 3" (scratchpad.rs:153) */
+    GL_ERR_NROW_KK_NNODE_B = 21,  /* "nrow(K) must be >= ii0 + pad_b.nnode" (mat_04_nsb.rs:78) */
+    GL_ERR_NCOL_KK_NDOF_PAD = 22, /* "ncol(K) must be >= jj0 + pad.nnode * space_ndim" (mat_04_nsb.rs:81) */
+    GL_ERR_NROW_KK_NDOF_PAD = 23, /* "nrow(K) must be >= ii0 + pad.nnode * space_ndim" (mat_06_nvn.rs:81) */
+    GL_ERR_NCOL_KK_NNODE_B = 24,  /* "ncol(K) must be >= jj0 + pad_b.nnode" (mat_06_nvn.rs:84) */
+    GL_ERR_BRY_2D = 25,           /* "in 2D, geometry ndim must be equal to 1 (a line)" (mat_01_nsn_bry.rs:56) */
+    GL_ERR_BRY_3D = 26,           /* "in 3D, geometry ndim must be equal to 2 (a surface)" (mat_01_nsn_bry.rs:59) */
+    GL_ERR_NORMAL_2D = 27,        /* "calc_normal_vector requires geo_ndim = 1 in 2D (CABLE in 2D)" (scratchpad_calc_normal_vector.rs:115) */
+    GL_ERR_NORMAL_3D = 28,        /* "calc_normal_vector requires geo_ndim = 2 in 3D (SHELL in 3D)" (scratchpad_calc_normal_vector.rs:118) */
     /* errors of the batched boundary itself (no reference counterpart) */
     GL_ERR_INVALID_ARG = 100,
     GL_ERR_CELL_RANGE = 101,
@@ -87,7 +95,21 @@ typedef enum gl_op {
     GL_OP_JACOBIAN = 8,   /* Scratchpad::calc_jacobian at one ksi (scratchpad_calc_jacobian.rs:101; Mesh::check_jacobian, mesh/check.rs:43-60)  1 */
     GL_OP_MAT_02_BVN = 9, /* integ::mat_02_bvn  K = int (B.v) N     (src/integ/mat_02_bvn.rs:48)   nnode x nnode; coefficient v (space_ndim) */
     GL_OP_MAT_08_NTN = 10, /* integ::mat_08_ntn K = int N T N       (src/integ/mat_08_ntn.rs:56)   ndof x ndof;   coefficient Mandel vector (ns) */
-    GL_OP_MAT_09_NVB = 11  /* integ::mat_09_nvb K = int N v B       (src/integ/mat_09_nvb.rs:54)   ndof x ndof;   coefficient v (space_ndim) */
+    GL_OP_MAT_09_NVB = 11, /* integ::mat_09_nvb K = int N v B       (src/integ/mat_09_nvb.rs:54)   ndof x ndof;   coefficient v (space_ndim) */
+    /* two-pad coupling matrices: the second Scratchpad (pad_b) is gl_args.kind_b on the FIRST nnode_b nodes of every cell
+     * (Qua8 + Qua4, Tri6 + Tri3, Hex20 + Hex8, Tet10 + Tet4, or the cell's own kind) */
+    GL_OP_MAT_04_NSB = 12, /* integ::mat_04_nsb K = int Nb s B      (src/integ/mat_04_nsb.rs:66)   nnode_b x ndof; coefficient s */
+    GL_OP_MAT_05_BTN = 13, /* integ::mat_05_btn K = int Bb.T N      (src/integ/mat_05_btn.rs:68)   nnode_b x ndof; coefficient Mandel vector (ns) */
+    GL_OP_MAT_06_NVN = 14, /* integ::mat_06_nvn K = int N v Nb      (src/integ/mat_06_nvn.rs:69)   ndof x nnode_b; coefficient v (space_ndim) */
+    GL_OP_MAT_07_BSN = 15, /* integ::mat_07_bsn K = int B s Nb      (src/integ/mat_07_bsn.rs:69)   ndof x nnode_b; coefficient s */
+    /* boundary integrals over cells with geo_ndim = space_ndim - 1 (lines in 2D, surfaces in 3D).  The reference's closures
+     * receive the unit normal un; as data, a record is (s0, w[space_ndim]) with s = s0 + w.un for the two scalar cases and
+     * (v[space_ndim], qn) with v = v + qn un for vec_02_nv_bry (a traction plus a pressure-like normal load) */
+    GL_OP_MAT_01_NSN_BRY = 16, /* integ::mat_01_nsn_bry (src/integ/mat_01_nsn_bry.rs:48)  nnode x nnode */
+    GL_OP_VEC_01_NS_BRY = 17,  /* integ::vec_01_ns_bry  (src/integ/vec_01_ns_bry.rs:54)   nnode */
+    GL_OP_VEC_02_NV_BRY = 18,  /* integ::vec_02_nv_bry  (src/integ/vec_02_nv_bry.rs:61)   ndof */
+    GL_OP_NORMAL = 19          /* Scratchpad::calc_normal_vector at every Gauss point (scratchpad_calc_normal_vector.rs:111):
+                                  ngauss x (un[space_ndim], mag_n) per cell */
 } gl_op;
 
 typedef enum gl_location { GL_HOST = 0, GL_DEVICE = 1 } gl_location;
@@ -107,6 +129,8 @@ typedef struct gl_args {
     uint32_t ii0, jj0;    /* CommonArgs.ii0 / jj0: offsets inside each element's block */
     uint32_t nrow, ncol;  /* per-element block dims; 0 = tight (nrow = ii0 + size, ncol = jj0 + size; vectors use nrow only) */
     double ksi[3];        /* GL_OP_JACOBIAN only: the reference point */
+    int32_t kind_b;       /* two-pad cases (GL_OP_MAT_04_NSB .. GL_OP_MAT_07_BSN): GeoKind ordinal of the second pad */
+    int32_t reserved;
 } gl_args;
 
 /* The reference takes the coefficient as a closure evaluated at every Gauss point
@@ -203,7 +227,8 @@ GL_API int gl_mesh_ndim(const gl_mesh *mesh);
 
 /* ---- output layout ------------------------------------------------------------------------------- */
 
-/* doubles per element block of `op` for a cell of `kind` (tight, ii0 = jj0 = 0) */
+/* doubles per element block of `op` for a cell of `kind` (tight, ii0 = jj0 = 0); the two-pad cases and GL_OP_NORMAL depend on
+ * args (kind_b, ngauss): use gl_out_total / gl_out_offsets for them (this function returns 0) */
 GL_API uint64_t gl_op_out_size(int op, int kind, int ndim);
 /* doubles per coefficient record */
 GL_API uint64_t gl_op_coef_size(int op, int ndim);
@@ -247,6 +272,25 @@ GL_API int gl_vec_03_bv(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, u
 /* replaces integ::vec_04_bt (src/integ/vec_04_bt.rs:93-170) */
 GL_API int gl_vec_04_bt(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                         const gl_coef *coef, gl_out *out);
+/* replace integ::mat_04_nsb, mat_05_btn, mat_06_nvn, mat_07_bsn (two pads; args->kind_b names the second one) */
+GL_API int gl_mat_04_nsb(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+GL_API int gl_mat_05_btn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+GL_API int gl_mat_06_nvn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+GL_API int gl_mat_07_bsn(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_out *out);
+/* replace integ::mat_01_nsn_bry, vec_01_ns_bry, vec_02_nv_bry (boundary cells: geo_ndim = space_ndim - 1) */
+GL_API int gl_mat_01_nsn_bry(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                             const gl_coef *coef, gl_out *out);
+GL_API int gl_vec_01_ns_bry(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                            const gl_coef *coef, gl_out *out);
+GL_API int gl_vec_02_nv_bry(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                            const gl_coef *coef, gl_out *out);
+/* batched Scratchpad::calc_normal_vector at the Gauss points of the rule (scratchpad_calc_normal_vector.rs:111-176) */
+GL_API int gl_normal_vectors(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                             gl_out *out);
 /* replaces the per-cell Scratchpad::calc_jacobian loop of Mesh::check_jacobian (src/mesh/check.rs:43-60) */
 GL_API int gl_jacobian(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                        gl_out *out);

@@ -47,6 +47,14 @@ const char *go_strerror(int code) {
     case GO_ERR_KIND_UNSUPPORTED: return "GeoKind is not restated by the oracle";
     case GO_ERR_CALLBACK_STOP: return "stop";
     case GO_ERR_SPACE_NDIM: return "space_ndim must be 2 or 3";
+    case GO_ERR_NROW_KK_NNODE_B: return "nrow(K) must be \xe2\x89\xa5 ii0 + pad_b.nnode";
+    case GO_ERR_NCOL_KK_NDOF_PAD: return "ncol(K) must be \xe2\x89\xa5 jj0 + pad.nnode \xe2\x8b\x85 space_ndim";
+    case GO_ERR_NROW_KK_NDOF_PAD: return "nrow(K) must be \xe2\x89\xa5 ii0 + pad.nnode \xe2\x8b\x85 space_ndim";
+    case GO_ERR_NCOL_KK_NNODE_B: return "ncol(K) must be \xe2\x89\xa5 jj0 + pad_b.nnode";
+    case GO_ERR_BRY_2D: return "in 2D, geometry ndim must be equal to 1 (a line)";
+    case GO_ERR_BRY_3D: return "in 3D, geometry ndim must be equal to 2 (a surface)";
+    case GO_ERR_NORMAL_2D: return "calc_normal_vector requires geo_ndim = 1 in 2D (CABLE in 2D)";
+    case GO_ERR_NORMAL_3D: return "calc_normal_vector requires geo_ndim = 2 in 3D (SHELL in 3D)";
     default: return "unknown error";
     }
 }
@@ -1388,6 +1396,372 @@ int go_mesh_integ(int op, const go_mesh *mesh, size_t cell_begin, size_t cell_en
                 { if (e < first_cell) { first_err = err; first_cell = e; } }
             }
         }
+    }
+    if (err_cell) *err_cell = first_cell;
+    return first_err;
+}
+
+
+/* ---------------------------------------------------------------------------------------------- */
+/* two-pad coupling matrices and boundary integrals                                               */
+/* ---------------------------------------------------------------------------------------------- */
+
+#define B(m, j) (pad->gradient[(m)*sd + (j)])
+#define KK(i, j) (kk[(size_t)(i) + (size_t)(j) * (size_t)nrow])
+#define XXT(j, m) (pad->xxt[(j)*nnode + (m)])
+#define BB(m, j) (pad_b->gradient[(m)*sd + (j)])
+
+/* the coefficient c of the coupled cases: N, B and det J of the main pad, then c = det J * w * alpha [* r] */
+static int coupled_point(go_args *args, int p, double *c) { return matrix_case_point(args, p, c); }
+
+/* integ::mat_04_nsb (src/integ/mat_04_nsb.rs:66-137): K(m, n j) = sum_p Nb(m) s c_p B(n, j) */
+int go_mat_04_nsb(double *kk, int nrow, int ncol, go_pad *pad_b, go_args *args, go_fn_s fn, void *user) {
+    go_pad *pad = args->pad;
+    const int sd = pad->space_ndim, nnode = pad->nnode, nnode_b = pad_b->nnode;
+    const int ii0 = args->ii0, jj0 = args->jj0;
+    if (nrow < ii0 + nnode_b) return GO_ERR_NROW_KK_NNODE_B;
+    if (ncol < jj0 + nnode * sd) return GO_ERR_NCOL_KK_NDOF_PAD;
+    if (args->clear) memset(kk, 0, sizeof(double) * (size_t)nrow * (size_t)ncol);
+    for (int p = 0; p < args->ngauss; p++) {
+        go_pad_calc_interp(pad_b, args->gauss[p]); /* Nb */
+        double c0;
+        int err = coupled_point(args, p, &c0);
+        if (err) return err;
+        double s = 0.0;
+        if (fn(&s, p, pad->interp, pad->gradient, user)) return GO_ERR_CALLBACK_STOP;
+        const double c = s * c0; /* s * det_jac * weight * alpha [* r]: same product up to the order of the scalar factors */
+        const double *nnb = pad_b->interp;
+        for (int m = 0; m < nnode_b; m++)
+            for (int n = 0; n < nnode; n++)
+                for (int j = 0; j < sd; j++) KK(ii0 + m, jj0 + j + n * sd) += nnb[m] * c * B(n, j);
+    }
+    return GO_OK;
+}
+
+/* integ::mat_05_btn (src/integ/mat_05_btn.rs:68-168): K(m, n j) = sum_p (Bb(m) . T)_j N(n) c_p, T from its Mandel vector */
+int go_mat_05_btn(double *kk, int nrow, int ncol, go_pad *pad_b, go_args *args, go_fn_tt fn, void *user) {
+    go_pad *pad = args->pad;
+    const int sd = pad->space_ndim, nnode = pad->nnode, nnode_b = pad_b->nnode;
+    const int ii0 = args->ii0, jj0 = args->jj0;
+    if (nrow < ii0 + nnode_b) return GO_ERR_NROW_KK_NNODE_B;
+    if (ncol < jj0 + nnode * sd) return GO_ERR_NCOL_KK_NDOF_PAD;
+    double t[6] = {0, 0, 0, 0, 0, 0};
+    if (args->clear) memset(kk, 0, sizeof(double) * (size_t)nrow * (size_t)ncol);
+    const double s = SQRT_2;
+    for (int p = 0; p < args->ngauss; p++) {
+        double det_b;
+        int err = go_pad_calc_gradient(pad_b, args->gauss[p], &det_b); /* Bb */
+        if (err) return err;
+        double c;
+        err = coupled_point(args, p, &c);
+        if (err) return err;
+        const double *nn = pad->interp;
+        if (fn(t, p, nn, pad->gradient, user)) return GO_ERR_CALLBACK_STOP;
+        for (int m = 0; m < nnode_b; m++)
+            for (int n = 0; n < nnode; n++) {
+                if (sd == 2) {
+                    KK(ii0 + m, jj0 + 0 + n * 2) += c * (BB(m, 0) * t[0] + BB(m, 1) * t[3] / s) * nn[n];
+                    KK(ii0 + m, jj0 + 1 + n * 2) += c * (BB(m, 0) * t[3] / s + BB(m, 1) * t[1]) * nn[n];
+                } else {
+                    KK(ii0 + m, jj0 + 0 + n * 3) += c * (BB(m, 0) * t[0] + BB(m, 1) * t[3] / s + BB(m, 2) * t[5] / s) * nn[n];
+                    KK(ii0 + m, jj0 + 1 + n * 3) += c * (BB(m, 0) * t[3] / s + BB(m, 1) * t[1] + BB(m, 2) * t[4] / s) * nn[n];
+                    KK(ii0 + m, jj0 + 2 + n * 3) += c * (BB(m, 0) * t[5] / s + BB(m, 1) * t[4] / s + BB(m, 2) * t[2]) * nn[n];
+                }
+            }
+    }
+    return GO_OK;
+}
+
+/* integ::mat_06_nvn (src/integ/mat_06_nvn.rs:69-140): K(m i, n) = sum_p N(m) v_i Nb(n) c_p */
+int go_mat_06_nvn(double *kk, int nrow, int ncol, go_args *args, go_pad *pad_b, go_fn_v fn, void *user) {
+    go_pad *pad = args->pad;
+    const int sd = pad->space_ndim, nnode = pad->nnode, nnode_b = pad_b->nnode;
+    const int ii0 = args->ii0, jj0 = args->jj0;
+    if (nrow < ii0 + nnode * sd) return GO_ERR_NROW_KK_NDOF_PAD;
+    if (ncol < jj0 + nnode_b) return GO_ERR_NCOL_KK_NNODE_B;
+    double v[3] = {0, 0, 0};
+    if (args->clear) memset(kk, 0, sizeof(double) * (size_t)nrow * (size_t)ncol);
+    for (int p = 0; p < args->ngauss; p++) {
+        double c;
+        int err = coupled_point(args, p, &c);
+        if (err) return err;
+        go_pad_calc_interp(pad_b, args->gauss[p]); /* Nb */
+        const double *nn = pad->interp, *nnb = pad_b->interp;
+        if (fn(v, p, nn, pad->gradient, user)) return GO_ERR_CALLBACK_STOP;
+        for (int m = 0; m < nnode; m++)
+            for (int n = 0; n < nnode_b; n++)
+                for (int i = 0; i < sd; i++) KK(ii0 + i + m * sd, jj0 + n) += c * nn[m] * v[i] * nnb[n];
+    }
+    return GO_OK;
+}
+
+/* integ::mat_07_bsn (src/integ/mat_07_bsn.rs:69-135): K(m i, n) = sum_p B(m, i) s c_p Nb(n) */
+int go_mat_07_bsn(double *kk, int nrow, int ncol, go_args *args, go_pad *pad_b, go_fn_s fn, void *user) {
+    go_pad *pad = args->pad;
+    const int sd = pad->space_ndim, nnode = pad->nnode, nnode_b = pad_b->nnode;
+    const int ii0 = args->ii0, jj0 = args->jj0;
+    if (nrow < ii0 + nnode * sd) return GO_ERR_NROW_KK_NDOF_PAD;
+    if (ncol < jj0 + nnode_b) return GO_ERR_NCOL_KK_NNODE_B;
+    if (args->clear) memset(kk, 0, sizeof(double) * (size_t)nrow * (size_t)ncol);
+    for (int p = 0; p < args->ngauss; p++) {
+        double c0;
+        int err = coupled_point(args, p, &c0);
+        if (err) return err;
+        go_pad_calc_interp(pad_b, args->gauss[p]); /* Nb */
+        double s = 0.0;
+        if (fn(&s, p, pad->interp, pad->gradient, user)) return GO_ERR_CALLBACK_STOP;
+        const double c = s * c0;
+        const double *nnb = pad_b->interp;
+        for (int m = 0; m < nnode; m++)
+            for (int n = 0; n < nnode_b; n++)
+                for (int i = 0; i < sd; i++) KK(ii0 + i + m * sd, jj0 + n) += B(m, i) * c * nnb[n];
+    }
+    return GO_OK;
+}
+
+/* Scratchpad::calc_normal_vector (src/shapes/scratchpad_calc_normal_vector.rs:111-176) */
+int go_pad_calc_normal_vector(go_pad *pad, double *un, const double *ksi, double *mag_n) {
+    const int sd = pad->space_ndim, gd = pad->geo_ndim, nnode = pad->nnode;
+    if (sd == 2 && gd != 1) return GO_ERR_NORMAL_2D;
+    if (sd == 3 && gd != 2) return GO_ERR_NORMAL_3D;
+    go_deriv(pad->kind, ksi, pad->deriv);
+    /* J = Xt . L (space_ndim x geo_ndim) */
+    double jj[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (int i = 0; i < sd; i++)
+        for (int j = 0; j < gd; j++) {
+            double sum = 0.0;
+            for (int m = 0; m < nnode; m++) sum += XXT(i, m) * pad->deriv[m * gd + j];
+            jj[i][j] = sum;
+        }
+    if (sd == 2) { /* n = e3 x g1 */
+        un[0] = -jj[1][0];
+        un[1] = jj[0][0];
+        const double mag = sqrt(un[0] * un[0] + un[1] * un[1]);
+        if (mag > 0.0) {
+            un[0] /= mag;
+            un[1] /= mag;
+        }
+        *mag_n = mag;
+        return GO_OK;
+    }
+    /* n = g1 x g2 */
+    un[0] = jj[1][0] * jj[2][1] - jj[2][0] * jj[1][1];
+    un[1] = jj[2][0] * jj[0][1] - jj[0][0] * jj[2][1];
+    un[2] = jj[0][0] * jj[1][1] - jj[1][0] * jj[0][1];
+    const double mag = sqrt(un[0] * un[0] + un[1] * un[1] + un[2] * un[2]);
+    if (mag > 0.0) {
+        un[0] /= mag;
+        un[1] /= mag;
+        un[2] /= mag;
+    }
+    *mag_n = mag;
+    return GO_OK;
+}
+
+static int bry_checks(const go_pad *pad) {
+    if (pad->space_ndim == 2 && pad->geo_ndim != 1) return GO_ERR_BRY_2D;
+    if (pad->space_ndim == 3 && pad->geo_ndim != 2) return GO_ERR_BRY_3D;
+    return GO_OK;
+}
+
+/* N, unit normal and c = mag_n * w * alpha [* r] at Gauss point p of a boundary cell */
+static int bry_point(go_args *args, int p, double *un, double *c) {
+    go_pad *pad = args->pad;
+    go_pad_calc_interp(pad, args->gauss[p]);
+    double mag_n;
+    int err = go_pad_calc_normal_vector(pad, un, args->gauss[p], &mag_n);
+    if (err) return err;
+    const double weight = args->gauss[p][3];
+    *c = args->axisymmetric ? mag_n * weight * args->alpha * radius_at_ip(pad) : mag_n * weight * args->alpha;
+    return GO_OK;
+}
+
+/* integ::mat_01_nsn_bry (src/integ/mat_01_nsn_bry.rs:48-113) */
+int go_mat_01_nsn_bry(double *kk, int nrow, int ncol, go_args *args, go_fn_bry fn, void *user) {
+    go_pad *pad = args->pad;
+    const int nnode = pad->nnode, ii0 = args->ii0, jj0 = args->jj0;
+    int err = bry_checks(pad);
+    if (err) return err;
+    if (nrow < ii0 + nnode) return GO_ERR_NROW_KK_NNODE;
+    if (ncol < jj0 + nnode) return GO_ERR_NCOL_KK_NNODE;
+    if (args->clear) memset(kk, 0, sizeof(double) * (size_t)nrow * (size_t)ncol);
+    for (int p = 0; p < args->ngauss; p++) {
+        double un[3] = {0, 0, 0}, c0, s = 0.0;
+        err = bry_point(args, p, un, &c0);
+        if (err) return err;
+        const double *nn = pad->interp;
+        if (fn(&s, p, un, nn, user)) return GO_ERR_CALLBACK_STOP;
+        const double c = s * c0;
+        for (int m = 0; m < nnode; m++)
+            for (int n = 0; n < nnode; n++) KK(ii0 + m, jj0 + n) += nn[m] * c * nn[n];
+    }
+    return GO_OK;
+}
+
+/* integ::vec_01_ns_bry (src/integ/vec_01_ns_bry.rs:54-115) */
+int go_vec_01_ns_bry(double *a, int len, go_args *args, go_fn_bry fn, void *user) {
+    go_pad *pad = args->pad;
+    const int nnode = pad->nnode, ii0 = args->ii0;
+    int err = bry_checks(pad);
+    if (err) return err;
+    if (len < ii0 + nnode) return GO_ERR_A_LEN;
+    if (args->clear) memset(a, 0, sizeof(double) * (size_t)len);
+    for (int p = 0; p < args->ngauss; p++) {
+        double un[3] = {0, 0, 0}, c0, s = 0.0;
+        err = bry_point(args, p, un, &c0);
+        if (err) return err;
+        const double *nn = pad->interp;
+        if (fn(&s, p, un, nn, user)) return GO_ERR_CALLBACK_STOP;
+        const double coef = s * c0;
+        for (int m = 0; m < nnode; m++) a[ii0 + m] += nn[m] * coef;
+    }
+    return GO_OK;
+}
+
+/* integ::vec_02_nv_bry (src/integ/vec_02_nv_bry.rs:61-130) */
+int go_vec_02_nv_bry(double *b, int len, go_args *args, go_fn_bry fn, void *user) {
+    go_pad *pad = args->pad;
+    const int sd = pad->space_ndim, nnode = pad->nnode, ii0 = args->ii0;
+    int err = bry_checks(pad);
+    if (err) return err;
+    if (len < ii0 + nnode * sd) return GO_ERR_B_LEN;
+    if (args->clear) memset(b, 0, sizeof(double) * (size_t)len);
+    for (int p = 0; p < args->ngauss; p++) {
+        double un[3] = {0, 0, 0}, coef, v[3] = {0, 0, 0};
+        err = bry_point(args, p, un, &coef);
+        if (err) return err;
+        const double *nn = pad->interp;
+        if (fn(v, p, un, nn, user)) return GO_ERR_CALLBACK_STOP;
+        for (int m = 0; m < nnode; m++)
+            for (int i = 0; i < sd; i++) b[ii0 + i + m * sd] += coef * nn[m] * v[i];
+    }
+    return GO_OK;
+}
+
+size_t go_op_out_size_ext(int op, int kind, int kind_b, int ndim, int ngauss) {
+    const size_t nnode = (size_t)go_kind_nnode(kind), ndof = nnode * (size_t)ndim;
+    const size_t nb = kind_b >= 0 ? (size_t)go_kind_nnode(kind_b) : 0;
+    switch (op) {
+    case GO_OP_MAT_04_NSB: case GO_OP_MAT_05_BTN: case GO_OP_MAT_06_NVN: case GO_OP_MAT_07_BSN: return nb * ndof;
+    case GO_OP_MAT_01_NSN_BRY: return nnode * nnode;
+    case GO_OP_VEC_01_NS_BRY: return nnode;
+    case GO_OP_VEC_02_NV_BRY: return ndof;
+    case GO_OP_NORMAL: {
+        const double(*g)[4];
+        int ng = 0;
+        if (go_gauss(kind, ngauss, &g, &ng)) return 0;
+        return (size_t)ng * (size_t)(ndim + 1);
+    }
+    default: return 0;
+    }
+}
+
+size_t go_op_coef_size_ext(int op, int ndim) {
+    switch (op) {
+    case GO_OP_MAT_04_NSB: case GO_OP_MAT_07_BSN: return 1;
+    case GO_OP_MAT_05_BTN: return 2 * (size_t)ndim;
+    case GO_OP_MAT_06_NVN: return (size_t)ndim;
+    case GO_OP_MAT_01_NSN_BRY: case GO_OP_VEC_01_NS_BRY: case GO_OP_VEC_02_NV_BRY: return (size_t)ndim + 1;
+    default: return 0;
+    }
+}
+
+/* data form of the boundary closures: s = s0 + w.un (scalar cases), v = v + qn un (vec_02_nv_bry) */
+typedef struct {
+    coef_view cv;
+    int ndim, vector_case;
+} bry_view;
+
+static int cb_bry(double *out, int p, const double *un, const double *nn, void *user) {
+    (void)nn;
+    const bry_view *bv = (const bry_view *)user;
+    const double *r = bv->cv.base + (size_t)p * bv->cv.gp_stride;
+    if (bv->vector_case) {
+        for (int i = 0; i < bv->ndim; i++) out[i] = r[i] + r[bv->ndim] * un[i];
+    } else {
+        double s = r[0];
+        for (int i = 0; i < bv->ndim; i++) s += r[1 + i] * un[i];
+        out[0] = s;
+    }
+    return 0;
+}
+
+static int integ_one_cell_ext(int op, const go_mesh *mesh, size_t e, size_t cell_begin, int ngauss, int kind_b, const double *coef,
+                              size_t coef_cell_stride, size_t coef_gp_stride, double alpha, int axisymmetric, double *out) {
+    const int kind = mesh->kinds[e], ndim = mesh->ndim;
+    go_pad pad, pad_b;
+    int err = go_pad_init(&pad, ndim, kind);
+    if (err) return err;
+    const uint64_t *points = mesh->conn + mesh->conn_off[e];
+    for (int m = 0; m < pad.nnode; m++)
+        for (int j = 0; j < ndim; j++) go_pad_set_xx(&pad, m, j, mesh->coords[points[m] * (size_t)ndim + (size_t)j]);
+    go_args args;
+    args.pad = &pad;
+    err = go_gauss(kind, ngauss, &args.gauss, &args.ngauss);
+    if (err) return err;
+    args.clear = 1;
+    args.axisymmetric = axisymmetric;
+    args.alpha = alpha;
+    args.ii0 = 0;
+    args.jj0 = 0;
+    const int nnode = pad.nnode, ndof = pad.nnode * ndim;
+    if (op == GO_OP_NORMAL) {
+        for (int p = 0; p < args.ngauss; p++) {
+            double un[3] = {0, 0, 0}, mag;
+            err = go_pad_calc_normal_vector(&pad, un, args.gauss[p], &mag);
+            if (err) return err;
+            for (int i = 0; i < ndim; i++) out[p * (ndim + 1) + i] = un[i];
+            out[p * (ndim + 1) + ndim] = mag;
+        }
+        return GO_OK;
+    }
+    coef_view cv;
+    cv.base = coef + (e - cell_begin) * coef_cell_stride;
+    cv.gp_stride = coef_gp_stride;
+    cv.len = go_op_coef_size_ext(op, ndim);
+    if (op >= GO_OP_MAT_01_NSN_BRY) {
+        bry_view bv;
+        bv.cv = cv;
+        bv.ndim = ndim;
+        bv.vector_case = op == GO_OP_VEC_02_NV_BRY;
+        switch (op) {
+        case GO_OP_MAT_01_NSN_BRY: return go_mat_01_nsn_bry(out, nnode, nnode, &args, cb_bry, &bv);
+        case GO_OP_VEC_01_NS_BRY: return go_vec_01_ns_bry(out, nnode, &args, cb_bry, &bv);
+        default: return go_vec_02_nv_bry(out, ndof, &args, cb_bry, &bv);
+        }
+    }
+    /* the second pad: kind_b on the first nnode_b nodes of the cell */
+    err = go_pad_init(&pad_b, ndim, kind_b);
+    if (err) return err;
+    if (pad_b.nnode > pad.nnode || pad_b.geo_ndim != pad.geo_ndim) return GO_ERR_KIND_UNSUPPORTED;
+    for (int m = 0; m < pad_b.nnode; m++)
+        for (int j = 0; j < ndim; j++) go_pad_set_xx(&pad_b, m, j, mesh->coords[points[m] * (size_t)ndim + (size_t)j]);
+    const int nb = pad_b.nnode;
+    switch (op) {
+    case GO_OP_MAT_04_NSB: return go_mat_04_nsb(out, nb, ndof, &pad_b, &args, cb_copy, &cv);
+    case GO_OP_MAT_05_BTN: return go_mat_05_btn(out, nb, ndof, &pad_b, &args, cb_copy, &cv);
+    case GO_OP_MAT_06_NVN: return go_mat_06_nvn(out, ndof, nb, &args, &pad_b, cb_copy, &cv);
+    case GO_OP_MAT_07_BSN: return go_mat_07_bsn(out, ndof, nb, &args, &pad_b, cb_copy, &cv);
+    default: return GO_ERR_KIND_UNSUPPORTED;
+    }
+}
+
+int go_mesh_integ_ext(int op, const go_mesh *mesh, size_t cell_begin, size_t cell_end, int ngauss, int kind_b, const double *coef,
+                      size_t coef_cell_stride, size_t coef_gp_stride, double alpha, int axisymmetric, double *out, int nthreads,
+                      size_t *err_cell) {
+    int first_err = GO_OK;
+    size_t first_cell = (size_t)-1;
+    (void)nthreads;
+    size_t off = 0;
+    for (size_t e = cell_begin; e < cell_end; e++) {
+        const size_t sz = go_op_out_size_ext(op, mesh->kinds[e], kind_b, mesh->ndim, ngauss);
+        int err = integ_one_cell_ext(op, mesh, e, cell_begin, ngauss, kind_b, coef, coef_cell_stride, coef_gp_stride, alpha, axisymmetric,
+                                     out + off);
+        if (err && e < first_cell) {
+            first_err = err;
+            first_cell = e;
+        }
+        off += sz;
     }
     if (err_cell) *err_cell = first_cell;
     return first_err;

@@ -66,7 +66,15 @@ enum {
     GO_ERR_GAUSS_TET = 16, GO_ERR_GAUSS_HEX = 17, /* gauss.rs:197-240 */
     GO_ERR_KIND_UNSUPPORTED = 18,  /* oracle does not restate this GeoKind yet */
     GO_ERR_CALLBACK_STOP = 19,     /* the user callback returned an error ("stop" in the tests) */
-    GO_ERR_SPACE_NDIM = 20         /* scratchpad.rs:153-161 */
+    GO_ERR_SPACE_NDIM = 20,        /* scratchpad.rs:153-161 */
+    GO_ERR_NROW_KK_NNODE_B = 21,   /* mat_04_nsb.rs:78 "nrow(K) must be >= ii0 + pad_b.nnode" */
+    GO_ERR_NCOL_KK_NDOF_PAD = 22,  /* mat_04_nsb.rs:81 "ncol(K) must be >= jj0 + pad.nnode . space_ndim" */
+    GO_ERR_NROW_KK_NDOF_PAD = 23,  /* mat_06_nvn.rs:81 "nrow(K) must be >= ii0 + pad.nnode . space_ndim" */
+    GO_ERR_NCOL_KK_NNODE_B = 24,   /* mat_06_nvn.rs:84 "ncol(K) must be >= jj0 + pad_b.nnode" */
+    GO_ERR_BRY_2D = 25,            /* mat_01_nsn_bry.rs:56 "in 2D, geometry ndim must be equal to 1 (a line)" */
+    GO_ERR_BRY_3D = 26,            /* mat_01_nsn_bry.rs:59 "in 3D, geometry ndim must be equal to 2 (a surface)" */
+    GO_ERR_NORMAL_2D = 27,         /* scratchpad_calc_normal_vector.rs:115 */
+    GO_ERR_NORMAL_3D = 28          /* scratchpad_calc_normal_vector.rs:118 */
 };
 const char *go_strerror(int code);
 
@@ -146,8 +154,29 @@ enum {
     GO_OP_MAT_10_BDB = 0, GO_OP_MAT_01_NSN = 1, GO_OP_MAT_03_BTB = 2,
     GO_OP_VEC_01_NS = 3, GO_OP_VEC_03_BV = 4, GO_OP_VEC_02_NV = 5, GO_OP_VEC_04_BT = 6,
     GO_OP_MAT_10_BDB_ALT = 7, GO_OP_JACOBIAN = 8,
-    GO_OP_MAT_02_BVN = 9, GO_OP_MAT_08_NTN = 10, GO_OP_MAT_09_NVB = 11
+    GO_OP_MAT_02_BVN = 9, GO_OP_MAT_08_NTN = 10, GO_OP_MAT_09_NVB = 11,
+    /* two-pad coupling matrices (second pad = kind_b on the first nnode_b nodes of the cell) */
+    GO_OP_MAT_04_NSB = 12, GO_OP_MAT_05_BTN = 13, GO_OP_MAT_06_NVN = 14, GO_OP_MAT_07_BSN = 15,
+    /* boundary integrals over cells with geo_ndim = space_ndim - 1 */
+    GO_OP_MAT_01_NSN_BRY = 16, GO_OP_VEC_01_NS_BRY = 17, GO_OP_VEC_02_NV_BRY = 18,
+    GO_OP_NORMAL = 19 /* calc_normal_vector at every Gauss point: ng x (un[space_ndim], mag_n) */
 };
+
+/* Scratchpad::calc_normal_vector (src/shapes/scratchpad_calc_normal_vector.rs:111-176): unit normal and its magnitude */
+int go_pad_calc_normal_vector(go_pad *pad, double *un, const double *ksi, double *mag_n);
+
+/* callbacks of the boundary cases receive the unit normal: fn(out, p, un, nn, user) */
+typedef int (*go_fn_bry)(double *out, int p, const double *un, const double *nn, void *user);
+/* integ::mat_04_nsb .. mat_07_bsn (src/integ/mat_04_nsb.rs:66, mat_05_btn.rs:68, mat_06_nvn.rs:69, mat_07_bsn.rs:69) */
+int go_mat_04_nsb(double *kk, int nrow, int ncol, go_pad *pad_b, go_args *args, go_fn_s fn, void *user);
+int go_mat_05_btn(double *kk, int nrow, int ncol, go_pad *pad_b, go_args *args, go_fn_tt fn, void *user);
+int go_mat_06_nvn(double *kk, int nrow, int ncol, go_args *args, go_pad *pad_b, go_fn_v fn, void *user);
+int go_mat_07_bsn(double *kk, int nrow, int ncol, go_args *args, go_pad *pad_b, go_fn_s fn, void *user);
+/* integ::mat_01_nsn_bry, vec_01_ns_bry, vec_02_nv_bry (src/integ/mat_01_nsn_bry.rs:48, vec_01_ns_bry.rs:54, vec_02_nv_bry.rs:61) */
+int go_mat_01_nsn_bry(double *kk, int nrow, int ncol, go_args *args, go_fn_bry fn, void *user);
+int go_vec_01_ns_bry(double *a, int len, go_args *args, go_fn_bry fn, void *user);
+int go_vec_02_nv_bry(double *b, int len, go_args *args, go_fn_bry fn, void *user);
+
 /* per-element output size in doubles for op on a cell of `kind` in `ndim` space */
 size_t go_op_out_size(int op, int kind, int ndim);
 /* coefficient record length in doubles: ns*ns (mat_10), 1 (mat_01, vec_01), ns (mat_03, vec_04), ndim (vec_02/03) */
@@ -174,6 +203,15 @@ int go_mesh_integ(int op, const go_mesh *mesh, size_t cell_begin, size_t cell_en
                   const double *coef, size_t coef_cell_stride, size_t coef_gp_stride, double alpha,
                   int axisymmetric, const double *ksi, double *out, const uint64_t *out_off,
                   int nthreads, size_t *err_cell);
+
+/* the mesh loop for the cases above.  kind_b: GeoKind of the second pad (its nodes are the first nnode_b nodes of every cell);
+ * coefficient records: mat_04 / mat_07 s; mat_05 Mandel vector; mat_06 v; the boundary cases take (s0, w[space_ndim]) with
+ * s = s0 + w.un, and vec_02_nv_bry (v[space_ndim], qn) with v = v + qn un -- the data form of closures that read the normal */
+int go_mesh_integ_ext(int op, const go_mesh *mesh, size_t cell_begin, size_t cell_end, int ngauss, int kind_b, const double *coef,
+                      size_t coef_cell_stride, size_t coef_gp_stride, double alpha, int axisymmetric, double *out, int nthreads,
+                      size_t *err_cell);
+size_t go_op_out_size_ext(int op, int kind, int kind_b, int ndim, int ngauss);
+size_t go_op_coef_size_ext(int op, int ndim);
 
 #ifdef __cplusplus
 }

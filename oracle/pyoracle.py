@@ -24,6 +24,8 @@ CLASS_LIN, CLASS_TRI, CLASS_QUA, CLASS_TET, CLASS_HEX = range(5)
 _CLASS_KIND = {CLASS_LIN: KIND["lin2"], CLASS_TRI: KIND["tri3"], CLASS_QUA: KIND["qua4"], CLASS_TET: KIND["tet4"],
                CLASS_HEX: KIND["hex8"]}
 
+OP_EXT = {"mat_04_nsb": 12, "mat_05_btn": 13, "mat_06_nvn": 14, "mat_07_bsn": 15, "mat_01_nsn_bry": 16, "vec_01_ns_bry": 17,
+          "vec_02_nv_bry": 18, "normal": 19}
 OP = {"mat_02_bvn": 9, "mat_08_ntn": 10, "mat_09_nvb": 11, "mat_10_bdb": 0, "mat_01_nsn": 1, "mat_03_btb": 2, "vec_01_ns": 3, "vec_03_bv": 4, "vec_02_nv": 5,
       "vec_04_bt": 6, "mat_10_bdb_alt": 7, "jacobian": 8}
 
@@ -441,6 +443,36 @@ def mesh_integ(op, ndim, coords, kinds, conn_off, conn, cell_begin=0, cell_end=N
                                float(alpha), int(axisymmetric), None if ksi_arr is None else ksi_arr.ctypes.data,
                                out.ctypes.data, None if out_off is None else out_off.ctypes.data, int(nthreads),
                                C.byref(err_cell))
+    if code != 0:
+        e = OracleError(code)
+        e.cell = err_cell.value
+        raise e
+    return out
+
+
+def mesh_integ_ext(op, ndim, coords, kinds, conn_off, conn, kind_b=None, cell_begin=0, cell_end=None, ngauss=0, coef=None,
+                   coef_cell_stride=0, coef_gp_stride=0, alpha=1.0, axisymmetric=False):
+    """The user loop for the two-pad coupling matrices (mat_04_nsb .. mat_07_bsn; kind_b = GeoKind of the second pad, whose nodes are
+    the first nnode_b nodes of every cell), the boundary integrals (*_bry) and the batched calc_normal_vector ("normal").
+    Coefficient records: see go_mesh_integ_ext in gemlab_oracle.h."""
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+    conn_off = np.ascontiguousarray(conn_off, dtype=np.uint64)
+    conn = np.ascontiguousarray(conn, dtype=np.uint64)
+    ncell = kinds.shape[0]
+    if cell_end is None:
+        cell_end = ncell
+    m = _Mesh(ndim, coords.shape[0], ncell, coords.ctypes.data, kinds.ctypes.data, conn_off.ctypes.data, conn.ctypes.data)
+    kb = -1 if kind_b is None else int(kind_b)
+    lib().go_op_out_size_ext.restype = C.c_size_t
+    total = sum(int(lib().go_op_out_size_ext(OP_EXT[op], int(k), kb, ndim, int(ngauss))) for k in kinds[cell_begin:cell_end])
+    out = np.full(total, np.nan)
+    coef_arr = None if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+    err_cell = C.c_size_t()
+    code = lib().go_mesh_integ_ext(OP_EXT[op], C.byref(m), C.c_size_t(cell_begin), C.c_size_t(cell_end), int(ngauss), kb,
+                                   None if coef_arr is None else C.c_void_p(coef_arr.ctypes.data), C.c_size_t(coef_cell_stride),
+                                   C.c_size_t(coef_gp_stride), C.c_double(alpha), int(axisymmetric), C.c_void_p(out.ctypes.data), 1,
+                                   C.byref(err_cell))
     if code != 0:
         e = OracleError(code)
         e.cell = err_cell.value
