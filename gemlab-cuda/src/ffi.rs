@@ -100,6 +100,8 @@ extern "C" {
     pub fn gl_kind_supported(kind: c_int) -> c_int;
     pub fn gl_gauss_rule(kind: c_int, ngauss: c_int, npoint: *mut c_int, data: *mut *const c_double) -> c_int;
     pub fn gl_shape_eval(kind: c_int, ksi: *const c_double, nn: *mut c_double, ll: *mut c_double) -> c_int;
+    pub fn gl_kind_reference_coords(kind: c_int, m: c_int, ksi: *mut c_double) -> c_int;
+    pub fn gl_extrap_matrix(kind: c_int, ngauss: c_int, ee: *mut c_double) -> c_int;
 
     pub fn gl_mesh_upload(
         ctx: *mut gl_ctx,

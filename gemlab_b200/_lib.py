@@ -57,6 +57,8 @@ SYMBOLS = {
     "gl_kind_supported": (C.c_int, [C.c_int]),
     "gl_gauss_rule": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),
     "gl_shape_eval": (C.c_int, [C.c_int, _P, _P, _P]),
+    "gl_kind_reference_coords": (C.c_int, [C.c_int, C.c_int, _P]),
+    "gl_extrap_matrix": (C.c_int, [C.c_int, C.c_int, _P]),
     "gl_mesh_upload": (C.c_int, [_P, C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, C.POINTER(_P)]),
     "gl_mesh_upload_homogeneous": (C.c_int, [_P, C.c_int, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, C.POINTER(_P)]),
     "gl_mesh_update_coords": (C.c_int, [_P, _P, _P, C.c_int]),

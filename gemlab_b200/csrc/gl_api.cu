@@ -457,6 +457,15 @@ int gl_shape_eval(int kind, const double *ksi, double *nn, double *ll) {
     return shape_eval(kind, ksi, nn, ll);
 }
 
+int gl_kind_reference_coords(int kind, int m, double *ksi) {
+    if (!ksi) return GL_ERR_INVALID_ARG;
+    return kind_reference_coords(kind, m, ksi);
+}
+int gl_extrap_matrix(int kind, int ngauss, double *ee) {
+    if (!ee) return GL_ERR_INVALID_ARG;
+    return extrap_matrix(kind, ngauss, ee);
+}
+
 void gl_args_default(gl_args *a) {
     if (!a) return;
     std::memset(a, 0, sizeof(*a));

@@ -35,6 +35,8 @@ const char *kind_name(int kind);
 int kind_from_name(const char *name);
 bool kind_supported(int kind);
 int shape_eval(int kind, const double *ksi, double *nn, double *ll);
+int kind_reference_coords(int kind, int m, double *ksi);
+int extrap_matrix(int kind, int ngauss, double *ee); // nnode x npoint, column-major
 int gauss_rule(int kind, int ngauss, int *npoint, const double **data);
 const double *shape_table(int kind, int ng); // N[ng][nnode] | L[ng][nnode][gd], exact; nullptr if not tabulated
 const char *status_string(int status);

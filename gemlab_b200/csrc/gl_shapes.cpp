@@ -10,6 +10,10 @@
 // ORDER and reference coordinates are the reference's (NODE_REFERENCE_COORDS in each src/shapes/<kind>.rs), because the
 // order is part of the connectivity contract.  tests/test_shapes_tables.py checks these against the oracle's
 // node-by-node restatement.
+#include <cmath>
+#include <mutex>
+#include <vector>
+
 #include "gl_internal.hpp"
 
 #include <cmath>
@@ -19,6 +23,7 @@ namespace gl {
 
 #include "gauss_tables.inc"
 #include "shape_tables.inc"
+#include "ref_coords.inc"
 
 namespace {
 
@@ -185,8 +190,8 @@ int kind_from_name(const char *name) {
 // every GeoKind integrates: the kernels read N and L from the (kind, rule) tables of shape_tables.inc
 bool kind_supported(int kind) { return kind >= 0 && kind < GL_NKIND; }
 
-// kinds whose shape functions this library can also evaluate at an ARBITRARY point (gl_shape_eval, GL_OP_JACOBIAN); the
-// cubic / quartic kinds exist as tables at the reference's Gauss points only
+// kinds with closed family-wise formulas (eval_lin / eval_simplex / eval_qua / eval_hex above); the cubic and quartic kinds go
+// through their NODAL BASIS, built from the node coordinates alone (below)
 bool kind_has_formulas(int kind) {
     switch (kind) {
     case GL_LIN2: case GL_LIN3: case GL_TRI3: case GL_TRI6: case GL_QUA4: case GL_QUA8: case GL_QUA9:
@@ -197,8 +202,164 @@ bool kind_has_formulas(int kind) {
     }
 }
 
+// GeoKind::reference_coords (src/shapes/enums.rs:1049): natural coordinates of node m
+int kind_reference_coords(int kind, int m, double *ksi) {
+    if (kind < 0 || kind >= GL_NKIND || m < 0 || m >= NNODE[kind]) return GL_ERR_KIND_UNSUPPORTED;
+    for (int j = 0; j < GNDIM[kind]; j++) ksi[j] = REF_COORDS[REF_COORDS_OFFSET[kind] + m][j];
+    return GL_OK;
+}
+
+namespace {
+
+// Shape functions of Lin4/5, Tri10/15, Qua12/16/17, Tet20 and Hex32 at an ARBITRARY point.  A nodal finite element is fixed by
+// its nodes and its polynomial space: N_m is the member of the space that is 1 at node m and 0 at the others, i.e.
+// N(ksi) = C phi(ksi) with C = inv(Phi), Phi[k][m] = phi_k(node m), for any basis phi of the space.  The spaces are the
+// classical ones -- complete polynomials P_k on simplices and lines, the tensor space Q_3 for Qua16, the serendipity spaces
+// S_k (monomials of superlinear degree <= k) for Qua12, Qua17 and Hex32 -- and the result agrees with the reference's
+// node-by-node expressions (src/shapes/tri10.rs:94-120, hex32.rs:216-330, ...) to 1e-14 at every Gauss point of every rule
+// (tests/test_shape_tables.py), without restating them.  Built once per kind, in long double.
+struct NodalBasis {
+    int n = 0, gd = 0;
+    std::vector<int> expo;       // [n][3] monomial exponents
+    std::vector<long double> cc; // [n][n]: N_m = sum_k cc[m * n + k] phi_k
+    bool ok = false;
+};
+
+int superlinear_degree(int a, int b, int c) { return (a >= 2 ? a : 0) + (b >= 2 ? b : 0) + (c >= 2 ? c : 0); }
+
+void monomials_of(int kind, std::vector<int> &e) {
+    auto push = [&](int a, int b, int c) { e.push_back(a); e.push_back(b); e.push_back(c); };
+    switch (kind) {
+    case GL_LIN4: for (int a = 0; a < 4; a++) push(a, 0, 0); break;
+    case GL_LIN5: for (int a = 0; a < 5; a++) push(a, 0, 0); break;
+    case GL_TRI10: case GL_TRI15: {
+        const int k = kind == GL_TRI10 ? 3 : 4;
+        for (int a = 0; a <= k; a++)
+            for (int b = 0; a + b <= k; b++) push(a, b, 0);
+    } break;
+    case GL_QUA16:
+        for (int a = 0; a < 4; a++)
+            for (int b = 0; b < 4; b++) push(a, b, 0);
+        break;
+    case GL_QUA12: case GL_QUA17: {
+        const int k = kind == GL_QUA12 ? 3 : 4;
+        for (int a = 0; a <= k; a++)
+            for (int b = 0; a + b <= k; b++) push(a, b, 0);
+        push(k, 1, 0);
+        push(1, k, 0);
+    } break;
+    case GL_TET20:
+        for (int a = 0; a <= 3; a++)
+            for (int b = 0; a + b <= 3; b++)
+                for (int c = 0; a + b + c <= 3; c++) push(a, b, c);
+        break;
+    case GL_HEX32:
+        for (int a = 0; a < 4; a++)
+            for (int b = 0; b < 4; b++)
+                for (int c = 0; c < 4; c++)
+                    if (superlinear_degree(a, b, c) <= 3) push(a, b, c);
+        break;
+    default: break;
+    }
+}
+
+long double ipow(long double x, int k) {
+    long double r = 1.0L;
+    for (int i = 0; i < k; i++) r *= x;
+    return r;
+}
+
+// inverse of an n x n matrix (row-major) by Gauss-Jordan with partial pivoting; false if singular
+template <typename T>
+bool invert_dense(std::vector<T> &a, int n) {
+    std::vector<T> inv((size_t)n * n, (T)0);
+    for (int i = 0; i < n; i++) inv[(size_t)i * n + i] = (T)1;
+    for (int col = 0; col < n; col++) {
+        int piv = col;
+        for (int r = col + 1; r < n; r++)
+            if (std::fabs((double)a[(size_t)r * n + col]) > std::fabs((double)a[(size_t)piv * n + col])) piv = r;
+        if (std::fabs((double)a[(size_t)piv * n + col]) < 1e-13) return false;
+        if (piv != col)
+            for (int k = 0; k < n; k++) {
+                std::swap(a[(size_t)piv * n + k], a[(size_t)col * n + k]);
+                std::swap(inv[(size_t)piv * n + k], inv[(size_t)col * n + k]);
+            }
+        const T d = a[(size_t)col * n + col];
+        for (int k = 0; k < n; k++) {
+            a[(size_t)col * n + k] /= d;
+            inv[(size_t)col * n + k] /= d;
+        }
+        for (int r = 0; r < n; r++) {
+            if (r == col) continue;
+            const T f = a[(size_t)r * n + col];
+            if (f == (T)0) continue;
+            for (int k = 0; k < n; k++) {
+                a[(size_t)r * n + k] -= f * a[(size_t)col * n + k];
+                inv[(size_t)r * n + k] -= f * inv[(size_t)col * n + k];
+            }
+        }
+    }
+    a.swap(inv);
+    return true;
+}
+
+const NodalBasis &nodal_basis(int kind) {
+    static NodalBasis table[GL_NKIND];
+    static std::once_flag once[GL_NKIND];
+    std::call_once(once[kind], [kind]() {
+        NodalBasis &nb = table[kind];
+        nb.n = NNODE[kind];
+        nb.gd = GNDIM[kind];
+        monomials_of(kind, nb.expo);
+        if ((int)nb.expo.size() != 3 * nb.n) return;
+        const int n = nb.n;
+        std::vector<long double> phi((size_t)n * n); // [k][m] = phi_k(node m)
+        for (int k = 0; k < n; k++)
+            for (int m = 0; m < n; m++) {
+                const double *x = REF_COORDS[REF_COORDS_OFFSET[kind] + m];
+                phi[(size_t)k * n + m] = ipow(x[0], nb.expo[3 * k]) * ipow(x[1], nb.expo[3 * k + 1]) * ipow(x[2], nb.expo[3 * k + 2]);
+            }
+        if (!invert_dense(phi, n)) return; // phi := inv(Phi): [m][k]
+        nb.cc.swap(phi);
+        nb.ok = true;
+    });
+    return table[kind];
+}
+
+int eval_nodal(int kind, const double *ksi, double *nn, double *ll) {
+    const NodalBasis &nb = nodal_basis(kind);
+    if (!nb.ok) return GL_ERR_KIND_UNSUPPORTED;
+    const int n = nb.n, gd = nb.gd;
+    long double x[3] = {ksi[0], gd > 1 ? ksi[1] : 0.0, gd > 2 ? ksi[2] : 0.0};
+    std::vector<long double> phi(n), dphi((size_t)n * 3, 0.0L);
+    for (int k = 0; k < n; k++) {
+        const int *e = &nb.expo[3 * k];
+        phi[k] = ipow(x[0], e[0]) * ipow(x[1], e[1]) * ipow(x[2], e[2]);
+        for (int j = 0; j < gd; j++) {
+            if (e[j] == 0) continue;
+            long double v = (long double)e[j];
+            for (int i = 0; i < 3; i++) v *= ipow(x[i], i == j ? e[i] - 1 : e[i]);
+            dphi[(size_t)k * 3 + j] = v;
+        }
+    }
+    for (int m = 0; m < n; m++) {
+        long double s = 0.0L, d[3] = {0.0L, 0.0L, 0.0L};
+        for (int k = 0; k < n; k++) {
+            const long double c = nb.cc[(size_t)m * n + k];
+            s += c * phi[k];
+            for (int j = 0; j < gd; j++) d[j] += c * dphi[(size_t)k * 3 + j];
+        }
+        nn[m] = (double)s;
+        for (int j = 0; j < gd; j++) ll[m * gd + j] = (double)d[j];
+    }
+    return GL_OK;
+}
+
+} // namespace
+
 int shape_eval(int kind, const double *ksi, double *nn, double *ll) {
-    if (!kind_has_formulas(kind)) return GL_ERR_KIND_UNSUPPORTED;
+    if (kind < 0 || kind >= GL_NKIND) return GL_ERR_KIND_UNSUPPORTED;
+    if (!kind_has_formulas(kind)) return eval_nodal(kind, ksi, nn, ll);
     const int nnode = NNODE[kind];
     switch (KCLASS[kind]) {
     case 0: eval_lin(nnode, ksi, nn, ll); break;
@@ -207,6 +368,124 @@ int shape_eval(int kind, const double *ksi, double *nn, double *ll) {
     case 3: eval_simplex(3, nnode, ksi, nn, ll); break;
     default: eval_hex(nnode, ksi, nn, ll); break;
     }
+    return GL_OK;
+}
+
+// recovery::get_extrap_matrix (src/recovery/get_extrap_matrix.rs:129-200): E (nnode x npoint, COLUMN-major in `ee`) maps values at
+// the Gauss points of the rule to nodal values.  P[p][m] = N_m(ksi_p) (get_interp_matrix.rs):  npoint = nnode: E = inv(P);
+// npoint > nnode or npoint = 1: E = pinv(P);  otherwise E = hat_xi_nodes B + pinv(P) (I - hat_xi B) with B = pinv(hat_xi), hat_xi =
+// [ksi_p, 1] (the constant tables TR_PINV_HXI_* of the reference are B^T).
+int extrap_matrix(int kind, int ngauss, double *ee) {
+    if (kind < 0 || kind >= GL_NKIND) return GL_ERR_KIND_UNSUPPORTED;
+    int np = 0;
+    const double *g = nullptr;
+    int st = gauss_rule(kind, ngauss, &np, &g);
+    if (st) return st;
+    const int nv = NNODE[kind], gd = GNDIM[kind], nh = gd + 1;
+    std::vector<long double> pp((size_t)np * nv); // [p][m]
+    {
+        std::vector<double> nn(nv), ll((size_t)nv * gd);
+        for (int p = 0; p < np; p++) {
+            st = shape_eval(kind, g + 4 * p, nn.data(), ll.data());
+            if (st) return st;
+            for (int m = 0; m < nv; m++) pp[(size_t)p * nv + m] = nn[m];
+        }
+    }
+    // Moore-Penrose pseudo-inverse of an r x c matrix a (row-major) -> c x r, by one-sided (Hestenes) Jacobi SVD in long double;
+    // singular values below eps max(r, c) sigma_max count as zero (the sampled nodal basis is rank deficient for some rules,
+    // e.g. Qua12 at 3 x 3 points), as LAPACK-based pseudo-inverses do
+    auto pinv = [](const std::vector<long double> &a_in, int r_in, int c_in, std::vector<long double> &out) -> bool {
+        const bool tr = r_in < c_in; // work on the tall orientation
+        const int r = tr ? c_in : r_in, c = tr ? r_in : c_in;
+        std::vector<long double> a((size_t)r * c), v((size_t)c * c, 0.0L);
+        for (int i = 0; i < r; i++)
+            for (int j = 0; j < c; j++) a[(size_t)i * c + j] = tr ? a_in[(size_t)j * c_in + i] : a_in[(size_t)i * c_in + j];
+        for (int j = 0; j < c; j++) v[(size_t)j * c + j] = 1.0L;
+        for (int sweep = 0; sweep < 60; sweep++) {
+            long double off = 0.0L;
+            for (int p = 0; p < c - 1; p++)
+                for (int q = p + 1; q < c; q++) {
+                    long double alpha = 0.0L, beta = 0.0L, gamma = 0.0L;
+                    for (int i = 0; i < r; i++) {
+                        alpha += a[(size_t)i * c + p] * a[(size_t)i * c + p];
+                        beta += a[(size_t)i * c + q] * a[(size_t)i * c + q];
+                        gamma += a[(size_t)i * c + p] * a[(size_t)i * c + q];
+                    }
+                    if (gamma == 0.0L || alpha == 0.0L || beta == 0.0L) continue;
+                    off = std::max(off, fabsl(gamma) / sqrtl(alpha * beta));
+                    const long double zeta = (beta - alpha) / (2.0L * gamma);
+                    const long double t = (zeta >= 0.0L ? 1.0L : -1.0L) / (fabsl(zeta) + sqrtl(1.0L + zeta * zeta));
+                    const long double cs = 1.0L / sqrtl(1.0L + t * t), sn = cs * t;
+                    for (int i = 0; i < r; i++) {
+                        const long double x = a[(size_t)i * c + p], y = a[(size_t)i * c + q];
+                        a[(size_t)i * c + p] = cs * x - sn * y;
+                        a[(size_t)i * c + q] = sn * x + cs * y;
+                    }
+                    for (int i = 0; i < c; i++) {
+                        const long double x = v[(size_t)i * c + p], y = v[(size_t)i * c + q];
+                        v[(size_t)i * c + p] = cs * x - sn * y;
+                        v[(size_t)i * c + q] = sn * x + cs * y;
+                    }
+                }
+            if (off < 1e-19L) break;
+        }
+        std::vector<long double> sig(c);
+        long double smax = 0.0L;
+        for (int j = 0; j < c; j++) {
+            long double n2 = 0.0L;
+            for (int i = 0; i < r; i++) n2 += a[(size_t)i * c + j] * a[(size_t)i * c + j];
+            sig[j] = sqrtl(n2);
+            smax = std::max(smax, sig[j]);
+        }
+        const long double cutoff = 2.220446049250313e-16L * (long double)std::max(r, c) * smax;
+        // pinv(A) = V diag(1 / sigma) U^T with U = A_rotated / sigma: (c x r); entry (i, k) = sum_j v[i][j] a[k][j] / sigma_j^2
+        std::vector<long double> pi((size_t)c * r, 0.0L);
+        for (int j = 0; j < c; j++) {
+            if (sig[j] <= cutoff) continue;
+            const long double w = 1.0L / (sig[j] * sig[j]);
+            for (int i = 0; i < c; i++)
+                for (int k = 0; k < r; k++) pi[(size_t)i * r + k] += v[(size_t)i * c + j] * a[(size_t)k * c + j] * w;
+        }
+        // back to the caller's orientation: pinv(A^T) = pinv(A)^T
+        out.assign((size_t)c_in * r_in, 0.0L);
+        for (int i = 0; i < c_in; i++)
+            for (int k = 0; k < r_in; k++) out[(size_t)i * r_in + k] = tr ? pi[(size_t)k * r + i] : pi[(size_t)i * r + k];
+        return smax > 0.0L;
+    };
+    std::vector<long double> e((size_t)nv * np, 0.0L); // [m][p]
+    if (np == nv) {
+        std::vector<long double> inv = pp; // np x nv square
+        if (!invert_dense(inv, nv)) return GL_ERR_ZERO_DET;
+        e = inv; // inv(P): [m][p]
+    } else if (np > nv || np == 1) {
+        if (!pinv(pp, np, nv, e)) return GL_ERR_ZERO_DET;
+    } else {
+        std::vector<long double> ppi, hx((size_t)np * nh), bb;
+        if (!pinv(pp, np, nv, ppi)) return GL_ERR_ZERO_DET; // nv x np
+        for (int p = 0; p < np; p++) {
+            for (int k = 0; k < gd; k++) hx[(size_t)p * nh + k] = g[4 * p + k];
+            hx[(size_t)p * nh + gd] = 1.0L;
+        }
+        if (!pinv(hx, np, nh, bb)) return GL_ERR_ZERO_DET; // nh x np
+        std::vector<long double> aa((size_t)np * np);
+        for (int i = 0; i < np; i++)
+            for (int j = 0; j < np; j++) {
+                long double sum = 0.0L;
+                for (int k = 0; k < nh; k++) sum += hx[(size_t)i * nh + k] * bb[(size_t)k * np + j];
+                aa[(size_t)i * np + j] = (i == j ? 1.0L : 0.0L) - sum;
+            }
+        for (int i = 0; i < nv; i++) {
+            const double *rc = REF_COORDS[REF_COORDS_OFFSET[kind] + i];
+            for (int j = 0; j < np; j++) {
+                long double v = bb[(size_t)gd * np + j];
+                for (int k = 0; k < gd; k++) v += (long double)rc[k] * bb[(size_t)k * np + j];
+                for (int k = 0; k < np; k++) v += ppi[(size_t)i * np + k] * aa[(size_t)k * np + j];
+                e[(size_t)i * np + j] = v;
+            }
+        }
+    }
+    for (int m = 0; m < nv; m++)
+        for (int p = 0; p < np; p++) ee[m + (size_t)p * nv] = (double)e[(size_t)m * np + p];
     return GL_OK;
 }
 

@@ -193,10 +193,15 @@ GL_API const char *gl_kind_name(int kind);
 GL_API int gl_kind_supported(int kind);
 /* rule lookup: *npoint points, data = npoint x 4 doubles {r,s,t,w} (static storage) */
 GL_API int gl_gauss_rule(int kind, int ngauss, int *npoint, const double **data);
-/* N (nnode) and L = dN/dksi (nnode x geo_ndim, row-major) at an ARBITRARY point, from the library's own formulas:
- * available for Lin2/3, Tri3/6, Qua4/8/9, Tet4/10, Hex8/20; the cubic and quartic kinds (Lin4/5, Tri10/15, Qua12/16/17,
- * Tet20, Hex32) exist as tables at the reference's Gauss points only -> GL_ERR_KIND_UNSUPPORTED (also for gl_jacobian) */
+/* N (nnode) and L = dN/dksi (nnode x geo_ndim, row-major) at an ARBITRARY point, for all 20 GeoKinds (replaces
+ * Scratchpad::calc_interp / calc_deriv, src/shapes/scratchpad.rs): closed family-wise formulas for Lin2/3, Tri3/6, Qua4/8/9,
+ * Tet4/10, Hex8/20; the cubic and quartic kinds through their nodal basis (see gl_shapes.cpp) */
 GL_API int gl_shape_eval(int kind, const double *ksi, double *nn, double *ll);
+/* GeoKind::reference_coords (src/shapes/enums.rs:1049): natural coordinates (geo_ndim values) of node m */
+GL_API int gl_kind_reference_coords(int kind, int m, double *ksi);
+/* recovery::get_extrap_matrix (src/recovery/get_extrap_matrix.rs:129): the matrix E (nnode x npoint, column-major in `ee`) that
+ * extrapolates values at the Gauss points of the rule (ngauss = 0: the kind's default) to the nodes; host only */
+GL_API int gl_extrap_matrix(int kind, int ngauss, double *ee);
 
 /* ---- mesh (replaces Mesh/Point/Cell + Mesh::set_pad, src/mesh/mesh.rs:27-54,110-135,448-456) ------ */
 

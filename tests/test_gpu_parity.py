@@ -569,6 +569,14 @@ def test_higher_order_kinds(ctx, kind, space_ndim):
         got = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(ngauss=n), Coef.uniform(coef))
         ref = oracle_integ("mat_10_bdb", mesh, coef, ngauss=n)
         assert rel_err(got, ref, integ.out_offsets(dmesh, "mat_10_bdb", None, CommonArgs(ngauss=n))) <= TOL
+    # Mesh::check_jacobian's loop (src/mesh/check.rs:43-60) on these kinds too: det J at an arbitrary point comes from the nodal
+    # basis of gl_shapes.cpp; the oracle knows these kinds at the reference's Gauss points, so one of those is the probe
+    if solid:
+        gs = po.Gauss(kind, 0)
+        ksi = list(gs.coords(gs.npoint() // 2))[:space_ndim]
+        det = integ.jacobian(ctx, dmesh, None, ksi)
+        ref = oracle_integ("jacobian", mesh, ksi=np.array(ksi))
+        assert np.max(np.abs(det - ref)) <= 1e-12 * np.max(np.abs(ref))
     # volume check independent of the oracle: sum of vec_01_ns with s = 1 is the cell measure; refine the rule
     if solid:
         v1 = integ.vec_01_ns(ctx, dmesh, None, CommonArgs(), Coef.uniform([1.0])).sum()

@@ -57,11 +57,11 @@ def test_table_matches_oracle_bitwise_and_library_formulas(key):
         assert np.array_equal(N[p], np.asarray(po.interp(kind, ksi)))          # bit for bit
         assert np.array_equal(Lt[p], np.asarray(po.deriv(kind, ksi)).reshape(nn, gd))
         n2, l2 = np.zeros(nn), np.zeros(nn * gd)
-        if lib().gl_shape_eval(kid, ksi.ctypes.data, n2.ctypes.data, l2.ctypes.data) == 0:  # independent formulas
-            assert np.max(np.abs(n2 - N[p])) <= 1e-14
-            assert np.max(np.abs(l2.reshape(nn, gd) - Lt[p])) <= 1e-14
-        else:  # cubic / quartic kinds: tables only (evaluated from the reference's expressions by the generator)
-            assert kind in ("lin4", "lin5", "tri10", "tri15", "qua12", "qua16", "qua17", "tet20", "hex32")
+        # independent evaluation at an arbitrary point: family-wise formulas, and for the cubic / quartic kinds the nodal basis
+        # built from the node coordinates and the polynomial space alone (gl_shapes.cpp) -- for ALL 20 kinds
+        assert lib().gl_shape_eval(kid, ksi.ctypes.data, n2.ctypes.data, l2.ctypes.data) == 0
+        assert np.max(np.abs(n2 - N[p])) <= 1e-14
+        assert np.max(np.abs(l2.reshape(nn, gd) - Lt[p])) <= 1e-14
     # partition of unity and zero-sum derivatives (shapes.rs tests of the reference)
     assert np.max(np.abs(N.sum(axis=1) - 1.0)) <= 1e-14
     assert np.max(np.abs(Lt.sum(axis=1))) <= 1e-13
