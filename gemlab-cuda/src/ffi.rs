@@ -72,6 +72,28 @@ pub struct gl_out {
     pub capacity: u64,
 }
 
+/// `struct gl_slab` -- a batched output that stays on its device
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct gl_slab {
+    pub ptr: *mut c_double,
+    pub capacity: u64,
+    pub size: u64,
+    pub cell_begin: u64,
+    pub cell_end: u64,
+    pub device: i32,
+    pub owned: i32,
+}
+
+#[repr(C)]
+pub struct gl_multi {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct gl_multi_mesh {
+    _private: [u8; 0],
+}
+
 #[repr(C)]
 pub struct gl_fused_item {
     pub op: i32,
@@ -205,4 +227,34 @@ extern "C" {
         vals: *mut c_double,
         missing: *mut u64,
     ) -> c_int;
+
+    // device-resident output slabs
+    pub fn gl_integ_slab(ctx: *mut gl_ctx, mesh: *const gl_mesh, op: c_int, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, slab: *mut gl_slab) -> c_int;
+    pub fn gl_slab_download(ctx: *mut gl_ctx, slab: *const gl_slab, host: *mut c_double) -> c_int;
+    pub fn gl_slab_free(slab: *mut gl_slab);
+
+    // single-process multi-GPU driver
+    pub fn gl_multi_create(devices: *const c_int, ndevice: c_int, multi: *mut *mut gl_multi) -> c_int;
+    pub fn gl_multi_destroy(multi: *mut gl_multi);
+    pub fn gl_multi_ndevice(multi: *const gl_multi) -> c_int;
+    pub fn gl_multi_ctx(multi: *mut gl_multi, g: c_int) -> *mut gl_ctx;
+    pub fn gl_multi_last_error(multi: *const gl_multi) -> *const c_char;
+    pub fn gl_multi_partition(cell_begin: u64, cell_end: u64, ndevice: c_int, g: c_int, piece_begin: *mut u64, piece_end: *mut u64);
+    pub fn gl_multi_mesh_upload(
+        multi: *mut gl_multi,
+        ndim: c_int,
+        npoint: u64,
+        coords: *const c_double,
+        ncell: u64,
+        kinds: *const u8,
+        markers: *const i32,
+        conn_off: *const u64,
+        conn: *const u64,
+        mesh: *mut *mut gl_multi_mesh,
+    ) -> c_int;
+    pub fn gl_multi_mesh_free(multi: *mut gl_multi, mesh: *mut gl_multi_mesh);
+    pub fn gl_multi_mesh_replica(mesh: *const gl_multi_mesh, g: c_int) -> *const gl_mesh;
+    pub fn gl_multi_integ(multi: *mut gl_multi, mesh: *const gl_multi_mesh, op: c_int, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
+    pub fn gl_multi_integ_slabs(multi: *mut gl_multi, mesh: *const gl_multi_mesh, op: c_int, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, slabs: *mut gl_slab) -> c_int;
+    pub fn gl_multi_sync(multi: *mut gl_multi) -> c_int;
 }

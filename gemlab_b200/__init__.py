@@ -8,8 +8,9 @@ from . import integ
 from ._lib import LIB_PATH, lib
 from .geo import Gauss, GemlabError, GeoClass, GeoKind
 from .integ import CommonArgs, Coef, Context, DeviceMesh, lin_elasticity, mandel_matrix, partition
+from .multi import DeviceSlab, MultiContext, integ_slab
 from .mesh import Block, GemlabTextError, Mesh, jitter_interior_points, split_hex_cells_into_tet10
 
 __all__ = ["integ", "lib", "LIB_PATH", "Gauss", "GemlabError", "GeoClass", "GeoKind", "CommonArgs", "Coef", "Context",
-           "DeviceMesh", "lin_elasticity", "mandel_matrix", "partition", "Block", "Mesh", "GemlabTextError", "jitter_interior_points",
+           "DeviceMesh", "DeviceSlab", "MultiContext", "integ_slab", "lin_elasticity", "mandel_matrix", "partition", "Block", "Mesh", "GemlabTextError", "jitter_interior_points",
            "split_hex_cells_into_tet10"]

@@ -37,6 +37,13 @@ class GlFusedItem(C.Structure):
     _fields_ = [("op", C.c_int32), ("reserved", C.c_int32), ("coef", C.POINTER(GlCoef)), ("out", C.POINTER(GlOut))]
 
 
+class GlSlab(C.Structure):
+    """struct gl_slab: a batched output that stays on its device."""
+
+    _fields_ = [("ptr", C.c_void_p), ("capacity", C.c_uint64), ("size", C.c_uint64), ("cell_begin", C.c_uint64),
+                ("cell_end", C.c_uint64), ("device", C.c_int32), ("owned", C.c_int32)]
+
+
 # every symbol include/gemlab_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -84,6 +91,23 @@ SYMBOLS = {
     "gl_bench_fp64_peak": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gl_bench_hbm_write": (C.c_int, [_P, C.c_int, _P, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
 }
+SYMBOLS.update({
+    "gl_integ_slab": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlSlab)]),
+    "gl_slab_download": (C.c_int, [_P, C.POINTER(GlSlab), _P]),
+    "gl_slab_free": (None, [C.POINTER(GlSlab)]),
+    "gl_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "gl_multi_destroy": (None, [_P]),
+    "gl_multi_ndevice": (C.c_int, [_P]),
+    "gl_multi_ctx": (_P, [_P, C.c_int]),
+    "gl_multi_last_error": (C.c_char_p, [_P]),
+    "gl_multi_partition": (None, [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "gl_multi_mesh_upload": (C.c_int, [_P, C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, C.POINTER(_P)]),
+    "gl_multi_mesh_free": (None, [_P, _P]),
+    "gl_multi_mesh_replica": (_P, [_P, C.c_int]),
+    "gl_multi_integ": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlOut)]),
+    "gl_multi_integ_slabs": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlSlab)]),
+    "gl_multi_sync": (C.c_int, [_P]),
+})
 SYMBOLS["gl_normal_vectors"] = (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlOut)])
 for _name in ("gl_mat_04_nsb", "gl_mat_05_btn", "gl_mat_06_nvn", "gl_mat_07_bsn", "gl_mat_01_nsn_bry", "gl_vec_01_ns_bry", "gl_vec_02_nv_bry",
               "gl_mat_10_bdb", "gl_mat_01_nsn", "gl_mat_02_bvn", "gl_mat_03_btb", "gl_mat_08_ntn", "gl_mat_09_nvb", "gl_vec_01_ns", "gl_vec_02_nv", "gl_vec_03_bv",

@@ -908,6 +908,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         p.coef_len = cr.len;
         p.coef_pat = cr.pat;
         p.coef_pat_dev = cr.pat_dev;
+        p.pg_flag = ctx->d_coef_pat;
         std::memcpy(p.coef_uniform, cr.uniform, sizeof(p.coef_uniform));
         p.coef = cr.dev;
         p.coef_cell_stride = cr.cell_stride;
@@ -941,6 +942,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         p.sigma = d_sigma; // stiffness + internal force from one pass: only the Hex8 kernel takes them
         p.out_d = d_force;
         if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
+        if (nl == 0 && op == GL_OP_MAT_10_BDB && d_sigma == nullptr) nl = launch_hex8_gauss(p, ctx->stream);
         if (force_done) *force_done = nl > 0 && d_sigma != nullptr;
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_small2d(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_syrk(p, mesh->ndim, ctx->stream);

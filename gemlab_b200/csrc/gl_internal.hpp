@@ -81,6 +81,7 @@ struct IntegParams {
                               // (2 = symmetric with uncoupled normal / diagonal shear blocks, 1 = major-symmetric, 0 = unknown / general)
     const int *coef_pat_dev;  // device-resident records: their common structure, found by a probe kernel earlier on the stream;
                               // the launcher then enqueues every pattern variant and all but the matching one exit at once
+    int *pg_flag;             // PER_GAUSS moduli: device flag of the in-kernel symmetry check (see gl_kernels_bdb.cu), owned by the ctx
     double coef_uniform[36];
     // output
     double *out;
@@ -120,6 +121,7 @@ int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op, int nn
 
 // tuned kernels; return 0 if the configuration is not covered (caller falls back to the generic kernel)
 int launch_hex8_bdb(const IntegParams &p, void *stream);
+int launch_hex8_gauss(const IntegParams &p, void *stream); // Hex8, one modulus per Gauss point (gl_kernels_hex8pg.cu)
 int launch_bdb(const IntegParams &p, int sd, void *stream);
 int launch_bdb_small2d(const IntegParams &p, int sd, void *stream); // thread-per-cell variant for Tri3 / Qua4 (gl_kernels_small2d.cu)
 int launch_bdb_tile(const IntegParams &p, int sd, void *stream); // register-tiled variant for Hex20 / Tet10 (gl_kernels_tile.cu)

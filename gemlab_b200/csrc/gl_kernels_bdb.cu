@@ -47,20 +47,33 @@ constexpr int GP_UNROLL = GL_BDB_GP_UNROLL; // unroll factor of the Gauss-point 
 
 struct BdbConsts {
     double d[36]; // d'[a][b] = f_a f_b d[a][b] (row-major, ns x ns), f = 1 for normal rows, 1/sqrt(2) for shear rows
+    int gen;      // 1: general store epilogue (nrow / ncol / ii0 / jj0, clear = false, 8-byte aligned output) instead of the bulk copy
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int NN, int SD, int LPN, bool AXI, int PAT>
+// PG = one modulus per GAUSS POINT (the reference closure's natural use, mat_10_bdb.rs:156-159: every nonlinear material).  The
+// Gauss sum can no longer move inside, so phase C accumulates the element blocks themselves,
+//   T(n) = c_p D'_p M(n)  (NS x SD, once per column node and Gauss point),   K(m,n) += M(m)^T T(n)  (SD col_n FMA per entry),
+// exploiting the sparsity of the strain-displacement columns (3 non-zeros of 6 in 3D), which a dense tensor-core tiling of
+// K = sum_p M_p^T (c_p D_p) M_p cannot (Hex8: 24 kflop per cell here against 55 kflop as 8x8x4 DMMA tiles on the same pipe).
+// PAT 1 = every D_p is major-symmetric (circulant half + mirror), PAT 0 = general (all NN distances, no mirror).  The PAT 1
+// variant compares D_p with its transpose while staging it and lowers *p.pg_flag when a record is not symmetric; the PAT 0
+// variant is enqueued right behind it and returns at once unless that happened -- no probe pass, no host synchronisation.
+template <int NN, int SD, int LPN, bool AXI, int PAT, bool PG = false>
 __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const BdbConsts cst, const int CPC, const int nthreads_used, const int alias_g) {
-    if (p.coef_pat_dev != nullptr && *p.coef_pat_dev != PAT) return; // another pattern variant owns this call (see launcher)
+    if constexpr (PG) {
+        if (PAT == 0 && *p.pg_flag != 0) return; // every record was symmetric: the PAT 1 variant's result stands
+    } else {
+        if (p.coef_pat_dev != nullptr && *p.coef_pat_dev != PAT) return; // another pattern variant owns this call (see launcher)
+    }
     constexpr bool SYM = PAT >= 1;
     constexpr int NS = 2 * SD;
     constexpr int NDOF = NN * SD;
     // circulant distances 0 .. ND-1 (NN odd: (NN+1)/2 = NN/2+1 too).  The half is enough for EVERY pattern: P(n,m) = P(m,n)^T, and for a
     // non-symmetric D the `transposed` store of phase D contracts that transpose itself.  (With ND = NN every off-diagonal block
     // was written twice, by two lanes whose values round differently: a shared-memory write race.)
-    constexpr int ND = NN / 2 + 1;
+    constexpr int ND = (PG && !SYM) ? NN : NN / 2 + 1;
     constexpr int NSLOT = (ND + LPN - 1) / LPN;        // blocks per lane
     constexpr int GS = (1 + NN * SD + (AXI ? NN : 0)) | 1; // record per (cell, gauss point): c | B | N/r ; odd stride
     constexpr int XS = (NN * SD) | 1;
@@ -76,9 +89,11 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     double *s_X = s_L + ng * LS;                      // [CPC][XS]
     // [CPC][ng][GS]; when a cell's records fit inside its element block they ALIAS the K staging (dead before K is staged,
     // see gl_kernels_tile.cu) -- roughly halves the shared memory of a CTA, i.e. doubles the resident warps
-    const bool drec = p.coef != nullptr;              // one modulus record per marker / per cell instead of a uniform D
+    const bool drec = !PG && p.coef != nullptr;       // one modulus record per marker / per cell instead of a uniform D
     double *s_D = s_X + CPC * XS;                     // [CPC][NS*NS] d' of every cell of the tile (record moduli only)
     double *s_G = alias_g ? smem : s_D + (drec ? CPC * NS * NS : 0);
+    // PG: [CPC][ng][NS*NS] d'_p of every (cell, Gauss point), row-major, at an even (16-byte aligned) offset behind the records
+    double *s_DG = smem + ((((int)(s_G - smem) + CPC * ng * GS) + 1) & ~1);
 
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < ng * (1 + NN); i += nt) s_w[i] = p.rule[i];
@@ -145,6 +160,25 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                                                             : (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
                 s_D[c * NS * NS + idx] = p.coef[rec * p.coef_cell_stride + a + b * NS] * (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
             }
+        }
+        if constexpr (PG) {
+            // the modulus records of the tile's Gauss points (ns x ns Mandel matrices, column-major), read in address order; the
+            // 1/sqrt(2) factors of the shear rows are folded in and the record is stored row-major.  The symmetric variant checks
+            // every entry against its transpose (same 128/288-byte record: an L1 hit)
+            const double hs = 0.70710678118654752440084436210484903928;
+            bool asym = false;
+            for (int t = tid; t < ncell_tile * ng * NS * NS; t += nt) {
+                const int cg = t / (NS * NS), idx = t - cg * (NS * NS);
+                const int c = cg / ng, gp = cg - c * ng;
+                const int b = idx / NS, a = idx - b * NS;
+                const unsigned long long cell = cell0 + c;
+                const unsigned long long rec = (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
+                const double *D = p.coef + rec * p.coef_cell_stride + (unsigned long long)gp * p.coef_gp_stride;
+                const double v = D[a + b * NS];
+                if (SYM && v != D[b + a * NS]) asym = true;
+                s_DG[cg * NS * NS + a * NS + b] = v * (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
+            }
+            if (SYM && asym) *p.pg_flag = 0;
         }
         // ---- phase B: geometry per (cell, gauss point), SD lanes per pair ------------------------------------------------
         // lane `sub` of a pair accumulates row `sub` of J = Xt.L, the rows are exchanged with shuffles, every lane inverts J
@@ -255,6 +289,22 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
 #pragma unroll
                 for (int k = 0; k < SD; k++) vn[k] = G[1 + n * SD + k] * c;
                 if constexpr (AXI) vn[SD] = G[1 + NN * SD + n] * c;
+                double T[NS][SD]; // PG: T(n) = c_p D'_p M(n); rows the strain-displacement columns never touch are dead code
+                if constexpr (PG) {
+                    const double *Dp = s_DG + (cs * ng + gp) * NS * NS; // the same address for every lane of the cell: broadcast
+#pragma unroll
+                    for (int a = 0; a < NS; a++)
+#pragma unroll
+                        for (int j = 0; j < SD; j++) {
+                            double t = 0.0;
+#pragma unroll
+                            for (int q = 0; q < col_n(SD, AXI, j); q++) {
+                                const double dv = Dp[a * NS + col_row(SD, j, q)], bv = vn[col_comp(SD, j, q)];
+                                t = q == 0 ? dv * bv : fma(dv, bv, t);
+                            }
+                            T[a][j] = t;
+                        }
+                }
 #pragma unroll
                 for (int s = 0; s < NSLOT; s++) {
                     // a slot beyond the last distance (only in the last slot of some lanes) recomputes distance 0 and is
@@ -266,17 +316,50 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
 #pragma unroll
                     for (int k = 0; k < SD; k++) vm[k] = G[1 + m * SD + k];
                     if constexpr (AXI) vm[SD] = G[1 + NN * SD + m];
+                    if constexpr (PG) {
+                        // K(m,n)[i][j] += sum_q M(m)[row(i,q)][i] T[row(i,q)][j]   (add_to_kk / add_to_kk_axisymmetric, mat_10_bdb.rs:179-233)
 #pragma unroll
-                    for (int l = 0; l < VD; l++)
+                        for (int j = 0; j < SD; j++)
 #pragma unroll
-                        for (int k = 0; k < VD; k++) acc[s][k + VD * l] = fma(vm[k], vn[l], acc[s][k + VD * l]);
+                            for (int i = 0; i < SD; i++)
+#pragma unroll
+                                for (int q = 0; q < col_n(SD, AXI, i); q++)
+                                    acc[s][i + SD * j] = fma(vm[col_comp(SD, i, q)], T[col_row(SD, i, q)][j], acc[s][i + SD * j]);
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < VD; l++)
+#pragma unroll
+                            for (int k = 0; k < VD; k++) acc[s][k + VD * l] = fma(vm[k], vn[l], acc[s][k + VD * l]);
+                    }
                 }
             }
         }
 
         // ---- phase D: contract with D', stage and ship ------------------------------------------------------------------
         __syncthreads(); // every lane has finished reading G (it may alias the staging)
-        if (worker && cs < ncell_tile) {
+        if constexpr (PG) {
+            // the accumulators are the element blocks: stage them (mirrored in the symmetric variant)
+            if (worker && cs < ncell_tile) {
+                double *Kc = s_K + cs * NDOF * NDOF;
+#pragma unroll
+                for (int s = 0; s < NSLOT; s++) {
+                    const int b = LPN == 1 ? s : s * LPN + h;
+                    if (b >= ND) continue;
+                    int m = n + b;
+                    if (m >= NN) m -= NN;
+                    const bool half = (NN % 2 == 0) && b == NN / 2; // lane n + NN/2 holds the transposed pair itself
+                    const bool mirror = SYM && b != 0 && !half;
+#pragma unroll
+                    for (int j = 0; j < SD; j++)
+#pragma unroll
+                        for (int i = 0; i < SD; i++) {
+                            const double v = acc[s][i + SD * j];
+                            Kc[(SD * m + i) + NDOF * (SD * n + j)] = v;
+                            if (mirror) Kc[(SD * n + j) + NDOF * (SD * m + i)] = v;
+                        }
+                }
+            }
+        } else if (worker && cs < ncell_tile) {
             double *Kc = s_K + cs * NDOF * NDOF;
             double dl[NS * NS]; // d' of this lane's cell: the constant bank (uniform D) or the tile's record table
 #pragma unroll
@@ -318,7 +401,26 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                     }
             }
         }
-        if (p.cell_ids == nullptr) {
+        if (cst.gen) {
+            // general blocks (CommonArgs nrow / ncol / ii0 / jj0), clear = false (accumulate into `out`), 8-byte aligned outputs:
+            // the tile's blocks are swept in address order; entries outside the integrated extent are zero-filled when clearing
+            __syncthreads();
+            const unsigned int block = p.nrow * p.ncol;
+            for (unsigned int idx = tid; idx < (unsigned int)ncell_tile * block; idx += nt) {
+                const unsigned int c = idx / block, q = idx - c * block;
+                const unsigned int col = q / p.nrow, row = q - col * p.nrow;
+                const unsigned long long cell = cell0 + c;
+                const unsigned long long orig = p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell;
+                double *dst = p.out + (p.out_off ? (p.out_off[cell] - p.out_base) : (orig - p.cell_begin) * block) + q;
+                const bool inside = row >= p.ii0 && row < p.ii0 + NDOF && col >= p.jj0 && col < p.jj0 + NDOF;
+                if (!inside) {
+                    if (p.clear) *dst = 0.0;
+                    continue;
+                }
+                const double v = s_K[c * NDOF * NDOF + (row - p.ii0) + NDOF * (col - p.jj0)];
+                *dst = p.clear ? v : *dst + v;
+            }
+        } else if (p.cell_ids == nullptr) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             if (tid == 0) {
@@ -347,22 +449,32 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int NN, int SD, int LPN>
-bool bdb_alias(int ng, bool axi) { return (size_t)ng * ((1 + NN * SD + (axi ? NN : 0)) | 1) <= (size_t)NN * SD * NN * SD; }
+// doubles of the per-(cell, Gauss point) records of one cell: c | B | N/r, plus (PG) the ns x ns modulus of every Gauss point
+template <int NN, int SD>
+size_t bdb_record_doubles(int ng, bool axi, bool pg) {
+    return (size_t)ng * ((1 + NN * SD + (axi ? NN : 0)) | 1) + (pg ? (size_t)ng * 4 * SD * SD : 0);
+}
 
 template <int NN, int SD, int LPN>
-size_t bdb_smem(int ng, int cpc, bool axi, bool drec) {
-    const int gs = (1 + NN * SD + (axi ? NN : 0)) | 1;
+bool bdb_alias(int ng, int cpc, bool axi, bool pg) {
+    return (size_t)cpc * bdb_record_doubles<NN, SD>(ng, axi, pg) + (pg ? 2 : 0) <= (size_t)cpc * NN * SD * NN * SD;
+}
+
+template <int NN, int SD, int LPN>
+size_t bdb_smem(int ng, int cpc, bool axi, bool drec, bool pg) {
     const int xs = (NN * SD) | 1;
     const int ls = (NN * SD + 6) / 16 * 16 + 9;
-    const size_t g = bdb_alias<NN, SD, LPN>(ng, axi) ? 0 : (size_t)cpc * ng * gs;
+    const size_t g = bdb_alias<NN, SD, LPN>(ng, cpc, axi, pg) ? 0 : (size_t)cpc * bdb_record_doubles<NN, SD>(ng, axi, pg) + (pg ? 2 : 0);
     const size_t dsz = drec ? (size_t)cpc * 4 * SD * SD : 0;
     return sizeof(double) * ((size_t)cpc * NN * SD * NN * SD + (size_t)ng * (1 + NN + ls) + (size_t)cpc * xs + dsz + g);
 }
 
+__global__ void pg_flag_reset_kernel(int *flag) { *flag = 1; }
+
 template <int NN, int SD, int LPN>
-int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *stream) {
+int launch_kind(const IntegParams &p, BdbConsts cst, int pat, void *stream) {
     const bool axi = p.axisym != 0;
+    const bool pg = p.coef != nullptr && p.coef_gp_stride != 0;
     // cells per CTA: fill ~256 threads, at most ~110 KB of shared memory (two CTAs per SM)
     int cpc = 256 / (NN * LPN);
     // measured (cells per CTA swept, `profiles/r01_bdb_cells_per_cta_sweep.txt`): small CTAs -- more of them resident, cheaper
@@ -374,19 +486,30 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     if (const char *e = tuning_env("GL_BDB_CPC")) cpc = atoi(e); // tuning knob: cells per CTA
     if (cpc * NN * LPN > 256) cpc = 256 / (NN * LPN); // __launch_bounds__(256)
     if (cpc < 1) cpc = 1;
-    const bool drec = p.coef != nullptr;
-    while (cpc > 1 && bdb_smem<NN, SD, LPN>(p.ng, cpc, axi, drec) > 110 * 1024) cpc--;
-    const size_t smem = bdb_smem<NN, SD, LPN>(p.ng, cpc, axi, drec);
+    const bool drec = p.coef != nullptr && !pg;
+    while (cpc > 1 && bdb_smem<NN, SD, LPN>(p.ng, cpc, axi, drec, pg) > 110 * 1024) cpc--;
+    const size_t smem = bdb_smem<NN, SD, LPN>(p.ng, cpc, axi, drec, pg);
     if (smem > 200 * 1024) return 0;
     const int used = cpc * NN * LPN;
     const int threads = (used + 31) / 32 * 32;
     typedef void (*kern_t)(const IntegParams, const BdbConsts, const int, const int, const int);
     auto pick = [&](int pat) -> kern_t {
-        if constexpr (SD == 2) {
-            if (axi) return pat == 2 ? bdb_kernel<NN, SD, LPN, true, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, true, 1> : bdb_kernel<NN, SD, LPN, true, 0>);
+        if (pg) {
+            if constexpr (SD == 2) {
+                if (axi) return pat >= 1 ? bdb_kernel<NN, SD, LPN, true, 1, true> : bdb_kernel<NN, SD, LPN, true, 0, true>;
+            }
+            return pat >= 1 ? bdb_kernel<NN, SD, LPN, false, 1, true> : bdb_kernel<NN, SD, LPN, false, 0, true>;
         }
-        return pat == 2 ? bdb_kernel<NN, SD, LPN, false, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, false, 1> : bdb_kernel<NN, SD, LPN, false, 0>);
+        if constexpr (NN == 20 && LPN == 2) {
+            return nullptr; // this lane split is instantiated for the per-Gauss-point variants only
+        } else {
+            if constexpr (SD == 2) {
+                if (axi) return pat == 2 ? bdb_kernel<NN, SD, LPN, true, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, true, 1> : bdb_kernel<NN, SD, LPN, true, 0>);
+            }
+            return pat == 2 ? bdb_kernel<NN, SD, LPN, false, 2> : (pat == 1 ? bdb_kernel<NN, SD, LPN, false, 1> : bdb_kernel<NN, SD, LPN, false, 0>);
+        }
     };
+    if (NN == 20 && LPN == 2 && !pg) return 0;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -401,6 +524,22 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     if (const char *e = tuning_env("GL_BDB_GRID")) grid = (unsigned long long)atoi(e); // tuning knob
     if (grid > ntile) grid = ntile;
     if (grid == 0) return 0;
+    const int alias = bdb_alias<NN, SD, LPN>(p.ng, cpc, axi, pg) ? 1 : 0;
+    if (pg) {
+        // symmetric variant first (it checks the records it stages), the general one behind it runs only if a record was not symmetric
+        pg_flag_reset_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p.pg_flag);
+        int first = 1;
+        if (const char *e = tuning_env("GL_BDB_PATTERN")) first = atoi(e) >= 1 ? 1 : 0; // testing knob: 0 = general variant only
+        if (first == 0) cudaMemsetAsync(p.pg_flag, 0, sizeof(int), (cudaStream_t)stream);
+        for (int pt = first; pt >= 0; pt--) {
+            kern_t kern = pick(pt);
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, cst, cpc, used, alias);
+        }
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        note_kernel("bdb<nn=%d,sd=%d,axi=%d,gauss%s>", NN, SD, axi ? 1 : 0, cst.gen ? ",gen" : "");
+        return 2 + first;
+    }
     // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
     const bool probe = drec && p.coef_pat_dev != nullptr && tuning_env("GL_BDB_PATTERN") == nullptr;
     IntegParams q = p;
@@ -408,11 +547,11 @@ int launch_kind(const IntegParams &p, const BdbConsts &cst, int pat, void *strea
     for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt++) {
         kern_t kern = pick(pt);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(q, cst, cpc, used, bdb_alias<NN, SD, LPN>(p.ng, axi) ? 1 : 0);
+        kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(q, cst, cpc, used, alias);
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    note_kernel("bdb<nn=%d,sd=%d,axi=%d,pat=%d%s>", NN, SD, axi ? 1 : 0, pat, drec ? ",rec" : "");
-    return 1;
+    note_kernel("bdb<nn=%d,sd=%d,axi=%d,pat=%d%s%s>", NN, SD, axi ? 1 : 0, pat, drec ? ",rec" : "", cst.gen ? ",gen" : "");
+    return probe ? 3 : 1;
 }
 
 } // namespace
@@ -430,17 +569,20 @@ int launch_bdb_2d(const IntegParams &p, void *stream) {
 int launch_bdb_3d(const IntegParams &p, void *stream) {
     const int sd = 3;
 #endif
-    // covered: D uniform or one record per marker / per cell, tight blocks, overwrite; homogeneous or mixed layout; 16-byte
-    // aligned output
-    if (p.op != GL_OP_MAT_10_BDB || !p.clear) return 0;
-    if (p.coef != nullptr && (p.coef_gp_stride != 0 || p.coef_cell_stride != (unsigned long long)(4 * sd * sd))) return 0; // PER_GAUSS: generic kernel
+    // covered: D uniform, one record per marker / per cell, or one per Gauss point; homogeneous or mixed layout; tight blocks
+    // leave by bulk copy, everything else (nrow / ncol / ii0 / jj0, clear = false, 8-byte aligned output) by the general epilogue
+    if (p.op != GL_OP_MAT_10_BDB) return 0;
+    const bool pg = p.coef != nullptr && p.coef_gp_stride != 0;
+    if (p.coef != nullptr && !pg && p.coef_cell_stride != (unsigned long long)(4 * sd * sd)) return 0;
+    if (pg && (p.coef_gp_stride != (unsigned long long)(4 * sd * sd) || p.coef_index != nullptr || p.pg_flag == nullptr)) return 0;
     const unsigned ndof = (unsigned)p.nnode * (unsigned)sd;
-    if (p.nrow != ndof || p.ncol != ndof || p.ii0 != 0 || p.jj0 != 0) return 0;
-    if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
+    if (p.size_r != ndof || p.size_c != ndof) return 0;
+    const bool tight = p.nrow == ndof && p.ncol == ndof && p.ii0 == 0 && p.jj0 == 0;
     if (tuning_env("GL_DISABLE_BDB")) return 0; // testing knob: force the generic kernel
 
     const int ns = 2 * sd;
     BdbConsts cst;
+    cst.gen = !(tight && p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
     const double hs = 0.70710678118654752440084436210484903928;
     bool sym = true;
     for (int a = 0; a < ns; a++)
@@ -475,7 +617,11 @@ int launch_bdb_3d(const IntegParams &p, void *stream) {
     case 4: return launch_kind<4, 3, 1>(p, cst, pat, stream);
     case 8: return launch_kind<8, 3, 1>(p, cst, pat, stream);
     case 10: return launch_kind<10, 3, 1>(p, cst, pat, stream);
-    case 20: return launch_kind<20, 3, 4>(p, cst, pat, stream); // 11 circulant blocks per column node split over 4 lanes
+    case 20:
+        // one modulus per Gauss point: every lane of a column node recomputes T(n) = D'_p M(n), so fewer, fatter lanes win
+        // (2 lanes x 6 blocks: 216 DFMA per lane and Gauss point, 8,640 per cell; 4 lanes x 3 blocks: 10,800 per cell)
+        if (pg && !tuning_env("GL_BDB_PG_LPN4")) return launch_kind<20, 3, 2>(p, cst, pat, stream);
+        return launch_kind<20, 3, 4>(p, cst, pat, stream); // 11 circulant blocks per column node split over 4 lanes
     default: return 0;
     }
 #endif

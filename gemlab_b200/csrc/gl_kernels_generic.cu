@@ -475,11 +475,8 @@ __global__ void __launch_bounds__(NT) integ_generic_kernel(const IntegParams p) 
 template <int SD, int GD>
 int launch_t(const IntegParams &p, void *stream) {
     const size_t smem = generic_smem_bytes(SD, GD, p.nnode, p.ng, p.op, p.cells_per_cta, p.nnode_b);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(integ_generic_kernel<SD, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
-        attr_set = true;
-    }
+    // per launch: the attribute is per device, and one process may drive several (gl_multi_*)
+    if (cudaFuncSetAttribute(integ_generic_kernel<SD, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
     const unsigned long long ntile = (p.hi - p.lo + p.cells_per_cta - 1) / p.cells_per_cta;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);

@@ -350,6 +350,54 @@ GL_API void gl_args_default(gl_args *args);
  * (ns x ns column-major; ns = 4 if two_dim else 6) -- convenience for callers without russell_tensor */
 GL_API void gl_lin_elasticity(double young, double poisson, int two_dim, int plane_stress, double *dd);
 
+/* ---- device-resident output slabs (no reference counterpart: the reference's output is one host Matrix per cell) ----------
+ * The batched output of one call that STAYS on its device: element e of [cell_begin, cell_end) at ptr[off[e - cell_begin]],
+ * off from gl_out_offsets (homogeneous meshes: (e - cell_begin) * block).  This is the type the host wrappers hand out
+ * (gemlab_cuda::DeviceSlab, gemlab::DeviceSlab) so that a caller can feed gl_triplet_indices / its own kernels / a sparse
+ * solver without the element matrices ever crossing PCIe. */
+typedef struct gl_slab {
+    double *ptr;         /* DEVICE pointer; NULL on input = the library allocates (cudaMalloc) and owns it until gl_slab_free */
+    uint64_t capacity;   /* doubles available at ptr (input when ptr != NULL) */
+    uint64_t size;       /* out: doubles written */
+    uint64_t cell_begin; /* out: the cells this slab holds */
+    uint64_t cell_end;
+    int32_t device;      /* out: CUDA device ordinal */
+    int32_t owned;       /* out: 1 if the library allocated ptr */
+} gl_slab;
+/* gl_integ into a slab (asynchronous on the ctx stream like every device-output call; gl_ctx_sync reports zero determinants) */
+GL_API int gl_integ_slab(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                         const gl_coef *coef, gl_slab *slab);
+/* copies slab->size doubles to HOST memory and synchronises the ctx */
+GL_API int gl_slab_download(gl_ctx *ctx, const gl_slab *slab, double *host);
+GL_API void gl_slab_free(gl_slab *slab);
+
+/* ---- single-process multi-GPU driver (no reference counterpart: the reference is single threaded) ------------
+ * One gl_ctx + stream + host thread per device; the mesh is replicated, the CELL RANGE is split into contiguous pieces
+ *     piece g of [b, e) = [b + floor(g n / G), b + floor((g + 1) n / G)),  n = e - b     (gl_multi_partition)
+ * and there is no collective: cells are independent.  Host outputs land concatenated in cell order -- bit-identical to the
+ * single-device call; device outputs stay on their devices, one gl_slab per device.  Coefficient records must be on the HOST
+ * (PER_CELL / PER_GAUSS records are advanced to each piece); UNIFORM and PER_MARKER tables are replicated. */
+typedef struct gl_multi gl_multi;
+typedef struct gl_multi_mesh gl_multi_mesh;
+GL_API int gl_multi_create(const int *devices, int ndevice, gl_multi **multi);
+GL_API void gl_multi_destroy(gl_multi *multi);
+GL_API int gl_multi_ndevice(const gl_multi *multi);
+GL_API gl_ctx *gl_multi_ctx(gl_multi *multi, int g); /* ctx of the g-th device (gl_last_error_cell, gl_ctx_last_kernel, ...) */
+GL_API const char *gl_multi_last_error(const gl_multi *multi);
+GL_API void gl_multi_partition(uint64_t cell_begin, uint64_t cell_end, int ndevice, int g, uint64_t *piece_begin, uint64_t *piece_end);
+/* arguments as gl_mesh_upload; the replicas are uploaded concurrently */
+GL_API int gl_multi_mesh_upload(gl_multi *multi, int ndim, uint64_t npoint, const double *coords, uint64_t ncell, const uint8_t *kinds,
+                                const int32_t *markers, const uint64_t *conn_off, const uint64_t *conn, gl_multi_mesh **mesh);
+GL_API void gl_multi_mesh_free(gl_multi *multi, gl_multi_mesh *mesh);
+GL_API const gl_mesh *gl_multi_mesh_replica(const gl_multi_mesh *mesh, int g);
+/* out->location must be GL_HOST (one buffer for the whole range); returns after every device has finished */
+GL_API int gl_multi_integ(gl_multi *multi, const gl_multi_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end,
+                          const gl_args *args, const gl_coef *coef, gl_out *out);
+/* slabs[0 .. ndevice): piece g stays on device g (ptr == NULL: allocated by the library).  Asynchronous: gl_multi_sync waits. */
+GL_API int gl_multi_integ_slabs(gl_multi *multi, const gl_multi_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end,
+                                const gl_args *args, const gl_coef *coef, gl_slab *slabs);
+GL_API int gl_multi_sync(gl_multi *multi);
+
 /* ---- micro-benchmarks used to measure the FP64 roofline denominators on the device (bench.py) ---- */
 /* runs `iters` dependent-chain DFMA (kind 0) or DMMA m8n8k4 (kind 1) per thread on the whole device and returns the
  * achieved TFLOP/s measured with CUDA events; kind 2 interleaves both */

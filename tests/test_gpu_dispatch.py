@@ -215,3 +215,98 @@ def test_packed_upper_triangles(ctx, kind, op):
     np.testing.assert_allclose(sym, full, rtol=0, atol=1e-12 * np.max(np.abs(full)))
     with pytest.raises(g.GemlabError):
         getattr(integ, op)(ctx, dmesh, None, CommonArgs(packed=True, clear=False), Coef.uniform(coef), out=np.zeros(mesh.ncell * tri))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# one modulus per Gauss point (the reference closure's natural use, mat_10_bdb.rs:156-159) on the tuned kernels
+# ---------------------------------------------------------------------------------------------------------------
+
+PG_KINDS = ["tri3", "tri6", "qua4", "qua8", "qua9", "tet4", "tet10", "hex8", "hex20"]
+
+
+@pytest.mark.parametrize("kind", PG_KINDS)
+@pytest.mark.parametrize("structure", ["symmetric", "general", "one_general_record"])
+def test_stiffness_with_one_modulus_per_gauss_point(ctx, kind, structure):
+    """D_p differs at every Gauss point: K = sum_p c_p M_p^T D_p M_p (add_to_kk, mat_10_bdb.rs:179-233).  Symmetric records run
+    the mirrored variant, a single non-symmetric record anywhere in the range makes the general variant redo the call (the
+    check happens on the device); both must match the oracle and stay off the generic kernel."""
+    import torch
+
+    mesh = make_mesh(kind, n=4)
+    ng = g.Gauss.new(GeoKind.from_str(kind)).npoint()
+    rng = np.random.default_rng(23)
+    ncell, ns = mesh.ncell, 2 * mesh.ndim
+    recs = random_coef("mat_10_bdb", mesh.ndim, ncell * ng, rng, spd=(structure != "general"))
+    if structure == "one_general_record":
+        recs[(ncell * ng * 2) // 3, 1] += 0.25  # D[1,0] != D[0,1] in one record only
+    dmesh = ctx.upload(mesh)
+    bs = integ.op_out_size("mat_10_bdb", GeoKind.from_str(kind), mesh.ndim)
+    sizes = np.arange(ncell + 1) * bs
+    for axisym in ([False, True] if mesh.ndim == 2 else [False]):
+        args = CommonArgs(axisymmetric=axisym, alpha=1.3)
+        ref = oracle_integ("mat_10_bdb", mesh, recs, cell_stride=ng * ns * ns, gp_stride=ns * ns, axisymmetric=axisym, alpha=1.3)
+        got = integ.mat_10_bdb(ctx, dmesh, None, args, Coef.per_gauss(recs))
+        fam = ctx.last_kernel()
+        assert fam.startswith("hex8_gauss") or (fam.startswith("bdb<") and ",gauss" in fam), f"{kind}: ran {fam!r}"
+        assert rel_err(got, ref, sizes) <= TOL, f"{kind} {structure} axisym={axisym}"
+        # device-resident records, device output, a sub-range that does not start at a tile boundary
+        b, e = 3, ncell - 2
+        out = torch.full(((e - b) * bs,), 7.0, dtype=torch.float64, device="cuda")
+        integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.per_gauss(torch.from_numpy(recs[b * ng:e * ng]).cuda()), out=out)
+        ctx.sync()
+        assert rel_err(out.cpu().numpy(), ref[b * bs:e * bs], sizes[: e - b + 1]) <= TOL, f"{kind} {structure} axisym={axisym} range"
+
+
+def test_per_gauss_moduli_constant_records_equal_uniform_path(ctx):
+    """The same D at every Gauss point must reproduce the uniform-D kernels (another algebra: geometric tensors) to rounding."""
+    for kind in ["hex8", "qua8", "tet10"]:
+        mesh = make_mesh(kind, n=3)
+        ng = g.Gauss.new(GeoKind.from_str(kind)).npoint()
+        dd = iso(mesh.ndim)
+        dmesh = ctx.upload(mesh)
+        uni = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.uniform(dd))
+        pg = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), Coef.per_gauss(np.tile(np.asarray(dd).ravel(), (mesh.ncell * ng, 1))))
+        bs = integ.op_out_size("mat_10_bdb", GeoKind.from_str(kind), mesh.ndim)
+        assert rel_err(pg, uni, np.arange(mesh.ncell + 1) * bs) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["hex8", "tet10", "qua8", "tri6", "tet4", "qua9"])
+@pytest.mark.parametrize("mode", ["uniform", "per_gauss"])
+def test_general_blocks_and_accumulation_on_the_register_blocked_kernel(ctx, kind, mode):
+    """CommonArgs nrow / ncol / ii0 / jj0 and clear = false (src/integ/common_args.rs:5-43; kk.fill(0.0) clears the WHOLE block,
+    mat_10_bdb.rs:141-143) are served by the store epilogue of the tuned kernel, not by the generic one."""
+    mesh = make_mesh(kind, n=3)
+    dmesh = ctx.upload(mesh)
+    gk = GeoKind.from_str(kind)
+    nd = gk.nnode() * mesh.ndim
+    ng = g.Gauss.new(gk).npoint()
+    rng = np.random.default_rng(4)
+    ns = 2 * mesh.ndim
+    if mode == "uniform":
+        coef = Coef.uniform(iso(mesh.ndim))
+    else:
+        coef = Coef.per_gauss(random_coef("mat_10_bdb", mesh.ndim, mesh.ncell * ng, rng))
+    base = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), coef).reshape(mesh.ncell, nd, nd)
+    out = np.full(base.size, 12.5)
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(clear=False), coef, out=out)
+    fam = ctx.last_kernel()
+    assert not fam.startswith("generic"), fam
+    assert fam.endswith(",gen>"), fam
+    np.testing.assert_allclose(out.reshape(base.shape), base + 12.5, rtol=1e-13, atol=0)
+    nrow, ncol = nd + 5, nd + 2
+    args = CommonArgs(ii0=3, jj0=1, nrow=nrow, ncol=ncol)
+    out = np.full(mesh.ncell * nrow * ncol, 99.0)
+    integ.mat_10_bdb(ctx, dmesh, None, args, coef, out=out)
+    assert ctx.last_kernel().endswith(",gen>"), ctx.last_kernel()
+    blk = out.reshape(mesh.ncell, ncol, nrow)  # [cell][col][row]
+    np.testing.assert_allclose(blk[:, 1:1 + nd, 3:3 + nd], base, rtol=1e-13, atol=0)
+    outside = blk.copy()
+    outside[:, 1:1 + nd, 3:3 + nd] = 0.0
+    assert np.count_nonzero(outside) == 0
+    out2 = np.full(out.size, 2.0)
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(ii0=3, jj0=1, nrow=nrow, ncol=ncol, clear=False), coef, out=out2)
+    blk2 = out2.reshape(mesh.ncell, ncol, nrow)
+    np.testing.assert_allclose(blk2[:, 1:1 + nd, 3:3 + nd], base + 2.0, rtol=1e-13, atol=0)
+    rest = blk2.copy()
+    rest[:, 1:1 + nd, 3:3 + nd] = 2.0
+    assert np.all(rest == 2.0)
