@@ -86,6 +86,10 @@ pub struct gl_slab {
 }
 
 #[repr(C)]
+pub struct gl_asm_plan {
+    _private: [u8; 0],
+}
+#[repr(C)]
 pub struct gl_multi {
     _private: [u8; 0],
 }
@@ -257,4 +261,22 @@ extern "C" {
     pub fn gl_multi_integ(multi: *mut gl_multi, mesh: *const gl_multi_mesh, op: c_int, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, out: *mut gl_out) -> c_int;
     pub fn gl_multi_integ_slabs(multi: *mut gl_multi, mesh: *const gl_multi_mesh, op: c_int, cell_begin: u64, cell_end: u64, args: *const gl_args, coef: *const gl_coef, slabs: *mut gl_slab) -> c_int;
     pub fn gl_multi_sync(multi: *mut gl_multi) -> c_int;
+
+    // planned assembly (position map computed once; stiffness blocks go from shared memory straight into the CSR values)
+    pub fn gl_assemble_plan_create(
+        ctx: *mut gl_ctx,
+        mesh: *const gl_mesh,
+        op: c_int,
+        cell_begin: u64,
+        cell_end: u64,
+        args: *const gl_args,
+        eq: *const i32,
+        eq_location: c_int,
+        rowptr: *const i64,
+        colidx: *const i32,
+        missing: *mut u64,
+        plan: *mut *mut gl_asm_plan,
+    ) -> c_int;
+    pub fn gl_assemble_planned(ctx: *mut gl_ctx, plan: *const gl_asm_plan, coef: *const gl_coef, vals: *mut c_double) -> c_int;
+    pub fn gl_assemble_plan_free(ctx: *mut gl_ctx, plan: *mut gl_asm_plan);
 }

@@ -107,6 +107,10 @@ SYMBOLS.update({
     "gl_multi_integ": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlOut)]),
     "gl_multi_integ_slabs": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlSlab)]),
     "gl_multi_sync": (C.c_int, [_P]),
+    "gl_assemble_plan_create": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), _P, C.c_int, _P, _P, C.POINTER(C.c_uint64),
+                                          C.POINTER(_P)]),
+    "gl_assemble_planned": (C.c_int, [_P, _P, C.POINTER(GlCoef), _P]),
+    "gl_assemble_plan_free": (None, [_P, _P]),
 })
 SYMBOLS["gl_normal_vectors"] = (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlOut)])
 for _name in ("gl_mat_04_nsb", "gl_mat_05_btn", "gl_mat_06_nvn", "gl_mat_07_bsn", "gl_mat_01_nsn_bry", "gl_vec_01_ns_bry", "gl_vec_02_nv_bry",

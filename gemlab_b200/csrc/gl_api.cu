@@ -827,7 +827,8 @@ static int ensure_point_major(gl_ctx *ctx, gl_mesh *mesh) {
 // launches the kernels that integrate original cells [b, e) into the DEVICE buffer d_out (block of cell b at d_out[0])
 static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a,
                         const CoefResolved &cr, uint64_t coef_begin, double *d_out, const double *d_sigma = nullptr,
-                        double *d_force = nullptr, bool *force_done = nullptr) {
+                        double *d_force = nullptr, bool *force_done = nullptr, const uint32_t *sc_pos = nullptr, double *sc_vals = nullptr,
+                        int only_bucket = -1) {
     if (b == e) return GL_OK;
     const bool explicit_block = a->nrow != 0 || (op_is_matrix(op) && a->ncol != 0);
     const std::vector<uint64_t> *pre = nullptr;
@@ -837,7 +838,9 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         pre = mesh_prefix(mesh, op, a, &key, &st);
         if (st) return fail(ctx, st);
     }
-    for (auto &bk : mesh->buckets) {
+    for (size_t bi = 0; bi < mesh->buckets.size(); bi++) {
+        auto &bk = mesh->buckets[bi];
+        if (only_bucket >= 0 && (int)bi != only_bucket) continue;
         uint64_t lo, hi;
         bucket_range(mesh, bk, b, e, lo, hi);
         if (lo >= hi) continue;
@@ -941,6 +944,18 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         int nl = 0;
         p.sigma = d_sigma; // stiffness + internal force from one pass: only the Hex8 kernel takes them
         p.out_d = d_force;
+        if (sc_pos) {
+            // fused assembly (gl_assemble_planned): only the kernels with a scatter epilogue; the caller checked stiffness_fusable()
+            p.scatter_pos = sc_pos;
+            p.scatter_vals = sc_vals;
+            nl = launch_hex8_bdb(p, ctx->stream);
+            if (nl == 0) nl = launch_bdb(p, mesh->ndim, ctx->stream);
+            if (nl == 0) return fail(ctx, GL_ERR_INVALID_ARG, "internal: no kernel with a scatter epilogue took the configuration");
+            if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
+            ctx->launches += (uint64_t)nl;
+            ctx->last_kernel = noted_kernel();
+            continue;
+        }
         if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && d_sigma == nullptr) nl = launch_hex8_gauss(p, ctx->stream);
         if (force_done) *force_done = nl > 0 && d_sigma != nullptr;
@@ -1810,6 +1825,214 @@ int gl_assemble(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t 
     if (st) return st;
     if (sync) return sync;
     if (h_missing) return fail(ctx, GL_ERR_INVALID_ARG, "sparsity pattern lacks entries of the element blocks");
+    return GL_OK;
+}
+
+} // extern "C"
+
+// =====================================================================================================
+// planned assembly: the position of every element-block entry in the global matrix is computed ONCE; after that
+// integrate-and-assemble is one kernel per GeoKind for the stiffness matrix (the blocks go from shared memory straight into the
+// CSR values, RED.ADD.F64 -- the element-matrix slab is never materialised) and slab + position-map scatter for the other cases
+// =====================================================================================================
+struct gl_asm_plan {
+    gl_mesh *mesh = nullptr;
+    int op = 0;
+    uint64_t b = 0, e = 0, total = 0;
+    gl_args args{};
+    bool is_mat = true;
+    uint32_t *d_pos = nullptr; // [total] position in vals of entry (row, col) of every block, ROW-major inside the block; 0xFFFFFFFF = skip
+};
+
+namespace {
+
+constexpr uint32_t NOPOS = 0xFFFFFFFFu;
+
+__global__ void plan_positions_kernel(const ScatterParams s, const long long *rowptr, const int32_t *colidx, uint32_t *pos,
+                                      unsigned long long *missing) {
+    const unsigned int bs = (unsigned int)s.nr * (unsigned int)s.nc;
+    const unsigned long long total = (s.hi - s.lo) * (unsigned long long)bs;
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long cl = s.lo + idx / bs;
+        const unsigned int q = (unsigned int)(idx % bs);
+        const unsigned int ii = q / (unsigned int)s.nc, jj = q - ii * (unsigned int)s.nc; // row-major inside the block
+        const unsigned long long orig = s.cell_ids ? (unsigned long long)s.cell_ids[cl] : cl;
+        const unsigned long long o = (s.out_off ? (s.out_off[cl] - s.out_base) : (orig - s.cell_begin) * bs) + q;
+        const unsigned int pr = s.conn[(unsigned long long)(ii / s.npd) * s.ncell_k + cl];
+        const int r = s.eq[(unsigned long long)pr * s.npd + ii % s.npd];
+        uint32_t u = NOPOS;
+        if (s.nc == 1) {
+            if (r >= 0) u = (uint32_t)r;
+        } else {
+            const unsigned int pc = s.conn[(unsigned long long)(jj / s.npd) * s.ncell_k + cl];
+            const int c = s.eq[(unsigned long long)pc * s.npd + jj % s.npd];
+            if (r >= 0 && c >= 0) {
+                long long a = rowptr[r], b = rowptr[r + 1];
+                const long long end = b;
+                while (a < b) {
+                    const long long mid = (a + b) >> 1;
+                    if (colidx[mid] < c) a = mid + 1;
+                    else b = mid;
+                }
+                if (a < end && colidx[a] == c && a < (long long)NOPOS) u = (uint32_t)a;
+                else atomicAdd(missing, 1ull);
+            }
+        }
+        pos[o] = u;
+    }
+}
+
+// slab path: blocks are column-major in `blocks`, the position map is row-major inside the block
+__global__ void planned_scatter_kernel(const ScatterParams s, const double *blocks, const uint32_t *pos, unsigned long long pos_base, double *vals) {
+    const unsigned int bs = (unsigned int)s.nr * (unsigned int)s.nc;
+    const unsigned long long total = (s.hi - s.lo) * (unsigned long long)bs;
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long cl = s.lo + idx / bs;
+        const unsigned int q = (unsigned int)(idx % bs);
+        const unsigned int ii = q / (unsigned int)s.nc, jj = q - ii * (unsigned int)s.nc;
+        const unsigned long long orig = s.cell_ids ? (unsigned long long)s.cell_ids[cl] : cl;
+        const unsigned long long base = s.out_off ? (s.out_off[cl] - s.out_base) : (orig - s.cell_begin) * bs;
+        const uint32_t u = pos[pos_base + base + q];
+        if (u != NOPOS) atomicAdd(vals + u, blocks[base + ii + (unsigned long long)jj * s.nr]);
+    }
+}
+
+// can the stiffness of this bucket go through a kernel with a scatter epilogue (gl_kernels_hex8.cu / gl_kernels_bdb.cu)?
+bool stiffness_fusable(const gl_mesh *mesh, const gl_mesh_bucket &bk, int op, const gl_args *a, const gl_coef *coef) {
+    if (op != GL_OP_MAT_10_BDB || kind_geo_ndim(bk.kind) != mesh->ndim) return false;
+    if (a->axisymmetric && mesh->ndim != 2) return false;
+    int ng = 0;
+    const double *data = nullptr;
+    if (gauss_rule(bk.kind, a->ngauss, &ng, &data)) return false;
+    const bool pg = coef->mode == GL_COEF_PER_GAUSS;
+    const bool drec = !pg && coef->mode != GL_COEF_UNIFORM;
+    return bdb_covers(bk.nnode, mesh->ndim, ng, a->axisymmetric != 0, drec, pg);
+}
+
+} // namespace
+
+extern "C" {
+
+int gl_assemble_plan_create(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t b, uint64_t e, const gl_args *a, const int32_t *eq,
+                            int eq_location, const int64_t *rowptr, const int32_t *colidx, uint64_t *missing, gl_asm_plan **out) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
+    int st = assemble_checks(ctx, mesh, op, b, e, a);
+    if (st) return st;
+    const bool is_mat = op_is_matrix(op);
+    if (!eq || !out || (is_mat && (!rowptr || !colidx))) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    if (missing) *missing = 0;
+    cudaSetDevice(ctx->device);
+    gl_args args = *a;
+    args.clear = 1;
+    uint64_t total = 0;
+    st = range_layout(mesh, op, b, e, &args, &total, nullptr);
+    if (st) return fail(ctx, st);
+    auto *plan = new gl_asm_plan();
+    plan->mesh = mesh;
+    plan->op = op;
+    plan->b = b;
+    plan->e = e;
+    plan->total = total;
+    plan->args = args;
+    plan->is_mat = is_mat;
+    if (total == 0) {
+        *out = plan;
+        return GL_OK;
+    }
+    if (cudaMalloc(&plan->d_pos, total * sizeof(uint32_t)) != cudaSuccess) {
+        delete plan;
+        return cuda_fail(ctx, cudaGetLastError(), "cudaMalloc (position map)");
+    }
+    const int32_t *d_eq = nullptr;
+    bool owned = false;
+    st = eq_on_device(ctx, mesh, op_dofs_per_node(op, mesh->ndim), eq, eq_location, &d_eq, &owned);
+    unsigned long long *d_missing = nullptr;
+    if (!st && cudaMalloc(&d_missing, sizeof(unsigned long long)) != cudaSuccess) st = cuda_fail(ctx, cudaGetLastError(), "cudaMalloc");
+    if (!st) {
+        cudaMemsetAsync(d_missing, 0, sizeof(unsigned long long), (cudaStream_t)ctx->stream);
+        for (auto &bk : mesh->buckets) {
+            ScatterParams s;
+            bool empty;
+            st = scatter_params(ctx, mesh, bk, op, &args, b, e, d_eq, s, empty);
+            if (st) break;
+            if (empty) continue;
+            plan_positions_kernel<<<scatter_grid(s), 256, 0, (cudaStream_t)ctx->stream>>>(s, (const long long *)rowptr, colidx, plan->d_pos, d_missing);
+            ctx->launches++;
+        }
+    }
+    unsigned long long h_missing = 0;
+    if (d_missing) cudaMemcpyAsync(&h_missing, d_missing, sizeof(h_missing), cudaMemcpyDeviceToHost, (cudaStream_t)ctx->stream);
+    const cudaError_t ce = cudaStreamSynchronize((cudaStream_t)ctx->stream);
+    if (d_missing) cudaFree(d_missing);
+    if (owned) cudaFree(const_cast<int32_t *>(d_eq));
+    if (missing) *missing = h_missing;
+    if (!st && ce != cudaSuccess) st = cuda_fail(ctx, ce, "position map");
+    if (!st && h_missing) st = fail(ctx, GL_ERR_INVALID_ARG, "sparsity pattern lacks entries of the element blocks");
+    if (st) {
+        cudaFree(plan->d_pos);
+        delete plan;
+        return st;
+    }
+    *out = plan;
+    return GL_OK;
+}
+
+void gl_assemble_plan_free(gl_ctx *ctx, gl_asm_plan *plan) {
+    if (!plan) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (plan->d_pos) cudaFree(plan->d_pos);
+    delete plan;
+}
+
+int gl_assemble_planned(gl_ctx *ctx, const gl_asm_plan *plan, const gl_coef *coef, double *vals) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    if (!plan || !coef || !vals) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    gl_mesh *mesh = plan->mesh;
+    if (mesh->device != ctx->device) return fail(ctx, GL_ERR_INVALID_ARG, "plan belongs to another device");
+    if (plan->total == 0) return GL_OK;
+    cudaSetDevice(ctx->device);
+    const int op = plan->op;
+    const uint64_t b = plan->b, e = plan->e;
+    const gl_args *a = &plan->args;
+    CoefResolved cr;
+    int st = resolve_coef(ctx, mesh, op, b, e, a, coef, cr);
+    if (st) return st;
+    for (size_t bi = 0; bi < mesh->buckets.size(); bi++) {
+        auto &bk = mesh->buckets[bi];
+        uint64_t lo, hi;
+        bucket_range(mesh, bk, b, e, lo, hi);
+        if (lo >= hi) continue;
+        if (stiffness_fusable(mesh, bk, op, a, coef)) {
+            st = launch_range(ctx, mesh, op, b, e, a, cr, b, nullptr, nullptr, nullptr, nullptr, plan->d_pos, vals, (int)bi);
+            if (st) return st;
+            continue;
+        }
+        // everything else: chunks of cells through the scratch slab, then the position-map scatter
+        const size_t avg = (size_t)std::max<uint64_t>(plan->total / (e - b), 1) * sizeof(double);
+        const uint64_t per_chunk = std::max<uint64_t>(((size_t)256 << 20) / avg, 1);
+        for (uint64_t cb = b; cb < e; cb += per_chunk) {
+            const uint64_t ce = std::min(e, cb + per_chunk);
+            uint64_t t = 0, before = 0;
+            st = range_layout(mesh, op, cb, ce, a, &t, nullptr);
+            if (!st) st = range_layout(mesh, op, b, cb, a, &before, nullptr);
+            if (st) return fail(ctx, st);
+            st = ensure_buffer(ctx, &ctx->d_full, &ctx->full_bytes, t * sizeof(double));
+            if (st) return st;
+            st = launch_range(ctx, mesh, op, cb, ce, a, cr, b, ctx->d_full, nullptr, nullptr, nullptr, nullptr, nullptr, (int)bi);
+            if (st) return st;
+            ScatterParams s;
+            bool empty;
+            st = scatter_params(ctx, mesh, bk, op, a, cb, ce, nullptr, s, empty);
+            if (st) return st;
+            if (empty) continue;
+            planned_scatter_kernel<<<scatter_grid(s), 256, 0, (cudaStream_t)ctx->stream>>>(s, ctx->d_full, plan->d_pos, before, vals);
+            ctx->launches++;
+        }
+    }
+    if (cudaGetLastError() != cudaSuccess) return cuda_fail(ctx, cudaGetLastError(), "planned assembly");
     return GL_OK;
 }
 

@@ -93,6 +93,10 @@ struct IntegParams {
     // and the output d[(e - cell_begin)*ndof ..]; nullptr = not requested
     const double *sigma;
     double *out_d;
+    // fused assembly (gl_assemble_planned): instead of writing the element blocks, add entry (row, col) of the block of the cell with
+    // original id e to scatter_vals[scatter_pos[off(e) + row * ncol + col]] (0xFFFFFFFF = not assembled); off(e) as for `out`
+    const uint32_t *scatter_pos;
+    double *scatter_vals;
     // failure reporting: smallest original id of a cell with |det J| <= 1e-15
     unsigned long long *err_cell;
     // kernels whose warps draw cells from a queue (gl_kernels_syrk.cu): a counter owned by the ctx, zeroed by the launcher
@@ -123,6 +127,7 @@ int generic_pick_cells_per_cta(int sd, int gd, int nnode, int ng, int op, int nn
 int launch_hex8_bdb(const IntegParams &p, void *stream);
 int launch_hex8_gauss(const IntegParams &p, void *stream); // Hex8, one modulus per Gauss point (gl_kernels_hex8pg.cu)
 int launch_bdb(const IntegParams &p, int sd, void *stream);
+bool bdb_covers(int nnode, int sd, int ng, bool axisym, bool record_moduli, bool per_gauss); // would launch_bdb take this stiffness configuration?
 int launch_bdb_small2d(const IntegParams &p, int sd, void *stream); // thread-per-cell variant for Tri3 / Qua4 (gl_kernels_small2d.cu)
 int launch_bdb_tile(const IntegParams &p, int sd, void *stream); // register-tiled variant for Hex20 / Tet10 (gl_kernels_tile.cu)
 int launch_bdb_syrk(const IntegParams &p, int sd, void *stream); // FP64 tensor-core (DMMA) symmetric rank-ng update for Hex20 / Tet10 (gl_kernels_syrk.cu)

@@ -48,6 +48,8 @@ constexpr int GP_UNROLL = GL_BDB_GP_UNROLL; // unroll factor of the Gauss-point 
 struct BdbConsts {
     double d[36]; // d'[a][b] = f_a f_b d[a][b] (row-major, ns x ns), f = 1 for normal rows, 1/sqrt(2) for shear rows
     int gen;      // 1: general store epilogue (nrow / ncol / ii0 / jj0, clear = false, 8-byte aligned output) instead of the bulk copy
+                  // 2: fused assembly -- blocks are staged transposed (row-major) and every entry is added to its slot of the global
+                  //    matrix (IntegParams::scatter_pos / scatter_vals); no element block is written
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -162,23 +164,34 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
             }
         }
         if constexpr (PG) {
-            // the modulus records of the tile's Gauss points (ns x ns Mandel matrices, column-major), read in address order; the
-            // 1/sqrt(2) factors of the shear rows are folded in and the record is stored row-major.  The symmetric variant checks
-            // every entry against its transpose (same 128/288-byte record: an L1 hit)
+            // the modulus records of the tile's Gauss points (ns x ns Mandel matrices, column-major), read in address order, eight
+            // loads in flight per thread; the 1/sqrt(2) factors of the shear rows are folded in and the record is stored row-major
             const double hs = 0.70710678118654752440084436210484903928;
-            bool asym = false;
-            for (int t = tid; t < ncell_tile * ng * NS * NS; t += nt) {
-                const int cg = t / (NS * NS), idx = t - cg * (NS * NS);
-                const int c = cg / ng, gp = cg - c * ng;
-                const int b = idx / NS, a = idx - b * NS;
-                const unsigned long long cell = cell0 + c;
-                const unsigned long long rec = (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
-                const double *D = p.coef + rec * p.coef_cell_stride + (unsigned long long)gp * p.coef_gp_stride;
-                const double v = D[a + b * NS];
-                if (SYM && v != D[b + a * NS]) asym = true;
-                s_DG[cg * NS * NS + a * NS + b] = v * (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
+            const int nval = ncell_tile * ng * NS * NS;
+            for (int t0 = tid; t0 < nval; t0 += 8 * nt) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int t = t0 + u * nt;
+                    v[u] = 0.0;
+                    if (t < nval) {
+                        const int cg = t / (NS * NS), idx = t - cg * (NS * NS);
+                        const int c = cg / ng, gp = cg - c * ng;
+                        const unsigned long long cell = cell0 + c;
+                        const unsigned long long rec = (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
+                        v[u] = __ldcs(p.coef + rec * p.coef_cell_stride + (unsigned long long)gp * p.coef_gp_stride + idx);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int t = t0 + u * nt;
+                    if (t < nval) {
+                        const int cg = t / (NS * NS), idx = t - cg * (NS * NS);
+                        const int b = idx / NS, a = idx - b * NS;
+                        s_DG[cg * NS * NS + a * NS + b] = v[u] * ((a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs));
+                    }
+                }
             }
-            if (SYM && asym) *p.pg_flag = 0;
         }
         // ---- phase B: geometry per (cell, gauss point), SD lanes per pair ------------------------------------------------
         // lane `sub` of a pair accumulates row `sub` of J = Xt.L, the rows are exchanged with shuffles, every lane inverts J
@@ -269,6 +282,22 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
             }
         }
         __syncthreads();
+        if constexpr (PG && SYM) {
+            // every staged record against its transpose (the scaling is symmetric, so d' is symmetric iff D is); shared memory only
+            constexpr int NP = NS * (NS - 1) / 2;
+            bool asym = false;
+            for (int t = tid; t < ncell_tile * ng * NP; t += nt) {
+                const int cg = t / NP;
+                int q = t - cg * NP, a = 0;
+                while (q >= NS - 1 - a) {
+                    q -= NS - 1 - a;
+                    a++;
+                }
+                const int b = a + 1 + q;
+                if (s_DG[cg * NS * NS + a * NS + b] != s_DG[cg * NS * NS + b * NS + a]) asym = true;
+            }
+            if (asym) *p.pg_flag = 0;
+        }
 
         // ---- phase C: geometric tensors of the node pairs ------------------------------------------------------------------
         // P(m,n)[k][l] = sum_p c_p v(m)[k] v(n)[l] with v(m) = (B(m,0..SD-1) [, N(m)/r]).  D is the same at every Gauss point,
@@ -337,6 +366,8 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
 
         // ---- phase D: contract with D', stage and ship ------------------------------------------------------------------
         __syncthreads(); // every lane has finished reading G (it may alias the staging)
+        const bool tr = cst.gen == 2;
+        auto kidx = [&](int r, int c) -> int { return tr ? c + NDOF * r : r + NDOF * c; };
         if constexpr (PG) {
             // the accumulators are the element blocks: stage them (mirrored in the symmetric variant)
             if (worker && cs < ncell_tile) {
@@ -354,8 +385,8 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
 #pragma unroll
                         for (int i = 0; i < SD; i++) {
                             const double v = acc[s][i + SD * j];
-                            Kc[(SD * m + i) + NDOF * (SD * n + j)] = v;
-                            if (mirror) Kc[(SD * n + j) + NDOF * (SD * m + i)] = v;
+                            Kc[kidx(SD * m + i, SD * n + j)] = v;
+                            if (mirror) Kc[kidx(SD * n + j, SD * m + i)] = v;
                         }
                 }
             }
@@ -395,13 +426,36 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                                 if (!SYM) u = have ? fma(dl[rb * NS + ra], pv, u) : dl[rb * NS + ra] * pv;
                                 have = true;
                             }
-                        Kc[(SD * m + i) + NDOF * (SD * n + j)] = v;
-                        if (mirror_all || (tri && i < j)) Kc[(SD * n + j) + NDOF * (SD * m + i)] = v;
-                        if (transposed) Kc[(SD * n + j) + NDOF * (SD * m + i)] = u;
+                        Kc[kidx(SD * m + i, SD * n + j)] = v;
+                        if (mirror_all || (tri && i < j)) Kc[kidx(SD * n + j, SD * m + i)] = v;
+                        if (transposed) Kc[kidx(SD * n + j, SD * m + i)] = u;
                     }
             }
         }
-        if (cst.gen) {
+        if (cst.gen == 2) {
+            // fused assembly: sweep the tile's (row-major) blocks and add every entry to its slot of the global matrix
+            __syncthreads();
+            // eight position-map loads in flight per thread before their adds (a RED must not wait on the map)
+            const unsigned int total = (unsigned int)ncell_tile * (NDOF * NDOF);
+            for (unsigned int idx0 = tid; idx0 < total; idx0 += 8 * nt) {
+                uint32_t u[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const unsigned int idx = idx0 + k * nt;
+                    u[k] = 0xFFFFFFFFu;
+                    if (idx < total) {
+                        const unsigned int c = idx / (NDOF * NDOF), q = idx - c * (NDOF * NDOF);
+                        const unsigned long long cell = cell0 + c;
+                        const unsigned long long orig = p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell;
+                        const unsigned long long base = p.out_off ? (p.out_off[cell] - p.out_base) : (orig - p.cell_begin) * (unsigned long long)(NDOF * NDOF);
+                        u[k] = __ldcs(p.scatter_pos + base + q);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (u[k] != 0xFFFFFFFFu) atomicAdd(p.scatter_vals + u[k], s_K[idx0 + k * nt]);
+            }
+        } else if (cst.gen) {
             // general blocks (CommonArgs nrow / ncol / ii0 / jj0), clear = false (accumulate into `out`), 8-byte aligned outputs:
             // the tile's blocks are swept in address order; entries outside the integrated extent are zero-filled when clearing
             __syncthreads();
@@ -537,7 +591,7 @@ int launch_kind(const IntegParams &p, BdbConsts cst, int pat, void *stream) {
             kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(p, cst, cpc, used, alias);
         }
         if (cudaGetLastError() != cudaSuccess) return -1;
-        note_kernel("bdb<nn=%d,sd=%d,axi=%d,gauss%s>", NN, SD, axi ? 1 : 0, cst.gen ? ",gen" : "");
+        note_kernel("bdb<nn=%d,sd=%d,axi=%d,gauss%s>", NN, SD, axi ? 1 : 0, cst.gen == 2 ? ",scatter" : (cst.gen ? ",gen" : ""));
         return 2 + first;
     }
     // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
@@ -550,7 +604,7 @@ int launch_kind(const IntegParams &p, BdbConsts cst, int pat, void *stream) {
         kern<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(q, cst, cpc, used, alias);
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    note_kernel("bdb<nn=%d,sd=%d,axi=%d,pat=%d%s%s>", NN, SD, axi ? 1 : 0, pat, drec ? ",rec" : "", cst.gen ? ",gen" : "");
+    note_kernel("bdb<nn=%d,sd=%d,axi=%d,pat=%d%s%s>", NN, SD, axi ? 1 : 0, pat, drec ? ",rec" : "", cst.gen == 2 ? ",scatter" : (cst.gen ? ",gen" : ""));
     return probe ? 3 : 1;
 }
 
@@ -583,6 +637,10 @@ int launch_bdb_3d(const IntegParams &p, void *stream) {
     const int ns = 2 * sd;
     BdbConsts cst;
     cst.gen = !(tight && p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
+    if (p.scatter_pos != nullptr) {
+        if (!tight) return 0;
+        cst.gen = 2;
+    }
     const double hs = 0.70710678118654752440084436210484903928;
     bool sym = true;
     for (int a = 0; a < ns; a++)
@@ -627,7 +685,34 @@ int launch_bdb_3d(const IntegParams &p, void *stream) {
 #endif
 }
 
+#if GL_BDB_SD == 2
+bool bdb_covers_2d(int nnode, int ng, bool axi, bool drec, bool pg) {
+    switch (nnode) {
+    case 3: return bdb_smem<3, 2, 1>(ng, 1, axi, drec, pg) <= 200 * 1024;
+    case 4: return bdb_smem<4, 2, 1>(ng, 1, axi, drec, pg) <= 200 * 1024;
+    case 6: return bdb_smem<6, 2, 1>(ng, 1, axi, drec, pg) <= 200 * 1024;
+    case 8: return bdb_smem<8, 2, 1>(ng, 1, axi, drec, pg) <= 200 * 1024;
+    case 9: return bdb_smem<9, 2, 1>(ng, 1, axi, drec, pg) <= 200 * 1024;
+    default: return false;
+    }
+}
+#else
+bool bdb_covers_3d(int nnode, int ng, bool drec, bool pg) {
+    switch (nnode) {
+    case 4: return bdb_smem<4, 3, 1>(ng, 1, false, drec, pg) <= 200 * 1024;
+    case 8: return bdb_smem<8, 3, 1>(ng, 1, false, drec, pg) <= 200 * 1024;
+    case 10: return bdb_smem<10, 3, 1>(ng, 1, false, drec, pg) <= 200 * 1024;
+    case 20: return bdb_smem<20, 3, 4>(ng, 1, false, drec, pg) <= 200 * 1024;
+    default: return false;
+    }
+}
+#endif
+
 #ifdef GL_BDB_MAIN
+bool bdb_covers_2d(int nnode, int ng, bool axi, bool drec, bool pg);
+bool bdb_covers(int nnode, int sd, int ng, bool axisym, bool record_moduli, bool per_gauss) {
+    return sd == 2 ? bdb_covers_2d(nnode, ng, axisym, record_moduli, per_gauss) : (!axisym && bdb_covers_3d(nnode, ng, record_moduli, per_gauss));
+}
 int launch_bdb_2d(const IntegParams &p, void *stream);
 int launch_bdb(const IntegParams &p, int sd, void *stream) { return sd == 2 ? launch_bdb_2d(p, stream) : launch_bdb_3d(p, stream); }
 #endif

@@ -65,7 +65,7 @@ __host__ __device__ constexpr bool d_nz(int pat, int a, int b) { return pat < 2 
 __host__ __device__ constexpr int col_row(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 3 : 5)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 3 : 4)) : (t == 0 ? 2 : (t == 1 ? 4 : 5))); }
 __host__ __device__ constexpr int col_comp(int j, int t) { return j == 0 ? (t == 0 ? 0 : (t == 1 ? 1 : 2)) : (j == 1 ? (t == 0 ? 1 : (t == 1 ? 0 : 2)) : (t == 0 ? 2 : (t == 1 ? 1 : 0))); }
 
-template <int PAT, int PF, int DBG = 0, bool DREC = false, bool FD = false>
+template <int PAT, int PF, int DBG = 0, bool DREC = false, bool FD = false, bool SC = false>
 __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegParams p, const Hex8Consts cst) {
     if (DREC && p.coef_pat_dev != nullptr && *p.coef_pat_dev != PAT) return; // another pattern variant owns this call
     constexpr bool SYM = PAT >= 1;
@@ -274,9 +274,28 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
                 d[2] = dn[2];
             }
         }
+        // SC: position-map slots of the warp's next cell to scatter (lane l owns entries l, l + 32, .. of the row-major block)
+        uint32_t sc_next[SC ? 18 : 1];
+        auto sc_load = [&](unsigned long long wc) {
+            if constexpr (SC) {
+                if (wc < p.hi) {
+                    const unsigned long long orig = p.cell_ids ? (unsigned long long)p.cell_ids[wc] : wc;
+                    const uint32_t *pos = p.scatter_pos + (orig - p.cell_begin) * 576ull + (tid & 31);
+#pragma unroll
+                    for (int k = 0; k < 18; k++) sc_next[k] = __ldcs(pos + 32 * k);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 18; k++) sc_next[k] = 0xFFFFFFFFu;
+                }
+            }
+        };
+        if constexpr (SC) sc_load(p.lo + batch * H8_CELLS + wq * 4);
         // ---- phase 3: contract with D', stage the blocks column-major, ship every cell with one bulk copy -------------
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the warp's previous copies have left s_K (no-op for lanes that issued none)
         __syncwarp();
+        // SC (fused assembly): the block is staged TRANSPOSED (row-major), so that consecutive lanes of the scatter sweep walk along
+        // one global row -- the three dofs of a node are adjacent columns of the CSR row
+        auto kidx = [](int r, int c) -> int { return SC ? c + 24 * r : r + 24 * c; };
 #pragma unroll
         for (int b = 0; b < (DBG >= 3 && DBG <= 4 ? 0 : 5); b++) {
             const int m = (g + b) & 7;
@@ -305,9 +324,9 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
                                 v = have ? fma(dv, pv, v) : dv * pv;
                                 have = true;
                             }
-                    Kc[(3 * m + i) + 24 * (3 * g + j)] = v;
+                    Kc[kidx(3 * m + i, 3 * g + j)] = v;
                     // mirrored entry K(n,m)^T: whole blocks at distance 1..3, strict upper triangles of the b = 0 / b = 4 blocks
-                    if (SYM && ((b >= 1 && b <= 3) || (tri && i < j))) Kc[(3 * g + j) + 24 * (3 * m + i)] = v;
+                    if (SYM && ((b >= 1 && b <= 3) || (tri && i < j))) Kc[kidx(3 * g + j, 3 * m + i)] = v;
                     if (!SYM && b >= 1 && b <= 3) {
                         // general D: K(3n+j, 3m+i) = sum_qr d'[row(j,r)][row(i,q)] P(n,m)[comp(j,r)][comp(i,q)], P(n,m) = P(m,n)^T
                         double u = 0.0;
@@ -320,9 +339,32 @@ __global__ void __launch_bounds__(H8_THREADS, 2) hex8_bdb_kernel(const IntegPara
                                 u = hv ? fma(dv, pv, u) : dv * pv;
                                 hv = true;
                             }
-                        Kc[(3 * g + j) + 24 * (3 * m + i)] = u;
+                        Kc[kidx(3 * g + j, 3 * m + i)] = u;
                     }
                 }
+        }
+        if constexpr (SC) {
+            // fused assembly: the warp sweeps its four staged blocks and adds every entry to its slot of the global matrix (RED.ADD.F64);
+            // the element matrices never reach HBM.  The 18 slots a lane needs per cell are loaded as one batch, one cell ahead of
+            // the adds (the first batch was issued before the contraction), so that no RED waits on the position map.
+            __syncwarp();
+            const unsigned long long wcell = p.lo + batch * H8_CELLS + wq * 4;
+            const int lane = tid & 31;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t u[18];
+#pragma unroll
+                for (int k = 0; k < 18; k++) u[k] = sc_next[k];
+                if (c + 1 < 4) sc_load(wcell + c + 1);
+                if (wcell + c < p.hi) {
+                    const double *src = s_K + (wq * 4 + c) * K_STRIDE + lane;
+#pragma unroll
+                    for (int k = 0; k < 18; k++)
+                        if (u[k] != 0xFFFFFFFFu) atomicAdd(p.scatter_vals + u[k], src[32 * k]);
+                }
+            }
+            __syncwarp();
+            continue;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -366,9 +408,11 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
     const bool drec = p.coef != nullptr;
     const bool fd = p.sigma != nullptr && p.out_d != nullptr; // fused internal-force vector (gl_integ_fused)
     if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 36)) return 0; // PER_GAUSS moduli: generic kernel
-    if (p.axisym || !p.clear || p.out_off != nullptr) return 0;
+    const bool sc = p.scatter_pos != nullptr; // fused assembly: no element blocks are written
+    if (sc && fd) return 0;
+    if (p.axisym || (!p.clear && !sc) || p.out_off != nullptr) return 0;
     if (p.nrow != 24 || p.ncol != 24 || p.ii0 != 0 || p.jj0 != 0 || p.size_r != 24) return 0;
-    if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
+    if (!sc && (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return 0;
 
     Hex8Consts cst;
     static int flags = -1;
@@ -418,6 +462,8 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
             }
         }
 #endif
+        if (sc && drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true, false, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true, false, true> : hex8_bdb_kernel<0, P, 0, true, false, true>);
+        if (sc) return pat == 2 ? hex8_bdb_kernel<2, P, 0, false, false, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, false, false, true> : hex8_bdb_kernel<0, P, 0, false, false, true>);
         if (fd && drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true, true> : hex8_bdb_kernel<0, P, 0, true, true>);
         if (fd) return pat == 2 ? hex8_bdb_kernel<2, P, 0, false, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, false, true> : hex8_bdb_kernel<0, P, 0, false, true>);
         if (drec) return pat == 2 ? hex8_bdb_kernel<2, P, 0, true> : (pat == 1 ? hex8_bdb_kernel<1, P, 0, true> : hex8_bdb_kernel<0, P, 0, true>);
@@ -445,7 +491,7 @@ int launch_hex8_bdb(const IntegParams &p, void *stream) {
         kern<<<(unsigned)grid, H8_THREADS, H8_SMEM, (cudaStream_t)stream>>>(q, cst);
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    note_kernel("hex8_bdb<pat=%d%s%s>", pat, drec ? ",rec" : "", fd ? ",fd" : "");
+    note_kernel("hex8_bdb<pat=%d%s%s%s>", pat, drec ? ",rec" : "", fd ? ",fd" : "", sc ? ",scatter" : "");
     return 1;
 }
 

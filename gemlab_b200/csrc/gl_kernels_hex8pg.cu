@@ -108,6 +108,21 @@ __global__ void __launch_bounds__(PG_THREADS, 2) hex8_gauss_kernel(const IntegPa
         if (c1 < p.hi) pid_next = ldpid(c1);
     }
     bool asym = false;
+    // the modulus record of Gauss point g of this lane's cell (18 LDG.128), loaded ONE BATCH AHEAD: issued right after the
+    // accumulation of the previous batch, in flight during its staging / copy issue and this batch's gather and geometry
+    double2 dr[18];
+    auto load_record = [&](unsigned long long c) {
+        if (c < p.hi) {
+            const unsigned long long rec = ((p.cell_ids ? (unsigned long long)p.cell_ids[c] : c) - p.coef_begin) * 8ull + g;
+            const double2 *D = reinterpret_cast<const double2 *>(p.coef + rec * 36ull);
+#pragma unroll
+            for (int i = 0; i < 18; i++) dr[i] = __ldcs(D + i); // streamed once
+        } else {
+#pragma unroll
+            for (int i = 0; i < 18; i++) dr[i] = make_double2(0.0, 0.0);
+        }
+    };
+    load_record(cell_of(0));
 
     for (unsigned long long it = 0;; it++) {
         const unsigned long long batch = (unsigned long long)blockIdx.x + it * gridDim.x;
@@ -124,17 +139,7 @@ __global__ void __launch_bounds__(PG_THREADS, 2) hex8_gauss_kernel(const IntegPa
             if (c1 < p.hi) ldp(pid_next, qx, qy, qz);
             if (c2 < p.hi) pid_next = ldpid(c2);
         }
-        // ---- phase 1: the modulus record of Gauss point g (loads first), then the geometry --------------------------------
-        double2 dr[18];
-        if (active) {
-            const unsigned long long rec = ((p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin) * 8ull + g;
-            const double2 *D = reinterpret_cast<const double2 *>(p.coef + rec * 36ull);
-#pragma unroll
-            for (int i = 0; i < 18; i++) dr[i] = __ldcs(D + i); // streamed once
-        } else {
-#pragma unroll
-            for (int i = 0; i < 18; i++) dr[i] = make_double2(0.0, 0.0);
-        }
+        // ---- phase 1: geometry at Gauss point g; then the modulus record (already in flight) goes to shared memory ------------
         __syncwarp();
         {
             double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
@@ -196,28 +201,36 @@ __global__ void __launch_bounds__(PG_THREADS, 2) hex8_gauss_kernel(const IntegPa
                 const int m = (g + b) & 7;
                 const double bm[3] = {Bg[m * 3 + 0], Bg[m * 3 + 1], Bg[m * 3 + 2]};
                 // K(3m+i, 3n+j) += sum_t M(m)[row(i,t)][i] T[row(i,t)][j]   (add_to_kk, mat_10_bdb.rs:179-208)
+                // symmetric D_p: the diagonal block (b = 0) is symmetric and the block at distance 4 is also held, transposed, by
+                // lane g+4 -- both lanes compute only i <= j and the mirror of phase 3 supplies the rest
+                const bool tri = SYM && (b == 0 || b == 4);
 #pragma unroll
                 for (int j = 0; j < 3; j++)
 #pragma unroll
-                    for (int i = 0; i < 3; i++)
+                    for (int i = 0; i < 3; i++) {
+                        if (tri && i > j) continue;
 #pragma unroll
                         for (int t = 0; t < 3; t++) acc[b][i + 3 * j] = fma(bm[col_comp(i, t)], T[col_row(i, t)][j], acc[b][i + 3 * j]);
+                    }
             }
         }
+        load_record(cell_of(it + 1)); // next batch's records
         __syncwarp(); // every lane of the warp has finished reading the records that alias the staging
 
         // ---- phase 3: stage column-major, one bulk copy per cell ----------------------------------------------------------
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             const int m = (g + b) & 7;
-            const bool mirror = SYM && b >= 1 && b <= 3; // distance 4 is held (transposed) by lane g+4 itself
+            const bool tri = SYM && (b == 0 || b == 4);
+            const bool mirror = SYM && b >= 1 && b <= 3;
 #pragma unroll
             for (int j = 0; j < 3; j++)
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
+                    if (tri && i > j) continue;
                     const double v = acc[b][i + 3 * j];
                     Kc[(3 * m + i) + 24 * (3 * g + j)] = v;
-                    if (mirror) Kc[(3 * g + j) + 24 * (3 * m + i)] = v;
+                    if (mirror || (tri && i < j)) Kc[(3 * g + j) + 24 * (3 * m + i)] = v;
                 }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -555,3 +555,42 @@ def assemble(ctx, dmesh, op, cell_range, args, coef, eq, vals, rowptr=None, coli
     if st:
         ctx._raise(st)
     return vals
+
+
+class AssemblyPlan:
+    """gl_asm_plan: the slot of every element-block entry in the global CSR matrix / vector, computed once (gl_assemble_plan_create).
+    `assemble(coef, vals)` integrates and adds (gl_assemble_planned; the stiffness matrix of solid kinds in ONE kernel per GeoKind,
+    element blocks never written to HBM).  Asynchronous on the ctx stream."""
+
+    def __init__(self, ctx, dmesh, op, cell_range, args, eq, rowptr=None, colidx=None):
+        b, e = _range(dmesh, cell_range)
+        a = args._c()
+        keep = []
+        ptr, loc = _marshal_eq(eq, keep)
+        missing = C.c_uint64()
+        h = C.c_void_p()
+        st = lib().gl_assemble_plan_create(ctx._h, dmesh._h, OPS[op], b, e, C.byref(a), ptr, loc,
+                                           None if rowptr is None else rowptr.data_ptr(), None if colidx is None else colidx.data_ptr(),
+                                           C.byref(missing), C.byref(h))
+        if st:
+            ctx._raise(st)
+        self.ctx, self._h, self._dmesh = ctx, h, dmesh
+
+    def assemble(self, coef, vals):
+        keep = []
+        c = _marshal_coef(coef, keep)
+        st = lib().gl_assemble_planned(self.ctx._h, self._h, C.byref(c), vals.data_ptr())
+        if st:
+            self.ctx._raise(st)
+        return vals
+
+    def free(self):
+        if self._h:
+            lib().gl_assemble_plan_free(self.ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -337,6 +337,21 @@ GL_API int gl_assemble(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_b
                        const gl_coef *coef, const int32_t *eq, int eq_location, const int64_t *rowptr, const int32_t *colidx,
                        double *vals, uint64_t *missing);
 
+/* Planned assembly (what a Newton loop does: the same mesh, equation table and sparsity pattern at every iteration).
+ * gl_assemble_plan_create finds, ONCE, the slot of every element-block entry in the CSR value array (or the global vector) and
+ * keeps that position map on the device (4 bytes per entry); gl_assemble_planned then integrates `op` and adds the blocks:
+ *   - mat_10_bdb on every solid kind (uniform / per-marker / per-cell / per-Gauss moduli): ONE kernel per GeoKind -- the element
+ *     blocks go from shared memory straight into `vals` (RED.ADD.F64); the element-matrix slab is never written to HBM;
+ *   - the other cases: element blocks through a bounded scratch slab, then a position-map scatter (no binary search).
+ * Asynchronous on the ctx stream (gl_ctx_sync reports zero determinants); `vals` is accumulated into, not cleared.
+ * *missing (may be NULL): entries the pattern lacks (then GL_ERR_INVALID_ARG and no plan).  nnz must be < 2^32 - 1. */
+typedef struct gl_asm_plan gl_asm_plan;
+GL_API int gl_assemble_plan_create(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
+                                   const int32_t *eq, int eq_location, const int64_t *rowptr, const int32_t *colidx, uint64_t *missing,
+                                   gl_asm_plan **plan);
+GL_API int gl_assemble_planned(gl_ctx *ctx, const gl_asm_plan *plan, const gl_coef *coef, double *vals);
+GL_API void gl_assemble_plan_free(gl_ctx *ctx, gl_asm_plan *plan);
+
 /* legacy (gemlab <= 1.x) names used by BASELINE.json's north_star: G was renamed to B in v2 */
 GL_API int gl_mat_10_gdg(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                          const gl_coef *coef, gl_out *out); /* = gl_mat_10_bdb */

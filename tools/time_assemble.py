@@ -12,6 +12,7 @@ import gemlab_b200 as g
 from gemlab_b200 import Coef, CommonArgs, Context, GeoKind, integ
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+planned_only = len(sys.argv) > 2 and sys.argv[2] == "planned-only"  # for profiling the fused kernel alone
 ctx = Context(0)
 dm = ctx.block(GeoKind.Hex8, (n, n, n))
 ncell, npoint = dm.ncell, dm.npoint
@@ -29,15 +30,38 @@ colidx = (keys % neq).to(torch.int32)
 del keys, rows, cols
 vals = torch.zeros(colidx.numel(), dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
-integ.assemble(ctx, dm, "mat_10_bdb", None, CommonArgs(), Coef.uniform(dd), eq, vals, rowptr, colidx)
-torch.cuda.synchronize()
-vals.zero_()
-t0 = time.perf_counter()
-integ.assemble(ctx, dm, "mat_10_bdb", None, CommonArgs(), Coef.uniform(dd), eq, vals, rowptr, colidx)
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
+dt = 1.0
+if not planned_only:
+    integ.assemble(ctx, dm, "mat_10_bdb", None, CommonArgs(), Coef.uniform(dd), eq, vals, rowptr, colidx)
+    torch.cuda.synchronize()
+    vals.zero_()
+    t0 = time.perf_counter()
+    integ.assemble(ctx, dm, "mat_10_bdb", None, CommonArgs(), Coef.uniform(dd), eq, vals, rowptr, colidx)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
 # K.1 = 0 for rigid translations: row sums of the assembled matrix vanish (relative to the largest entry)
 rs = torch.zeros(neq, dtype=torch.float64, device="cuda")
 rs.index_add_(0, torch.repeat_interleave(torch.arange(neq, device="cuda"), rowptr[1:] - rowptr[:-1]), vals)
 print(f"n={n}: {ncell} cells, {neq} equations, nnz {colidx.numel()}; triplet indices {t_trip*1e3:.1f} ms; "
       f"assemble {dt*1e3:.1f} ms = {ncell/dt/1e6:.1f} M elements/s; max |row sum| / max |K| = {float(rs.abs().max() / vals.abs().max()):.1e}")
+
+# planned assembly: position map once, then integrate + scatter fused into the stiffness kernel (no element-matrix slab)
+t0 = time.perf_counter()
+plan = integ.AssemblyPlan(ctx, dm, "mat_10_bdb", None, CommonArgs(), eq, rowptr, colidx)
+torch.cuda.synchronize()
+t_plan = time.perf_counter() - t0
+ref_vals = vals.clone()
+vals.zero_()
+plan.assemble(Coef.uniform(dd), vals)
+torch.cuda.synchronize()
+err = float((vals - ref_vals).abs().max() / ref_vals.abs().max()) if not planned_only else float("nan")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+vals.zero_()
+e0.record()
+for _ in range(5):
+    plan.assemble(Coef.uniform(dd), vals)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+print(f"planned: plan {t_plan*1e3:.1f} ms (once); integrate + assemble {ms:.3f} ms = {ncell/ms/1e3:.1f} M elements/s; kernel {ctx.last_kernel()}; "
+      f"max |planned - unplanned| / max |K| = {err:.1e}")
