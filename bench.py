@@ -488,10 +488,27 @@ def main():
 
         what = (f"{nx}x{ny}x{layers} cells per GPU per step ({n_e2e} cells): gl_mesh_upload (pinned host coords + 64-bit connectivity) + "
                 f"gl_mat_10_bdb into a pinned host buffer; chunked, kernels hidden behind the device->host copy")
+        # what the host link gives: one 1 GiB pinned device->host copy per rank, all ranks at once (the e2e legs move 2.4 / 4.6 KB
+        # per element over this link and are bound by it; on a box whose ranks share host bandwidth the sum does not scale with N)
+        link_src = torch.empty(1 << 27, dtype=torch.float64, device="cuda")
+        link_dst = host_out[: 1 << 27]
+        link_dst.copy_(link_src, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            link_dst.copy_(link_src, non_blocking=True)
+        torch.cuda.synchronize()
+        link_gbs_rank = 3 * link_src.numel() * 8 / (time.perf_counter() - t0) / 1e9
+        barrier()
+        link_all = world * 3 * link_src.numel() * 8 / max_over_ranks(time.perf_counter() - t0) / 1e9
+        del link_src
         v, d2h, buf = e2e_leg(packed=True)
         e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "output": "packed upper triangles (gl_args.packed): 300 doubles per element -- K is symmetric (D is major-symmetric)",
-               "workload": what, "numa_node": numa_node}
+               "workload": what, "numa_node": numa_node,
+               "d2h_link_gbs": {"this_rank_alone_in_its_share": link_gbs_rank, "all_ranks_concurrently": link_all,
+                                "note": "measured pinned device->host copy rate; value * d2h_bytes / n_cells is bounded by it"},
+               "frac_of_link": v * (d2h / n_e2e) / 1e9 / link_all}
         if rank == 0:
             e2e["parity_max_rel_err"], e2e["parity_cells"] = e2e_parity(buf, True)
         v, d2h, buf = e2e_leg(packed=False)

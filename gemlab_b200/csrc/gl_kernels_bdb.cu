@@ -488,15 +488,32 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {
-            // mixed-kind mesh: every cell has its own destination (prefix of block sizes); cooperative 16-byte copy
+            // mixed-kind mesh: every cell has its own destination (prefix of block sizes).  Block sizes of all kinds are even, so the
+            // destinations are 16-byte aligned like `out`: one bulk copy per cell.  The lanes of warp 0 look the destinations up in
+            // parallel, lane 0 issues the copies (a per-lane issue is serialised by ptxas into a loop that waits on the copy unit)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
-            constexpr int V = NDOF * NDOF / 2; // double2 per cell (NDOF*NDOF is even for every supported kind)
-            for (int idx = tid; idx < ncell_tile * V; idx += nt) {
-                const int c = idx / V, q = idx - c * V;
-                const unsigned long long cell = cell0 + c;
-                double *dst = p.out + (p.out_off ? (p.out_off[cell] - p.out_base)
-                                                 : ((unsigned long long)p.cell_ids[cell] - p.cell_begin) * (unsigned long long)(NDOF * NDOF));
-                reinterpret_cast<double2 *>(dst)[q] = reinterpret_cast<const double2 *>(s_K + c * NDOF * NDOF)[q];
+            if (tid < 32) {
+                unsigned long long pol;
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                for (int c0 = 0; c0 < ncell_tile; c0 += 32) {
+                    const int c = c0 + tid;
+                    unsigned long long off = 0;
+                    if (c < ncell_tile) {
+                        const unsigned long long cell = cell0 + c;
+                        off = p.out_off ? (p.out_off[cell] - p.out_base)
+                                        : ((unsigned long long)p.cell_ids[cell] - p.cell_begin) * (unsigned long long)(NDOF * NDOF);
+                    }
+                    const int nb = min(32, ncell_tile - c0);
+                    for (int k = 0; k < nb; k++) {
+                        const unsigned long long o = __shfl_sync(0xffffffffu, off, k);
+                        if (tid == 0)
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(p.out + o),
+                                         "r"(smem_u32(s_K + (c0 + k) * NDOF * NDOF)), "r"((unsigned)(NDOF * NDOF * sizeof(double))), "l"(pol)
+                                         : "memory");
+                    }
+                }
+                if (tid == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
     }
