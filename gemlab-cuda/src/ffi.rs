@@ -86,6 +86,12 @@ pub struct gl_slab {
 }
 
 #[repr(C)]
+pub struct gl_host_mesh {
+    _private: [u8; 0],
+}
+pub const GL_MESH_FORMAT_MSH: c_int = 0;
+pub const GL_MESH_FORMAT_JSON: c_int = 1;
+#[repr(C)]
 pub struct gl_asm_plan {
     _private: [u8; 0],
 }
@@ -279,4 +285,25 @@ extern "C" {
     ) -> c_int;
     pub fn gl_assemble_planned(ctx: *mut gl_ctx, plan: *const gl_asm_plan, coef: *const gl_coef, vals: *mut c_double) -> c_int;
     pub fn gl_assemble_plan_free(ctx: *mut gl_ctx, plan: *mut gl_asm_plan);
+
+    // mesh ingestion: gemlab's MSH text and JSON formats, parsed on the host (the reference's grammar and error strings)
+    pub fn gl_host_mesh_parse(text: *const c_char, len: u64, format: c_int, mesh: *mut *mut gl_host_mesh) -> c_int;
+    pub fn gl_host_mesh_read(path: *const c_char, format: c_int, mesh: *mut *mut gl_host_mesh) -> c_int;
+    pub fn gl_host_mesh_free(mesh: *mut gl_host_mesh);
+    pub fn gl_mesh_text_last_error() -> *const c_char;
+    pub fn gl_host_mesh_ndim(mesh: *const gl_host_mesh) -> c_int;
+    pub fn gl_host_mesh_npoint(mesh: *const gl_host_mesh) -> u64;
+    pub fn gl_host_mesh_ncell(mesh: *const gl_host_mesh) -> u64;
+    pub fn gl_host_mesh_nmarked_edge(mesh: *const gl_host_mesh) -> u64;
+    pub fn gl_host_mesh_nmarked_face(mesh: *const gl_host_mesh) -> u64;
+    pub fn gl_host_mesh_coords(mesh: *const gl_host_mesh) -> *const c_double;
+    pub fn gl_host_mesh_point_markers(mesh: *const gl_host_mesh) -> *const i32;
+    pub fn gl_host_mesh_kinds(mesh: *const gl_host_mesh) -> *const u8;
+    pub fn gl_host_mesh_markers(mesh: *const gl_host_mesh) -> *const i32;
+    pub fn gl_host_mesh_conn_off(mesh: *const gl_host_mesh) -> *const u64;
+    pub fn gl_host_mesh_conn(mesh: *const gl_host_mesh) -> *const u64;
+    pub fn gl_host_mesh_marked_edges(mesh: *const gl_host_mesh) -> *const i64;
+    pub fn gl_host_mesh_marked_faces(mesh: *const gl_host_mesh) -> *const i64;
+    pub fn gl_mesh_upload_host(ctx: *mut gl_ctx, host: *const gl_host_mesh, mesh: *mut *mut gl_mesh) -> c_int;
+    pub fn gl_mesh_from_text(ctx: *mut gl_ctx, text: *const c_char, len: u64, format: c_int, mesh: *mut *mut gl_mesh) -> c_int;
 }

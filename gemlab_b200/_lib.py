@@ -107,6 +107,25 @@ SYMBOLS.update({
     "gl_multi_integ": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlOut)]),
     "gl_multi_integ_slabs": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), C.POINTER(GlCoef), C.POINTER(GlSlab)]),
     "gl_multi_sync": (C.c_int, [_P]),
+    "gl_host_mesh_parse": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(_P)]),
+    "gl_host_mesh_read": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "gl_host_mesh_free": (None, [_P]),
+    "gl_mesh_text_last_error": (C.c_char_p, []),
+    "gl_host_mesh_ndim": (C.c_int, [_P]),
+    "gl_host_mesh_npoint": (C.c_uint64, [_P]),
+    "gl_host_mesh_ncell": (C.c_uint64, [_P]),
+    "gl_host_mesh_nmarked_edge": (C.c_uint64, [_P]),
+    "gl_host_mesh_nmarked_face": (C.c_uint64, [_P]),
+    "gl_host_mesh_coords": (C.POINTER(C.c_double), [_P]),
+    "gl_host_mesh_point_markers": (C.POINTER(C.c_int32), [_P]),
+    "gl_host_mesh_kinds": (C.POINTER(C.c_uint8), [_P]),
+    "gl_host_mesh_markers": (C.POINTER(C.c_int32), [_P]),
+    "gl_host_mesh_conn_off": (C.POINTER(C.c_uint64), [_P]),
+    "gl_host_mesh_conn": (C.POINTER(C.c_uint64), [_P]),
+    "gl_host_mesh_marked_edges": (C.POINTER(C.c_int64), [_P]),
+    "gl_host_mesh_marked_faces": (C.POINTER(C.c_int64), [_P]),
+    "gl_mesh_upload_host": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "gl_mesh_from_text": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(_P)]),
     "gl_assemble_plan_create": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(GlArgs), _P, C.c_int, _P, _P, C.POINTER(C.c_uint64),
                                           C.POINTER(_P)]),
     "gl_assemble_planned": (C.c_int, [_P, _P, C.POINTER(GlCoef), _P]),

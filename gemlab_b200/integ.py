@@ -200,6 +200,18 @@ class Context:
             self._raise(st)
         return DeviceMesh(self, h, mesh.ndim, mesh.ncell, mesh.npoint, mesh.kinds.copy())
 
+    def mesh_from_text(self, text, fmt="msh"):
+        """gl_mesh_from_text: parse gemlab's MSH text (fmt="msh") or JSON (fmt="json") mesh format with the library's own parser and
+        upload it (Mesh::read / Mesh::read_json followed by the per-cell Mesh::set_pad gather, in one call)."""
+        data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        st = lib().gl_mesh_from_text(self._h, data, len(data), {"msh": 0, "json": 1}[fmt], C.byref(h))
+        if st:
+            self._raise(st)
+        ncell, npoint, ndim = int(lib().gl_mesh_ncell(h)), int(lib().gl_mesh_npoint(h)), int(lib().gl_mesh_ndim(h))
+        kinds = Mesh.from_text_native(text, fmt).kinds
+        return DeviceMesh(self, h, ndim, ncell, npoint, kinds)
+
     def block(self, kind, ndiv, xmin=None, xmax=None, marker=1):
         """Device-side lattice generator (gl_mesh_block): the mesh of Block::new(box).set_ndiv(ndiv).subdivide(kind) for an
         axis-aligned box, built in HBM with the reference's cell order and first-touch point numbering."""

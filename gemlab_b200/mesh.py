@@ -201,6 +201,81 @@ class Mesh:
         mesh.marked_faces = faces
         return mesh
 
+    # ---- the same formats through the C ABI (gl_host_mesh_parse: the parser a Rust / C++ host links) ---------------------------
+
+    @staticmethod
+    def _from_host_handle(h):
+        import ctypes as C
+
+        from ._lib import lib
+
+        L = lib()
+        try:
+            ndim, npoint, ncell = L.gl_host_mesh_ndim(h), L.gl_host_mesh_npoint(h), L.gl_host_mesh_ncell(h)
+            ne, nf = L.gl_host_mesh_nmarked_edge(h), L.gl_host_mesh_nmarked_face(h)
+
+            def arr(ptr, n, dtype):
+                return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True) if n else np.zeros(0, dtype)
+
+            conn_off = arr(L.gl_host_mesh_conn_off(h), ncell + 1, np.uint64)
+            mesh = Mesh(ndim, arr(L.gl_host_mesh_coords(h), npoint * ndim, np.float64).reshape(npoint, ndim),
+                        arr(L.gl_host_mesh_kinds(h), ncell, np.uint8), conn_off,
+                        arr(L.gl_host_mesh_conn(h), int(conn_off[-1]) if ncell else 0, np.uint64), arr(L.gl_host_mesh_markers(h), ncell, np.int32))
+            mesh.point_markers = arr(L.gl_host_mesh_point_markers(h), npoint, np.int32)
+            ed = arr(L.gl_host_mesh_marked_edges(h), ne * 3, np.int64).reshape(ne, 3)
+            fa = arr(L.gl_host_mesh_marked_faces(h), nf * 5, np.int64).reshape(nf, 5)
+            mesh.marked_edges = [tuple(int(v) for v in r) for r in ed]
+            mesh.marked_faces = [tuple(int(v) for v in r if v >= 0 or v == r[0]) if r[4] >= 0 else (int(r[0]), int(r[1]), int(r[2]), int(r[3]))
+                                 for r in fa]
+            return mesh
+        finally:
+            L.gl_host_mesh_free(h)
+
+    @staticmethod
+    def from_text_native(text, fmt="msh"):
+        """Parses MSH text (fmt="msh") or the JSON image of Mesh (fmt="json", Mesh::read_json, src/mesh/mesh.rs:245) with the C++
+        parser behind the C ABI (gl_host_mesh_parse) -- the reference's grammar and error strings."""
+        import ctypes as C
+
+        from ._lib import lib
+
+        data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        st = lib().gl_host_mesh_parse(data, len(data), {"msh": 0, "json": 1}[fmt], C.byref(h))
+        if st:
+            raise GemlabTextError(lib().gl_mesh_text_last_error().decode("utf-8"))
+        return Mesh._from_host_handle(h)
+
+    @staticmethod
+    def read_native(path, fmt=None):
+        """Mesh::read / Mesh::read_json through the C ABI (gl_host_mesh_read); fmt defaults to the file extension."""
+        import ctypes as C
+
+        from ._lib import lib
+
+        fmt = fmt or ("json" if str(path).lower().endswith(".json") else "msh")
+        h = C.c_void_p()
+        st = lib().gl_host_mesh_read(str(path).encode("utf-8"), {"msh": 0, "json": 1}[fmt], C.byref(h))
+        if st:
+            raise GemlabTextError(lib().gl_mesh_text_last_error().decode("utf-8"))
+        return Mesh._from_host_handle(h)
+
+    def to_json(self):
+        """serde_json's image of the reference's Mesh (Mesh::write_json, src/mesh/mesh.rs:263): GeoKind as its variant name, the
+        missing fourth point of a triangular marked face as usize::MAX."""
+        import json
+
+        pm = getattr(self, "point_markers", np.zeros(self.npoint, dtype=np.int32))
+        variant = lambda k: (lambda s: s[0].upper() + s[1:])(GeoKind(int(k)).to_string())
+        return json.dumps({
+            "ndim": self.ndim,
+            "points": [{"id": i, "marker": int(pm[i]), "coords": [float(v) for v in self.coords[i]]} for i in range(self.npoint)],
+            "cells": [{"id": e, "marker": int(self.markers[e]), "kind": variant(self.kinds[e]), "points": [int(p) for p in self.cell_points(e)]}
+                      for e in range(self.ncell)],
+            "marked_edges": [[int(v) for v in ed] for ed in getattr(self, "marked_edges", [])],
+            "marked_faces": [[int(v) for v in fa] + [18446744073709551615] * (5 - len(fa)) for fa in getattr(self, "marked_faces", [])],
+        })
+
     @staticmethod
     def read(path):
         """Mesh::read (src/mesh/read_text_mesh.rs:312)."""

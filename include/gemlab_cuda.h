@@ -230,6 +230,35 @@ GL_API uint64_t gl_mesh_ncell(const gl_mesh *mesh);
 GL_API uint64_t gl_mesh_npoint(const gl_mesh *mesh);
 GL_API int gl_mesh_ndim(const gl_mesh *mesh);
 
+/* ---- mesh ingestion: gemlab's MSH text format (Mesh::read / Mesh::from_text, src/mesh/read_text_mesh.rs:312-450,
+ * README "MSH file format") and its JSON format (Mesh::read_json, src/mesh/mesh.rs:245-256: the serde image of Mesh).  Host code;
+ * grammar and error strings are the reference's ("cannot parse point id", "the id and index of cells must equal each other",
+ * "not all marked faces have been found", "cannot parse JSON file", ...).  On failure the functions return GL_ERR_MESH and
+ * gl_mesh_text_last_error() (thread-local) holds the string. */
+enum { GL_MESH_FORMAT_MSH = 0, GL_MESH_FORMAT_JSON = 1 };
+typedef struct gl_host_mesh gl_host_mesh;
+GL_API int gl_host_mesh_parse(const char *text, uint64_t len, int format, gl_host_mesh **mesh);
+GL_API int gl_host_mesh_read(const char *path, int format, gl_host_mesh **mesh); /* "cannot open file" like Mesh::read */
+GL_API void gl_host_mesh_free(gl_host_mesh *mesh);
+GL_API const char *gl_mesh_text_last_error(void);
+GL_API int gl_host_mesh_ndim(const gl_host_mesh *mesh);
+GL_API uint64_t gl_host_mesh_npoint(const gl_host_mesh *mesh);
+GL_API uint64_t gl_host_mesh_ncell(const gl_host_mesh *mesh);
+GL_API uint64_t gl_host_mesh_nmarked_edge(const gl_host_mesh *mesh);
+GL_API uint64_t gl_host_mesh_nmarked_face(const gl_host_mesh *mesh);
+/* flat arrays in the layout gl_mesh_upload takes (owned by the handle) */
+GL_API const double *gl_host_mesh_coords(const gl_host_mesh *mesh);         /* npoint x ndim */
+GL_API const int32_t *gl_host_mesh_point_markers(const gl_host_mesh *mesh); /* npoint */
+GL_API const uint8_t *gl_host_mesh_kinds(const gl_host_mesh *mesh);         /* ncell GeoKind ordinals */
+GL_API const int32_t *gl_host_mesh_markers(const gl_host_mesh *mesh);       /* ncell */
+GL_API const uint64_t *gl_host_mesh_conn_off(const gl_host_mesh *mesh);     /* ncell + 1 */
+GL_API const uint64_t *gl_host_mesh_conn(const gl_host_mesh *mesh);
+GL_API const int64_t *gl_host_mesh_marked_edges(const gl_host_mesh *mesh);  /* nmarked_edge x (marker, p1, p2) */
+GL_API const int64_t *gl_host_mesh_marked_faces(const gl_host_mesh *mesh);  /* nmarked_face x (marker, p1, p2, p3, p4); p4 = -1 for triangles */
+GL_API int gl_mesh_upload_host(gl_ctx *ctx, const gl_host_mesh *host, gl_mesh **mesh);
+/* parse + upload in one call; the error string is also left in gl_last_error(ctx) */
+GL_API int gl_mesh_from_text(gl_ctx *ctx, const char *text, uint64_t len, int format, gl_mesh **mesh);
+
 /* ---- output layout ------------------------------------------------------------------------------- */
 
 /* doubles per element block of `op` for a cell of `kind` (tight, ii0 = jj0 = 0); the two-pad cases and GL_OP_NORMAL depend on

@@ -100,6 +100,78 @@ def test_error_strings_are_the_references(text, msg):
     assert str(e.value) == msg
 
 
+def _same(a, b):
+    return (a.ndim == b.ndim and np.array_equal(a.coords, b.coords) and np.array_equal(a.conn, b.conn) and np.array_equal(a.conn_off, b.conn_off)
+            and np.array_equal(a.kinds, b.kinds) and np.array_equal(a.markers, b.markers) and np.array_equal(a.point_markers, b.point_markers)
+            and a.marked_edges == b.marked_edges and a.marked_faces == b.marked_faces)
+
+
+def test_c_abi_parser_agrees_with_the_python_reader():
+    """gl_host_mesh_parse (the parser a Rust / C++ host links) against the Python reader, MSH and JSON."""
+    for text in (TWO_CUBES, MIXED_2D):
+        a = Mesh.from_text(text)
+        b = Mesh.from_text_native(text)
+        assert _same(a, b)
+        c = Mesh.from_text_native(a.to_json(), "json")  # Mesh::write_json -> Mesh::read_json round trip
+        assert _same(a, c)
+    js = Mesh.from_text(TWO_CUBES).to_json()
+    assert '"kind": "Hex8"' in js and "18446744073709551615" in js  # serde's image: variant names, usize::MAX for a missing p4
+
+
+@pytest.mark.parametrize("text,msg", [
+    ("", "file is empty or header is missing"),
+    ("2 4", "cannot read ncell"),
+    ("2 x 1 0 0", "cannot parse npoint"),
+    ("2 2 1 0 0\n0 0 0.0 0.0\n", "not all points have been found"),
+    ("2 2 1 0 0\n0 0 0.0 0.0\n2 0 1.0 0.0\n", "the id and index of points must equal each other"),
+    ("2 1 0 0 0\n0 0 0.0 0.0 0.0\n", "point data contains extra values"),
+    ("2 1 0 0 0\n0 0 0.0\n", "cannot read point y coordinate"),
+    ("2 1 0 0 0\n0 0 0.0 abc\n", "cannot parse point y coordinate"),
+    ("2 3 1 0 0\n0 0 0 0\n1 0 1 0\n2 0 0 1\n", "not all cells have been found"),
+    ("2 3 1 0 0\n0 0 0 0\n1 0 1 0\n2 0 0 1\n0 1 tri4 0 1 2\n", "string representation of GeoKind is incorrect"),
+    ("2 3 1 0 0\n0 0 0 0\n1 0 1 0\n2 0 0 1\n0 1 tri3 0 1\n", "cannot read cell point id"),
+    ("2 3 1 0 0\n0 0 0 0\n1 0 1 0\n2 0 0 1\n0 1 tri3 0 1 2 3\n", "cell data contains extra values"),
+    ("2 3 1 0 0\n0 0 0 0\n1 0 1 0\n2 0 0 1\n1 1 tri3 0 1 2\n", "the id and index of cells must equal each other"),
+    ("2 3 1 1 0\n0 0 0 0\n1 0 1 0\n2 0 0 1\n0 1 tri3 0 1 2\n", "not all marked edges have been found"),
+    ("2 3 1 0 1\n0 0 0 0\n1 0 1 0\n2 0 0 1\n0 1 tri3 0 1 2\n-1 0 1\n", "cannot read p3 of marked face"),
+])
+def test_c_abi_parser_error_strings(text, msg):
+    with pytest.raises(GemlabTextError) as e:
+        Mesh.from_text_native(text)
+    assert str(e.value) == msg
+
+
+def test_c_abi_json_errors_and_files(tmp_path):
+    for bad in ("", "{", '{"ndim": 2}', '{"ndim":2,"points":[],"cells":[{"id":0,"marker":1,"kind":"Tri9","points":[0,1,2]}],"marked_edges":[],"marked_faces":[]}'):
+        with pytest.raises(GemlabTextError) as e:
+            Mesh.from_text_native(bad, "json")
+        assert str(e.value) == "cannot parse JSON file"  # Mesh::read_json maps every serde error to this string (mesh.rs:253)
+    with pytest.raises(GemlabTextError) as e:
+        Mesh.read_native("/nonexistent/dir/mesh.json")
+    assert str(e.value) == "cannot open file"
+    m = Mesh.from_text(TWO_CUBES)
+    (tmp_path / "m.json").write_text(m.to_json())
+    (tmp_path / "m.msh").write_text(m.to_text())
+    assert _same(m, Mesh.read_native(tmp_path / "m.json")) and _same(m, Mesh.read_native(tmp_path / "m.msh"))
+
+
+@pytest.mark.skipif(not Path("/root/reference/data/meshes").exists(), reason="reference tree is only present in the authoring container")
+def test_c_abi_parser_on_the_reference_mesh_files():
+    ref = Path("/root/reference/data/meshes")
+    n = 0
+    for f in sorted(ref.glob("*.msh")):
+        try:
+            a = Mesh.read(f)
+        except GemlabTextError as ea:
+            with pytest.raises(GemlabTextError) as eb:
+                Mesh.read_native(f)
+            assert str(eb.value) == str(ea), f.name
+            continue
+        assert _same(a, Mesh.read_native(f)), f.name
+        n += 1
+    assert n >= 10
+
+
 def test_missing_file():
     with pytest.raises(GemlabTextError) as e:
         Mesh.read("/nonexistent/dir/mesh.msh")
@@ -149,4 +221,22 @@ def test_text_mesh_drives_the_gpu_path():
             assert np.max(np.abs(got[pos:pos + ref.size] - ref)) <= 1e-12 * np.max(np.abs(ref))
             pos += ref.size
         assert pos == got.size
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gl_mesh_from_text_uploads_what_it_parses():
+    from oracle import pyoracle as po
+
+    ctx = g.Context(0)
+    for text, two_dim in ((TWO_CUBES, False), (MIXED_2D, True)):
+        mesh = Mesh.from_text(text)
+        dd = g.lin_elasticity(480.0, 1.0 / 3.0, two_dim)
+        ref = po.mesh_integ("mat_10_bdb", mesh.ndim, mesh.coords, mesh.kinds, mesh.conn_off, mesh.conn, coef=dd.ravel(order="F"))
+        for fmt, payload in (("msh", text), ("json", mesh.to_json())):
+            dm = ctx.mesh_from_text(payload, fmt)
+            got = integ.mat_10_bdb(ctx, dm, None, CommonArgs(), Coef.uniform(g.mandel_matrix(dd)))
+            assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref)), fmt
+    with pytest.raises(g.GemlabError, match="not all cells have been found"):
+        ctx.mesh_from_text("2 3 1 0 0\n0 0 0 0\n1 0 1 0\n2 0 0 1\n")
     ctx.close()
