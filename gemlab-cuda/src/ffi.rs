@@ -205,6 +205,7 @@ extern "C" {
     pub fn gl_lin_elasticity(young: c_double, poisson: c_double, two_dim: c_int, plane_stress: c_int, dd: *mut c_double);
     pub fn gl_bench_fp64_peak(ctx: *mut gl_ctx, kind: c_int, iters: c_int, tflops: *mut c_double) -> c_int;
     pub fn gl_mesh_block(ctx: *mut gl_ctx, kind: c_int, ndiv: *const u32, xmin: *const c_double, xmax: *const c_double, marker: i32, mesh: *mut *mut gl_mesh) -> c_int;
+    pub fn gl_mesh_block_general(ctx: *mut gl_ctx, kind: c_int, ndiv: *const u32, ncontrol: c_int, control: *const c_double, marker: i32, mesh: *mut *mut gl_mesh) -> c_int;
     pub fn gl_mesh_download(ctx: *mut gl_ctx, mesh: *const gl_mesh, coords: *mut c_double, conn: *mut u32) -> c_int;
     pub fn gl_bench_hbm_write(ctx: *mut gl_ctx, kind: c_int, dev: *mut c_double, nbytes: u64, warps_per_sm: c_int, gbs: *mut c_double) -> c_int;
 

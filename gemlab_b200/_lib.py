@@ -70,6 +70,7 @@ SYMBOLS = {
     "gl_mesh_upload_homogeneous": (C.c_int, [_P, C.c_int, C.c_uint64, _P, C.c_uint64, C.c_int, _P, _P, C.POINTER(_P)]),
     "gl_mesh_update_coords": (C.c_int, [_P, _P, _P, C.c_int]),
     "gl_mesh_block": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int32, C.POINTER(_P)]),
+    "gl_mesh_block_general": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int32, C.POINTER(_P)]),
     "gl_mesh_download": (C.c_int, [_P, _P, _P, _P]),
     "gl_mesh_free": (None, [_P, _P]),
     "gl_mesh_ncell": (C.c_uint64, [_P]),

@@ -2049,6 +2049,12 @@ int gl_assemble_planned(gl_ctx *ctx, const gl_asm_plan *plan, const gl_coef *coe
 // host Block (which is pinned by the reference's sample meshes).
 namespace {
 
+// natural coordinates of the Qua9 / Hex20 nodes (src/shapes/qua9.rs, hex20.rs): lattice offsets of the targets, control points of a block
+const signed char QUA_REF[9][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}, {0, -1}, {1, 0}, {0, 1}, {-1, 0}, {0, 0}};
+const signed char HEX_REF[20][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1},
+                                    {0, -1, -1}, {1, 0, -1}, {0, 1, -1}, {-1, 0, -1}, {0, -1, 1}, {1, 0, 1}, {0, 1, 1}, {-1, 0, 1},
+                                    {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}};
+
 __device__ __constant__ int LOC_HEX8[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
 __device__ __constant__ int LOC_QUA4[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
 
@@ -2127,7 +2133,15 @@ int gl_mesh_block(gl_ctx *ctx, int kind, const uint32_t *ndiv, const double *xmi
     if (!ctx) return GL_ERR_INVALID_ARG;
     if (!out || !ndiv || !xmin || !xmax) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
     *out = nullptr;
-    if (kind != GL_QUA4 && kind != GL_HEX8) return fail(ctx, GL_ERR_KIND_UNSUPPORTED, "the device lattice generator builds Qua4 and Hex8 meshes");
+    if (kind == GL_QUA8 || kind == GL_QUA9 || kind == GL_HEX20) {
+        // quadratic targets: the general generator on the box's corners (the closed form below covers the linear targets)
+        const int nd = kind == GL_HEX20 ? 3 : 2;
+        double corners[8 * 3];
+        for (int q = 0; q < (nd == 2 ? 4 : 8); q++)
+            for (int d = 0; d < nd; d++) corners[q * nd + d] = (nd == 2 ? QUA_REF[q][d] : HEX_REF[q][d]) < 0 ? xmin[d] : xmax[d];
+        return gl_mesh_block_general(ctx, kind, ndiv, nd == 2 ? 4 : 8, corners, marker, out);
+    }
+    if (kind != GL_QUA4 && kind != GL_HEX8) return fail(ctx, GL_ERR_KIND_UNSUPPORTED, "the device lattice generator builds Qua4, Qua8, Qua9, Hex8 and Hex20 meshes");
     const int ndim = kind == GL_HEX8 ? 3 : 2;
     BlockGen g;
     g.ndim = ndim;
@@ -2162,6 +2176,221 @@ int gl_mesh_block(gl_ctx *ctx, int kind, const uint32_t *ndiv, const double *xmi
     block_coords_kernel<<<1184, 256, 0, st>>>(g, mesh->d_coords);
     ctx->launches += 2;
     if (cudaGetLastError() != cudaSuccess) return cuda_fail(ctx, cudaGetLastError(), "lattice generator");
+    mesh->buckets.push_back(std::move(bk));
+    *out = mesh.release();
+    return GL_OK;
+}
+
+} // extern "C"
+
+// ---- general lattice generator: every Block target (Qua4 / Qua8 / Qua9 / Hex8 / Hex20) on a straight-edged or curved block ------------
+// The reference walks the cells in id order and gives a point the next free id the first time a cell touches it (GridSearch,
+// src/mesh/block.rs:749-812).  On the device the same numbering comes from three passes over a lattice with f = 1 (linear targets)
+// or 2 (quadratic) steps per cell: (1) atomicMin of the key cell * nnode + m at every lattice point a cell touches; (2) per cell, the
+// number of nodes whose key won = the points the cell introduces, turned into an exclusive prefix over the cells; (3) the cell's new
+// points get prefix + rank in local order, their coordinates come from the block's own interpolation (bi/tri-linear map of the
+// corners, or the Qua8 / Hex20 serendipity map of a curved block: block.rs:794).
+namespace {
+
+struct LatGen {
+    int ndim, nnode, f, ncontrol;
+    unsigned nx, ny, nz;
+    unsigned long long lat0, lat1, lat2, ncell;
+    signed char off[20][3]; // lattice offsets of the local nodes, in 0 .. f
+    signed char ref[20][3]; // natural coordinates of the block's control points (-1, 0, 1)
+    double ctrl[20][3];
+};
+
+__device__ __forceinline__ unsigned long long lat_index(const LatGen &g, unsigned long long e, int m) {
+    const unsigned long long i = e % g.nx, j = (e / g.nx) % g.ny, k = e / ((unsigned long long)g.nx * g.ny);
+    const unsigned long long a = g.f * i + g.off[m][0], b = g.f * j + g.off[m][1], c = g.ndim == 3 ? g.f * k + g.off[m][2] : 0ull;
+    return a + g.lat0 * (b + g.lat1 * c);
+}
+
+__global__ void lat_first_kernel(const LatGen g, unsigned long long *first) {
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < g.ncell * g.nnode;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = t / g.nnode;
+        const int m = (int)(t - e * g.nnode);
+        atomicMin(first + lat_index(g, e, m), t);
+    }
+}
+
+__global__ void lat_count_kernel(const LatGen g, const unsigned long long *first, unsigned int *count) {
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < g.ncell;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned int n = 0;
+        for (int m = 0; m < g.nnode; m++) n += first[lat_index(g, e, m)] == e * g.nnode + m ? 1u : 0u;
+        count[e] = n;
+    }
+}
+
+// single-CTA exclusive scan in chunks (the generator is not on the hot path; 10^7 cells take well under a millisecond)
+__global__ void lat_scan_kernel(const unsigned int *count, unsigned int *prefix, unsigned long long n) {
+    __shared__ unsigned int warp_sum[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (unsigned long long base = 0; base < n; base += blockDim.x) {
+        const unsigned long long i = base + threadIdx.x;
+        const unsigned int v = i < n ? count[i] : 0u;
+        unsigned int x = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int w = lane < (int)(blockDim.x >> 5) ? warp_sum[lane] : 0u;
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += y;
+            }
+            warp_sum[lane] = w; // inclusive sums of the warps
+        }
+        __syncthreads();
+        const unsigned int before = carry + (wid > 0 ? warp_sum[wid - 1] : 0u);
+        if (i < n) prefix[i] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + x;
+        __syncthreads();
+    }
+}
+
+__device__ void block_interp(const LatGen &g, const double *ksi, double *x) {
+    for (int d = 0; d < g.ndim; d++) x[d] = 0.0;
+    const int nd = g.ndim;
+    const int ncorner = nd == 2 ? 4 : 8;
+    for (int q = 0; q < g.ncontrol; q++) {
+        double w;
+        if (g.ncontrol == ncorner) { // straight-edged block: bi / tri-linear map of the corners
+            w = nd == 2 ? 0.25 : 0.125;
+            for (int d = 0; d < nd; d++) w *= 1.0 + ksi[d] * (double)g.ref[q][d];
+        } else if (q < ncorner) { // serendipity corner
+            double prod = 1.0, gsum = -(double)(nd - 1);
+            for (int d = 0; d < nd; d++) {
+                prod *= 1.0 + ksi[d] * (double)g.ref[q][d];
+                gsum += ksi[d] * (double)g.ref[q][d];
+            }
+            w = prod * gsum / (nd == 2 ? 4.0 : 8.0);
+        } else { // serendipity mid-edge node
+            w = 1.0;
+            for (int d = 0; d < nd; d++) w *= g.ref[q][d] == 0 ? (1.0 - ksi[d] * ksi[d]) : (1.0 + ksi[d] * (double)g.ref[q][d]);
+            w /= nd == 2 ? 2.0 : 4.0;
+        }
+        for (int d = 0; d < nd; d++) x[d] += w * g.ctrl[q][d];
+    }
+}
+
+__global__ void lat_number_kernel(const LatGen g, const unsigned long long *first, const unsigned int *prefix, uint32_t *point_of_lattice,
+                                  double *coords, unsigned long long npoint) {
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < g.ncell;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned int id = prefix[e];
+        for (int m = 0; m < g.nnode; m++) {
+            const unsigned long long li = lat_index(g, e, m);
+            if (first[li] != e * g.nnode + m) continue;
+            point_of_lattice[li] = id;
+            const unsigned long long a = li % g.lat0, b = (li / g.lat0) % g.lat1, c = li / (g.lat0 * g.lat1);
+            double ksi[3], x[3];
+            ksi[0] = -1.0 + 2.0 * (double)a / (double)(g.f * g.nx);
+            ksi[1] = -1.0 + 2.0 * (double)b / (double)(g.f * g.ny);
+            ksi[2] = g.ndim == 3 ? -1.0 + 2.0 * (double)c / (double)(g.f * g.nz) : 0.0;
+            block_interp(g, ksi, x);
+            for (int d = 0; d < g.ndim; d++) coords[(unsigned long long)d * npoint + id] = x[d];
+            id++;
+        }
+    }
+}
+
+__global__ void lat_conn_kernel(const LatGen g, const uint32_t *point_of_lattice, uint32_t *conn) {
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < g.ncell * g.nnode;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = t / g.nnode;
+        const int m = (int)(t - e * g.nnode);
+        conn[(unsigned long long)m * g.ncell + e] = point_of_lattice[lat_index(g, e, m)];
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int gl_mesh_block_general(gl_ctx *ctx, int kind, const uint32_t *ndiv, int ncontrol, const double *control, int32_t marker, gl_mesh **out) {
+    if (!ctx) return GL_ERR_INVALID_ARG;
+    if (!out || !ndiv || !control) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    *out = nullptr;
+    if (kind != GL_QUA4 && kind != GL_QUA8 && kind != GL_QUA9 && kind != GL_HEX8 && kind != GL_HEX20)
+        return fail(ctx, GL_ERR_KIND_UNSUPPORTED, "the lattice generator builds Qua4, Qua8, Qua9, Hex8 and Hex20 meshes");
+    const int ndim = kind_geo_ndim(kind);
+    if (!((ndim == 2 && (ncontrol == 4 || ncontrol == 8)) || (ndim == 3 && (ncontrol == 8 || ncontrol == 20))))
+        return fail(ctx, GL_ERR_INVALID_ARG, "a block has 4 corners or 8 Qua8 nodes in 2D, 8 corners or 20 Hex20 nodes in 3D");
+    LatGen g;
+    std::memset(&g, 0, sizeof(g));
+    g.ndim = ndim;
+    g.nnode = kind_nnode(kind);
+    g.f = (kind == GL_QUA4 || kind == GL_HEX8) ? 1 : 2;
+    g.ncontrol = ncontrol;
+    g.nx = ndiv[0];
+    g.ny = ndiv[1];
+    g.nz = ndim == 3 ? ndiv[2] : 1;
+    if (g.nx == 0 || g.ny == 0 || g.nz == 0) return fail(ctx, GL_ERR_INVALID_ARG, "ndiv must be >= 1");
+    g.ncell = (unsigned long long)g.nx * g.ny * g.nz;
+    g.lat0 = (unsigned long long)g.f * g.nx + 1;
+    g.lat1 = (unsigned long long)g.f * g.ny + 1;
+    g.lat2 = ndim == 3 ? (unsigned long long)g.f * g.nz + 1 : 1;
+    for (int m = 0; m < g.nnode; m++)
+        for (int d = 0; d < ndim; d++) g.off[m][d] = (signed char)(((ndim == 2 ? QUA_REF[m][d] : HEX_REF[m][d]) + 1) * g.f / 2);
+    for (int q = 0; q < ncontrol; q++)
+        for (int d = 0; d < ndim; d++) {
+            g.ref[q][d] = ndim == 2 ? QUA_REF[q][d] : HEX_REF[q][d];
+            g.ctrl[q][d] = control[q * ndim + d];
+        }
+    const unsigned long long nlat = g.lat0 * g.lat1 * g.lat2;
+    const unsigned long long nx = g.nx, ny = g.ny, nz = g.nz;
+    unsigned long long npoint = nlat; // Qua4 / Hex8 / Qua9: every lattice point
+    if (kind == GL_QUA8) npoint = nlat - nx * ny; // no cell centres
+    if (kind == GL_HEX20) npoint = (nx + 1) * (ny + 1) * (nz + 1) + nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz;
+    if (npoint > 0xffffffffull || g.ncell > 0xffffffffull) return fail(ctx, GL_ERR_MESH, "npoint/ncell must fit in 32 bits");
+    cudaSetDevice(ctx->device);
+    auto mesh = std::make_unique<gl_mesh>();
+    mesh->ndim = ndim;
+    mesh->npoint = npoint;
+    mesh->ncell = g.ncell;
+    mesh->device = ctx->device;
+    mesh->homogeneous = true;
+    mesh->marker_values.assign(1, marker);
+    gl_mesh_bucket bk;
+    bk.kind = kind;
+    bk.nnode = g.nnode;
+    bk.ncell = g.ncell;
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &mesh->d_coords, (size_t)npoint * ndim * sizeof(double)));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &bk.d_conn, (size_t)g.ncell * bk.nnode * sizeof(uint32_t)));
+    unsigned long long *first = nullptr;
+    uint32_t *pol = nullptr;
+    unsigned int *count = nullptr, *prefix = nullptr;
+    const size_t b_first = nlat * sizeof(unsigned long long), b_pol = nlat * sizeof(uint32_t), b_cnt = g.ncell * sizeof(unsigned int);
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &first, b_first));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &pol, b_pol));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &count, b_cnt));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &prefix, b_cnt));
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    CUDA_TRY(ctx, cudaMemsetAsync(first, 0xff, b_first, st));
+    lat_first_kernel<<<1184, 256, 0, st>>>(g, first);
+    lat_count_kernel<<<1184, 256, 0, st>>>(g, first, count);
+    lat_scan_kernel<<<1, 1024, 0, st>>>(count, prefix, g.ncell);
+    lat_number_kernel<<<1184, 256, 0, st>>>(g, first, prefix, pol, mesh->d_coords, npoint);
+    lat_conn_kernel<<<1184, 256, 0, st>>>(g, pol, bk.d_conn);
+    ctx->launches += 5;
+    const cudaError_t ce = cudaGetLastError();
+    // the scratch arrays go back to the pool; everything that touches them is ordered on the ctx stream
+    pool_free(ctx, first, b_first);
+    pool_free(ctx, pol, b_pol);
+    pool_free(ctx, count, b_cnt);
+    pool_free(ctx, prefix, b_cnt);
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "lattice generator");
     mesh->buckets.push_back(std::move(bk));
     *out = mesh.release();
     return GL_OK;

@@ -224,8 +224,22 @@ class Context:
         st = lib().gl_mesh_block(self._h, int(kind), nd, lo, hi, int(marker), C.byref(h))
         if st:
             self._raise(st)
-        ncell = int(np.prod([int(v) for v in ndiv[:ndim]]))
-        npoint = int(np.prod([int(v) + 1 for v in ndiv[:ndim]]))
+        ncell = int(lib().gl_mesh_ncell(h))
+        npoint = int(lib().gl_mesh_npoint(h))
+        return DeviceMesh(self, h, ndim, ncell, npoint, np.full(ncell, int(kind), dtype=np.uint8))
+
+    def block_general(self, kind, ndiv, control, marker=1):
+        """gl_mesh_block_general: Block::new(control).set_ndiv(ndiv).subdivide(kind) on the device for any Block target and a
+        straight-edged (corners) or curved (Qua8 / Hex20 nodes) block."""
+        kind = GeoKind(kind)
+        ndim = kind.ndim()
+        ctrl = np.ascontiguousarray(control, dtype=np.float64)
+        nd = (C.c_uint32 * 3)(*[int(v) for v in list(ndiv) + [1] * (3 - len(ndiv))])
+        h = C.c_void_p()
+        st = lib().gl_mesh_block_general(self._h, int(kind), nd, int(ctrl.shape[0]), ctrl.ctypes.data, int(marker), C.byref(h))
+        if st:
+            self._raise(st)
+        ncell, npoint = int(lib().gl_mesh_ncell(h)), int(lib().gl_mesh_npoint(h))
         return DeviceMesh(self, h, ndim, ncell, npoint, np.full(ncell, int(kind), dtype=np.uint8))
 
     def download(self, dmesh):

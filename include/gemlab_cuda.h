@@ -219,9 +219,16 @@ GL_API int gl_mesh_update_coords(gl_ctx *ctx, gl_mesh *mesh, const double *coord
 /* Device-side lattice generator: the mesh that Block::new(box).set_ndiv(ndiv).subdivide(kind) returns for an axis-aligned
  * box [xmin, xmax] -- cell id = i + nx*(j + ny*k), first-touch point numbering (src/mesh/block.rs:749-812; fixtures
  * src/mesh/samples.rs:1407, 1901) -- built directly in HBM from a closed form of that numbering: no host arrays, no upload.
- * kind: Qua4 (ndiv[0..1], 2D) or Hex8 (ndiv[0..2], 3D); every cell gets `marker`. */
+ * kind: Qua4 / Qua8 / Qua9 (ndiv[0..1], 2D) or Hex8 / Hex20 (ndiv[0..2], 3D); every cell gets `marker`. */
 GL_API int gl_mesh_block(gl_ctx *ctx, int kind, const uint32_t *ndiv, const double *xmin, const double *xmax, int32_t marker,
                          gl_mesh **mesh);
+/* The same for every Block target -- Qua4, Qua8, Qua9 (2D), Hex8, Hex20 (3D) -- and for a GENERAL block: `control` holds the block's
+ * 4 corners or 8 Qua8 nodes (2D), 8 corners or 20 Hex20 nodes (3D), AoS ncontrol x ndim in the reference's local node order; points
+ * are placed by the block's own interpolation (Block::subdivide, src/mesh/block.rs:661-812), numbered by first touch in cell order
+ * (three passes over the lattice: atomicMin of the touching (cell, node) key, per-cell count + prefix, numbering).
+ * gl_mesh_block accepts the quadratic targets as well (box corners). */
+GL_API int gl_mesh_block_general(gl_ctx *ctx, int kind, const uint32_t *ndiv, int ncontrol, const double *control, int32_t marker,
+                                 gl_mesh **mesh);
 /* Copies a device mesh back to HOST arrays (either pointer may be NULL): coords npoint x ndim (AoS, as Mesh.points),
  * conn ncell x nnode 32-bit point ids (single-kind meshes only). */
 GL_API int gl_mesh_download(gl_ctx *ctx, const gl_mesh *mesh, double *coords, uint32_t *conn);

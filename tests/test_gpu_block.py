@@ -51,3 +51,50 @@ def test_large_block_is_generated_without_host_arrays(ctx):
     got = ctx.download(dm)
     assert np.array_equal(got.conn_matrix(), host.conn_matrix())
     assert dt < 1.0
+
+
+@pytest.mark.parametrize("kind,ndiv", [("qua8", (2, 2)), ("qua8", (5, 3)), ("qua9", (2, 2)), ("qua9", (4, 7)), ("hex20", (2, 2, 2)),
+                                       ("hex20", (3, 1, 4)), ("qua4", (3, 2)), ("hex8", (2, 3, 2))])
+def test_quadratic_targets_and_general_blocks(ctx, kind, ndiv):
+    """gl_mesh_block for the quadratic targets and gl_mesh_block_general for straight-edged and curved blocks against the host
+    Block (first-touch numbering pinned by Samples::block_2d_four_qua8 / qua9 / block_3d_eight_hex20, src/mesh/samples.rs:1466,
+    1530, 2043 through tests/golden/block_samples.json)."""
+    k = GeoKind.from_str(kind)
+    nd = k.ndim()
+    host = (Block.new_cube(2.0) if nd == 3 else Block.new_square(2.0)).set_ndiv(list(ndiv)).subdivide(k)
+    got = ctx.download(ctx.block(k, ndiv, xmin=[0.0] * nd, xmax=[2.0] * nd))
+    assert got.npoint == host.npoint
+    assert np.array_equal(got.conn_matrix(), host.conn_matrix())
+    assert np.max(np.abs(got.coords - host.coords)) <= 1e-15 * 2.0
+    # a skewed straight-edged block given by its corners
+    rng = np.random.default_rng(3)
+    ref = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], dtype=float)
+    corners = (ref[:4, :2] if nd == 2 else ref) + 0.2 * rng.uniform(-1, 1, (4 if nd == 2 else 8, nd))
+    host = Block(_block_nodes(corners, nd)).set_ndiv(list(ndiv)).subdivide(k)
+    got = ctx.download(ctx.block_general(k, ndiv, corners))
+    assert np.array_equal(got.conn_matrix(), host.conn_matrix())
+    assert np.max(np.abs(got.coords - host.coords)) <= 1e-14
+    # a curved block (mid-edge nodes off their edges): the Qua8 / Hex20 serendipity map
+    nodes = _block_nodes(corners, nd)
+    nodes[4 if nd == 2 else 8:] += 0.05 * rng.uniform(-1, 1, nodes[4 if nd == 2 else 8:].shape)
+    host = Block(nodes).set_ndiv(list(ndiv)).subdivide(k)
+    got = ctx.download(ctx.block_general(k, ndiv, nodes))
+    assert np.array_equal(got.conn_matrix(), host.conn_matrix())
+    assert np.max(np.abs(got.coords - host.coords)) <= 1e-14
+
+
+def _block_nodes(corners, nd):
+    """Qua8 / Hex20 nodes of a straight-edged block: corners plus edge midpoints in the reference's local order."""
+    if nd == 2:
+        edges = [(0, 1), (1, 2), (2, 3), (3, 0)]
+    else:
+        edges = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+    return np.vstack([corners, [(corners[a] + corners[b]) / 2 for a, b in edges]])
+
+
+def test_hex20_block_of_config_2_is_generated_on_the_device(ctx):
+    dm = ctx.block(GeoKind.Hex20, (40, 40, 40))
+    ctx.sync()
+    host = Block.new_cube(1.0).set_ndiv([40, 40, 40]).subdivide(GeoKind.Hex20)
+    got = ctx.download(dm)
+    assert np.array_equal(got.conn_matrix(), host.conn_matrix())
