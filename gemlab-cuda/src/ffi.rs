@@ -26,6 +26,14 @@ pub const GL_OP_JACOBIAN: c_int = 8;
 pub const GL_OP_MAT_02_BVN: c_int = 9;
 pub const GL_OP_MAT_08_NTN: c_int = 10;
 pub const GL_OP_MAT_09_NVB: c_int = 11;
+pub const GL_OP_MAT_04_NSB: c_int = 12;
+pub const GL_OP_MAT_05_BTN: c_int = 13;
+pub const GL_OP_MAT_06_NVN: c_int = 14;
+pub const GL_OP_MAT_07_BSN: c_int = 15;
+pub const GL_OP_MAT_01_NSN_BRY: c_int = 16;
+pub const GL_OP_VEC_01_NS_BRY: c_int = 17;
+pub const GL_OP_VEC_02_NV_BRY: c_int = 18;
+pub const GL_OP_NORMAL: c_int = 19;
 
 pub const GL_HOST: i32 = 0;
 pub const GL_DEVICE: i32 = 1;

@@ -451,6 +451,19 @@ def test_cpp_host_mirror(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
 
 
+def test_cpp_host_mirror_device_paths(tmp_path):
+    """DeviceSlab, MultiContext, the device Block, the MSH reader and gl_integ_fused through cpp/gemlab.hpp."""
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "test_device_paths"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-o", str(exe), str(root / "tests" / "cpp" / "test_device_paths.cpp"),
+                    "-L", str(root / "gemlab_b200"), "-lgemlab_cuda", f"-Wl,-rpath,{root / 'gemlab_b200'}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("kind", ["tri3", "qua8", "tet10", "hex8"])
 def test_fused_scalar_cases_share_one_geometry_pass(ctx, kind):
     """gl_integ_fused: mat_01_nsn + mat_03_btb + vec_01_ns + vec_03_bv from one kernel == the four separate calls

@@ -167,3 +167,56 @@ def test_rust_ffi_declares_every_abi_symbol():
     names = set(re.findall(r"GL_API\s+[\w\s\*]+?\b(gl_\w+)\s*\(", hdr))
     ffi = set(re.findall(r"pub fn (gl_\w+)", (root / "gemlab-cuda" / "src" / "ffi.rs").read_text()))
     assert names and not (names - ffi), sorted(names - ffi)
+
+
+def test_cpp_host_mirror_compiles_and_links():
+    """cpp/gemlab.hpp and its two test programs build against the in-tree library (they RUN in the -m gpu suite)."""
+    import subprocess
+    import tempfile
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in ("test_batch", "test_device_paths"):
+            subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-o", str(Path(tmp) / name), str(root / "tests" / "cpp" / f"{name}.cpp"),
+                            "-L", str(root / "gemlab_b200"), "-lgemlab_cuda", f"-Wl,-rpath,{root / 'gemlab_b200'}"], check=True)
+
+
+def test_rust_crate_uses_only_declared_ffi_items_and_matches_the_header_enums():
+    """gemlab-cuda cannot be compiled here (no cargo): at least every `ffi::name` lib.rs uses must exist in ffi.rs, the op / format
+    constants must equal the header's enums, and the repr(C) structs must list the header's fields in order."""
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    lib_rs = (root / "gemlab-cuda" / "src" / "lib.rs").read_text()
+    ffi_rs = (root / "gemlab-cuda" / "src" / "ffi.rs").read_text()
+    hdr = (root / "include" / "gemlab_cuda.h").read_text()
+    declared = set(re.findall(r"pub (?:fn|const|struct) (\w+)", ffi_rs))
+    used = set(re.findall(r"ffi::(\w+)", lib_rs))
+    assert not (used - declared), sorted(used - declared)
+    for name, val in re.findall(r"pub const (GL_OP_\w+): c_int = (\d+);", ffi_rs):
+        m = re.search(rf"\b{name} = (\d+)", hdr)
+        assert m and int(m.group(1)) == int(val), name
+    for name, val in re.findall(r"pub const (GL_MESH_FORMAT_\w+): c_int = (\d+);", ffi_rs):
+        m = re.search(rf"\b{name} = (\d+)", hdr)
+        assert m and int(m.group(1)) == int(val), name
+    # struct field order: gl_slab, gl_args, gl_coef, gl_out
+    for st in ("gl_slab", "gl_args", "gl_coef", "gl_out", "gl_fused_item"):
+        c_body = re.search(rf"typedef struct {st} \{{(.*?)\}} {st};", hdr, re.S).group(1)
+        c_body = re.sub(r"/\*.*?\*/", "", c_body, flags=re.S)
+        c_fields = [re.sub(r"\[.*", "", f.strip().split()[-1]).lstrip("*") for f in c_body.split(";") if f.strip()]
+        c_fields = [f for decl in c_fields for f in decl.split(",")]
+        r_body = re.search(rf"pub struct {st} \{{(.*?)\n\}}", ffi_rs, re.S).group(1)
+        r_fields = re.findall(r"pub (\w+):", r_body)
+        flat_c = []
+        for f in c_body.split(";"):
+            f = f.strip()
+            if not f:
+                continue
+            names = f.split(None, 1)[1] if " " in f else f
+            # "const double *data" / "uint32_t ii0, jj0" / "double ksi[3]"
+            names = re.sub(r"^(?:const\s+)?\w+\s+", "", f)
+            for n in names.split(","):
+                flat_c.append(re.sub(r"\[.*", "", n.strip().lstrip("*").strip()))
+        assert flat_c == r_fields, (st, flat_c, r_fields)
