@@ -552,8 +552,7 @@ int launch_kind(const IntegParams &p, BdbConsts cst, int pat, void *stream) {
     // barriers -- win where the element block is large against the arithmetic per lane
     if (NN == 10 && SD == 3) cpc = 4;  // Tet10: 266 -> 301 M el/s
     if (NN >= 8 && NN <= 9 && SD == 2) cpc = 16; // Qua8: 1.87 -> 1.99 G el/s, Qua9: 1.12 -> 1.22 G el/s
-    // (axisymmetric Qua4 also measured faster at 16 than at the default 64 -- 4.65 vs 3.83 G el/s -- not yet adopted: the
-    // parity suite has not run on that default)
+    if (NN == 4 && SD == 2 && axi) cpc = 8; // axisymmetric Qua4: 4.63 (8), 4.37 (16), 4.11 (32), 3.68 (64) G el/s
     if (const char *e = tuning_env("GL_BDB_CPC")) cpc = atoi(e); // tuning knob: cells per CTA
     if (cpc * NN * LPN > 256) cpc = 256 / (NN * LPN); // __launch_bounds__(256)
     if (cpc < 1) cpc = 1;

@@ -467,7 +467,8 @@ int launch_bdb_syrk(const IntegParams &p, int sd, void *stream) {
     const bool drec = p.coef != nullptr;
     if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 36)) return 0; // PER_GAUSS moduli: not a rank-ng update
     if (tuning_env("GL_DISABLE_SYRK")) return 0;
-    if (p.nnode == 10 && !tuning_env("GL_SYRK_TET10")) return 0; // Tet10 stays on gl_kernels_bdb.cu until measured
+    // Tet10: measured 448 M el/s here against 263 M el/s on gl_kernels_bdb.cu (750 000 cells, profiles/r02_tet10_dmma_vs_register_blocked.txt)
+    if (p.nnode == 10 && tuning_env("GL_DISABLE_SYRK_TET10")) return 0;
     const unsigned ndof = (unsigned)p.nnode * 3u;
     const bool tight = p.nrow == ndof && p.ncol == ndof && p.ii0 == 0 && p.jj0 == 0;
     const bool gen = !(tight && p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);

@@ -35,7 +35,9 @@ FAMILIES = [
     ("hex20", "mat_10_bdb", {"ngauss": 64}, "bdb<nn=20,sd=3"),
     ("hex20", "mat_10_bdb", {"clear": False}, "syrk_dmma<nn=20,pat=2,gen>"),
     ("hex20", "mat_10_bdb", {"ii0": 1, "jj0": 2, "nrow": 64, "ncol": 63}, "syrk_dmma<nn=20,pat=2,gen>"),
-    ("tet10", "mat_10_bdb", {}, "bdb<nn=10,sd=3"),
+    ("tet10", "mat_10_bdb", {}, "syrk_dmma<nn=10,pat=2>"),
+    ("tet10", "mat_10_bdb", {"ngauss": 24}, "bdb<nn=10,sd=3"),
+    ("tet10", "mat_10_bdb", {"clear": False}, "syrk_dmma<nn=10,pat=2,gen>"),
     ("tet4", "mat_10_bdb", {}, "bdb<nn=4,sd=3"),
     ("qua4", "mat_10_bdb", {}, "small2d<nn=4,axi=0"),
     ("tri3", "mat_10_bdb", {}, "small2d<nn=3,axi=0"),
@@ -310,3 +312,20 @@ def test_general_blocks_and_accumulation_on_the_register_blocked_kernel(ctx, kin
     rest = blk2.copy()
     rest[:, 1:1 + nd, 3:3 + nd] = 2.0
     assert np.all(rest == 2.0)
+
+
+@pytest.mark.parametrize("rule", [1, 4, 5, 8, 14, 15])
+@pytest.mark.parametrize("structure", ["isotropic", "symmetric", "general"])
+def test_tet10_tensor_core_stiffness(ctx, rule, structure):
+    """Tet10 mat_10_bdb through the DMMA rank-ng kernel (30 dofs -> 4 x 4 dof tiles, 14 cell slots per CTA) vs the oracle, every rule it
+    accepts, the three modulus patterns, ranges that do not fill the slots."""
+    mesh = make_mesh("tet10", n=3)
+    rng = np.random.default_rng(77)
+    dd = iso(3) if structure == "isotropic" else random_coef("mat_10_bdb", 3, 1, rng, spd=(structure == "symmetric"))[0]
+    dmesh = ctx.upload(mesh)
+    ref = oracle_integ("mat_10_bdb", mesh, dd, ngauss=rule)
+    pat = {"isotropic": 2, "symmetric": 1, "general": 0}[structure]
+    for b, e in [(0, mesh.ncell), (0, 1), (3, 9), (5, 40), (1, mesh.ncell - 1)]:
+        got = integ.mat_10_bdb(ctx, dmesh, (b, e), CommonArgs(ngauss=rule), Coef.uniform(dd))
+        assert ctx.last_kernel() == f"syrk_dmma<nn=10,pat={pat}>"
+        assert rel_err(got, ref[b * 900:e * 900], np.arange(e - b + 1) * 900) <= TOL, f"rule {rule} range {b}:{e}"
