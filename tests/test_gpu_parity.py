@@ -680,3 +680,71 @@ def test_fused_stiffness_and_internal_force_hex8(ctx):
     ctx.sync()
     ref_k27 = oracle_integ("mat_10_bdb", mesh, dd, ngauss=27)
     assert rel_err(out_k.cpu().numpy(), ref_k27, np.arange(ncell + 1) * 576) <= TOL
+
+
+@pytest.mark.parametrize("guard", [1024, 1025])
+@pytest.mark.parametrize("kind", ["tri3", "qua4", "qua8", "qua9", "tet4", "tet10", "hex8", "hex20"])
+def test_round2_kernels_write_only_their_own_blocks(ctx, kind, guard):
+    """Guard bands around the outputs of the round-2 paths: one modulus per Gauss point (hex8_gauss / bdb<..,gauss>), the general
+    store epilogue (nrow / ncol / ii0 / jj0, clear = false) and the planned assembly (vals and nothing else is touched)."""
+    import scipy.sparse as sp
+    import torch
+
+    mesh = make_mesh(kind, n=4)
+    dmesh = ctx.upload(mesh)
+    gk = GeoKind.from_str(kind)
+    ng = g.Gauss.new(gk).npoint()
+    nd = gk.nnode() * mesh.ndim
+    rng = np.random.default_rng(8)
+    sentinel = -3.5
+    b, e = 2, mesh.ncell - 3
+    recs = random_coef("mat_10_bdb", mesh.ndim, (e - b) * ng, rng)
+    ns2 = (2 * mesh.ndim) ** 2
+    sub = mesh.permuted(np.arange(b, e))
+    ref = oracle_integ("mat_10_bdb", sub, recs, cell_stride=ng * ns2, gp_stride=ns2).reshape(e - b, nd, nd)
+    # 1. per-Gauss moduli, tight blocks
+    total = (e - b) * nd * nd
+    buf = torch.full((total + 2 * guard,), sentinel, dtype=torch.float64, device="cuda")
+    integ.mat_10_bdb(ctx, dmesh, (b, e), CommonArgs(), Coef.per_gauss(torch.from_numpy(recs).cuda()), out=buf[guard:guard + total])
+    ctx.sync()
+    assert "gauss" in ctx.last_kernel()
+    assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + total:] == sentinel).all()), kind
+    got = buf[guard:guard + total].cpu().numpy().reshape(e - b, nd, nd)
+    assert rel_err(got.ravel(), ref.ravel(), np.arange(e - b + 1) * nd * nd) <= TOL
+    # 2. per-Gauss moduli accumulated into an offset window of larger blocks
+    nrow, ncol = nd + 3, nd + 4
+    total = (e - b) * nrow * ncol
+    buf = torch.full((total + 2 * guard,), sentinel, dtype=torch.float64, device="cuda")
+    buf[guard:guard + total] = 1.0
+    integ.mat_10_bdb(ctx, dmesh, (b, e), CommonArgs(ii0=2, jj0=1, nrow=nrow, ncol=ncol, clear=False),
+                     Coef.per_gauss(torch.from_numpy(recs).cuda()), out=buf[guard:guard + total])
+    ctx.sync()
+    assert ctx.last_kernel().endswith(",gen>"), ctx.last_kernel()
+    assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + total:] == sentinel).all()), kind
+    blk = buf[guard:guard + total].cpu().numpy().reshape(e - b, ncol, nrow)
+    inner = blk[:, 1:1 + nd, 2:2 + nd]
+    np.testing.assert_allclose(inner, ref + 1.0, rtol=1e-12, atol=1e-12 * np.abs(ref).max())  # both are [cell][column][row]
+    rest = blk.copy()
+    rest[:, 1:1 + nd, 2:2 + nd] = 1.0
+    assert np.all(rest == 1.0)
+    # 3. planned assembly: only `vals` changes
+    eq = np.arange(mesh.npoint * mesh.ndim, dtype=np.int32)
+    rows, cols = integ.triplet_indices(ctx, dmesh, "mat_10_bdb", (b, e), CommonArgs(), eq)
+    rr, cc = rows.cpu().numpy(), cols.cpu().numpy()
+    pat = sp.coo_matrix((np.ones(rr.size), (rr, cc)), shape=(eq.size, eq.size)).tocsr()
+    pat.sum_duplicates()
+    pat.sort_indices()
+    rowptr = torch.tensor(pat.indptr.astype(np.int64), device="cuda")
+    colidx = torch.tensor(pat.indices.astype(np.int32), device="cuda")
+    vbuf = torch.full((pat.nnz + 2 * guard,), sentinel, dtype=torch.float64, device="cuda")
+    vbuf[guard:guard + pat.nnz] = 0.0
+    plan = integ.AssemblyPlan(ctx, dmesh, "mat_10_bdb", (b, e), CommonArgs(), eq, rowptr, colidx)
+    plan.assemble(Coef.per_gauss(torch.from_numpy(recs).cuda()), vbuf[guard:guard + pat.nnz])
+    ctx.sync()
+    assert bool((vbuf[:guard] == sentinel).all()) and bool((vbuf[guard + pat.nnz:] == sentinel).all()), kind
+    # column-major blocks: entry q = ii + jj * nd of element e is ref[e, jj, ii]
+    want = sp.coo_matrix((ref.ravel(), (rr, cc)), shape=(eq.size, eq.size)).tocsr()
+    want.sum_duplicates()
+    want.sort_indices()
+    assert np.max(np.abs(vbuf[guard:guard + pat.nnz].cpu().numpy() - want.data)) <= 2e-12 * np.abs(want.data).max()
+    plan.free()
