@@ -1849,7 +1849,7 @@ namespace {
 constexpr uint32_t NOPOS = 0xFFFFFFFFu;
 
 __global__ void plan_positions_kernel(const ScatterParams s, const long long *rowptr, const int32_t *colidx, uint32_t *pos,
-                                      unsigned long long *missing) {
+                                      unsigned long long *missing, const int upper_only) {
     const unsigned int bs = (unsigned int)s.nr * (unsigned int)s.nc;
     const unsigned long long total = (s.hi - s.lo) * (unsigned long long)bs;
     for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
@@ -1867,7 +1867,7 @@ __global__ void plan_positions_kernel(const ScatterParams s, const long long *ro
         } else {
             const unsigned int pc = s.conn[(unsigned long long)(jj / s.npd) * s.ncell_k + cl];
             const int c = s.eq[(unsigned long long)pc * s.npd + jj % s.npd];
-            if (r >= 0 && c >= 0) {
+            if (r >= 0 && c >= 0 && !(upper_only && r > c)) { // symmetric storage: the strictly lower entries are not assembled
                 long long a = rowptr[r], b = rowptr[r + 1];
                 const long long end = b;
                 while (a < b) {
@@ -1919,14 +1919,17 @@ int gl_assemble_plan_create(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t 
                             int eq_location, const int64_t *rowptr, const int32_t *colidx, uint64_t *missing, gl_asm_plan **out) {
     if (!ctx) return GL_ERR_INVALID_ARG;
     gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
-    int st = assemble_checks(ctx, mesh, op, b, e, a);
+    if (!a) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
+    gl_args args = *a;
+    const int upper_only = args.packed ? 1 : 0; // for a plan, `packed` selects symmetric storage: only entries with row <= col are assembled
+    args.packed = 0;
+    args.clear = 1;
+    int st = assemble_checks(ctx, mesh, op, b, e, &args);
     if (st) return st;
     const bool is_mat = op_is_matrix(op);
     if (!eq || !out || (is_mat && (!rowptr || !colidx))) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
     if (missing) *missing = 0;
     cudaSetDevice(ctx->device);
-    gl_args args = *a;
-    args.clear = 1;
     uint64_t total = 0;
     st = range_layout(mesh, op, b, e, &args, &total, nullptr);
     if (st) return fail(ctx, st);
@@ -1959,7 +1962,8 @@ int gl_assemble_plan_create(gl_ctx *ctx, const gl_mesh *cmesh, int op, uint64_t 
             st = scatter_params(ctx, mesh, bk, op, &args, b, e, d_eq, s, empty);
             if (st) break;
             if (empty) continue;
-            plan_positions_kernel<<<scatter_grid(s), 256, 0, (cudaStream_t)ctx->stream>>>(s, (const long long *)rowptr, colidx, plan->d_pos, d_missing);
+            plan_positions_kernel<<<scatter_grid(s), 256, 0, (cudaStream_t)ctx->stream>>>(s, (const long long *)rowptr, colidx, plan->d_pos, d_missing,
+                                                                                          is_mat ? upper_only : 0);
             ctx->launches++;
         }
     }

@@ -380,7 +380,9 @@ GL_API int gl_assemble(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_b
  *     blocks go from shared memory straight into `vals` (RED.ADD.F64); the element-matrix slab is never written to HBM;
  *   - the other cases: element blocks through a bounded scratch slab, then a position-map scatter (no binary search).
  * Asynchronous on the ctx stream (gl_ctx_sync reports zero determinants); `vals` is accumulated into, not cleared.
- * *missing (may be NULL): entries the pattern lacks (then GL_ERR_INVALID_ARG and no plan).  nnz must be < 2^32 - 1. */
+ * *missing (may be NULL): entries the pattern lacks (then GL_ERR_INVALID_ARG and no plan).  nnz must be < 2^32 - 1.
+ * args->packed = 1 selects SYMMETRIC STORAGE: only entries with global row <= column are assembled (the pattern holds the upper
+ * triangle; strictly lower entries are skipped, not reported missing) -- half the adds, for solvers that keep one triangle. */
 typedef struct gl_asm_plan gl_asm_plan;
 GL_API int gl_assemble_plan_create(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_begin, uint64_t cell_end, const gl_args *args,
                                    const int32_t *eq, int eq_location, const int64_t *rowptr, const int32_t *colidx, uint64_t *missing,

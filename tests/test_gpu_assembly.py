@@ -233,3 +233,31 @@ def test_planned_assembly_of_the_other_cases(ctx):
     planv.assemble(Coef.uniform(bf), rhs)
     ctx.sync()
     assert np.max(np.abs(rhs.cpu().numpy() - refv)) <= 1e-12 * np.max(np.abs(refv))
+
+
+def test_planned_assembly_into_symmetric_storage(ctx):
+    """args.packed on a plan: only the upper triangle (global row <= column) of the matrix is assembled."""
+    import torch
+
+    mesh = g.jitter_interior_points(Block.new_cube(1.0).set_ndiv([4, 3, 5]).subdivide(GeoKind.Hex8), 0.02, 3)
+    dmesh = ctx.upload(mesh)
+    dd = g.mandel_matrix(g.lin_elasticity(480.0, 1.0 / 3.0, False))
+    rng = np.random.default_rng(5)
+    eq = rng.permutation(mesh.npoint * 3).astype(np.int32)
+    eq[::11] = -1
+    rr, cc, vv = reference_triplets(mesh, "mat_10_bdb", dd, 3, eq)
+    keep = (rr >= 0) & (cc >= 0) & (rr <= cc)
+    ref = sp.coo_matrix((vv[keep], (rr[keep], cc[keep])), shape=(eq.size, eq.size)).tocsr()
+    ref.sum_duplicates()
+    ref.sort_indices()
+    rowptr = torch.tensor(ref.indptr.astype(np.int64), device="cuda")
+    colidx = torch.tensor(ref.indices.astype(np.int32), device="cuda")
+    plan = integ.AssemblyPlan(ctx, dmesh, "mat_10_bdb", None, CommonArgs(packed=True), eq, rowptr, colidx)
+    vals = torch.zeros(ref.nnz, dtype=torch.float64, device="cuda")
+    plan.assemble(Coef.uniform(dd), vals)
+    ctx.sync()
+    assert ctx.last_kernel().endswith(",scatter>")
+    assert np.max(np.abs(vals.cpu().numpy() - ref.data)) <= 1e-12 * np.max(np.abs(ref.data))
+    # the full pattern is still required without the flag: an upper-only pattern then lacks entries
+    with pytest.raises(g.GemlabError):
+        integ.AssemblyPlan(ctx, dmesh, "mat_10_bdb", None, CommonArgs(), eq, rowptr, colidx)
