@@ -54,13 +54,32 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
 
     const unsigned long long ncell = p.hi - p.lo;
     const unsigned long long nbatch = (ncell + S2_THREADS - 1) / S2_THREADS;
-    // point ids of the NEXT batch are fetched while this one is integrated: one hop of the dependent gather is off the
-    // critical path
+    // software-pipelined gather: the COORDINATES of the next batch and the point ids of the batch after it are in flight while this
+    // one is integrated, so neither hop of the dependent gather is on the critical path (ncu, round 1: long-scoreboard stalls 3.2 per
+    // issued instruction with the coordinates loaded at the top of their own batch)
     unsigned int pid_next[NN];
+    double xn[NN][SD];
+    auto load_ids = [&](unsigned long long c) {
+#pragma unroll
+        for (int m = 0; m < NN; m++) pid_next[m] = c < p.hi ? p.conn[(unsigned long long)m * p.ncell_k + c] : 0u;
+    };
+    auto load_coords = [&](unsigned long long c) {
+#pragma unroll
+        for (int m = 0; m < NN; m++) {
+            xn[m][0] = xn[m][1] = 0.0;
+            if (c < p.hi) {
+                const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[pid_next[m]];
+                xn[m][0] = a.x;
+                xn[m][1] = a.y;
+            }
+        }
+    };
+    const unsigned long long cstep = (unsigned long long)gridDim.x * S2_THREADS;
     {
         const unsigned long long c0 = p.lo + (unsigned long long)blockIdx.x * S2_THREADS + tid;
-#pragma unroll
-        for (int m = 0; m < NN; m++) pid_next[m] = c0 < p.hi ? p.conn[(unsigned long long)m * p.ncell_k + c0] : 0u;
+        load_ids(c0);
+        load_coords(c0);
+        load_ids(c0 + cstep);
     }
     for (unsigned long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const unsigned long long wcell0 = p.lo + batch * S2_THREADS + (unsigned long long)wid * 32; // first cell of this warp
@@ -70,18 +89,11 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
         double x[NN][SD];
 #pragma unroll
         for (int m = 0; m < NN; m++) {
-            x[m][0] = x[m][1] = 0.0;
-            if (active) {
-                const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[pid_next[m]];
-                x[m][0] = a.x;
-                x[m][1] = a.y;
-            }
+            x[m][0] = xn[m][0];
+            x[m][1] = xn[m][1];
         }
-        {
-            const unsigned long long cn = cell + (unsigned long long)gridDim.x * S2_THREADS;
-#pragma unroll
-            for (int m = 0; m < NN; m++) pid_next[m] = cn < p.hi ? p.conn[(unsigned long long)m * p.ncell_k + cn] : 0u;
-        }
+        load_coords(cell + cstep);     // next batch (its point ids arrived during the previous iteration)
+        load_ids(cell + 2 * cstep);    // the batch after
         if (!active) { // a unit cell keeps the arithmetic finite; nothing of it is stored
             x[1 % NN][0] = 1.0;
             x[2 % NN][0] = NN == 3 ? 0.0 : 1.0;
@@ -236,7 +248,13 @@ int launch_small2d_kind(const IntegParams &p, const Small2dConsts &cst, int pat,
     if (ctas_per_sm > 4) ctas_per_sm = 4;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const unsigned long long nbatch = (p.hi - p.lo + S2_THREADS - 1) / S2_THREADS;
-    unsigned long long grid = (unsigned long long)nsm * ctas_per_sm * 8;
+    // CTAs per resident slot: 8 keeps the SMs out of lockstep on large meshes (9 M cells: 11.5 G el/s at 8, 10.1 at 2), but every CTA
+    // should still loop over ~8 batches for the gather pipeline to pay (10^6 cells: 10.1 G el/s at 2, 9.3 at 8)
+    const unsigned long long slots = (unsigned long long)nsm * ctas_per_sm;
+    unsigned long long mult = nbatch / (slots * 8);
+    mult = mult < 1 ? 1 : (mult > 8 ? 8 : mult);
+    unsigned long long grid = slots * mult;
+    if (const char *e = tuning_env("GL_SMALL2D_GRID_MULT")) grid = (unsigned long long)nsm * ctas_per_sm * (unsigned long long)atoi(e); // tuning knob
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     // records whose structure only the device knows: every variant is enqueued, the probe's verdict selects the one that runs
