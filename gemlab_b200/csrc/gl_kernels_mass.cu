@@ -78,6 +78,13 @@ __global__ void __launch_bounds__(MASS_THREADS) mass_kernel(const IntegParams p,
     double *Cw = s_C + wid * 32 * CS;
     const unsigned long long ncell = p.hi - p.lo;
     const unsigned long long nbatch = (ncell + MASS_THREADS - 1) / MASS_THREADS;
+    // the point ids of the NEXT batch are fetched while this one is integrated: one hop of the dependent gather off the critical path
+    unsigned int pid_next[NN];
+    auto load_ids = [&](unsigned long long c) {
+#pragma unroll
+        for (int m = 0; m < NN; m++) pid_next[m] = c < p.hi ? p.conn[(unsigned long long)m * p.ncell_k + c] : 0u;
+    };
+    load_ids(p.lo + (unsigned long long)blockIdx.x * MASS_THREADS + tid);
     for (unsigned long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const unsigned long long cell = p.lo + batch * MASS_THREADS + tid;
         const bool active = cell < p.hi;
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(MASS_THREADS) mass_kernel(const IntegParams p,
         if (active) {
 #pragma unroll
             for (int m = 0; m < NN; m++) {
-                const unsigned int pid = p.conn[(unsigned long long)m * p.ncell_k + cell];
+                const unsigned int pid = pid_next[m];
                 if (p.coords_pm) { // one 32-byte (3D) / 16-byte (2D) record per point: a single sector instead of SD
                     if constexpr (SD == 2) {
                         const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[pid];
@@ -111,6 +118,7 @@ __global__ void __launch_bounds__(MASS_THREADS) mass_kernel(const IntegParams p,
 #pragma unroll
                 for (int j = 0; j < SD; j++) x[m][j] = 0.0;
         }
+        load_ids(cell + (unsigned long long)gridDim.x * MASS_THREADS);
         bool bad = false;
 #pragma unroll 1
         for (int gp = 0; gp < ng; gp++) {

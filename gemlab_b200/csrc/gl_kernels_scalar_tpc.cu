@@ -53,30 +53,60 @@ __global__ void __launch_bounds__(TPC_THREADS) scalar_tpc_kernel(const IntegPara
 
     const unsigned long long ncell = p.hi - p.lo;
     const unsigned long long nbatch = (ncell + TPC_THREADS - 1) / TPC_THREADS;
+    // software-pipelined gather (Mesh::set_pad): the coordinates of the next batch and the point ids of the batch after it are in
+    // flight while this one is integrated (see gl_kernels_small2d.cu)
+    constexpr bool PFX = NN * SD <= 16; // the larger kinds have no registers left for a second set of coordinates: ids only
+    unsigned int pid_next[NN];
+    double xn[NN][SD];
+    auto load_ids = [&](unsigned long long c) {
+#pragma unroll
+        for (int m = 0; m < NN; m++) pid_next[m] = c < p.hi ? p.conn[(unsigned long long)m * p.ncell_k + c] : 0u;
+    };
+    auto load_coords = [&](unsigned long long c) {
+#pragma unroll
+        for (int m = 0; m < NN; m++) {
+#pragma unroll
+            for (int j = 0; j < SD; j++) xn[m][j] = 0.0;
+            if (c < p.hi) {
+                if constexpr (SD == 2) {
+                    const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[pid_next[m]];
+                    xn[m][0] = a.x;
+                    xn[m][1] = a.y;
+                } else {
+                    const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[2ull * pid_next[m]];
+                    const double2 c2 = reinterpret_cast<const double2 *>(p.coords_pm)[2ull * pid_next[m] + 1];
+                    xn[m][0] = a.x;
+                    xn[m][1] = a.y;
+                    xn[m][2] = c2.x;
+                }
+            }
+        }
+    };
+    const unsigned long long cstep = (unsigned long long)gridDim.x * TPC_THREADS;
+    {
+        const unsigned long long c0 = p.lo + (unsigned long long)blockIdx.x * TPC_THREADS + tid;
+        load_ids(c0);
+        if constexpr (PFX) {
+            load_coords(c0);
+            load_ids(c0 + cstep);
+        }
+    }
     for (unsigned long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const unsigned long long wcell0 = p.lo + batch * TPC_THREADS + (unsigned long long)wid * 32; // first cell of this warp
         const unsigned long long cell = wcell0 + lane;
         const bool active = cell < p.hi;
 
+        if constexpr (!PFX) load_coords(cell); // with the ids fetched during the previous batch
         double x[NN][SD];
 #pragma unroll
-        for (int m = 0; m < NN; m++) {
+        for (int m = 0; m < NN; m++)
 #pragma unroll
-            for (int j = 0; j < SD; j++) x[m][j] = 0.0;
-            if (active) {
-                const unsigned int pid = p.conn[(unsigned long long)m * p.ncell_k + cell];
-                if constexpr (SD == 2) {
-                    const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[pid];
-                    x[m][0] = a.x;
-                    x[m][1] = a.y;
-                } else {
-                    const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[2ull * pid];
-                    const double2 c = reinterpret_cast<const double2 *>(p.coords_pm)[2ull * pid + 1];
-                    x[m][0] = a.x;
-                    x[m][1] = a.y;
-                    x[m][2] = c.x;
-                }
-            }
+            for (int j = 0; j < SD; j++) x[m][j] = xn[m][j];
+        if constexpr (PFX) {
+            load_coords(cell + cstep);  // next batch (its point ids arrived during the previous iteration)
+            load_ids(cell + 2 * cstep); // the batch after
+        } else {
+            load_ids(cell + cstep);
         }
 
         double acc[NPAIR], av[NN];
@@ -221,7 +251,11 @@ int launch_tpc_kind(const IntegParams &p, const ScalarFused &f, void *stream) {
     if (ctas_per_sm > 4) ctas_per_sm = 4;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const unsigned long long nbatch = (p.hi - p.lo + TPC_THREADS - 1) / TPC_THREADS;
-    unsigned long long grid = (unsigned long long)nsm * ctas_per_sm * 8;
+    // 8 CTAs per resident slot on large meshes, fewer on small ones so that every CTA still loops over ~8 batches (gl_kernels_small2d.cu)
+    const unsigned long long slots = (unsigned long long)nsm * ctas_per_sm;
+    unsigned long long mult = nbatch / (slots * 8);
+    mult = mult < 1 ? 1 : (mult > 8 ? 8 : mult);
+    unsigned long long grid = slots * mult;
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     kern<<<(unsigned)grid, TPC_THREADS, smem, (cudaStream_t)stream>>>(p, f);

@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
     // software-pipelined gather: the COORDINATES of the next batch and the point ids of the batch after it are in flight while this
     // one is integrated, so neither hop of the dependent gather is on the critical path (ncu, round 1: long-scoreboard stalls 3.2 per
     // issued instruction with the coordinates loaded at the top of their own batch)
+    // (not for the axisymmetric Tri3 variant: the second set of coordinates costs it a resident CTA -- 168 -> 194 registers, measured
+    // 0.60 -> 0.66 ms on the Tri3 half of configs[4]; it keeps the ids one batch ahead only)
+    constexpr bool PFX = !AXI;
     unsigned int pid_next[NN];
     double xn[NN][SD];
     auto load_ids = [&](unsigned long long c) {
@@ -78,22 +81,29 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
     {
         const unsigned long long c0 = p.lo + (unsigned long long)blockIdx.x * S2_THREADS + tid;
         load_ids(c0);
-        load_coords(c0);
-        load_ids(c0 + cstep);
+        if constexpr (PFX) {
+            load_coords(c0);
+            load_ids(c0 + cstep);
+        }
     }
     for (unsigned long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const unsigned long long wcell0 = p.lo + batch * S2_THREADS + (unsigned long long)wid * 32; // first cell of this warp
         const unsigned long long cell = wcell0 + lane;
         const bool active = cell < p.hi;
 
+        if constexpr (!PFX) load_coords(cell); // with the ids fetched during the previous batch
         double x[NN][SD];
 #pragma unroll
         for (int m = 0; m < NN; m++) {
             x[m][0] = xn[m][0];
             x[m][1] = xn[m][1];
         }
-        load_coords(cell + cstep);     // next batch (its point ids arrived during the previous iteration)
-        load_ids(cell + 2 * cstep);    // the batch after
+        if constexpr (PFX) {
+            load_coords(cell + cstep);  // next batch (its point ids arrived during the previous iteration)
+            load_ids(cell + 2 * cstep); // the batch after
+        } else {
+            load_ids(cell + cstep);
+        }
         if (!active) { // a unit cell keeps the arithmetic finite; nothing of it is stored
             x[1 % NN][0] = 1.0;
             x[2 % NN][0] = NN == 3 ? 0.0 : 1.0;
