@@ -527,32 +527,57 @@ __global__ void coords_to_point_major_kernel(const double *__restrict__ soa, dou
 }
 
 // uploads a homogeneous mesh: raw host arrays go to the device as they are and are transposed there
+// Homogeneous upload in two halves so that the caller can validate its host arrays while the copies are in flight:
+// begin() enqueues the H2D copies and the SoA / narrowing kernels on the ctx stream, finish() waits and reports out-of-range ids.
+struct PendingUpload {
+    void *d_raw = nullptr;
+    int *d_bad = nullptr;
+    size_t raw_bytes = 0;
+    int *h_bad = nullptr; // pinned
+};
+
 template <typename IdT>
-int upload_homogeneous_device(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, const double *coords, const IdT *conn) {
+int upload_homogeneous_begin(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, const double *coords, const IdT *conn, PendingUpload &pu) {
     cudaStream_t st = (cudaStream_t)ctx->stream;
     const size_t conn_bytes = (size_t)bk.ncell * bk.nnode * sizeof(IdT);
     const size_t coord_bytes = (size_t)mesh->npoint * mesh->ndim * sizeof(double);
-    void *d_raw = nullptr;
-    int *d_bad = nullptr;
-    CUDA_TRY(ctx, pool_alloc(ctx, &d_raw, std::max(conn_bytes, coord_bytes)));
-    CUDA_TRY(ctx, pool_alloc_t(ctx, &d_bad, sizeof(int)));
-    CUDA_TRY(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    const size_t conn_at = (coord_bytes + 255) & ~(size_t)255;
+    pu.raw_bytes = conn_at + conn_bytes; // two staging areas: the second copy does not wait for the first kernel
+    CUDA_TRY(ctx, pool_alloc(ctx, &pu.d_raw, pu.raw_bytes));
+    CUDA_TRY(ctx, pool_alloc_t(ctx, &pu.d_bad, sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(pu.d_bad, 0, sizeof(int), st));
     CUDA_TRY(ctx, pool_alloc_t(ctx, &mesh->d_coords, coord_bytes));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_raw, coords, coord_bytes, cudaMemcpyHostToDevice, st));
-    coords_to_soa_kernel<<<1184, 256, 0, st>>>((const double *)d_raw, mesh->d_coords, mesh->npoint, mesh->ndim);
+    CUDA_TRY(ctx, cudaMemcpyAsync(pu.d_raw, coords, coord_bytes, cudaMemcpyHostToDevice, st));
+    coords_to_soa_kernel<<<1184, 256, 0, st>>>((const double *)pu.d_raw, mesh->d_coords, mesh->npoint, mesh->ndim);
     if (bk.ncell) {
+        char *d_conn_raw = (char *)pu.d_raw + conn_at;
         CUDA_TRY(ctx, pool_alloc_t(ctx, &bk.d_conn, (size_t)bk.ncell * bk.nnode * sizeof(uint32_t)));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_raw, conn, conn_bytes, cudaMemcpyHostToDevice, st));
-        conn_to_soa_kernel<IdT><<<1184, 256, 0, st>>>((const IdT *)d_raw, bk.d_conn, bk.ncell, bk.nnode, mesh->npoint, d_bad);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_conn_raw, conn, conn_bytes, cudaMemcpyHostToDevice, st));
+        conn_to_soa_kernel<IdT><<<1184, 256, 0, st>>>((const IdT *)d_conn_raw, bk.d_conn, bk.ncell, bk.nnode, mesh->npoint, pu.d_bad);
     }
-    int bad = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     ctx->launches += bk.ncell ? 2 : 1;
-    pool_free(ctx, d_raw, std::max(conn_bytes, coord_bytes));
-    pool_free(ctx, d_bad, sizeof(int));
+    return GL_OK;
+}
+
+int upload_homogeneous_finish(gl_ctx *ctx, PendingUpload &pu) {
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    int bad = 0;
+    cudaError_t ce = cudaMemcpyAsync(&bad, pu.d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    pool_free(ctx, pu.d_raw, pu.raw_bytes);
+    pool_free(ctx, pu.d_bad, sizeof(int));
+    pu = PendingUpload();
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "mesh upload");
     if (bad) return fail(ctx, GL_ERR_MESH, "point id out of range");
     return GL_OK;
+}
+
+template <typename IdT>
+int upload_homogeneous_device(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, const double *coords, const IdT *conn) {
+    PendingUpload pu;
+    int st = upload_homogeneous_begin<IdT>(ctx, mesh, bk, coords, conn, pu);
+    if (st) return st;
+    return upload_homogeneous_finish(ctx, pu);
 }
 
 } // namespace
@@ -612,14 +637,78 @@ int gl_mesh_upload(gl_ctx *ctx, int ndim, uint64_t npoint, const double *coords,
     if (ndim < 2 || ndim > 3) return fail(ctx, GL_ERR_SPACE_NDIM);
     if (npoint == 0 || npoint > 0xffffffffull || ncell > 0xffffffffull) return fail(ctx, GL_ERR_MESH, "npoint/ncell must fit in 32 bits");
     cudaSetDevice(ctx->device);
-    // validate and count per kind
-    uint64_t count[GL_NKIND] = {0};
-    for (uint64_t e = 0; e < ncell; e++) {
-        const int k = kinds[e];
+    // Single-kind meshes (the common case, and every step of a host-driven loop): the copies and the device-side transposition are
+    // enqueued FIRST, the host-side validation of kinds / offsets / markers runs while they are in flight.
+    bool one_kind = ncell > 0;
+    for (uint64_t e = 1; e < ncell && one_kind; e++) one_kind = kinds[e] == kinds[0];
+    if (one_kind) {
+        const int k = kinds[0];
         if (k >= GL_NKIND || !kind_supported(k)) return fail(ctx, GL_ERR_KIND_UNSUPPORTED);
         if (kind_geo_ndim(k) > ndim) return fail(ctx, GL_ERR_MESH, "geo_ndim cannot be greater than space_ndim");
-        if (conn_off[e + 1] - conn_off[e] != (uint64_t)kind_nnode(k)) return fail(ctx, GL_ERR_MESH, "cell connectivity length != nnode");
-        count[k]++;
+        auto mesh = std::make_unique<gl_mesh>();
+        mesh->ndim = ndim;
+        mesh->npoint = npoint;
+        mesh->ncell = ncell;
+        mesh->device = ctx->device;
+        mesh->homogeneous = true;
+        gl_mesh_bucket bk;
+        bk.kind = k;
+        bk.nnode = kind_nnode(k);
+        bk.ncell = ncell;
+        PendingUpload pu;
+        int st = upload_homogeneous_begin<uint64_t>(ctx, mesh.get(), bk, coords, conn + conn_off[0], pu);
+        bool offsets_ok = true;
+        if (!st) {
+            const uint64_t nn = (uint64_t)bk.nnode;
+            uint64_t prev = conn_off[0];
+            for (uint64_t e = 0; e < ncell; e++) {
+                const uint64_t next = conn_off[e + 1];
+                offsets_ok = offsets_ok && (next - prev == nn);
+                prev = next;
+            }
+        }
+        std::vector<uint32_t> marker_idx;
+        if (!st) build_markers(ctx, mesh.get(), markers, marker_idx);
+        if (pu.d_raw) {
+            const int st2 = upload_homogeneous_finish(ctx, pu);
+            if (!st) st = st2;
+        }
+        if (!st && !offsets_ok) st = fail(ctx, GL_ERR_MESH, "cell connectivity length != nnode");
+        if (!st && !marker_idx.empty()) {
+            if (cudaMalloc(&bk.d_marker_idx, marker_idx.size() * sizeof(uint32_t)) != cudaSuccess ||
+                cudaMemcpy(bk.d_marker_idx, marker_idx.data(), marker_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+                st = cuda_fail(ctx, cudaGetLastError(), "marker table");
+        }
+        mesh->buckets.push_back(std::move(bk));
+        if (st) {
+            gl_mesh_free(ctx, mesh.release());
+            return st;
+        }
+        *out = mesh.release();
+        return GL_OK;
+    }
+    // validate and count per kind
+    uint64_t count[GL_NKIND] = {0};
+    {
+        uint64_t nn_of[256];
+        unsigned char ok_of[256];
+        for (int k = 0; k < 256; k++) {
+            const bool known = k < GL_NKIND && kind_supported(k);
+            nn_of[k] = known ? (uint64_t)kind_nnode(k) : 0;
+            ok_of[k] = !known ? 0 : (kind_geo_ndim(k) > ndim ? 1 : 2);
+        }
+        uint64_t prev = conn_off[0];
+        for (uint64_t e = 0; e < ncell; e++) {
+            const unsigned k = kinds[e];
+            const uint64_t next = conn_off[e + 1];
+            if (ok_of[k] != 2 || next - prev != nn_of[k]) {
+                if (ok_of[k] == 0) return fail(ctx, GL_ERR_KIND_UNSUPPORTED);
+                if (ok_of[k] == 1) return fail(ctx, GL_ERR_MESH, "geo_ndim cannot be greater than space_ndim");
+                return fail(ctx, GL_ERR_MESH, "cell connectivity length != nnode");
+            }
+            prev = next;
+            count[k]++;
+        }
     }
     auto mesh = std::make_unique<gl_mesh>();
     mesh->ndim = ndim;
@@ -631,22 +720,6 @@ int gl_mesh_upload(gl_ctx *ctx, int ndim, uint64_t npoint, const double *coords,
     mesh->homogeneous = nkinds <= 1;
     std::vector<uint32_t> marker_idx;
     build_markers(ctx, mesh.get(), markers, marker_idx);
-    if (mesh->homogeneous && ncell > 0) {
-        // one GeoKind: conn is already a dense [ncell][nnode] table -> transposed and range-checked on the device
-        gl_mesh_bucket bk;
-        bk.kind = kinds[0];
-        bk.nnode = kind_nnode(bk.kind);
-        bk.ncell = ncell;
-        int st = upload_homogeneous_device<uint64_t>(ctx, mesh.get(), bk, coords, conn + conn_off[0]);
-        if (st) return st;
-        if (!marker_idx.empty()) {
-            CUDA_TRY(ctx, cudaMalloc(&bk.d_marker_idx, marker_idx.size() * sizeof(uint32_t)));
-            CUDA_TRY(ctx, cudaMemcpy(bk.d_marker_idx, marker_idx.data(), marker_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        }
-        mesh->buckets.push_back(std::move(bk));
-        *out = mesh.release();
-        return GL_OK;
-    }
     if (!mesh->homogeneous) mesh->h_kinds.assign(kinds, kinds + ncell);
     for (int k = 0; k < GL_NKIND; k++) {
         if (!count[k]) continue;
