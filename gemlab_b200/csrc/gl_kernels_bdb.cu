@@ -321,18 +321,18 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                 double T[NS][SD]; // PG: T(n) = c_p D'_p M(n); rows the strain-displacement columns never touch are dead code
                 if constexpr (PG) {
                     const double *Dp = s_DG + (cs * ng + gp) * NS * NS; // the same address for every lane of the cell: broadcast
+                    // term by term over ALL entries (q outermost): consecutive FMAs are independent, so a warp does not wait on its own
+                    // previous result (ncu: fixed-latency "wait" stalls were a third of the samples with q innermost)
 #pragma unroll
-                    for (int a = 0; a < NS; a++)
+                    for (int q = 0; q < 3; q++)
 #pragma unroll
-                        for (int j = 0; j < SD; j++) {
-                            double t = 0.0;
+                        for (int a = 0; a < NS; a++)
 #pragma unroll
-                            for (int q = 0; q < col_n(SD, AXI, j); q++) {
+                            for (int j = 0; j < SD; j++) {
+                                if (q >= col_n(SD, AXI, j)) continue;
                                 const double dv = Dp[a * NS + col_row(SD, j, q)], bv = vn[col_comp(SD, j, q)];
-                                t = q == 0 ? dv * bv : fma(dv, bv, t);
+                                T[a][j] = q == 0 ? dv * bv : fma(dv, bv, T[a][j]);
                             }
-                            T[a][j] = t;
-                        }
                 }
 #pragma unroll
                 for (int s = 0; s < NSLOT; s++) {
@@ -348,12 +348,14 @@ __global__ void __launch_bounds__(256) bdb_kernel(const IntegParams p, const Bdb
                     if constexpr (PG) {
                         // K(m,n)[i][j] += sum_q M(m)[row(i,q)][i] T[row(i,q)][j]   (add_to_kk / add_to_kk_axisymmetric, mat_10_bdb.rs:179-233)
 #pragma unroll
-                        for (int j = 0; j < SD; j++)
+                        for (int q = 0; q < 3; q++)
 #pragma unroll
-                            for (int i = 0; i < SD; i++)
+                            for (int j = 0; j < SD; j++)
 #pragma unroll
-                                for (int q = 0; q < col_n(SD, AXI, i); q++)
+                                for (int i = 0; i < SD; i++) {
+                                    if (q >= col_n(SD, AXI, i)) continue;
                                     acc[s][i + SD * j] = fma(vm[col_comp(SD, i, q)], T[col_row(SD, i, q)][j], acc[s][i + SD * j]);
+                                }
                     } else {
 #pragma unroll
                         for (int l = 0; l < VD; l++)

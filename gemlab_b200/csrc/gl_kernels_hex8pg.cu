@@ -193,8 +193,11 @@ __global__ void __launch_bounds__(PG_THREADS, 2) hex8_gauss_kernel(const IntegPa
                 const double2 d01 = Dp[a * 3 + 0], d23 = Dp[a * 3 + 1], d45 = Dp[a * 3 + 2];
                 const double d[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};
 #pragma unroll
-                for (int j = 0; j < 3; j++)
-                    T[a][j] = fma(d[col_row(j, 2)], vn[col_comp(j, 2)], fma(d[col_row(j, 1)], vn[col_comp(j, 1)], d[col_row(j, 0)] * vn[col_comp(j, 0)]));
+                for (int j = 0; j < 3; j++) T[a][j] = d[col_row(j, 0)] * vn[col_comp(j, 0)];
+#pragma unroll
+                for (int j = 0; j < 3; j++) T[a][j] = fma(d[col_row(j, 1)], vn[col_comp(j, 1)], T[a][j]);
+#pragma unroll
+                for (int j = 0; j < 3; j++) T[a][j] = fma(d[col_row(j, 2)], vn[col_comp(j, 2)], T[a][j]);
             }
 #pragma unroll
             for (int b = 0; b < NB; b++) {
@@ -204,14 +207,16 @@ __global__ void __launch_bounds__(PG_THREADS, 2) hex8_gauss_kernel(const IntegPa
                 // symmetric D_p: the diagonal block (b = 0) is symmetric and the block at distance 4 is also held, transposed, by
                 // lane g+4 -- both lanes compute only i <= j and the mirror of phase 3 supplies the rest
                 const bool tri = SYM && (b == 0 || b == 4);
+                // (t outermost: consecutive FMAs go to different accumulators)
 #pragma unroll
-                for (int j = 0; j < 3; j++)
+                for (int t = 0; t < 3; t++)
 #pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        if (tri && i > j) continue;
+                    for (int j = 0; j < 3; j++)
 #pragma unroll
-                        for (int t = 0; t < 3; t++) acc[b][i + 3 * j] = fma(bm[col_comp(i, t)], T[col_row(i, t)][j], acc[b][i + 3 * j]);
-                    }
+                        for (int i = 0; i < 3; i++) {
+                            if (tri && i > j) continue;
+                            acc[b][i + 3 * j] = fma(bm[col_comp(i, t)], T[col_row(i, t)][j], acc[b][i + 3 * j]);
+                        }
             }
         }
         load_record(cell_of(it + 1)); // next batch's records

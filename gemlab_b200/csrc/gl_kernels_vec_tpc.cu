@@ -39,6 +39,14 @@ __global__ void __launch_bounds__(VT_THREADS) vec_tpc_kernel(const IntegParams p
 
     const unsigned long long ncell = p.hi - p.lo;
     const unsigned long long nbatch = (ncell + VT_THREADS - 1) / VT_THREADS;
+    // the point ids of the NEXT batch are fetched while this one is integrated (gl_kernels_small2d.cu): one hop of the dependent gather
+    // off the critical path
+    unsigned int pid_next[NN];
+    auto load_ids = [&](unsigned long long c) {
+#pragma unroll
+        for (int m = 0; m < NN; m++) pid_next[m] = c < p.hi ? p.conn[(unsigned long long)m * p.ncell_k + c] : 0u;
+    };
+    load_ids(p.lo + (unsigned long long)blockIdx.x * VT_THREADS + tid);
     for (unsigned long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const unsigned long long wcell0 = p.lo + batch * VT_THREADS + (unsigned long long)wid * 32; // first cell of this warp
         const unsigned long long cell = wcell0 + lane;
@@ -51,7 +59,7 @@ __global__ void __launch_bounds__(VT_THREADS) vec_tpc_kernel(const IntegParams p
 #pragma unroll
             for (int j = 0; j < SD; j++) x[m][j] = 0.0;
             if (active) {
-                const unsigned int pid = p.conn[(unsigned long long)m * p.ncell_k + cell];
+                const unsigned int pid = pid_next[m];
                 if constexpr (SD == 2) {
                     const double2 a = reinterpret_cast<const double2 *>(p.coords_pm)[pid];
                     x[m][0] = a.x;
@@ -65,6 +73,7 @@ __global__ void __launch_bounds__(VT_THREADS) vec_tpc_kernel(const IntegParams p
                 }
             }
         }
+        load_ids(cell + (unsigned long long)gridDim.x * VT_THREADS);
 
         double acc[NN][SD];
 #pragma unroll
@@ -181,7 +190,11 @@ int launch_vt_kind(const IntegParams &p, void *stream) {
     if (ctas_per_sm > 4) ctas_per_sm = 4;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const unsigned long long nbatch = (p.hi - p.lo + VT_THREADS - 1) / VT_THREADS;
-    unsigned long long grid = (unsigned long long)nsm * ctas_per_sm * 8;
+    // 8 CTAs per resident slot on large meshes, fewer on small ones so that every CTA still loops over ~8 batches (gl_kernels_small2d.cu)
+    const unsigned long long slots = (unsigned long long)nsm * ctas_per_sm;
+    unsigned long long mult = nbatch / (slots * 8);
+    mult = mult < 1 ? 1 : (mult > 8 ? 8 : mult);
+    unsigned long long grid = slots * mult;
     if (grid > nbatch) grid = nbatch;
     if (grid == 0) return 0;
     kern<<<(unsigned)grid, VT_THREADS, smem, (cudaStream_t)stream>>>(p);

@@ -108,7 +108,9 @@ int gl_integ_slab(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t b, uint64_t
     slab->cell_end = e;
     slab->size = total;
     gl_out out{slab->ptr, GL_DEVICE, 0, slab->capacity};
-    return gl_integ(ctx, mesh, op, b, e, a, coef, &out);
+    st = gl_integ(ctx, mesh, op, b, e, a, coef, &out);
+    if (st && slab->owned) gl_slab_free(slab); // nothing half-made is handed back
+    return st;
 }
 
 int gl_slab_download(gl_ctx *ctx, const gl_slab *slab, double *host) {

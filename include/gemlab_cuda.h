@@ -379,7 +379,8 @@ GL_API int gl_assemble(gl_ctx *ctx, const gl_mesh *mesh, int op, uint64_t cell_b
  *   - mat_10_bdb on every solid kind (uniform / per-marker / per-cell / per-Gauss moduli): ONE kernel per GeoKind -- the element
  *     blocks go from shared memory straight into `vals` (RED.ADD.F64); the element-matrix slab is never written to HBM;
  *   - the other cases: element blocks through a bounded scratch slab, then a position-map scatter (no binary search).
- * Asynchronous on the ctx stream (gl_ctx_sync reports zero determinants); `vals` is accumulated into, not cleared.
+ * Asynchronous on the ctx stream (gl_ctx_sync reports zero determinants); `vals` is accumulated into, not cleared.  A plan refers
+ * to its mesh: free the plan before the mesh.
  * *missing (may be NULL): entries the pattern lacks (then GL_ERR_INVALID_ARG and no plan).  nnz must be < 2^32 - 1.
  * args->packed = 1 selects SYMMETRIC STORAGE: only entries with global row <= column are assembled (the pattern holds the upper
  * triangle; strictly lower entries are skipped, not reported missing) -- half the adds, for solvers that keep one triangle. */
