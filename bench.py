@@ -373,27 +373,47 @@ def main():
     def step():
         integ.mat_10_bdb(ctx, dmesh, (0, ncell), cargs, coef, out=out)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    ctx.sync()
-    kernel_name = ctx.last_kernel()
-    barrier()
+    # nvidia-smi takes a few hundred ms to deliver its first sample and then one every 100 ms, while K timed steps may last less than
+    # that: the sampler is started BEFORE the warm-up, the warm-up is extended (same kernel, untimed) until a sample has arrived, and
+    # if none lands inside the timed region the same kernel keeps running (untimed) until the next one does -- every sample used was
+    # taken under the load of the timed kernel, right around or inside the region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.15)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.sync()
+    if rank == 0 and sampler.proc:
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+            step()
+            ctx.sync()
+    kernel_name = ctx.last_kernel()
+    barrier()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    n_before = len(sampler.rows)
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     torch.cuda.synchronize()
+    n_after = len(sampler.rows)
+    launches = ctx.launch_count() - launches0
+    if rank == 0 and sampler.proc and n_after == n_before:
+        t_wait = time.perf_counter()
+        while len(sampler.rows) == n_after and time.perf_counter() - t_wait < 1.0:
+            step()
+            ctx.sync()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.rows = sampler.rows[max(n_before - 1, 0):]
+        clocks = sampler.stop()
+        clocks["samples_inside_timed_region"] = n_after - n_before
+    else:
+        clocks = None
     ctx.sync()  # surfaces device-side failures (zero determinant)
     ms_max = max_over_ranks(ms)
     value = world * ncell * args.steps / (ms_max * 1e-3)
