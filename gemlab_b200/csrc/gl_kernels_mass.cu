@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(MASS_THREADS) mass_kernel(const IntegParams p,
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const bool m01 = f.mask & 1, v01 = f.mask & 4;
+    // 16-byte stores of the accumulator pairs: block starts (multiples of NN^2 resp. NN) and the K / vector boundary must be even
+    const bool vec2 = NN % 2 == 0 && f.moff == nullptr && f.voff == nullptr && (!m01 || (reinterpret_cast<uintptr_t>(f.out_m01) & 15) == 0) &&
+                      (!v01 || (reinterpret_cast<uintptr_t>(f.out_v01) & 15) == 0) && p.cell_ids == nullptr;
     for (int i = tid; i < ng; i += MASS_THREADS) s_w[i] = p.rule[i];
     for (int i = tid; i < ng * NN; i += MASS_THREADS) s_N[i] = p.rule[ng + i];
     for (int i = tid; i < ng * LS; i += MASS_THREADS) s_L[i] = p.rule[ng * (1 + NN) + i];
@@ -157,14 +160,33 @@ __global__ void __launch_bounds__(MASS_THREADS) mass_kernel(const IntegParams p,
         // ---- phase 2 + 3: [K | a] = C . W on the tensor cores, stored from the accumulator fragments -----------------------
         const int ar = lane >> 2, ak = lane & 3; // fragment coordinates: row (cell / output entry) and k index
         const int nks = KP / 4;
+        // the A fragments (this warp's 32 x KP coefficient matrix) do not depend on the column tile: rules of up to 16 points keep them in
+        // registers for the whole sweep instead of re-reading them from shared memory for each of the EP / 8 column tiles
+        const bool a_in_regs = nks <= 4;
+        double afr[4][4];
+#pragma unroll
+        for (int rt = 0; rt < 4; rt++)
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) afr[rt][ks] = (a_in_regs && ks < nks) ? Cw[(8 * rt + ar) * CS + 4 * ks + ak] : 0.0;
         for (int ct = 0; ct < EP / 8; ct++) {
             double acc[4][2];
 #pragma unroll
             for (int rt = 0; rt < 4; rt++) acc[rt][0] = acc[rt][1] = 0.0;
-            for (int ks = 0; ks < nks; ks++) {
-                const double b = s_W[(4 * ks + ak) * WS + 8 * ct + ar];
+            if (a_in_regs) {
 #pragma unroll
-                for (int rt = 0; rt < 4; rt++) dmma_m8n8k4(acc[rt][0], acc[rt][1], Cw[(8 * rt + ar) * CS + 4 * ks + ak], b);
+                for (int ks = 0; ks < 4; ks++) {
+                    if (ks < nks) {
+                        const double b = s_W[(4 * ks + ak) * WS + 8 * ct + ar];
+#pragma unroll
+                        for (int rt = 0; rt < 4; rt++) dmma_m8n8k4(acc[rt][0], acc[rt][1], afr[rt][ks], b);
+                    }
+                }
+            } else {
+                for (int ks = 0; ks < nks; ks++) {
+                    const double b = s_W[(4 * ks + ak) * WS + 8 * ct + ar];
+#pragma unroll
+                    for (int rt = 0; rt < 4; rt++) dmma_m8n8k4(acc[rt][0], acc[rt][1], Cw[(8 * rt + ar) * CS + 4 * ks + ak], b);
+                }
             }
             const int q0 = 8 * ct + 2 * ak;
 #pragma unroll
@@ -173,6 +195,15 @@ __global__ void __launch_bounds__(MASS_THREADS) mass_kernel(const IntegParams p,
                 const unsigned long long mo = __shfl_sync(0xffffffffu, moff, src), vo = __shfl_sync(0xffffffffu, voff, src);
                 const bool row_active = p.lo + batch * MASS_THREADS + (unsigned long long)(wid * 32 + src) < p.hi;
                 if (!row_active) continue;
+                if (vec2) {
+                    // even NN on a single-kind mesh: the lane's two entries (columns q0, q0 + 1) are one aligned 16-byte store
+                    if (q0 < KK) {
+                        if (m01) *reinterpret_cast<double2 *>(f.out_m01 + mo + q0) = make_double2(acc[rt][0], acc[rt][1]);
+                    } else if (q0 < KK + NN) {
+                        if (v01) *reinterpret_cast<double2 *>(f.out_v01 + vo + (q0 - KK)) = make_double2(acc[rt][0], acc[rt][1]);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int q = q0 + e;
