@@ -1034,6 +1034,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         if (force_done) *force_done = nl > 0 && d_sigma != nullptr;
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_small2d(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_syrk(p, mesh->ndim, ctx->stream);
+        if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_qua8(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_tile(p, mesh->ndim, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb(p, mesh->ndim, ctx->stream);
         if (nl == 0 && gd == mesh->ndim && cr.dev == nullptr && a->clear && a->ii0 == 0 && (a->jj0 == 0 || !op_is_matrix(op)) &&

@@ -131,6 +131,7 @@ bool bdb_covers(int nnode, int sd, int ng, bool axisym, bool record_moduli, bool
 int launch_bdb_small2d(const IntegParams &p, int sd, void *stream); // thread-per-cell variant for Tri3 / Qua4 (gl_kernels_small2d.cu)
 int launch_bdb_tile(const IntegParams &p, int sd, void *stream); // register-tiled variant for Hex20 / Tet10 (gl_kernels_tile.cu)
 int launch_bdb_syrk(const IntegParams &p, int sd, void *stream); // FP64 tensor-core (DMMA) symmetric rank-ng update for Hex20 / Tet10 (gl_kernels_syrk.cu)
+int launch_bdb_qua8(const IntegParams &p, int sd, void *stream); // FP64 tensor-core (DMMA) geometric tensors for Qua8, plane / axisymmetric (gl_kernels_qua8.cu)
 
 // fused scalar-dof cases (gl_kernels_scalar.cu): any subset of mat_01_nsn (bit 0), mat_03_btb (bit 1), vec_01_ns (bit 2),
 // vec_03_bv (bit 3) from one geometry pass; uniform coefficients

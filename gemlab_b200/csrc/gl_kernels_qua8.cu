@@ -1,0 +1,339 @@
+// gl_kernels_qua8.cu -- Qua8 stiffness on the FP64 TENSOR CORES, plane and axisymmetric: integ::mat_10_bdb
+// (src/integ/mat_10_bdb.rs:121-233, the axisymmetric branch :213-233) with a uniform modulus D.  The heavier half of
+// BASELINE.json configs[4] (mixed Tri3 / Qua8, axisymmetric).
+//
+// Algebra (gl_kernels_bdb.cu): with the per-node vector g(m) = (B(m,0), B(m,1) [, N(m)/r]) and c' = det.w.alpha [.r],
+//     P[k][l](m,n) = sum_p c'_p g_p(m)[k] g_p(n)[l],        K(2m+i, 2n+j) = sum_kl D'_(ik)(jl) P[k][l](m,n)   (once per node pair).
+// The register-blocked kernel accumulates P with DFMA from per-node records in shared memory and is bound by the shared-memory
+// pipe (ncu, profiles/r02_ncu_full_qua8_axisym_bdb_summary.json: LDS wavefronts 78 % of peak, FP64 pipe 35 %, a quarter of the
+// stall samples at CTA barriers).  Here P = V^T diag(c') V is formed by mma.sync.m8n8k4.f64 with the columns of V ordered
+// COMPONENT-MAJOR, V[p][8k + m] = g_p(m)[k]: Qua8 has exactly eight nodes, so the 8 x 8 tile (I, J) of P is P[I][J](., .) and its
+// accumulator fragment gives lane (ar, ak) the entries (m, n) = (2ak + e, ar), e = 0, 1, of EVERY component pair -- the lane owns
+// the complete geometric tensors of two node pairs and contracts them with D' in registers (compile-time sparsity pattern); no
+// second trip through shared memory, no pair table.  Only the upper tiles (I <= J) are computed (6 of 9 axisymmetric, 3 of 4
+// plane); P[J][I](m,n) = P[I][J](n,m) sits in lane (2ak + e, ar >> 1) as element ar & 1 and is fetched with shuffles.
+//
+// Mapping: ONE WARP PER THREE CELLS, no barrier wider than a warp, 8 warps per CTA, 2 CTAs per SM.  Per triple:
+//   A  gather (Mesh::set_pad, src/mesh/mesh.rs:448-456): lane = (cell, node); point ids two triples ahead, coordinates one;
+//   B  geometry, lane = (cell, Gauss point), in the ORACLE'S operation order (gl_geom.cuh): J = Xt.L, closed-form inverse, det,
+//      r = sum N.x0; B = L.inv(J), N/r -> V (shared memory, dof-major, conflict-free strides), c';
+//   C  per cell: ceil(ng/4) k-steps of 6 (3) DMMA, the scaled operand c' V formed in registers; transposed tiles by shuffle;
+//      contraction with D'; the lane's two 2 x 2 blocks go to the staged element block as 16-byte stores (odd fragment rows
+//      store their upper half first: conflict-free);
+//   D  the triple (3 x 2,048 contiguous bytes on single-kind meshes; runs of consecutive blocks on mixed ones) leaves with bulk
+//      async copies (L2 evict-first).
+// Covered: uniform D (any pattern), rules of at most 10 points, tight blocks that overwrite a 16-byte aligned buffer; everything
+// else stays on gl_kernels_bdb.cu.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "gl_geom.cuh"
+#include "gl_internal.hpp"
+
+namespace gl {
+
+namespace {
+
+// strain-displacement column (node, j) in 2D: entries q -> (Mandel row, component of g); component 2 is the hoop value N/r
+// (calc_bb_matrix, src/integ/mat_10_bdb.rs:238-278)
+__host__ __device__ constexpr int q8_col_n(bool axi, int j) { return j == 0 ? (axi ? 3 : 2) : 2; }
+__host__ __device__ constexpr int q8_col_row(int j, int q) { return j == 0 ? (q == 0 ? 0 : (q == 1 ? 3 : 2)) : (q == 0 ? 1 : 3); }
+__host__ __device__ constexpr int q8_col_comp(int j, int q) { return j == 0 ? (q == 0 ? 0 : (q == 1 ? 1 : 2)) : (q == 0 ? 1 : 0); }
+// PAT 0 general, PAT 2 symmetric with uncoupled normal / diagonal shear blocks (exact zeros)
+__host__ __device__ constexpr bool q8_nz(int pat, int a, int b) { return pat < 2 ? true : ((a < 3 && b < 3) || a == b); }
+
+struct Qua8Consts {
+    double d[16]; // d'[a][b] = f_a f_b d[a][b] (row-major 4 x 4), f = 1 for the normal rows, 1/sqrt(2) for the shear row
+};
+
+__device__ __forceinline__ unsigned q8_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void q8_dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double q8_select(int c, double a, double b) { // c ? a : b
+    double r;
+    asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\nselp.f64 %0, %1, %2, p;\n}" : "=d"(r) : "d"(a), "d"(b), "r"(c));
+    return r;
+}
+
+constexpr int Q8_G = 3;        // cells per warp
+constexpr int Q8_WARPS = 8;    // warps per CTA
+constexpr int Q8_CTAS = 2;     // CTAs per SM
+constexpr int Q8_PS = 12;      // V is stored dof-major, Vt[col][p] at col PS + p; PS = 12 (mod 16): the fragment loads of a half-warp
+                               // (4 columns x 4 Gauss points) hit 16 distinct bank pairs
+constexpr int Q8_XS = 18;      // coordinates of a cell (16 doubles + 2): the three cells of a warp read distinct banks
+constexpr int Q8_KB = 256;     // element block
+
+template <bool AXI>
+struct Qua8Dims {
+    static constexpr int VD = AXI ? 3 : 2;
+    static constexpr int NV = 8 * VD;
+    static constexpr int CS = NV * Q8_PS + 9; // = 9 (mod 16): the (cell, Gauss point) lanes of a half-warp store one column conflict-free
+    static constexpr int VSZ = (Q8_G * CS + 1) & ~1;
+    static constexpr int WSZ = Q8_G * Q8_KB + VSZ + Q8_G * Q8_PS + Q8_G * Q8_XS; // doubles per warp (even)
+    static_assert(WSZ % 2 == 0, "16-byte aligned warp regions");
+};
+
+template <bool AXI, int PAT>
+__global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst) {
+    using T = Qua8Dims<AXI>;
+    constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = Q8_G, XS = Q8_XS, KB = Q8_KB;
+
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *Kst = smem + warp * T::WSZ; // [G][256]  staged element blocks (16-byte aligned: bulk copy source)
+    double *V = Kst + G * KB;           // [G][CS]   Vt[cell][8k + m][p]
+    double *cc = V + T::VSZ;            // [G][PS]   c'_p
+    double *Xs = cc + G * PS;           // [G][XS]   X[2m + j]
+
+    const int ng = p.ng;
+    const int KS = (ng + 3) >> 2;
+    const int ar = lane >> 2, ak = lane & 3;
+
+    // phase B role: lane = (cell of the triple, Gauss point); its rows of the reference-element table stay in registers
+    const bool vl = lane < G * ng;
+    const int bg = vl ? lane / ng : 0, bp = vl ? lane - bg * ng : 0;
+    double l[16], nsh[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) l[i] = p.rule[ng * 9 + bp * 16 + i];
+#pragma unroll
+    for (int m = 0; m < 8; m++) nsh[m] = AXI ? p.rule[ng + bp * 8 + m] : 0.0;
+    const double wgt = p.rule[bp];
+
+    // phase A role: lane = (cell of the triple, node)
+    const int ag = lane >> 3, am = lane & 7;
+    const unsigned long long ncell = p.hi - p.lo;
+    const unsigned long long ntriple = (ncell + G - 1) / G;
+    const unsigned long long tstride = (unsigned long long)gridDim.x * Q8_WARPS;
+    auto load_pid = [&](unsigned long long t) -> unsigned int {
+        const unsigned long long c = t * G + ag;
+        return (lane < 8 * G && t < ntriple && c < ncell) ? p.conn[(unsigned long long)am * p.ncell_k + p.lo + c] : 0u;
+    };
+    unsigned long long t = (unsigned long long)blockIdx.x * Q8_WARPS + warp;
+    unsigned int pid = load_pid(t);
+    double gx0 = 0.0, gx1 = 0.0;
+    if (lane < 8 * G) {
+        gx0 = p.coords[pid];
+        gx1 = p.coords[p.npoint + pid];
+    }
+    pid = load_pid(t + tstride);
+
+    unsigned long long pol; // the element matrices are written once: keep them from flushing the mesh out of L2
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+
+    for (; t < ntriple; t += tstride) {
+        const unsigned long long c0 = t * G; // first cell of the triple, relative to p.lo
+        const int nv = (int)(ncell - c0 < (unsigned long long)G ? ncell - c0 : (unsigned long long)G);
+        // ---- phase A: publish the coordinates, prefetch --------------------------------------------------------------------
+        if (lane < 8 * G) {
+            *reinterpret_cast<double2 *>(Xs + ag * XS + 2 * am) = make_double2(gx0, gx1);
+            gx0 = p.coords[pid];
+            gx1 = p.coords[p.npoint + pid];
+        }
+        pid = load_pid(t + 2 * tstride);
+        // destination of the lane's cell (lanes 0 .. nv-1), needed at the very end
+        unsigned long long off = 0;
+        if (lane < nv) {
+            const unsigned long long cell = p.lo + c0 + lane;
+            if (p.out_off) off = p.out_off[cell] - p.out_base;
+            else off = ((p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.cell_begin) * (unsigned long long)KB;
+        }
+        __syncwarp();
+
+        // ---- phase B: geometry, lane = (cell, Gauss point) ----------------------------------------------------------------
+        {
+            const double *X = Xs + bg * XS;
+            double J[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            double r = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const double2 xx = *reinterpret_cast<const double2 *>(X + 2 * m);
+                J[0][0] = geom::add(J[0][0], geom::mul(xx.x, l[2 * m]));
+                J[0][1] = geom::add(J[0][1], geom::mul(xx.x, l[2 * m + 1]));
+                J[1][0] = geom::add(J[1][0], geom::mul(xx.y, l[2 * m]));
+                J[1][1] = geom::add(J[1][1], geom::mul(xx.y, l[2 * m + 1]));
+                if constexpr (AXI) r = geom::add(r, geom::mul(nsh[m], xx.x)); // radius_at_ip: r = sum N.x0
+            }
+            double Ji[2][2];
+            const double det = geom::invert(J, Ji);
+            const bool live = vl && bg < nv;
+            if (live && fabs(det) <= ZERO_DETERMINANT) {
+                const unsigned long long cell = p.lo + c0 + bg;
+                atomicMin(p.err_cell, p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell);
+            }
+            double coef = det * wgt * p.alpha;
+            double rinv = 0.0;
+            if constexpr (AXI) {
+                rinv = 1.0 / r;
+                coef *= r;
+            }
+            if (vl) {
+                double *Vq = V + bg * CS + bp;
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    Vq[m * PS] = fma(l[2 * m + 1], Ji[1][0], l[2 * m] * Ji[0][0]);
+                    Vq[(8 + m) * PS] = fma(l[2 * m + 1], Ji[1][1], l[2 * m] * Ji[0][1]);
+                    if constexpr (AXI) Vq[(16 + m) * PS] = nsh[m] * rinv;
+                }
+                cc[bg * PS + bp] = coef;
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the previous bulk copies have left Kst
+        }
+        __syncwarp();
+
+        // ---- phase C: per cell, P on the tensor cores, contraction with D', staging ------------------------------------------
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            double P[VD][VD][2];
+#pragma unroll
+            for (int I = 0; I < VD; I++)
+#pragma unroll
+                for (int Jt = 0; Jt < VD; Jt++) P[I][Jt][0] = P[I][Jt][1] = 0.0;
+#pragma unroll 1
+            for (int ks = 0; ks < KS; ks++) {
+                const int row = 4 * ks + ak;
+                const bool ok = row < ng; // the padding Gauss points of the last k-step contribute zeros
+                const double c = ok ? cc[g * PS + row] : 0.0;
+                const double *vr = V + g * CS + ar * PS + row;
+                double v[VD], vs[VD];
+#pragma unroll
+                for (int k = 0; k < VD; k++) {
+                    v[k] = ok ? vr[8 * k * PS] : 0.0;
+                    vs[k] = v[k] * c;
+                }
+                // C[r][q] += sum_k A[r][k] B[k][q] with A[r][k] = V[k][8J + r], B[k][q] = c_k V[k][8I + q]: C[r][q] = P[I][J](m = q, n = r)
+#pragma unroll
+                for (int I = 0; I < VD; I++)
+#pragma unroll
+                    for (int Jt = I; Jt < VD; Jt++) q8_dmma(P[I][Jt][0], P[I][Jt][1], v[Jt], vs[I]);
+            }
+            // the lane holds P[I][J](2ak + e, ar), I <= J.  P[J][I](2ak + e, ar) = P[I][J](ar, 2ak + e): lane (2ak + e, ar >> 1), element ar & 1
+#pragma unroll
+            for (int I = 0; I < VD; I++)
+#pragma unroll
+                for (int Jt = I + 1; Jt < VD; Jt++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int src = (2 * ak + e) * 4 + (ar >> 1);
+                        const double t0 = __shfl_sync(0xffffffffu, P[I][Jt][0], src);
+                        const double t1 = __shfl_sync(0xffffffffu, P[I][Jt][1], src);
+                        P[Jt][I][e] = q8_select(ar & 1, t1, t0);
+                    }
+            // K(2m + i, 2n + j) = sum_qr d'[row(i,q)][row(j,r)] P[comp(i,q)][comp(j,r)](m,n)   (add_to_kk / add_to_kk_axisymmetric)
+            double Kb[2][2][2]; // [e][i][j]
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        double s = 0.0;
+                        bool have = false;
+#pragma unroll
+                        for (int q = 0; q < q8_col_n(AXI, i); q++)
+#pragma unroll
+                            for (int rr = 0; rr < q8_col_n(AXI, j); rr++) {
+                                const int ra = q8_col_row(i, q), rb = q8_col_row(j, rr);
+                                if (!q8_nz(PAT, ra, rb)) continue;
+                                const double pv = P[q8_col_comp(i, q)][q8_col_comp(j, rr)][e];
+                                s = have ? fma(cst.d[ra * 4 + rb], pv, s) : cst.d[ra * 4 + rb] * pv;
+                                have = true;
+                            }
+                        Kb[e][i][j] = s;
+                    }
+            // rows 4ak + 2e + i of columns 2ar + j, column-major 16 x 16; odd fragment rows store e = 1 first: the eight lanes of a
+            // quarter-warp then write eight distinct 16-byte slots of the 128-byte bank window
+            double *Kc = Kst + g * KB + 16 * (2 * ar) + 4 * ak;
+            const int e0 = ar & 1;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int e = e0 ^ s;
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const double a = q8_select(e, Kb[1][0][j], Kb[0][0][j]);
+                    const double b = q8_select(e, Kb[1][1][j], Kb[0][1][j]);
+                    *reinterpret_cast<double2 *>(Kc + 16 * j + 2 * e) = make_double2(a, b);
+                }
+            }
+        }
+
+        // ---- phase D: ship ---------------------------------------------------------------------------------------------------
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const unsigned long long o1 = __shfl_sync(0xffffffffu, off, 1), o2 = __shfl_sync(0xffffffffu, off, 2);
+        if (lane == 0) {
+            // runs of blocks that are consecutive in the output leave as one copy (always, on single-kind meshes)
+            const bool c01 = nv > 1 && o1 == off + KB, c12 = nv > 2 && o2 == o1 + KB;
+            auto ship = [&](unsigned long long o, int first, int count) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(p.out + o),
+                             "r"(q8_smem_u32(Kst + first * KB)), "r"((unsigned)(count * KB * sizeof(double))), "l"(pol)
+                             : "memory");
+            };
+            ship(off, 0, 1 + (c01 ? 1 : 0) + (c01 && c12 ? 1 : 0));
+            if (nv > 1 && !c01) ship(o1, 1, 1 + (c12 ? 1 : 0));
+            if (nv > 2 && !c12) ship(o2, 2, 1);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <bool AXI>
+int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, void *stream) {
+    using T = Qua8Dims<AXI>;
+    const size_t smem = sizeof(double) * (size_t)Q8_WARPS * T::WSZ;
+    typedef void (*kern_t)(const IntegParams, const Qua8Consts);
+    kern_t kern = pat == 2 ? qua8_kernel<AXI, 2> : qua8_kernel<AXI, 0>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long ntriple = (p.hi - p.lo + Q8_G - 1) / Q8_G;
+    unsigned long long grid = (unsigned long long)nsm * Q8_CTAS; // persistent: warps stride over the triples
+    if (const char *e = tuning_env("GL_QUA8_GRID")) grid = (unsigned long long)atoi(e);
+    const unsigned long long need = (ntriple + Q8_WARPS - 1) / Q8_WARPS;
+    if (grid > need) grid = need;
+    if (grid == 0) return 0;
+    kern<<<(unsigned)grid, 32 * Q8_WARPS, smem, (cudaStream_t)stream>>>(p, cst);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    note_kernel("qua8_dmma<axi=%d,pat=%d>", AXI ? 1 : 0, pat == 2 ? 2 : 0);
+    return 1;
+}
+
+} // namespace
+
+int launch_bdb_qua8(const IntegParams &p, int sd, void *stream) {
+    if (sd != 2 || p.op != GL_OP_MAT_10_BDB || p.nnode != 8) return 0;
+    if (p.coef != nullptr || p.scatter_pos != nullptr || p.sigma != nullptr) return 0; // record moduli, fused assembly: gl_kernels_bdb.cu
+    if (Q8_G * p.ng > 32) return 0;
+    if (p.size_r != 16 || p.size_c != 16) return 0;
+    const bool tight = p.nrow == 16 && p.ncol == 16 && p.ii0 == 0 && p.jj0 == 0;
+    if (!(tight && p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) return 0; // general store epilogue: gl_kernels_bdb.cu
+    if (tuning_env("GL_DISABLE_QUA8")) return 0;
+
+    Qua8Consts cst;
+    const double hs = 0.70710678118654752440084436210484903928;
+    bool sym = true;
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) {
+            const double fa = a < 3 ? 1.0 : hs, fb = b < 3 ? 1.0 : hs;
+            cst.d[a * 4 + b] = p.coef_uniform[a + b * 4] * fa * fb;
+            if (p.coef_uniform[a + b * 4] != p.coef_uniform[b + a * 4]) sym = false;
+        }
+    int pat = 0;
+    if (sym) {
+        pat = 2;
+        for (int a = 0; a < 4; a++)
+            for (int b = 0; b < 4; b++)
+                if (!q8_nz(2, a, b) && cst.d[a * 4 + b] != 0.0) pat = 0;
+    }
+    if (const char *e = tuning_env("GL_BDB_PATTERN")) {
+        if (atoi(e) < pat) pat = 0;
+    }
+    return p.axisym ? launch_qua8_kind<true>(p, cst, pat, stream) : launch_qua8_kind<false>(p, cst, pat, stream);
+}
+
+} // namespace gl

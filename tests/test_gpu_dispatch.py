@@ -41,8 +41,10 @@ FAMILIES = [
     ("tet4", "mat_10_bdb", {}, "bdb<nn=4,sd=3"),
     ("qua4", "mat_10_bdb", {}, "small2d<nn=4,axi=0"),
     ("tri3", "mat_10_bdb", {}, "small2d<nn=3,axi=0"),
-    ("qua8", "mat_10_bdb", {}, "bdb<nn=8,sd=2,axi=0"),
-    ("qua8", "mat_10_bdb", {"axisymmetric": True}, "bdb<nn=8,sd=2,axi=1"),
+    ("qua8", "mat_10_bdb", {}, "qua8_dmma<axi=0,pat=2>"),
+    ("qua8", "mat_10_bdb", {"axisymmetric": True}, "qua8_dmma<axi=1,pat=2>"),
+    ("qua8", "mat_10_bdb", {"ngauss": 16}, "bdb<nn=8,sd=2,axi=0"),
+    ("qua8", "mat_10_bdb", {"axisymmetric": True, "clear": False}, "bdb<nn=8,sd=2,axi=1,pat=2,gen>"),
     ("qua9", "mat_10_bdb", {}, "bdb<nn=9,sd=2"),
     ("tri6", "mat_10_bdb", {}, "bdb<nn=6,sd=2"),
     ("tet10", "mat_01_nsn", {}, "mass_dmma<nn=10,sd=3"),
@@ -96,6 +98,54 @@ def test_hex20_tensor_core_stiffness(ctx, rule, structure):
         got = integ.mat_10_bdb(ctx, dmesh, (b, e), CommonArgs(ngauss=rule), Coef.uniform(dd))
         assert ctx.last_kernel() == f"syrk_dmma<nn=20,pat={ {'isotropic': 2, 'symmetric': 1, 'general': 0}[structure] }>"
         assert rel_err(got, ref[b * 3600:e * 3600], np.arange(e - b + 1) * 3600) <= TOL, f"rule {rule} range {b}:{e}"
+
+
+@pytest.mark.parametrize("axisymmetric", [False, True])
+@pytest.mark.parametrize("rule", [1, 4, 9])
+@pytest.mark.parametrize("structure", ["isotropic", "symmetric", "general"])
+def test_qua8_tensor_core_stiffness(ctx, axisymmetric, rule, structure):
+    """mat_10_bdb on jittered Qua8 cells through the DMMA kernel of gl_kernels_qua8.cu vs the oracle (src/integ/mat_10_bdb.rs:179-233,
+    plane and axisymmetric), every rule it accepts, isotropic / symmetric / general moduli; ranges that do not fill the three
+    cells of a warp, and more triples than one CTA holds warps."""
+    mesh = make_mesh("qua8", n=7, seed=11)  # 56 cells
+    rng = np.random.default_rng(37)
+    dd = iso(2) if structure == "isotropic" else random_coef("mat_10_bdb", 2, 1, rng, spd=(structure == "symmetric"))[0]
+    dmesh = ctx.upload(mesh)
+    ref = oracle_integ("mat_10_bdb", mesh, dd, ngauss=rule, axisymmetric=axisymmetric)
+    for b, e in [(0, mesh.ncell), (0, 1), (3, 5), (5, 19), (1, 56), (2, 27)]:
+        got = integ.mat_10_bdb(ctx, dmesh, (b, e), CommonArgs(ngauss=rule, axisymmetric=axisymmetric), Coef.uniform(dd))
+        assert ctx.last_kernel() == f"qua8_dmma<axi={int(axisymmetric)},pat={2 if structure == 'isotropic' else 0}>"
+        assert rel_err(got, ref[b * 256:e * 256], np.arange(e - b + 1) * 256) <= TOL, f"rule {rule} range {b}:{e}"
+
+
+def test_qua8_tensor_core_on_mixed_mesh_and_guard_band(ctx):
+    """The Qua8 stripes of a mixed Tri3 / Qua8 mesh (BASELINE.json configs[4]) leave as runs of consecutive blocks; nothing
+    outside the integrated range is written; zero determinants are reported with the smallest cell id."""
+    from test_gpu_parity import mixed_mesh_2d
+    mesh = mixed_mesh_2d(n=7)
+    dmesh = ctx.upload(mesh)
+    dd = iso(2)
+    args = CommonArgs(axisymmetric=True)
+    off = integ.out_offsets(dmesh, "mat_10_bdb", None, args)
+    ref = oracle_integ("mat_10_bdb", mesh, dd, axisymmetric=True)
+    for b, e in [(0, mesh.ncell), (2, mesh.ncell - 3), (8, 30)]:
+        import torch
+        n = int(off[e] - off[b])
+        buf = torch.full((n + 64,), 7.25, dtype=torch.float64, device="cuda")
+        integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.uniform(dd), out=buf[32:32 + n])
+        got = buf.cpu().numpy()
+        assert np.all(got[:32] == 7.25) and np.all(got[32 + n:] == 7.25)
+        assert rel_err(got[32:32 + n], ref[int(off[b]):int(off[e])], off[b:e + 1] - off[b]) <= TOL
+    # homogeneous Qua8 mesh with a collapsed cell: the reference's error string and the smallest failing cell
+    q8 = make_mesh("qua8", n=4)
+    conn = q8.conn_matrix()
+    bad = 7
+    q8.coords[conn[bad].astype(np.int64)] = q8.coords[int(conn[bad][0])]
+    dq = ctx.upload(q8)
+    with pytest.raises(g.GemlabError, match="cannot compute inverse due to zero determinant") as ei:
+        integ.mat_10_bdb(ctx, dq, (2, q8.ncell), CommonArgs(), Coef.uniform(dd))
+    assert ctx.last_kernel().startswith("qua8_dmma")
+    assert ei.value.cell == bad
 
 
 def test_hex20_general_blocks_and_accumulation(ctx):
@@ -289,26 +339,28 @@ def test_general_blocks_and_accumulation_on_the_register_blocked_kernel(ctx, kin
     else:
         coef = Coef.per_gauss(random_coef("mat_10_bdb", mesh.ndim, mesh.ncell * ng, rng))
     base = integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), coef).reshape(mesh.ncell, nd, nd)
+    # the tight call may run on another kernel family (Qua8: the tensor-core kernel) whose sums round differently
+    tol = dict(rtol=1e-12, atol=1e-13 * float(np.abs(base).max()))
     out = np.full(base.size, 12.5)
     integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(clear=False), coef, out=out)
     fam = ctx.last_kernel()
     assert not fam.startswith("generic"), fam
     assert fam.endswith(",gen>"), fam
-    np.testing.assert_allclose(out.reshape(base.shape), base + 12.5, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(out.reshape(base.shape), base + 12.5, **tol)
     nrow, ncol = nd + 5, nd + 2
     args = CommonArgs(ii0=3, jj0=1, nrow=nrow, ncol=ncol)
     out = np.full(mesh.ncell * nrow * ncol, 99.0)
     integ.mat_10_bdb(ctx, dmesh, None, args, coef, out=out)
     assert ctx.last_kernel().endswith(",gen>"), ctx.last_kernel()
     blk = out.reshape(mesh.ncell, ncol, nrow)  # [cell][col][row]
-    np.testing.assert_allclose(blk[:, 1:1 + nd, 3:3 + nd], base, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(blk[:, 1:1 + nd, 3:3 + nd], base, **tol)
     outside = blk.copy()
     outside[:, 1:1 + nd, 3:3 + nd] = 0.0
     assert np.count_nonzero(outside) == 0
     out2 = np.full(out.size, 2.0)
     integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(ii0=3, jj0=1, nrow=nrow, ncol=ncol, clear=False), coef, out=out2)
     blk2 = out2.reshape(mesh.ncell, ncol, nrow)
-    np.testing.assert_allclose(blk2[:, 1:1 + nd, 3:3 + nd], base + 2.0, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(blk2[:, 1:1 + nd, 3:3 + nd], base + 2.0, **tol)
     rest = blk2.copy()
     rest[:, 1:1 + nd, 3:3 + nd] = 2.0
     assert np.all(rest == 2.0)
