@@ -271,17 +271,15 @@ def run_config_record(torch, ctx, po, idx, scale, hbm_peak, fp64_peak, threads):
     kernels = []
 
     def step(record=False):
-        # the stiffness matrix on its own; the scalar-dof cases (mass + source, conductivity + flux) from ONE geometry pass
-        fused = [(op, Coef.uniform(c), o) for (op, c), o in zip(cfg["cases"], outs) if op != "mat_10_bdb"]
-        for (op, c), o in zip(cfg["cases"], outs):
-            if op == "mat_10_bdb":
-                integ.mat_10_bdb(ctx, dm, None, a, Coef.uniform(c), out=o)
-                if record:
-                    kernels.append(ctx.last_kernel())
-        if fused:
-            integ.fused(ctx, dm, None, a, fused)
-            if record:
-                kernels.append(ctx.last_kernel())
+        # every case of the configuration from ONE gl_integ_fused call: the library shares the geometry pass where it has a kernel
+        # for it (mass + source; conductivity + flux; on Qua8 cells stiffness + conductivity + flux) and runs the rest in turn
+        items = [(op, Coef.uniform(c), o) for (op, c), o in zip(cfg["cases"], outs)]
+        if len(items) == 1:
+            integ.mat_10_bdb(ctx, dm, None, a, items[0][1], out=items[0][2])
+        else:
+            integ.fused(ctx, dm, None, a, items)
+        if record:
+            kernels.extend(ctx.last_kernel().split(" + "))
 
     launches0 = ctx.launch_count()
     step(record=True)

@@ -897,11 +897,55 @@ static int ensure_point_major(gl_ctx *ctx, gl_mesh *mesh) {
     return GL_OK;
 }
 
+// gl_ctx_last_kernel: the kernel of the most recent launch; inside gl_integ_fused, every distinct kernel of the call joined by " + "
+static void set_last_kernel(gl_ctx *ctx) {
+    const std::string k = noted_kernel();
+    if (!ctx->collect_kernels || ctx->last_kernel.empty()) {
+        ctx->last_kernel = k;
+        return;
+    }
+    const std::string hay = " + " + ctx->last_kernel + " + ";
+    if (hay.find(" + " + k + " + ") == std::string::npos) ctx->last_kernel += " + " + k;
+}
+struct KernelCollector { // scope of one gl_integ_fused call
+    gl_ctx *ctx;
+    explicit KernelCollector(gl_ctx *c) : ctx(c) {
+        ctx->collect_kernels = true;
+        ctx->last_kernel.clear();
+    }
+    ~KernelCollector() { ctx->collect_kernels = false; }
+};
+
+// block offsets of a bucket's cells on the device (mixed meshes), cached per block layout
+static int bucket_device_offsets(gl_ctx *ctx, gl_mesh_bucket &bk, const std::vector<uint64_t> *pre, const BlockKey &key,
+                                 const unsigned long long **out) {
+    auto it = bk.d_out_off.find(key);
+    if (it == bk.d_out_off.end()) {
+        std::vector<unsigned long long> offs(bk.ncell);
+        for (uint64_t c = 0; c < bk.ncell; c++) offs[c] = (*pre)[bk.h_cell_ids[c]];
+        unsigned long long *d = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&d, offs.size() * sizeof(unsigned long long)));
+        CUDA_TRY(ctx, cudaMemcpy(d, offs.data(), offs.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        it = bk.d_out_off.emplace(key, d).first;
+    }
+    *out = it->second;
+    return GL_OK;
+}
+
+// gl_integ_fused, stiffness + conductivity matrix + flux vector: the scalar cases the Qua8 buckets take from the stiffness kernel's
+// geometric tensors (gl_kernels_qua8.cu); `done` marks the buckets served that way
+struct Qua8Fusion {
+    const ScalarFused *f;
+    const std::vector<uint64_t> *mpre, *vpre;
+    BlockKey mkey, vkey;
+    std::vector<char> *done;
+};
+
 // launches the kernels that integrate original cells [b, e) into the DEVICE buffer d_out (block of cell b at d_out[0])
 static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t e, const gl_args *a,
                         const CoefResolved &cr, uint64_t coef_begin, double *d_out, const double *d_sigma = nullptr,
                         double *d_force = nullptr, bool *force_done = nullptr, const uint32_t *sc_pos = nullptr, double *sc_vals = nullptr,
-                        int only_bucket = -1) {
+                        int only_bucket = -1, Qua8Fusion *qf = nullptr) {
     if (b == e) return GL_OK;
     const bool explicit_block = a->nrow != 0 || (op_is_matrix(op) && a->ncol != 0);
     const std::vector<uint64_t> *pre = nullptr;
@@ -1026,10 +1070,25 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
             if (nl == 0) return fail(ctx, GL_ERR_INVALID_ARG, "internal: no kernel with a scatter epilogue took the configuration");
             if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
             ctx->launches += (uint64_t)nl;
-            ctx->last_kernel = noted_kernel();
+            set_last_kernel(ctx);
             continue;
         }
-        if (op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
+        if (qf && op == GL_OP_MAT_10_BDB && bk.kind == GL_QUA8 && mesh->ndim == 2) {
+            ScalarFused fb = *qf->f;
+            if (qf->mpre) {
+                st = bucket_device_offsets(ctx, bk, qf->mpre, qf->mkey, &fb.moff);
+                if (st) return st;
+                fb.mbase = (*qf->mpre)[b];
+            }
+            if (qf->vpre) {
+                st = bucket_device_offsets(ctx, bk, qf->vpre, qf->vkey, &fb.voff);
+                if (st) return st;
+                fb.vbase = (*qf->vpre)[b];
+            }
+            nl = launch_bdb_qua8(p, mesh->ndim, ctx->stream, &fb);
+            if (nl > 0) (*qf->done)[bi] = 1;
+        }
+        if (nl == 0 && op == GL_OP_MAT_10_BDB) nl = launch_hex8_bdb(p, ctx->stream);
         if (nl == 0 && op == GL_OP_MAT_10_BDB && d_sigma == nullptr) nl = launch_hex8_gauss(p, ctx->stream);
         if (force_done) *force_done = nl > 0 && d_sigma != nullptr;
         if (nl == 0 && op == GL_OP_MAT_10_BDB && gd == mesh->ndim) nl = launch_bdb_small2d(p, mesh->ndim, ctx->stream);
@@ -1059,7 +1118,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
         }
         if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
         ctx->launches += (uint64_t)nl;
-        ctx->last_kernel = noted_kernel();
+        set_last_kernel(ctx);
     }
     return GL_OK;
 }
@@ -1385,6 +1444,7 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
     gl_mesh *mesh = const_cast<gl_mesh *>(cmesh);
     if (!mesh || !a || !items || nitems <= 0) return fail(ctx, GL_ERR_INVALID_ARG, "null pointer");
     if (b > e || e > mesh->ncell) return fail(ctx, GL_ERR_CELL_RANGE);
+    KernelCollector collector(ctx);
     if (a->packed) { // packed matrices go through the pack pass of gl_integ
         for (int i = 0; i < nitems; i++) {
             int st = gl_integ(ctx, cmesh, items[i].op, b, e, a, items[i].coef, items[i].out);
@@ -1432,6 +1492,35 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
             return GL_OK;
         }
     }
+    // stiffness + scalar-dof cases in one call (BASELINE.json configs[4]: mat_10_bdb + mat_03_btb + vec_03_bv): the stiffness runs on
+    // its own kernels and the scalar cases share the fused scalar kernel -- except on Qua8 buckets, which take mat_03_btb / vec_03_bv
+    // from the geometric tensors of the tensor-core stiffness kernel (gl_kernels_qua8.cu)
+    const gl_fused_item *const all_items = items;
+    const int all_nitems = nitems;
+    const gl_fused_item *ik = nullptr;
+    gl_fused_item sitems[4];
+    {
+        int nk = 0, ns = 0;
+        bool ok = nitems >= 2 && nitems <= 5 && e > b;
+        for (int i = 0; i < nitems && ok; i++) {
+            if (items[i].op == GL_OP_MAT_10_BDB) {
+                nk++;
+                ik = &items[i];
+            } else if (scalar_family(items[i].op) && ns < 4) {
+                sitems[ns++] = items[i];
+            } else {
+                ok = false;
+            }
+        }
+        ok = ok && nk == 1 && ns >= 1 && ik->coef && ik->out && ik->coef->mode == GL_COEF_UNIFORM && ik->coef->data &&
+             ik->out->location == GL_DEVICE && ik->out->ptr;
+        if (ok) {
+            items = sitems;
+            nitems = ns;
+        } else {
+            ik = nullptr;
+        }
+    }
     // can the items share one kernel?
     bool fusable = nitems <= 4 && a->clear && a->ii0 == 0 && a->jj0 == 0 && a->nrow == 0 && a->ncol == 0 && e > b;
     int mask = 0;
@@ -1447,8 +1536,8 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
     for (auto &bk : mesh->buckets)
         if (kind_geo_ndim(bk.kind) != mesh->ndim) fusable = false;
     if (!fusable) {
-        for (int i = 0; i < nitems; i++) {
-            int st = gl_integ(ctx, cmesh, items[i].op, b, e, a, items[i].coef, items[i].out);
+        for (int i = 0; i < all_nitems; i++) {
+            int st = gl_integ(ctx, cmesh, all_items[i].op, b, e, a, all_items[i].coef, all_items[i].out);
             if (st) return st;
         }
         return GL_OK;
@@ -1478,20 +1567,22 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
         if (mat_op >= 0) mpre = mesh_prefix(mesh, mat_op, a, &mkey, &st);
         if (vec_op >= 0) vpre = mesh_prefix(mesh, vec_op, a, &vkey, &st);
     }
-    auto device_offsets = [&](gl_mesh_bucket &bk, const std::vector<uint64_t> *pre, const BlockKey &key, const unsigned long long **out) -> int {
-        auto it = bk.d_out_off.find(key);
-        if (it == bk.d_out_off.end()) {
-            std::vector<unsigned long long> offs(bk.ncell);
-            for (uint64_t c = 0; c < bk.ncell; c++) offs[c] = (*pre)[bk.h_cell_ids[c]];
-            unsigned long long *d = nullptr;
-            CUDA_TRY(ctx, cudaMalloc(&d, offs.size() * sizeof(unsigned long long)));
-            CUDA_TRY(ctx, cudaMemcpy(d, offs.data(), offs.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-            it = bk.d_out_off.emplace(key, d).first;
-        }
-        *out = it->second;
-        return GL_OK;
-    };
-    for (auto &bk : mesh->buckets) {
+    std::vector<char> done(mesh->buckets.size(), 0);
+    if (ik) {
+        uint64_t total = 0;
+        st = range_layout(mesh, GL_OP_MAT_10_BDB, b, e, a, &total, nullptr);
+        if (st) return fail(ctx, st);
+        if (ik->out->capacity < total) return fail(ctx, GL_ERR_OUT_CAPACITY);
+        CoefResolved crk;
+        st = resolve_coef(ctx, mesh, GL_OP_MAT_10_BDB, b, e, a, ik->coef, crk);
+        if (st) return st;
+        Qua8Fusion qf{&f, mpre, vpre, mkey, vkey, &done};
+        st = launch_range(ctx, mesh, GL_OP_MAT_10_BDB, b, e, a, crk, b, ik->out->ptr, nullptr, nullptr, nullptr, nullptr, nullptr, -1, &qf);
+        if (st) return st;
+    }
+    for (size_t bi = 0; bi < mesh->buckets.size(); bi++) {
+        if (done[bi]) continue; // served by the stiffness kernel
+        auto &bk = mesh->buckets[bi];
         uint64_t lo, hi;
         bucket_range(mesh, bk, b, e, lo, hi);
         if (lo >= hi) continue;
@@ -1522,12 +1613,12 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
         p.err_cell = ctx->d_err_cell;
         ScalarFused fb = f;
         if (mpre) {
-            st = device_offsets(bk, mpre, mkey, &fb.moff);
+            st = bucket_device_offsets(ctx, bk, mpre, mkey, &fb.moff);
             if (st) return st;
             fb.mbase = (*mpre)[b];
         }
         if (vpre) {
-            st = device_offsets(bk, vpre, vkey, &fb.voff);
+            st = bucket_device_offsets(ctx, bk, vpre, vkey, &fb.voff);
             if (st) return st;
             fb.vbase = (*vpre)[b];
         }
@@ -1535,7 +1626,7 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
         if (nl == 0) nl = launch_scalar_tpc(p, fb, mesh->ndim, ctx->stream);
         if (nl == 0) nl = launch_scalar_fused(p, fb, mesh->ndim, ctx->stream);
         if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");
-        if (nl > 0) ctx->last_kernel = noted_kernel();
+        if (nl > 0) set_last_kernel(ctx);
         if (nl == 0) { // kind not covered by the fused kernel: run the items one after the other for the whole range
             for (int i = 0; i < nitems; i++) {
                 int st2 = gl_integ(ctx, cmesh, items[i].op, b, e, a, items[i].coef, items[i].out);

@@ -131,7 +131,6 @@ bool bdb_covers(int nnode, int sd, int ng, bool axisym, bool record_moduli, bool
 int launch_bdb_small2d(const IntegParams &p, int sd, void *stream); // thread-per-cell variant for Tri3 / Qua4 (gl_kernels_small2d.cu)
 int launch_bdb_tile(const IntegParams &p, int sd, void *stream); // register-tiled variant for Hex20 / Tet10 (gl_kernels_tile.cu)
 int launch_bdb_syrk(const IntegParams &p, int sd, void *stream); // FP64 tensor-core (DMMA) symmetric rank-ng update for Hex20 / Tet10 (gl_kernels_syrk.cu)
-int launch_bdb_qua8(const IntegParams &p, int sd, void *stream); // FP64 tensor-core (DMMA) geometric tensors for Qua8, plane / axisymmetric (gl_kernels_qua8.cu)
 
 // fused scalar-dof cases (gl_kernels_scalar.cu): any subset of mat_01_nsn (bit 0), mat_03_btb (bit 1), vec_01_ns (bit 2),
 // vec_03_bv (bit 3) from one geometry pass; uniform coefficients
@@ -147,6 +146,9 @@ struct ScalarFused {
     unsigned long long vbase;
 };
 int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
+// FP64 tensor-core (DMMA) geometric tensors for Qua8 stiffness, plane / axisymmetric (gl_kernels_qua8.cu); `extra` (mask of mat_03_btb = 2,
+// vec_03_bv = 8) asks for the conductivity matrix and / or the flux vector from the same pass
+int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFused *extra = nullptr);
 // mat_01_nsn and/or vec_01_ns as a (cells x ng).(ng x entries) product on the FP64 tensor cores (gl_kernels_mass.cu); 0 if not covered
 // mat_03_btb and/or vec_03_bv, one thread per cell (gl_kernels_scalar_tpc.cu); 0 if not covered
 int launch_scalar_tpc(const IntegParams &p, const ScalarFused &f, int sd, void *stream);
@@ -195,6 +197,7 @@ struct gl_ctx {
     uint64_t last_error_cell = gl::NO_ERR_CELL;
     uint64_t launches = 0;
     std::string last_kernel; // kernel family of the most recent integration launch (gl_ctx_last_kernel)
+    bool collect_kernels = false; // inside gl_integ_fused: last_kernel accumulates every distinct kernel of the call
     unsigned long long *d_err_cell = nullptr;
     unsigned long long *d_work_counter = nullptr; // see IntegParams::work_counter
     int *d_coef_pat = nullptr; // result of the modulus-structure probe (device-resident PER_CELL moduli)

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "gl_geom.cuh"
 #include "gl_internal.hpp"
@@ -45,6 +46,17 @@ __host__ __device__ constexpr bool q8_nz(int pat, int a, int b) { return pat < 2
 
 struct Qua8Consts {
     double d[16]; // d'[a][b] = f_a f_b d[a][b] (row-major 4 x 4), f = 1 for the normal rows, 1/sqrt(2) for the shear row
+};
+
+// by-products of the same geometric tensors (gl_integ_fused: stiffness + conductivity matrix + flux vector, BASELINE.json configs[4]):
+//   mat_03_btb (src/integ/mat_03_btb.rs:50-131)  Kc(m,n) = t0 P[0][0] + t1 P[1][1] + t3/sqrt(2) (P[0][1] + P[1][0])   (same c', same alpha)
+//   vec_03_bv  (src/integ/vec_03_bv.rs)          b(m)    = sum_p c'_p (w0 B_p(m,0) + w1 B_p(m,1))
+struct Qua8Extra {
+    int mask; // 2: mat_03_btb, 8: vec_03_bv (the bits of ScalarFused::mask)
+    double t00, t11, t01, w0, w1;
+    double *out_m03, *out_v03;
+    const unsigned long long *moff, *voff; // mixed meshes: bucket-local cell -> absolute offset of its 8 x 8 block / 8-vector
+    unsigned long long mbase, vbase;
 };
 
 __device__ __forceinline__ unsigned q8_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -77,8 +89,8 @@ struct Qua8Dims {
     static_assert(WSZ % 2 == 0, "16-byte aligned warp regions");
 };
 
-template <bool AXI, int PAT>
-__global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst) {
+template <bool AXI, int PAT, bool EXTRA>
+__global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst, const Qua8Extra x) {
     using T = Qua8Dims<AXI>;
     constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = Q8_G, XS = Q8_XS, KB = Q8_KB;
 
@@ -127,20 +139,25 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
     for (; t < ntriple; t += tstride) {
         const unsigned long long c0 = t * G; // first cell of the triple, relative to p.lo
         const int nv = (int)(ncell - c0 < (unsigned long long)G ? ncell - c0 : (unsigned long long)G);
-        // ---- phase A: publish the coordinates, prefetch --------------------------------------------------------------------
+        // ---- phase A: destinations, publish the coordinates, prefetch ------------------------------------------------------
+        // destination of the lane's cell (lanes 0 .. nv-1), needed at the very end; computed BEFORE the prefetch loads are issued (the
+        // address arithmetic of a conditional offset load would otherwise wait on the scoreboard it shares with them)
+        unsigned long long off = 0, moffv = 0, voffv = 0;
+        if (lane < nv) {
+            const unsigned long long cell = p.lo + c0 + lane;
+            const unsigned long long rel = (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.cell_begin;
+            off = p.out_off ? p.out_off[cell] - p.out_base : rel * (unsigned long long)KB;
+            if constexpr (EXTRA) {
+                moffv = x.moff ? x.moff[cell] - x.mbase : rel * 64ull;
+                voffv = x.voff ? x.voff[cell] - x.vbase : rel * 8ull;
+            }
+        }
         if (lane < 8 * G) {
             *reinterpret_cast<double2 *>(Xs + ag * XS + 2 * am) = make_double2(gx0, gx1);
             gx0 = p.coords[pid];
             gx1 = p.coords[p.npoint + pid];
         }
         pid = load_pid(t + 2 * tstride);
-        // destination of the lane's cell (lanes 0 .. nv-1), needed at the very end
-        unsigned long long off = 0;
-        if (lane < nv) {
-            const unsigned long long cell = p.lo + c0 + lane;
-            if (p.out_off) off = p.out_off[cell] - p.out_base;
-            else off = ((p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.cell_begin) * (unsigned long long)KB;
-        }
         __syncwarp();
 
         // ---- phase B: geometry, lane = (cell, Gauss point) ----------------------------------------------------------------
@@ -184,6 +201,17 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
         }
         __syncwarp();
 
+        if constexpr (EXTRA) {
+            // flux vector: lane = (cell, node) sums its column pair of V over the Gauss points
+            const unsigned long long vo = __shfl_sync(0xffffffffu, voffv, ag < G ? ag : 0);
+            if ((x.mask & 8) && lane < 8 * G && ag < nv) {
+                const double *v0 = V + ag * CS + am * PS;
+                double sum = 0.0;
+                for (int q = 0; q < ng; q++) sum = fma(cc[ag * PS + q], fma(x.w1, v0[8 * PS + q], x.w0 * v0[q]), sum);
+                x.out_v03[vo + am] = sum;
+            }
+        }
+
         // ---- phase C: per cell, P on the tensor cores, contraction with D', staging ------------------------------------------
 #pragma unroll
         for (int g = 0; g < G; g++) {
@@ -222,6 +250,16 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
                         const double t1 = __shfl_sync(0xffffffffu, P[I][Jt][1], src);
                         P[Jt][I][e] = q8_select(ar & 1, t1, t0);
                     }
+            if constexpr (EXTRA) {
+                // conductivity block, column-major 8 x 8: rows 2ak, 2ak + 1 of column ar (8-byte stores: on mixed meshes the 3 x 3 blocks
+                // of the Tri3 cells leave the offsets odd)
+                const unsigned long long mo = __shfl_sync(0xffffffffu, moffv, g);
+                if ((x.mask & 2) && g < nv) {
+                    double *dst = x.out_m03 + mo + 8 * ar + 2 * ak;
+#pragma unroll
+                    for (int e = 0; e < 2; e++) dst[e] = fma(x.t11, P[1][1][e], fma(x.t01, P[0][1][e] + P[1][0][e], x.t00 * P[0][0][e]));
+                }
+            }
             // K(2m + i, 2n + j) = sum_qr d'[row(i,q)][row(j,r)] P[comp(i,q)][comp(j,r)](m,n)   (add_to_kk / add_to_kk_axisymmetric)
             double Kb[2][2][2]; // [e][i][j]
 #pragma unroll
@@ -282,11 +320,11 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
 }
 
 template <bool AXI>
-int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, void *stream) {
+int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, void *stream) {
     using T = Qua8Dims<AXI>;
     const size_t smem = sizeof(double) * (size_t)Q8_WARPS * T::WSZ;
-    typedef void (*kern_t)(const IntegParams, const Qua8Consts);
-    kern_t kern = pat == 2 ? qua8_kernel<AXI, 2> : qua8_kernel<AXI, 0>;
+    typedef void (*kern_t)(const IntegParams, const Qua8Consts, const Qua8Extra);
+    kern_t kern = x.mask ? (pat == 2 ? qua8_kernel<AXI, 2, true> : qua8_kernel<AXI, 0, true>) : (pat == 2 ? qua8_kernel<AXI, 2, false> : qua8_kernel<AXI, 0, false>);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
@@ -297,15 +335,16 @@ int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, void 
     const unsigned long long need = (ntriple + Q8_WARPS - 1) / Q8_WARPS;
     if (grid > need) grid = need;
     if (grid == 0) return 0;
-    kern<<<(unsigned)grid, 32 * Q8_WARPS, smem, (cudaStream_t)stream>>>(p, cst);
+    kern<<<(unsigned)grid, 32 * Q8_WARPS, smem, (cudaStream_t)stream>>>(p, cst, x);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    note_kernel("qua8_dmma<axi=%d,pat=%d>", AXI ? 1 : 0, pat == 2 ? 2 : 0);
+    if (x.mask) note_kernel("qua8_dmma<axi=%d,pat=%d,fused=%d>", AXI ? 1 : 0, pat == 2 ? 2 : 0, x.mask);
+    else note_kernel("qua8_dmma<axi=%d,pat=%d>", AXI ? 1 : 0, pat == 2 ? 2 : 0);
     return 1;
 }
 
 } // namespace
 
-int launch_bdb_qua8(const IntegParams &p, int sd, void *stream) {
+int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFused *extra) {
     if (sd != 2 || p.op != GL_OP_MAT_10_BDB || p.nnode != 8) return 0;
     if (p.coef != nullptr || p.scatter_pos != nullptr || p.sigma != nullptr) return 0; // record moduli, fused assembly: gl_kernels_bdb.cu
     if (Q8_G * p.ng > 32) return 0;
@@ -333,7 +372,24 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream) {
     if (const char *e = tuning_env("GL_BDB_PATTERN")) {
         if (atoi(e) < pat) pat = 0;
     }
-    return p.axisym ? launch_qua8_kind<true>(p, cst, pat, stream) : launch_qua8_kind<false>(p, cst, pat, stream);
+    Qua8Extra x;
+    std::memset(&x, 0, sizeof(x));
+    if (extra) { // mat_03_btb and / or vec_03_bv from the same pass (uniform coefficients, tight blocks, device outputs: checked by the caller)
+        if ((extra->mask & ~10) != 0 || extra->mask == 0) return 0;
+        x.mask = extra->mask;
+        x.t00 = extra->t[0];
+        x.t11 = extra->t[1];
+        x.t01 = extra->t[3] * hs;
+        x.w0 = extra->w[0];
+        x.w1 = extra->w[1];
+        x.out_m03 = extra->out_m03;
+        x.out_v03 = extra->out_v03;
+        x.moff = extra->moff;
+        x.mbase = extra->mbase;
+        x.voff = extra->voff;
+        x.vbase = extra->vbase;
+    }
+    return p.axisym ? launch_qua8_kind<true>(p, cst, pat, x, stream) : launch_qua8_kind<false>(p, cst, pat, x, stream);
 }
 
 } // namespace gl

@@ -180,7 +180,8 @@ GL_API uint64_t gl_ctx_launch_count(const gl_ctx *ctx);
 /* which kernel the most recent integration launch of this ctx used: "family<template parameters>", e.g. "hex8_bdb<pat=2>",
  * "syrk_dmma<nn=20,pat=2>", "mass_dmma<nn=10,sd=3,mask=5>", "generic<sd=3,gd=3>".  The dispatch tries the tuned kernels in
  * turn and ends at the generic one; tests and bench.py assert the family so that a tuned kernel that starts declining a
- * configuration cannot go unnoticed.  (No reference counterpart.) */
+ * configuration cannot go unnoticed.  After gl_integ_fused: every distinct kernel of that call, joined by " + " (one per
+ * GeoKind bucket and group of cases).  (No reference counterpart.) */
 GL_API const char *gl_ctx_last_kernel(const gl_ctx *ctx);
 
 /* ---- GeoKind / Gauss queries (host only; replace GeoKind::nnode, ndim, class and Gauss::new, new_sized, npoint, coords) ---- */
@@ -341,7 +342,9 @@ GL_API int gl_jacobian(gl_ctx *ctx, const gl_mesh *mesh, uint64_t cell_begin, ui
  * items into one kernel when it can -- today: any subset of mat_01_nsn, mat_03_btb, vec_01_ns, vec_03_bv with uniform
  * coefficients and device outputs (e.g. the mass matrix and the body-force vector of BASELINE.json config 4), and the pair
  * mat_10_bdb + vec_04_bt of a Hex8 mesh with the stress given per Gauss point (stiffness and internal-force vector, the two
- * sides of a Newton step) -- and otherwise runs them one after the other.  The reference has no counterpart: its callers invoke integ::mat_01_nsn and
+ * sides of a Newton step), and mat_10_bdb (uniform modulus) + mat_03_btb and / or vec_03_bv over a 2D mesh, whose Qua8 cells
+ * take all of them from the geometric tensors of the tensor-core stiffness kernel (stiffness, conductivity matrix and flux
+ * vector of BASELINE.json config 5) -- and otherwise runs them one after the other.  The reference has no counterpart: its callers invoke integ::mat_01_nsn and
  * integ::vec_01_ns separately, each recomputing the Jacobian (src/integ/mat_01_nsn.rs:75-76, vec_01_ns.rs:106-107). */
 typedef struct gl_fused_item {
     int32_t op; /* gl_op */

@@ -148,6 +148,48 @@ def test_qua8_tensor_core_on_mixed_mesh_and_guard_band(ctx):
     assert ei.value.cell == bad
 
 
+@pytest.mark.parametrize("axisymmetric", [False, True])
+@pytest.mark.parametrize("which", ["both", "mat_03_btb", "vec_03_bv"])
+@pytest.mark.parametrize("layout", ["mixed", "qua8"])
+def test_stiffness_conductivity_flux_from_one_pass(ctx, axisymmetric, which, layout):
+    """gl_integ_fused with mat_10_bdb + mat_03_btb and / or vec_03_bv (BASELINE.json configs[4]): the Qua8 cells take the scalar
+    cases from the geometric tensors of the tensor-core stiffness kernel, the Tri3 cells run their own kernels; results equal the
+    oracle's for every case (src/integ/mat_10_bdb.rs:179-233, mat_03_btb.rs:50-131, vec_03_bv.rs), ragged ranges included."""
+    import torch
+    from test_gpu_parity import mixed_mesh_2d
+    mesh = mixed_mesh_2d(n=7) if layout == "mixed" else make_mesh("qua8", n=5, seed=4)
+    dmesh = ctx.upload(mesh)
+    args = CommonArgs(axisymmetric=axisymmetric)
+    coefs = {"mat_10_bdb": iso(2), "mat_03_btb": np.array([2.0, 3.5, 0.0, 0.75]), "vec_03_bv": np.array([1.0, -2.0])}
+    ops = ["mat_10_bdb"] + (["mat_03_btb", "vec_03_bv"] if which == "both" else [which])
+    kw = {"axisymmetric": True} if axisymmetric else {}
+    for b, e in [(0, mesh.ncell), (3, mesh.ncell - 2), (1, 2)]:
+        outs, offs = [], []
+        for op in ops:
+            off = integ.out_offsets(dmesh, op, (b, e), args)
+            offs.append(off)
+            outs.append(torch.full((int(off[-1]) + 16,), 3.25, dtype=torch.float64, device="cuda"))
+        integ.fused(ctx, dmesh, (b, e), args, [(op, Coef.uniform(coefs[op]), o[8:-8]) for op, o in zip(ops, outs)])
+        ran = ctx.last_kernel().split(" + ")
+        mask = {"both": 10, "mat_03_btb": 2, "vec_03_bv": 8}[which]
+        assert f"qua8_dmma<axi={int(axisymmetric)},pat=2,fused={mask}>" in ran, ran
+        assert not any(k.startswith("scalar_tpc<nn=8") for k in ran), ran
+        sub = mesh.permuted(np.arange(b, e))
+        for op, o, off in zip(ops, outs, offs):
+            got = o.cpu().numpy()
+            assert np.all(got[:8] == 3.25) and np.all(got[-8:] == 3.25), op
+            ref = oracle_integ(op, sub, coefs[op], **kw)
+            assert rel_err(got[8:-8], ref, off) <= TOL, f"{op} range {b}:{e}"
+    # rules the tensor-core kernel does not take (16 points): the same call still answers, case by case
+    a16 = CommonArgs(axisymmetric=axisymmetric, ngauss=16) if layout == "qua8" else None
+    if a16 is not None:
+        res = integ.fused(ctx, dmesh, None, a16, [(op, Coef.uniform(coefs[op]), None) for op in ops])
+        for op, got in zip(ops, res):
+            ref = oracle_integ(op, mesh, coefs[op], ngauss=16, **kw)
+            bs = integ.op_out_size(op, GeoKind.Qua8, 2)
+            assert rel_err(np.asarray(got), ref, np.arange(mesh.ncell + 1) * bs) <= TOL, op
+
+
 def test_hex20_general_blocks_and_accumulation(ctx):
     """nrow / ncol / ii0 / jj0 and clear = false in the store epilogue of the tensor-core kernel (CommonArgs,
     src/integ/common_args.rs:5-43; kk.fill(0.0) clears the WHOLE block, mat_10_bdb.rs:141-143)."""

@@ -43,4 +43,7 @@ for name, mesh in meshes.items():
     ov = torch.empty(integ.out_total(dm, "vec_03_bv", None, a), dtype=torch.float64, device="cuda")
     t1 = timed(lambda: integ.mat_10_bdb(ctx, dm, None, a, Coef.uniform(dd), out=ok))
     t2 = timed(lambda: integ.fused(ctx, dm, None, a, [("mat_03_btb", Coef.uniform([2.0, 2.0, 0.0, 0.0]), oh), ("vec_03_bv", Coef.uniform([1.0, 2.0]), ov)]))
+    t3 = timed(lambda: integ.fused(ctx, dm, None, a, [("mat_10_bdb", Coef.uniform(dd), ok), ("mat_03_btb", Coef.uniform([2.0, 2.0, 0.0, 0.0]), oh),
+                                                       ("vec_03_bv", Coef.uniform([1.0, 2.0]), ov)]))
+    print(f"{name:10s} all three from one gl_integ_fused call: {t3:.3f} ms ({mesh.ncell / t3 / 1e6:.3f} G el/s)  [{ctx.last_kernel()}]")
     print(f"{name:10s} {mesh.ncell:8d} cells: mat_10_bdb {t1:.3f} ms ({ok.numel()*8/t1/1e6:.0f} GB/s out), fused btb+bv {t2:.3f} ms ({(oh.numel()+ov.numel())*8/t2/1e6:.0f} GB/s out)")
