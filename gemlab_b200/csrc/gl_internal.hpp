@@ -128,7 +128,6 @@ int launch_hex8_bdb(const IntegParams &p, void *stream);
 int launch_hex8_gauss(const IntegParams &p, void *stream); // Hex8, one modulus per Gauss point (gl_kernels_hex8pg.cu)
 int launch_bdb(const IntegParams &p, int sd, void *stream);
 bool bdb_covers(int nnode, int sd, int ng, bool axisym, bool record_moduli, bool per_gauss); // would launch_bdb take this stiffness configuration?
-int launch_bdb_small2d(const IntegParams &p, int sd, void *stream); // thread-per-cell variant for Tri3 / Qua4 (gl_kernels_small2d.cu)
 int launch_bdb_tile(const IntegParams &p, int sd, void *stream); // register-tiled variant for Hex20 / Tet10 (gl_kernels_tile.cu)
 int launch_bdb_syrk(const IntegParams &p, int sd, void *stream); // FP64 tensor-core (DMMA) symmetric rank-ng update for Hex20 / Tet10 (gl_kernels_syrk.cu)
 
@@ -149,6 +148,7 @@ int launch_scalar_fused(const IntegParams &p, const ScalarFused &f, int sd, void
 // FP64 tensor-core (DMMA) geometric tensors for Qua8 stiffness, plane / axisymmetric (gl_kernels_qua8.cu); `extra` (mask of mat_03_btb = 2,
 // vec_03_bv = 8) asks for the conductivity matrix and / or the flux vector from the same pass
 int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFused *extra = nullptr);
+int launch_bdb_small2d(const IntegParams &p, int sd, void *stream); // thread-per-cell variant for Tri3 / Qua4 (gl_kernels_small2d.cu)
 // mat_01_nsn and/or vec_01_ns as a (cells x ng).(ng x entries) product on the FP64 tensor cores (gl_kernels_mass.cu); 0 if not covered
 // mat_03_btb and/or vec_03_bv, one thread per cell (gl_kernels_scalar_tpc.cu); 0 if not covered
 int launch_scalar_tpc(const IntegParams &p, const ScalarFused &f, int sd, void *stream);

@@ -150,14 +150,15 @@ def test_qua8_tensor_core_on_mixed_mesh_and_guard_band(ctx):
 
 @pytest.mark.parametrize("axisymmetric", [False, True])
 @pytest.mark.parametrize("which", ["both", "mat_03_btb", "vec_03_bv"])
-@pytest.mark.parametrize("layout", ["mixed", "qua8"])
+@pytest.mark.parametrize("layout", ["mixed", "qua8", "tri3", "qua4"])
 def test_stiffness_conductivity_flux_from_one_pass(ctx, axisymmetric, which, layout):
     """gl_integ_fused with mat_10_bdb + mat_03_btb and / or vec_03_bv (BASELINE.json configs[4]): the Qua8 cells take the scalar
-    cases from the geometric tensors of the tensor-core stiffness kernel, the Tri3 cells run their own kernels; results equal the
-    oracle's for every case (src/integ/mat_10_bdb.rs:179-233, mat_03_btb.rs:50-131, vec_03_bv.rs), ragged ranges included."""
+    cases from the geometric tensors of the tensor-core stiffness kernel, the other kinds run their stiffness kernel and ONE fused
+    scalar kernel; results equal the oracle's for every case (src/integ/mat_10_bdb.rs:179-233, mat_03_btb.rs:50-131,
+    vec_03_bv.rs), ragged ranges included."""
     import torch
     from test_gpu_parity import mixed_mesh_2d
-    mesh = mixed_mesh_2d(n=7) if layout == "mixed" else make_mesh("qua8", n=5, seed=4)
+    mesh = mixed_mesh_2d(n=7) if layout == "mixed" else make_mesh(layout, n=5, seed=4)
     dmesh = ctx.upload(mesh)
     args = CommonArgs(axisymmetric=axisymmetric)
     coefs = {"mat_10_bdb": iso(2), "mat_03_btb": np.array([2.0, 3.5, 0.0, 0.75]), "vec_03_bv": np.array([1.0, -2.0])}
@@ -172,8 +173,13 @@ def test_stiffness_conductivity_flux_from_one_pass(ctx, axisymmetric, which, lay
         integ.fused(ctx, dmesh, (b, e), args, [(op, Coef.uniform(coefs[op]), o[8:-8]) for op, o in zip(ops, outs)])
         ran = ctx.last_kernel().split(" + ")
         mask = {"both": 10, "mat_03_btb": 2, "vec_03_bv": 8}[which]
-        assert f"qua8_dmma<axi={int(axisymmetric)},pat=2,fused={mask}>" in ran, ran
-        assert not any(k.startswith("scalar_tpc<nn=8") for k in ran), ran
+        if layout in ("mixed", "qua8"):
+            assert f"qua8_dmma<axi={int(axisymmetric)},pat=2,fused={mask}>" in ran, ran
+            assert not any(k.startswith("scalar_tpc<nn=8") for k in ran), ran
+        if layout == "tri3" or (layout == "mixed" and e - b > 1):
+            assert f"small2d<nn=3,axi={int(axisymmetric)},pat=2>" in ran and f"scalar_tpc<nn=3,sd=2,mask={mask}>" in ran, ran
+        if layout == "qua4":
+            assert f"scalar_tpc<nn=4,sd=2,mask={mask}>" in ran, ran
         sub = mesh.permuted(np.arange(b, e))
         for op, o, off in zip(ops, outs, offs):
             got = o.cpu().numpy()
@@ -186,7 +192,7 @@ def test_stiffness_conductivity_flux_from_one_pass(ctx, axisymmetric, which, lay
         res = integ.fused(ctx, dmesh, None, a16, [(op, Coef.uniform(coefs[op]), None) for op in ops])
         for op, got in zip(ops, res):
             ref = oracle_integ(op, mesh, coefs[op], ngauss=16, **kw)
-            bs = integ.op_out_size(op, GeoKind.Qua8, 2)
+            bs = integ.op_out_size(op, GeoKind.Qua8, 2)  # (layout == "qua8" here)
             assert rel_err(np.asarray(got), ref, np.arange(mesh.ncell + 1) * bs) <= TOL, op
 
 
