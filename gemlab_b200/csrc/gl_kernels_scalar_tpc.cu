@@ -206,13 +206,17 @@ __global__ void __launch_bounds__(TPC_THREADS) scalar_tpc_kernel(const IntegPara
                 vo = f.voff ? (f.voff[cell] - f.vbase) : (orig - p.cell_begin) * NN;
             }
             const int nc = wcell0 < p.hi ? (int)(p.hi - wcell0 < 32 ? p.hi - wcell0 : 32) : 0;
-            if (p.cell_ids == nullptr && f.moff == nullptr && f.voff == nullptr) { // single-kind mesh: one contiguous run
+            // one contiguous run per output: always on single-kind meshes; on mixed ones whenever the warp's cells lie inside one stripe
+            const unsigned long long mo0 = __shfl_sync(0xffffffffu, mo, 0), vo0 = __shfl_sync(0xffffffffu, vo, 0);
+            const bool single = p.cell_ids == nullptr && f.moff == nullptr && f.voff == nullptr;
+            const bool one_run = single || __all_sync(0xffffffffu, !active || (mo == mo0 + (unsigned long long)lane * KK && vo == vo0 + (unsigned long long)lane * NN));
+            if (one_run) {
                 if (m03 && nc > 0) {
-                    double *dst = f.out_m03 + (wcell0 - p.cell_begin) * KK;
+                    double *dst = f.out_m03 + mo0;
                     for (int w = lane; w < nc * KK; w += 32) dst[w] = Tw[(w % KK) * TS + w / KK];
                 }
                 if (v03 && nc > 0) {
-                    double *dst = f.out_v03 + (wcell0 - p.cell_begin) * NN;
+                    double *dst = f.out_v03 + vo0;
                     for (int w = lane; w < nc * NN; w += 32) dst[w] = Tw[(KK + w % NN) * TS + w / NN];
                 }
                 continue;

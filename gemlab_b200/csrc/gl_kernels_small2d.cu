@@ -223,9 +223,12 @@ __global__ void __launch_bounds__(S2_THREADS) small2d_kernel(const IntegParams p
             if (active) mo = p.out_off ? (p.out_off[cell] - p.out_base)
                                        : ((p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.cell_begin) * BS;
             const int nc = wcell0 < p.hi ? (int)(p.hi - wcell0 < 32 ? p.hi - wcell0 : 32) : 0;
-            if (p.cell_ids == nullptr && p.out_off == nullptr) { // single-kind mesh: one contiguous run
+            // one contiguous run: always on single-kind meshes; on mixed ones whenever the warp's cells lie inside one stripe
+            const unsigned long long mo0 = __shfl_sync(0xffffffffu, mo, 0);
+            const bool one_run = (p.cell_ids == nullptr && p.out_off == nullptr) || __all_sync(0xffffffffu, !active || mo == mo0 + (unsigned long long)lane * BS);
+            if (one_run) {
                 if (nc > 0) {
-                    double2 *dst = reinterpret_cast<double2 *>(p.out + (wcell0 - p.cell_begin) * BS);
+                    double2 *dst = reinterpret_cast<double2 *>(p.out + mo0);
                     for (int w = lane; w < nc * (BS / 2); w += 32) {
                         const int c = w / (BS / 2), q = 2 * (w - c * (BS / 2));
                         dst[w] = make_double2(Tw[q * TS + c], Tw[(q + 1) * TS + c]);
