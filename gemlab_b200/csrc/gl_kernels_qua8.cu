@@ -17,7 +17,8 @@
 //   A  gather (Mesh::set_pad, src/mesh/mesh.rs:448-456): lane = (cell, node); point ids two triples ahead, coordinates one;
 //   B  geometry, lane = (cell, Gauss point), in the ORACLE'S operation order (gl_geom.cuh): J = Xt.L, closed-form inverse, det,
 //      r = sum N.x0; B = L.inv(J), N/r -> V (shared memory, dof-major, conflict-free strides), c';
-//   C  per cell: ceil(ng/4) k-steps of 6 (3) DMMA, the scaled operand c' V formed in registers; transposed tiles by shuffle;
+//   C  per cell: k-steps of 6 (3) DMMA over four Gauss points each (a single leftover point by DFMA), the scaled operand c' V formed in
+//      registers; transposed tiles by shuffle;
 //      contraction with D'; the lane's two 2 x 2 blocks go to the staged element block as 16-byte stores (odd fragment rows
 //      store their upper half first: conflict-free);
 //   D  the triple (3 x 2,048 contiguous bytes on single-kind meshes; runs of consecutive blocks on mixed ones) leaves with bulk
@@ -102,7 +103,10 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
     double *Xs = cc + G * PS;           // [G][XS]   X[2m + j]
 
     const int ng = p.ng;
-    const int KS = (ng + 3) >> 2;
+    // Gauss points go through the tensor cores four at a time; a single leftover point (9 = 2 x 4 + 1, the default rule) is a rank-1
+    // update of the fragments with DFMA (12 + 3 instructions instead of a padded k-step of 6 DMMA = 48 DFMA slots of the same pipe)
+    const bool tail1 = (ng & 3) == 1;
+    const int KS = tail1 ? ng >> 2 : (ng + 3) >> 2;
     const int ar = lane >> 2, ak = lane & 3;
 
     // phase B role: lane = (cell of the triple, Gauss point); its rows of the reference-element table stay in registers
@@ -238,6 +242,24 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
 #pragma unroll
                     for (int Jt = I; Jt < VD; Jt++) q8_dmma(P[I][Jt][0], P[I][Jt][1], v[Jt], vs[I]);
             }
+            if (tail1) {
+                const double *vq = V + g * CS + (ng - 1);
+                const double c = cc[g * PS + ng - 1];
+                double gm[VD][2], gn[VD];
+#pragma unroll
+                for (int k = 0; k < VD; k++) {
+                    gn[k] = vq[(8 * k + ar) * PS] * c;
+                    gm[k][0] = vq[(8 * k + 2 * ak) * PS];
+                    gm[k][1] = vq[(8 * k + 2 * ak + 1) * PS];
+                }
+#pragma unroll
+                for (int I = 0; I < VD; I++)
+#pragma unroll
+                    for (int Jt = I; Jt < VD; Jt++) {
+                        P[I][Jt][0] = fma(gm[I][0], gn[Jt], P[I][Jt][0]);
+                        P[I][Jt][1] = fma(gm[I][1], gn[Jt], P[I][Jt][1]);
+                    }
+            }
             // the lane holds P[I][J](2ak + e, ar), I <= J.  P[J][I](2ak + e, ar) = P[I][J](ar, 2ak + e): lane (2ak + e, ar >> 1), element ar & 1
 #pragma unroll
             for (int I = 0; I < VD; I++)
@@ -251,8 +273,8 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
                         P[Jt][I][e] = q8_select(ar & 1, t1, t0);
                     }
             if constexpr (EXTRA) {
-                // conductivity block, column-major 8 x 8: rows 2ak, 2ak + 1 of column ar (8-byte stores: on mixed meshes the 3 x 3 blocks
-                // of the Tri3 cells leave the offsets odd)
+                // conductivity block, column-major 8 x 8: rows 2ak, 2ak + 1 of column ar.  8-byte stores: on mixed meshes the 3 x 3 blocks
+                // of the Tri3 cells can leave the offset odd, and one 16-byte store where it is even measured no faster
                 const unsigned long long mo = __shfl_sync(0xffffffffu, moffv, g);
                 if ((x.mask & 2) && g < nv) {
                     double *dst = x.out_m03 + mo + 8 * ar + 2 * ak;

@@ -196,6 +196,27 @@ def test_stiffness_conductivity_flux_from_one_pass(ctx, axisymmetric, which, lay
             assert rel_err(np.asarray(got), ref, np.arange(mesh.ncell + 1) * bs) <= TOL, op
 
 
+@pytest.mark.parametrize("kind", ["hex8", "tet10"])
+def test_stiffness_plus_scalar_cases_in_one_call_3d(ctx, kind):
+    """gl_integ_fused with the stiffness next to scalar-dof cases on a 3D mesh: the stiffness runs on its own kernel, the scalar cases
+    share one; same results as the separate calls (the fused call is defined as equivalent to them, include/gemlab_cuda.h)."""
+    import torch
+    mesh = make_mesh(kind, n=3)
+    dmesh = ctx.upload(mesh)
+    args = CommonArgs()
+    coefs = {"mat_10_bdb": iso(3), "mat_03_btb": np.array([2.0, 3.5, 1.5, 0.75, -0.25, 0.5]), "vec_03_bv": np.array([1.0, -2.0, 0.5]),
+             "mat_01_nsn": np.array([2.7])}
+    for ops in (["mat_10_bdb", "mat_03_btb", "vec_03_bv"], ["mat_01_nsn", "mat_10_bdb"]):
+        outs = [torch.empty(integ.out_total(dmesh, op, None, args), dtype=torch.float64, device="cuda") for op in ops]
+        integ.fused(ctx, dmesh, None, args, [(op, Coef.uniform(coefs[op]), o) for op, o in zip(ops, outs)])
+        ran = ctx.last_kernel().split(" + ")
+        assert len(ran) == 2 and not any(k.startswith("generic") for k in ran), ran
+        for op, o in zip(ops, outs):
+            ref = oracle_integ(op, mesh, coefs[op])
+            bs = integ.op_out_size(op, GeoKind.from_str(kind), 3)
+            assert rel_err(o.cpu().numpy(), ref, np.arange(mesh.ncell + 1) * bs) <= TOL, op
+
+
 def test_hex20_general_blocks_and_accumulation(ctx):
     """nrow / ncol / ii0 / jj0 and clear = false in the store epilogue of the tensor-core kernel (CommonArgs,
     src/integ/common_args.rs:5-43; kk.fill(0.0) clears the WHOLE block, mat_10_bdb.rs:141-143)."""
