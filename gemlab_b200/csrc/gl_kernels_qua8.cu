@@ -23,8 +23,8 @@
 //      store their upper half first: conflict-free);
 //   D  the triple (3 x 2,048 contiguous bytes on single-kind meshes; runs of consecutive blocks on mixed ones) leaves with bulk
 //      async copies (L2 evict-first).
-// Covered: uniform D (any pattern), rules of at most 10 points, tight blocks that overwrite a 16-byte aligned buffer; everything
-// else stays on gl_kernels_bdb.cu.
+// Covered: uniform D or one record per marker / per cell (any pattern), rules of at most 10 points, tight blocks that overwrite a
+// 16-byte aligned buffer; everything else (one modulus per Gauss point, general blocks, fused assembly) stays on gl_kernels_bdb.cu.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -80,19 +80,23 @@ constexpr int Q8_PS = 12;      // V is stored dof-major, Vt[col][p] at col PS + 
 constexpr int Q8_XS = 18;      // coordinates of a cell (16 doubles + 2): the three cells of a warp read distinct banks
 constexpr int Q8_KB = 256;     // element block
 
-template <bool AXI>
+template <bool AXI, bool DREC = false>
 struct Qua8Dims {
     static constexpr int VD = AXI ? 3 : 2;
     static constexpr int NV = 8 * VD;
     static constexpr int CS = NV * Q8_PS + 9; // = 9 (mod 16): the (cell, Gauss point) lanes of a half-warp store one column conflict-free
     static constexpr int VSZ = (Q8_G * CS + 1) & ~1;
-    static constexpr int WSZ = Q8_G * Q8_KB + VSZ + Q8_G * Q8_PS + Q8_G * Q8_XS; // doubles per warp (even)
+    static constexpr int WSZ = Q8_G * Q8_KB + VSZ + Q8_G * Q8_PS + Q8_G * Q8_XS + (DREC ? Q8_G * 16 : 0); // doubles per warp (even)
     static_assert(WSZ % 2 == 0, "16-byte aligned warp regions");
 };
 
-template <bool AXI, int PAT, bool EXTRA>
+// DREC = one modulus record per marker or per cell (multi-material meshes) instead of a uniform D: the records of the next triple are
+// fetched one iteration ahead (their indices two ahead), scaled into d' and staged per cell; with device-resident records whose
+// structure only the probe knows, every pattern variant is enqueued and all but the matching one return at once (gl_kernels_bdb.cu)
+template <bool AXI, int PAT, bool EXTRA, bool DREC = false>
 __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst, const Qua8Extra x) {
-    using T = Qua8Dims<AXI>;
+    if (DREC && p.coef_pat_dev != nullptr && (*p.coef_pat_dev == 2 ? 2 : 0) != PAT) return;
+    using T = Qua8Dims<AXI, DREC>;
     constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = Q8_G, XS = Q8_XS, KB = Q8_KB;
 
     extern __shared__ __align__(16) double smem[];
@@ -101,6 +105,7 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
     double *V = Kst + G * KB;           // [G][CS]   Vt[cell][8k + m][p]
     double *cc = V + T::VSZ;            // [G][PS]   c'_p
     double *Xs = cc + G * PS;           // [G][XS]   X[2m + j]
+    double *Dc = Xs + G * XS;           // [G][16]   d' of the cell, row-major (DREC only)
 
     const int ng = p.ng;
     // Gauss points go through the tensor cores four at a time; a single leftover point (9 = 2 x 4 + 1, the default rule) is a rank-1
@@ -136,6 +141,23 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
         gx1 = p.coords[p.npoint + pid];
     }
     pid = load_pid(t + tstride);
+    // modulus records: lane -> entry (lane & 15) of cell (lane >> 4) of the triple, lanes 0..15 also entry `lane` of its third cell
+    auto load_rec = [&](unsigned long long tt, int g) -> unsigned long long {
+        const unsigned long long c = tt * G + g;
+        if (!(tt < ntriple && c < ncell)) return 0ull;
+        const unsigned long long cell = p.lo + c;
+        return p.coef_index ? (unsigned long long)p.coef_index[cell] : (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
+    };
+    unsigned long long rec0 = 0, rec1 = 0;
+    double dv0 = 0.0, dv1 = 0.0;
+    if constexpr (DREC) {
+        rec0 = load_rec(t, lane >> 4);
+        rec1 = load_rec(t, 2);
+        dv0 = p.coef[rec0 * p.coef_cell_stride + (lane & 15)];
+        dv1 = p.coef[rec1 * p.coef_cell_stride + (lane & 15)];
+        rec0 = load_rec(t + tstride, lane >> 4);
+        rec1 = load_rec(t + tstride, 2);
+    }
 
     unsigned long long pol; // the element matrices are written once: keep them from flushing the mesh out of L2
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -162,6 +184,18 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
             gx1 = p.coords[p.npoint + pid];
         }
         pid = load_pid(t + 2 * tstride);
+        if constexpr (DREC) {
+            // record entry a + 4b (column-major ns x ns Mandel matrix) -> d'[a][b], the 1/sqrt(2) of the shear row folded in
+            const double hs = 0.70710678118654752440084436210484903928;
+            const int a = lane & 3, b = (lane >> 2) & 3;
+            const double fs = (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
+            Dc[(lane >> 4) * 16 + a * 4 + b] = dv0 * fs;
+            if (lane < 16) Dc[2 * 16 + a * 4 + b] = dv1 * fs;
+            dv0 = p.coef[rec0 * p.coef_cell_stride + (lane & 15)];
+            dv1 = p.coef[rec1 * p.coef_cell_stride + (lane & 15)];
+            rec0 = load_rec(t + 2 * tstride, lane >> 4);
+            rec1 = load_rec(t + 2 * tstride, 2);
+        }
         __syncwarp();
 
         // ---- phase B: geometry, lane = (cell, Gauss point) ----------------------------------------------------------------
@@ -299,7 +333,8 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
                                 const int ra = q8_col_row(i, q), rb = q8_col_row(j, rr);
                                 if (!q8_nz(PAT, ra, rb)) continue;
                                 const double pv = P[q8_col_comp(i, q)][q8_col_comp(j, rr)][e];
-                                s = have ? fma(cst.d[ra * 4 + rb], pv, s) : cst.d[ra * 4 + rb] * pv;
+                                const double dab = DREC ? Dc[g * 16 + ra * 4 + rb] : cst.d[ra * 4 + rb];
+                                s = have ? fma(dab, pv, s) : dab * pv;
                                 have = true;
                             }
                         Kb[e][i][j] = s;
@@ -342,12 +377,14 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
 }
 
 template <bool AXI>
-int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, void *stream) {
-    using T = Qua8Dims<AXI>;
-    const size_t smem = sizeof(double) * (size_t)Q8_WARPS * T::WSZ;
+int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, bool drec, void *stream) {
+    const size_t smem = sizeof(double) * (size_t)Q8_WARPS * (drec ? Qua8Dims<AXI, true>::WSZ : Qua8Dims<AXI, false>::WSZ);
     typedef void (*kern_t)(const IntegParams, const Qua8Consts, const Qua8Extra);
-    kern_t kern = x.mask ? (pat == 2 ? qua8_kernel<AXI, 2, true> : qua8_kernel<AXI, 0, true>) : (pat == 2 ? qua8_kernel<AXI, 2, false> : qua8_kernel<AXI, 0, false>);
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    auto pick = [&](int pt) -> kern_t {
+        if (drec) return pt == 2 ? qua8_kernel<AXI, 2, false, true> : qua8_kernel<AXI, 0, false, true>;
+        if (x.mask) return pt == 2 ? qua8_kernel<AXI, 2, true> : qua8_kernel<AXI, 0, true>;
+        return pt == 2 ? qua8_kernel<AXI, 2, false> : qua8_kernel<AXI, 0, false>;
+    };
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -357,18 +394,30 @@ int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const
     const unsigned long long need = (ntriple + Q8_WARPS - 1) / Q8_WARPS;
     if (grid > need) grid = need;
     if (grid == 0) return 0;
-    kern<<<(unsigned)grid, 32 * Q8_WARPS, smem, (cudaStream_t)stream>>>(p, cst, x);
+    // records whose structure only the device knows: both variants are enqueued, the probe's verdict selects the one that runs
+    const bool probe = drec && p.coef_pat_dev != nullptr;
+    IntegParams q = p;
+    if (!probe) q.coef_pat_dev = nullptr;
+    int nl = 0;
+    for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt += 2) {
+        kern_t kern = pick(pt);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        kern<<<(unsigned)grid, 32 * Q8_WARPS, smem, (cudaStream_t)stream>>>(q, cst, x);
+        nl++;
+    }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    if (x.mask) note_kernel("qua8_dmma<axi=%d,pat=%d,fused=%d>", AXI ? 1 : 0, pat == 2 ? 2 : 0, x.mask);
-    else note_kernel("qua8_dmma<axi=%d,pat=%d>", AXI ? 1 : 0, pat == 2 ? 2 : 0);
-    return 1;
+    if (x.mask) note_kernel("qua8_dmma<axi=%d,pat=%d,fused=%d>", AXI ? 1 : 0, pat, x.mask);
+    else note_kernel("qua8_dmma<axi=%d,pat=%d%s>", AXI ? 1 : 0, pat, drec ? ",rec" : "");
+    return nl;
 }
 
 } // namespace
 
 int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFused *extra) {
     if (sd != 2 || p.op != GL_OP_MAT_10_BDB || p.nnode != 8) return 0;
-    if (p.coef != nullptr || p.scatter_pos != nullptr || p.sigma != nullptr) return 0; // record moduli, fused assembly: gl_kernels_bdb.cu
+    if (p.scatter_pos != nullptr || p.sigma != nullptr) return 0; // fused assembly: gl_kernels_bdb.cu
+    const bool drec = p.coef != nullptr;
+    if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 16 || extra != nullptr)) return 0; // one modulus per Gauss point: gl_kernels_bdb.cu
     if (Q8_G * p.ng > 32) return 0;
     if (p.size_r != 16 || p.size_c != 16) return 0;
     const bool tight = p.nrow == 16 && p.ncol == 16 && p.ii0 == 0 && p.jj0 == 0;
@@ -391,6 +440,7 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
             for (int b = 0; b < 4; b++)
                 if (!q8_nz(2, a, b) && cst.d[a * 4 + b] != 0.0) pat = 0;
     }
+    if (drec) pat = p.coef_pat == 2 ? 2 : 0; // structure common to all records (0 when they live on the device only)
     if (const char *e = tuning_env("GL_BDB_PATTERN")) {
         if (atoi(e) < pat) pat = 0;
     }
@@ -411,7 +461,7 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
         x.voff = extra->voff;
         x.vbase = extra->vbase;
     }
-    return p.axisym ? launch_qua8_kind<true>(p, cst, pat, x, stream) : launch_qua8_kind<false>(p, cst, pat, x, stream);
+    return p.axisym ? launch_qua8_kind<true>(p, cst, pat, x, drec, stream) : launch_qua8_kind<false>(p, cst, pat, x, drec, stream);
 }
 
 } // namespace gl

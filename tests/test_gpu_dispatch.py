@@ -118,6 +118,41 @@ def test_qua8_tensor_core_stiffness(ctx, axisymmetric, rule, structure):
         assert rel_err(got, ref[b * 256:e * 256], np.arange(e - b + 1) * 256) <= TOL, f"rule {rule} range {b}:{e}"
 
 
+@pytest.mark.parametrize("axisymmetric", [False, True])
+def test_qua8_modulus_records_on_the_tensor_core_kernel(ctx, axisymmetric):
+    """One modulus per marker / per cell (multi-material meshes) on the Qua8 DMMA kernel: records fetched one triple ahead and staged
+    per cell; ragged ranges, host- and device-resident records (the latter through the structure probe: both pattern variants are
+    enqueued, one runs)."""
+    import torch
+    mesh = make_mesh("qua8", n=6, seed=8)
+    rng = np.random.default_rng(29)
+    mesh.markers[:] = rng.integers(1, 4, mesh.ncell)
+    dmesh = ctx.upload(mesh)
+    args = CommonArgs(axisymmetric=axisymmetric)
+    for structure in ("isotropic", "general"):
+        if structure == "isotropic":
+            recs = np.stack([g.mandel_matrix(g.lin_elasticity(100.0 * (k + 1), 0.1 * (k + 1), True)) for k in range(3)])
+        else:
+            recs = random_coef("mat_10_bdb", 2, 3, rng, spd=False)
+        per_cell = np.ascontiguousarray(recs[mesh.markers - 1])
+        ref = oracle_integ("mat_10_bdb", mesh, per_cell, cell_stride=16, axisymmetric=axisymmetric)
+        pat = 2 if structure == "isotropic" else 0
+        for b, e in [(0, mesh.ncell), (1, 2), (4, 21), (7, mesh.ncell)]:
+            sizes = np.arange(e - b + 1) * 256
+            got = integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.per_marker([1, 2, 3], recs))
+            assert ctx.last_kernel() == f"qua8_dmma<axi={int(axisymmetric)},pat={pat},rec>"
+            assert rel_err(got, ref[b * 256:e * 256], sizes) <= TOL, f"per_marker {structure} {b}:{e}"
+            got = integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.per_cell(per_cell[b:e]))
+            assert ctx.last_kernel() == f"qua8_dmma<axi={int(axisymmetric)},pat={pat},rec>"
+            assert rel_err(got, ref[b * 256:e * 256], sizes) <= TOL, f"per_cell {structure} {b}:{e}"
+            out = torch.full(((e - b) * 256 + 8,), -1.5, dtype=torch.float64, device="cuda")
+            integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.per_cell(torch.from_numpy(per_cell[b:e].copy()).cuda()), out=out[4:-4])
+            assert ctx.last_kernel().startswith(f"qua8_dmma<axi={int(axisymmetric)},pat=") and ctx.last_kernel().endswith(",rec>")
+            res = out.cpu().numpy()
+            assert np.all(res[:4] == -1.5) and np.all(res[-4:] == -1.5)
+            assert rel_err(res[4:-4], ref[b * 256:e * 256], sizes) <= TOL, f"per_cell device {structure} {b}:{e}"
+
+
 def test_qua8_tensor_core_on_mixed_mesh_and_guard_band(ctx):
     """The Qua8 stripes of a mixed Tri3 / Qua8 mesh (BASELINE.json configs[4]) leave as runs of consecutive blocks; nothing
     outside the integrated range is written; zero determinants are reported with the smallest cell id."""

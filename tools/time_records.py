@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Times mat_10_bdb on Qua4 / Hex20 / Tet10 with a uniform modulus, one modulus per marker and one per cell (device-resident
+"""Times mat_10_bdb on Qua4 / Qua8 / Hex20 / Tet10 with a uniform modulus, one modulus per marker and one per cell (device-resident
 outputs) and checks a sample of cells against the oracle.  GL_DISABLE_TILE=1 GL_DISABLE_SMALL2D=1 shows the register-blocked fallback."""
 import json
 import sys
@@ -22,10 +22,11 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 50
     ctx = Context(0)
     rng = np.random.default_rng(5)
-    for kind in ("qua4", "hex20", "tet10"):
-        two_dim = kind == "qua4"
+    kinds = sys.argv[2].split(",") if len(sys.argv) > 2 else ("qua4", "qua8", "hex20", "tet10")
+    for kind in kinds:
+        two_dim = kind in ("qua4", "qua8")
         if two_dim:
-            mesh = g.jitter_interior_points(Block.new_square(1.0).set_ndiv([20 * n, 20 * n]).subdivide(GeoKind.Qua4), 0.01 / n)
+            mesh = g.jitter_interior_points(Block.new_square(1.0).set_ndiv([20 * n, 20 * n]).subdivide(GeoKind.from_str(kind)), 0.01 / n)
         elif kind == "hex20":
             mesh = g.jitter_interior_points(Block.new_cube(1.0).set_ndiv([n, n, n]).subdivide(GeoKind.Hex20), 0.05 / n)
         else:
@@ -53,7 +54,7 @@ def main():
             ref = po.mesh_integ("mat_10_bdb", mesh.ndim, sub.coords, sub.kinds, sub.conn_off, sub.conn,
                                 coef=np.ascontiguousarray(ref_recs).reshape(-1), coef_cell_stride=ns2).reshape(len(sel), bs)
             err = float(np.max(np.abs(got - ref).max(axis=1) / np.abs(ref).max(axis=1)))
-            print(json.dumps({"kind": kind, "coef": name, "cells": mesh.ncell, "ms": ms,
+            print(json.dumps({"kind": kind, "coef": name, "kernel": ctx.last_kernel(), "cells": mesh.ncell, "ms": ms,
                               "elements_per_s": mesh.ncell / (ms * 1e-3), "max_rel_err": err}), flush=True)
 
 
