@@ -1073,7 +1073,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
             set_last_kernel(ctx);
             continue;
         }
-        if (qf && op == GL_OP_MAT_10_BDB && mesh->ndim == 2 && bk.kind == GL_QUA8) {
+        if (qf && op == GL_OP_MAT_10_BDB && mesh->ndim == 2 && (bk.kind == GL_QUA8 || bk.kind == GL_TRI6)) {
             ScalarFused fb = *qf->f;
             if (qf->mpre) {
                 st = bucket_device_offsets(ctx, bk, qf->mpre, qf->mkey, &fb.moff);

@@ -1,4 +1,4 @@
-// gl_kernels_qua8.cu -- Qua8 stiffness on the FP64 TENSOR CORES, plane and axisymmetric: integ::mat_10_bdb
+// gl_kernels_qua8.cu -- Qua8 (and Tri6) stiffness on the FP64 TENSOR CORES, plane and axisymmetric: integ::mat_10_bdb
 // (src/integ/mat_10_bdb.rs:121-233, the axisymmetric branch :213-233) with a uniform modulus D.  The heavier half of
 // BASELINE.json configs[4] (mixed Tri3 / Qua8, axisymmetric).
 //
@@ -23,6 +23,7 @@
 //      store their upper half first: conflict-free);
 //   D  the triple (3 x 2,048 contiguous bytes on single-kind meshes; runs of consecutive blocks on mixed ones) leaves with bulk
 //      async copies (L2 evict-first).
+// Tri6 runs on the same template with its six nodes in the first six node slots of the tiles.
 // Covered: uniform D or one record per marker / per cell (any pattern), rules of at most 10 points, tight blocks that overwrite a
 // 16-byte aligned buffer; everything else (one modulus per Gauss point, general blocks, fused assembly) stays on gl_kernels_bdb.cu.
 #include <cuda_runtime.h>
@@ -78,30 +79,34 @@ constexpr int Q8_CTAS = 2;     // CTAs per SM
 constexpr int Q8_PS = 12;      // V is stored dof-major, Vt[col][p] at col PS + p; PS = 12 (mod 16): the fragment loads of a half-warp
                                // (4 columns x 4 Gauss points) hit 16 distinct bank pairs
 constexpr int Q8_XS = 18;      // coordinates of a cell (16 doubles + 2): the three cells of a warp read distinct banks
-constexpr int Q8_KB = 256;     // element block
 
-template <bool AXI, bool DREC = false>
+// NN = 8 (Qua8) or 6 (Tri6: its six nodes occupy the first six of the eight node slots of a tile; the two padding columns of V are
+// never written and only reach entries of P that nobody reads -- an MMA output depends on its own row and column alone)
+template <int NN, bool AXI, bool DREC = false>
 struct Qua8Dims {
+    static constexpr int NDOF = 2 * NN;
+    static constexpr int KB = NDOF * NDOF;    // element block (doubles)
     static constexpr int VD = AXI ? 3 : 2;
     static constexpr int NV = 8 * VD;
     static constexpr int CS = NV * Q8_PS + 9; // = 9 (mod 16): the (cell, Gauss point) lanes of a half-warp store one column conflict-free
     static constexpr int VSZ = (Q8_G * CS + 1) & ~1;
-    static constexpr int WSZ = Q8_G * Q8_KB + VSZ + Q8_G * Q8_PS + Q8_G * Q8_XS + (DREC ? Q8_G * 16 : 0); // doubles per warp (even)
+    static constexpr int WSZ = Q8_G * KB + VSZ + Q8_G * Q8_PS + Q8_G * Q8_XS + (DREC ? Q8_G * 16 : 0); // doubles per warp (even)
+    static_assert(NN == 6 || NN == 8, "node slots per tile");
     static_assert(WSZ % 2 == 0, "16-byte aligned warp regions");
 };
 
 // DREC = one modulus record per marker or per cell (multi-material meshes) instead of a uniform D: the records of the next triple are
 // fetched one iteration ahead (their indices two ahead), scaled into d' and staged per cell; with device-resident records whose
 // structure only the probe knows, every pattern variant is enqueued and all but the matching one return at once (gl_kernels_bdb.cu)
-template <bool AXI, int PAT, bool EXTRA, bool DREC = false>
+template <int NN, bool AXI, int PAT, bool EXTRA, bool DREC = false>
 __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst, const Qua8Extra x) {
     if (DREC && p.coef_pat_dev != nullptr && (*p.coef_pat_dev == 2 ? 2 : 0) != PAT) return;
-    using T = Qua8Dims<AXI, DREC>;
-    constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = Q8_G, XS = Q8_XS, KB = Q8_KB;
+    using T = Qua8Dims<NN, AXI, DREC>;
+    constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = Q8_G, XS = Q8_XS, KB = T::KB, NDOF = T::NDOF;
 
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *Kst = smem + warp * T::WSZ; // [G][256]  staged element blocks (16-byte aligned: bulk copy source)
+    double *Kst = smem + warp * T::WSZ; // [G][KB]   staged element blocks (16-byte aligned: bulk copy source)
     double *V = Kst + G * KB;           // [G][CS]   Vt[cell][8k + m][p]
     double *cc = V + T::VSZ;            // [G][PS]   c'_p
     double *Xs = cc + G * PS;           // [G][XS]   X[2m + j]
@@ -117,26 +122,26 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
     // phase B role: lane = (cell of the triple, Gauss point); its rows of the reference-element table stay in registers
     const bool vl = lane < G * ng;
     const int bg = vl ? lane / ng : 0, bp = vl ? lane - bg * ng : 0;
-    double l[16], nsh[8];
+    double l[2 * NN], nsh[NN];
 #pragma unroll
-    for (int i = 0; i < 16; i++) l[i] = p.rule[ng * 9 + bp * 16 + i];
+    for (int i = 0; i < 2 * NN; i++) l[i] = p.rule[ng * (1 + NN) + bp * 2 * NN + i];
 #pragma unroll
-    for (int m = 0; m < 8; m++) nsh[m] = AXI ? p.rule[ng + bp * 8 + m] : 0.0;
+    for (int m = 0; m < NN; m++) nsh[m] = AXI ? p.rule[ng + bp * NN + m] : 0.0;
     const double wgt = p.rule[bp];
 
     // phase A role: lane = (cell of the triple, node)
-    const int ag = lane >> 3, am = lane & 7;
+    const int ag = lane / NN, am = lane - ag * NN;
     const unsigned long long ncell = p.hi - p.lo;
     const unsigned long long ntriple = (ncell + G - 1) / G;
     const unsigned long long tstride = (unsigned long long)gridDim.x * Q8_WARPS;
     auto load_pid = [&](unsigned long long t) -> unsigned int {
         const unsigned long long c = t * G + ag;
-        return (lane < 8 * G && t < ntriple && c < ncell) ? p.conn[(unsigned long long)am * p.ncell_k + p.lo + c] : 0u;
+        return (lane < NN * G && t < ntriple && c < ncell) ? p.conn[(unsigned long long)am * p.ncell_k + p.lo + c] : 0u;
     };
     unsigned long long t = (unsigned long long)blockIdx.x * Q8_WARPS + warp;
     unsigned int pid = load_pid(t);
     double gx0 = 0.0, gx1 = 0.0;
-    if (lane < 8 * G) {
+    if (lane < NN * G) {
         gx0 = p.coords[pid];
         gx1 = p.coords[p.npoint + pid];
     }
@@ -174,11 +179,11 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
             const unsigned long long rel = (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.cell_begin;
             off = p.out_off ? p.out_off[cell] - p.out_base : rel * (unsigned long long)KB;
             if constexpr (EXTRA) {
-                moffv = x.moff ? x.moff[cell] - x.mbase : rel * 64ull;
-                voffv = x.voff ? x.voff[cell] - x.vbase : rel * 8ull;
+                moffv = x.moff ? x.moff[cell] - x.mbase : rel * (unsigned long long)(NN * NN);
+                voffv = x.voff ? x.voff[cell] - x.vbase : rel * (unsigned long long)NN;
             }
         }
-        if (lane < 8 * G) {
+        if (lane < NN * G) {
             *reinterpret_cast<double2 *>(Xs + ag * XS + 2 * am) = make_double2(gx0, gx1);
             gx0 = p.coords[pid];
             gx1 = p.coords[p.npoint + pid];
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
             double J[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
             double r = 0.0;
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
+            for (int m = 0; m < NN; m++) {
                 const double2 xx = *reinterpret_cast<const double2 *>(X + 2 * m);
                 J[0][0] = geom::add(J[0][0], geom::mul(xx.x, l[2 * m]));
                 J[0][1] = geom::add(J[0][1], geom::mul(xx.x, l[2 * m + 1]));
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
             if (vl) {
                 double *Vq = V + bg * CS + bp;
 #pragma unroll
-                for (int m = 0; m < 8; m++) {
+                for (int m = 0; m < NN; m++) {
                     Vq[m * PS] = fma(l[2 * m + 1], Ji[1][0], l[2 * m] * Ji[0][0]);
                     Vq[(8 + m) * PS] = fma(l[2 * m + 1], Ji[1][1], l[2 * m] * Ji[0][1]);
                     if constexpr (AXI) Vq[(16 + m) * PS] = nsh[m] * rinv;
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
         if constexpr (EXTRA) {
             // flux vector: lane = (cell, node) sums its column pair of V over the Gauss points
             const unsigned long long vo = __shfl_sync(0xffffffffu, voffv, ag < G ? ag : 0);
-            if ((x.mask & 8) && lane < 8 * G && ag < nv) {
+            if ((x.mask & 8) && lane < NN * G && ag < nv) {
                 const double *v0 = V + ag * CS + am * PS;
                 double sum = 0.0;
                 for (int q = 0; q < ng; q++) sum = fma(cc[ag * PS + q], fma(x.w1, v0[8 * PS + q], x.w0 * v0[q]), sum);
@@ -307,11 +312,11 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
                         P[Jt][I][e] = q8_select(ar & 1, t1, t0);
                     }
             if constexpr (EXTRA) {
-                // conductivity block, column-major 8 x 8: rows 2ak, 2ak + 1 of column ar.  8-byte stores: on mixed meshes the 3 x 3 blocks
+                // conductivity block, column-major NN x NN: rows 2ak, 2ak + 1 of column ar.  8-byte stores: on mixed meshes the 3 x 3 blocks
                 // of the Tri3 cells can leave the offset odd, and one 16-byte store where it is even measured no faster
                 const unsigned long long mo = __shfl_sync(0xffffffffu, moffv, g);
-                if ((x.mask & 2) && g < nv) {
-                    double *dst = x.out_m03 + mo + 8 * ar + 2 * ak;
+                if ((x.mask & 2) && g < nv && (NN == 8 || (ar < NN && 2 * ak < NN))) {
+                    double *dst = x.out_m03 + mo + NN * ar + 2 * ak;
 #pragma unroll
                     for (int e = 0; e < 2; e++) dst[e] = fma(x.t11, P[1][1][e], fma(x.t01, P[0][1][e] + P[1][0][e], x.t00 * P[0][0][e]));
                 }
@@ -339,18 +344,21 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
                             }
                         Kb[e][i][j] = s;
                     }
-            // rows 4ak + 2e + i of columns 2ar + j, column-major 16 x 16; odd fragment rows store e = 1 first: the eight lanes of a
-            // quarter-warp then write eight distinct 16-byte slots of the 128-byte bank window
-            double *Kc = Kst + g * KB + 16 * (2 * ar) + 4 * ak;
-            const int e0 = ar & 1;
+            // rows 4ak + 2e + i of columns 2ar + j, column-major NDOF x NDOF; odd fragment rows store e = 1 first: with NDOF = 16 the eight
+            // lanes of a quarter-warp then write eight distinct 16-byte slots of the 128-byte bank window.  (Tri6: the lanes of the two
+            // padding node slots hold nothing.)
+            if (NN == 8 || (ar < NN && 2 * ak < NN)) {
+                double *Kc = Kst + g * KB + NDOF * (2 * ar) + 4 * ak;
+                const int e0 = ar & 1;
 #pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const int e = e0 ^ s;
+                for (int s = 0; s < 2; s++) {
+                    const int e = e0 ^ s;
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const double a = q8_select(e, Kb[1][0][j], Kb[0][0][j]);
-                    const double b = q8_select(e, Kb[1][1][j], Kb[0][1][j]);
-                    *reinterpret_cast<double2 *>(Kc + 16 * j + 2 * e) = make_double2(a, b);
+                    for (int j = 0; j < 2; j++) {
+                        const double a = q8_select(e, Kb[1][0][j], Kb[0][0][j]);
+                        const double b = q8_select(e, Kb[1][1][j], Kb[0][1][j]);
+                        *reinterpret_cast<double2 *>(Kc + NDOF * j + 2 * e) = make_double2(a, b);
+                    }
                 }
             }
         }
@@ -376,14 +384,14 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <bool AXI>
+template <int NN, bool AXI>
 int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, bool drec, void *stream) {
-    const size_t smem = sizeof(double) * (size_t)Q8_WARPS * (drec ? Qua8Dims<AXI, true>::WSZ : Qua8Dims<AXI, false>::WSZ);
+    const size_t smem = sizeof(double) * (size_t)Q8_WARPS * (drec ? Qua8Dims<NN, AXI, true>::WSZ : Qua8Dims<NN, AXI, false>::WSZ);
     typedef void (*kern_t)(const IntegParams, const Qua8Consts, const Qua8Extra);
     auto pick = [&](int pt) -> kern_t {
-        if (drec) return pt == 2 ? qua8_kernel<AXI, 2, false, true> : qua8_kernel<AXI, 0, false, true>;
-        if (x.mask) return pt == 2 ? qua8_kernel<AXI, 2, true> : qua8_kernel<AXI, 0, true>;
-        return pt == 2 ? qua8_kernel<AXI, 2, false> : qua8_kernel<AXI, 0, false>;
+        if (drec) return pt == 2 ? qua8_kernel<NN, AXI, 2, false, true> : qua8_kernel<NN, AXI, 0, false, true>;
+        if (x.mask) return pt == 2 ? qua8_kernel<NN, AXI, 2, true> : qua8_kernel<NN, AXI, 0, true>;
+        return pt == 2 ? qua8_kernel<NN, AXI, 2, false> : qua8_kernel<NN, AXI, 0, false>;
     };
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
@@ -406,21 +414,23 @@ int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const
         nl++;
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    if (x.mask) note_kernel("qua8_dmma<axi=%d,pat=%d,fused=%d>", AXI ? 1 : 0, pat, x.mask);
-    else note_kernel("qua8_dmma<axi=%d,pat=%d%s>", AXI ? 1 : 0, pat, drec ? ",rec" : "");
+    const char *family = NN == 8 ? "qua8_dmma" : "tri6_dmma";
+    if (x.mask) note_kernel("%s<axi=%d,pat=%d,fused=%d>", family, AXI ? 1 : 0, pat, x.mask);
+    else note_kernel("%s<axi=%d,pat=%d%s>", family, AXI ? 1 : 0, pat, drec ? ",rec" : "");
     return nl;
 }
 
 } // namespace
 
 int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFused *extra) {
-    if (sd != 2 || p.op != GL_OP_MAT_10_BDB || p.nnode != 8) return 0;
+    if (sd != 2 || p.op != GL_OP_MAT_10_BDB || (p.nnode != 8 && p.nnode != 6)) return 0;
     if (p.scatter_pos != nullptr || p.sigma != nullptr) return 0; // fused assembly: gl_kernels_bdb.cu
     const bool drec = p.coef != nullptr;
     if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 16 || extra != nullptr)) return 0; // one modulus per Gauss point: gl_kernels_bdb.cu
     if (Q8_G * p.ng > 32) return 0;
-    if (p.size_r != 16 || p.size_c != 16) return 0;
-    const bool tight = p.nrow == 16 && p.ncol == 16 && p.ii0 == 0 && p.jj0 == 0;
+    const unsigned ndof = 2u * (unsigned)p.nnode;
+    if (p.size_r != ndof || p.size_c != ndof) return 0;
+    const bool tight = p.nrow == ndof && p.ncol == ndof && p.ii0 == 0 && p.jj0 == 0;
     if (!(tight && p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) return 0; // general store epilogue: gl_kernels_bdb.cu
     if (tuning_env("GL_DISABLE_QUA8")) return 0;
 
@@ -461,7 +471,9 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
         x.voff = extra->voff;
         x.vbase = extra->vbase;
     }
-    return p.axisym ? launch_qua8_kind<true>(p, cst, pat, x, drec, stream) : launch_qua8_kind<false>(p, cst, pat, x, drec, stream);
+    if (p.nnode == 6)
+        return p.axisym ? launch_qua8_kind<6, true>(p, cst, pat, x, drec, stream) : launch_qua8_kind<6, false>(p, cst, pat, x, drec, stream);
+    return p.axisym ? launch_qua8_kind<8, true>(p, cst, pat, x, drec, stream) : launch_qua8_kind<8, false>(p, cst, pat, x, drec, stream);
 }
 
 } // namespace gl

@@ -46,7 +46,9 @@ FAMILIES = [
     ("qua8", "mat_10_bdb", {"ngauss": 16}, "bdb<nn=8,sd=2,axi=0"),
     ("qua8", "mat_10_bdb", {"axisymmetric": True, "clear": False}, "bdb<nn=8,sd=2,axi=1,pat=2,gen>"),
     ("qua9", "mat_10_bdb", {}, "bdb<nn=9,sd=2"),
-    ("tri6", "mat_10_bdb", {}, "bdb<nn=6,sd=2"),
+    ("tri6", "mat_10_bdb", {}, "tri6_dmma<axi=0,pat=2>"),
+    ("tri6", "mat_10_bdb", {"axisymmetric": True}, "tri6_dmma<axi=1,pat=2>"),
+    ("tri6", "mat_10_bdb", {"ngauss": 12}, "bdb<nn=6,sd=2"),
     ("tet10", "mat_01_nsn", {}, "mass_dmma<nn=10,sd=3"),
     ("tet10", "vec_01_ns", {}, "mass_dmma<nn=10,sd=3"),
     ("hex8", "mat_01_nsn", {}, "mass_dmma<nn=8,sd=3"),
@@ -101,30 +103,34 @@ def test_hex20_tensor_core_stiffness(ctx, rule, structure):
 
 
 @pytest.mark.parametrize("axisymmetric", [False, True])
-@pytest.mark.parametrize("rule", [1, 4, 9])
+@pytest.mark.parametrize("kind,rule", [("qua8", 1), ("qua8", 4), ("qua8", 9), ("tri6", 1), ("tri6", 3), ("tri6", 4), ("tri6", 6), ("tri6", 7)])
 @pytest.mark.parametrize("structure", ["isotropic", "symmetric", "general"])
-def test_qua8_tensor_core_stiffness(ctx, axisymmetric, rule, structure):
-    """mat_10_bdb on jittered Qua8 cells through the DMMA kernel of gl_kernels_qua8.cu vs the oracle (src/integ/mat_10_bdb.rs:179-233,
-    plane and axisymmetric), every rule it accepts, isotropic / symmetric / general moduli; ranges that do not fill the three
-    cells of a warp, and more triples than one CTA holds warps."""
-    mesh = make_mesh("qua8", n=7, seed=11)  # 56 cells
+def test_qua8_tensor_core_stiffness(ctx, axisymmetric, kind, rule, structure):
+    """mat_10_bdb on jittered Qua8 / Tri6 cells through the DMMA kernel of gl_kernels_qua8.cu vs the oracle
+    (src/integ/mat_10_bdb.rs:179-233, plane and axisymmetric), every rule it accepts (four Gauss points per k-step, a single leftover
+    point as a rank-1 update, other remainders as a padded step), isotropic / symmetric / general moduli; ranges that do not fill the
+    three cells of a warp, and more triples than one CTA holds warps."""
+    mesh = make_mesh(kind, n=7 if kind == "qua8" else 5, seed=11)  # 56 Qua8 / 50 Tri6 cells
     rng = np.random.default_rng(37)
     dd = iso(2) if structure == "isotropic" else random_coef("mat_10_bdb", 2, 1, rng, spd=(structure == "symmetric"))[0]
     dmesh = ctx.upload(mesh)
+    bs = 256 if kind == "qua8" else 144
     ref = oracle_integ("mat_10_bdb", mesh, dd, ngauss=rule, axisymmetric=axisymmetric)
-    for b, e in [(0, mesh.ncell), (0, 1), (3, 5), (5, 19), (1, 56), (2, 27)]:
+    for b, e in [(0, mesh.ncell), (0, 1), (3, 5), (5, 19), (1, mesh.ncell), (2, 27)]:
         got = integ.mat_10_bdb(ctx, dmesh, (b, e), CommonArgs(ngauss=rule, axisymmetric=axisymmetric), Coef.uniform(dd))
-        assert ctx.last_kernel() == f"qua8_dmma<axi={int(axisymmetric)},pat={2 if structure == 'isotropic' else 0}>"
-        assert rel_err(got, ref[b * 256:e * 256], np.arange(e - b + 1) * 256) <= TOL, f"rule {rule} range {b}:{e}"
+        assert ctx.last_kernel() == f"{kind}_dmma<axi={int(axisymmetric)},pat={2 if structure == 'isotropic' else 0}>"
+        assert rel_err(got, ref[b * bs:e * bs], np.arange(e - b + 1) * bs) <= TOL, f"rule {rule} range {b}:{e}"
 
 
 @pytest.mark.parametrize("axisymmetric", [False, True])
-def test_qua8_modulus_records_on_the_tensor_core_kernel(ctx, axisymmetric):
+@pytest.mark.parametrize("kind", ["qua8", "tri6"])
+def test_qua8_modulus_records_on_the_tensor_core_kernel(ctx, axisymmetric, kind):
     """One modulus per marker / per cell (multi-material meshes) on the Qua8 DMMA kernel: records fetched one triple ahead and staged
     per cell; ragged ranges, host- and device-resident records (the latter through the structure probe: both pattern variants are
     enqueued, one runs)."""
     import torch
-    mesh = make_mesh("qua8", n=6, seed=8)
+    mesh = make_mesh(kind, n=6 if kind == "qua8" else 4, seed=8)
+    bs = 256 if kind == "qua8" else 144
     rng = np.random.default_rng(29)
     mesh.markers[:] = rng.integers(1, 4, mesh.ncell)
     dmesh = ctx.upload(mesh)
@@ -138,19 +144,19 @@ def test_qua8_modulus_records_on_the_tensor_core_kernel(ctx, axisymmetric):
         ref = oracle_integ("mat_10_bdb", mesh, per_cell, cell_stride=16, axisymmetric=axisymmetric)
         pat = 2 if structure == "isotropic" else 0
         for b, e in [(0, mesh.ncell), (1, 2), (4, 21), (7, mesh.ncell)]:
-            sizes = np.arange(e - b + 1) * 256
+            sizes = np.arange(e - b + 1) * bs
             got = integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.per_marker([1, 2, 3], recs))
-            assert ctx.last_kernel() == f"qua8_dmma<axi={int(axisymmetric)},pat={pat},rec>"
-            assert rel_err(got, ref[b * 256:e * 256], sizes) <= TOL, f"per_marker {structure} {b}:{e}"
+            assert ctx.last_kernel() == f"{kind}_dmma<axi={int(axisymmetric)},pat={pat},rec>"
+            assert rel_err(got, ref[b * bs:e * bs], sizes) <= TOL, f"per_marker {structure} {b}:{e}"
             got = integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.per_cell(per_cell[b:e]))
-            assert ctx.last_kernel() == f"qua8_dmma<axi={int(axisymmetric)},pat={pat},rec>"
-            assert rel_err(got, ref[b * 256:e * 256], sizes) <= TOL, f"per_cell {structure} {b}:{e}"
-            out = torch.full(((e - b) * 256 + 8,), -1.5, dtype=torch.float64, device="cuda")
+            assert ctx.last_kernel() == f"{kind}_dmma<axi={int(axisymmetric)},pat={pat},rec>"
+            assert rel_err(got, ref[b * bs:e * bs], sizes) <= TOL, f"per_cell {structure} {b}:{e}"
+            out = torch.full(((e - b) * bs + 8,), -1.5, dtype=torch.float64, device="cuda")
             integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.per_cell(torch.from_numpy(per_cell[b:e].copy()).cuda()), out=out[4:-4])
-            assert ctx.last_kernel().startswith(f"qua8_dmma<axi={int(axisymmetric)},pat=") and ctx.last_kernel().endswith(",rec>")
+            assert ctx.last_kernel().startswith(f"{kind}_dmma<axi={int(axisymmetric)},pat=") and ctx.last_kernel().endswith(",rec>")
             res = out.cpu().numpy()
             assert np.all(res[:4] == -1.5) and np.all(res[-4:] == -1.5)
-            assert rel_err(res[4:-4], ref[b * 256:e * 256], sizes) <= TOL, f"per_cell device {structure} {b}:{e}"
+            assert rel_err(res[4:-4], ref[b * bs:e * bs], sizes) <= TOL, f"per_cell device {structure} {b}:{e}"
 
 
 def test_qua8_tensor_core_on_mixed_mesh_and_guard_band(ctx):
@@ -185,7 +191,7 @@ def test_qua8_tensor_core_on_mixed_mesh_and_guard_band(ctx):
 
 @pytest.mark.parametrize("axisymmetric", [False, True])
 @pytest.mark.parametrize("which", ["both", "mat_03_btb", "vec_03_bv"])
-@pytest.mark.parametrize("layout", ["mixed", "qua8", "tri3", "qua4"])
+@pytest.mark.parametrize("layout", ["mixed", "qua8", "tri6", "tri3", "qua4"])
 def test_stiffness_conductivity_flux_from_one_pass(ctx, axisymmetric, which, layout):
     """gl_integ_fused with mat_10_bdb + mat_03_btb and / or vec_03_bv (BASELINE.json configs[4]): the Qua8 cells take the scalar
     cases from the geometric tensors of the tensor-core stiffness kernel, the other kinds run their stiffness kernel and ONE fused
@@ -211,6 +217,8 @@ def test_stiffness_conductivity_flux_from_one_pass(ctx, axisymmetric, which, lay
         if layout in ("mixed", "qua8"):
             assert f"qua8_dmma<axi={int(axisymmetric)},pat=2,fused={mask}>" in ran, ran
             assert not any(k.startswith("scalar_tpc<nn=8") for k in ran), ran
+        if layout == "tri6":
+            assert ran == [f"tri6_dmma<axi={int(axisymmetric)},pat=2,fused={mask}>"], ran
         if layout == "tri3" or (layout == "mixed" and e - b > 1):
             assert f"small2d<nn=3,axi={int(axisymmetric)},pat=2>" in ran and f"scalar_tpc<nn=3,sd=2,mask={mask}>" in ran, ran
         if layout == "qua4":
