@@ -73,8 +73,6 @@ __device__ __forceinline__ double q8_select(int c, double a, double b) { // c ? 
     return r;
 }
 
-constexpr int Q8_G = 3;        // cells per warp
-constexpr int Q8_WARPS = 8;    // warps per CTA
 constexpr int Q8_CTAS = 2;     // CTAs per SM
 constexpr int Q8_PS = 12;      // V is stored dof-major, Vt[col][p] at col PS + p; PS = 12 (mod 16): the fragment loads of a half-warp
                                // (4 columns x 4 Gauss points) hit 16 distinct bank pairs
@@ -86,11 +84,16 @@ template <int NN, bool AXI, bool DREC = false>
 struct Qua8Dims {
     static constexpr int NDOF = 2 * NN;
     static constexpr int KB = NDOF * NDOF;    // element block (doubles)
+    // cells per warp: G x ng geometry lanes (27 of 32 with the 9-point Qua8 rule, 28 with the 7-point Tri6 rule).  Axisymmetric Tri6
+    // keeps three: four would leave room for seven warps per CTA only, measured slower (2.00 against 2.05 G el/s)
+    static constexpr int G = (NN == 6 && !AXI) ? 4 : 3;
     static constexpr int VD = AXI ? 3 : 2;
     static constexpr int NV = 8 * VD;
     static constexpr int CS = NV * Q8_PS + 9; // = 9 (mod 16): the (cell, Gauss point) lanes of a half-warp store one column conflict-free
-    static constexpr int VSZ = (Q8_G * CS + 1) & ~1;
-    static constexpr int WSZ = Q8_G * KB + VSZ + Q8_G * Q8_PS + Q8_G * Q8_XS + (DREC ? Q8_G * 16 : 0); // doubles per warp (even)
+    static constexpr int VSZ = (G * CS + 1) & ~1;
+    static constexpr int WSZ = G * KB + VSZ + G * Q8_PS + G * Q8_XS + (DREC ? G * 16 : 0); // doubles per warp (even)
+    // warps per CTA: eight if two CTAs of eight fit an SM (228 KB, 1 KB reserved per CTA), else seven
+    static constexpr int WARPS = 2 * (8 * WSZ * 8 + 1024) <= 228 * 1024 ? 8 : 7;
     static_assert(NN == 6 || NN == 8, "node slots per tile");
     static_assert(WSZ % 2 == 0, "16-byte aligned warp regions");
 };
@@ -99,10 +102,10 @@ struct Qua8Dims {
 // fetched one iteration ahead (their indices two ahead), scaled into d' and staged per cell; with device-resident records whose
 // structure only the probe knows, every pattern variant is enqueued and all but the matching one return at once (gl_kernels_bdb.cu)
 template <int NN, bool AXI, int PAT, bool EXTRA, bool DREC = false>
-__global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst, const Qua8Extra x) {
+__global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst, const Qua8Extra x) {
     if (DREC && p.coef_pat_dev != nullptr && (*p.coef_pat_dev == 2 ? 2 : 0) != PAT) return;
     using T = Qua8Dims<NN, AXI, DREC>;
-    constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = Q8_G, XS = Q8_XS, KB = T::KB, NDOF = T::NDOF;
+    constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = T::G, XS = Q8_XS, KB = T::KB, NDOF = T::NDOF, WARPS = T::WARPS;
 
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -133,12 +136,12 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
     const int ag = lane / NN, am = lane - ag * NN;
     const unsigned long long ncell = p.hi - p.lo;
     const unsigned long long ntriple = (ncell + G - 1) / G;
-    const unsigned long long tstride = (unsigned long long)gridDim.x * Q8_WARPS;
+    const unsigned long long tstride = (unsigned long long)gridDim.x * WARPS;
     auto load_pid = [&](unsigned long long t) -> unsigned int {
         const unsigned long long c = t * G + ag;
         return (lane < NN * G && t < ntriple && c < ncell) ? p.conn[(unsigned long long)am * p.ncell_k + p.lo + c] : 0u;
     };
-    unsigned long long t = (unsigned long long)blockIdx.x * Q8_WARPS + warp;
+    unsigned long long t = (unsigned long long)blockIdx.x * WARPS + warp;
     unsigned int pid = load_pid(t);
     double gx0 = 0.0, gx1 = 0.0;
     if (lane < NN * G) {
@@ -146,10 +149,10 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
         gx1 = p.coords[p.npoint + pid];
     }
     pid = load_pid(t + tstride);
-    // modulus records: lane -> entry (lane & 15) of cell (lane >> 4) of the triple, lanes 0..15 also entry `lane` of its third cell
+    // modulus records: lane -> entry (lane & 15) of cells (lane >> 4) and 2 + (lane >> 4) of the warp's cells
     auto load_rec = [&](unsigned long long tt, int g) -> unsigned long long {
         const unsigned long long c = tt * G + g;
-        if (!(tt < ntriple && c < ncell)) return 0ull;
+        if (!(g < G && tt < ntriple && c < ncell)) return 0ull;
         const unsigned long long cell = p.lo + c;
         return p.coef_index ? (unsigned long long)p.coef_index[cell] : (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.coef_begin;
     };
@@ -157,11 +160,11 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
     double dv0 = 0.0, dv1 = 0.0;
     if constexpr (DREC) {
         rec0 = load_rec(t, lane >> 4);
-        rec1 = load_rec(t, 2);
+        rec1 = load_rec(t, 2 + (lane >> 4));
         dv0 = p.coef[rec0 * p.coef_cell_stride + (lane & 15)];
         dv1 = p.coef[rec1 * p.coef_cell_stride + (lane & 15)];
         rec0 = load_rec(t + tstride, lane >> 4);
-        rec1 = load_rec(t + tstride, 2);
+        rec1 = load_rec(t + tstride, 2 + (lane >> 4));
     }
 
     unsigned long long pol; // the element matrices are written once: keep them from flushing the mesh out of L2
@@ -195,11 +198,11 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
             const int a = lane & 3, b = (lane >> 2) & 3;
             const double fs = (a < 3 ? 1.0 : hs) * (b < 3 ? 1.0 : hs);
             Dc[(lane >> 4) * 16 + a * 4 + b] = dv0 * fs;
-            if (lane < 16) Dc[2 * 16 + a * 4 + b] = dv1 * fs;
+            if (2 + (lane >> 4) < G) Dc[(2 + (lane >> 4)) * 16 + a * 4 + b] = dv1 * fs;
             dv0 = p.coef[rec0 * p.coef_cell_stride + (lane & 15)];
             dv1 = p.coef[rec1 * p.coef_cell_stride + (lane & 15)];
             rec0 = load_rec(t + 2 * tstride, lane >> 4);
-            rec1 = load_rec(t + 2 * tstride, 2);
+            rec1 = load_rec(t + 2 * tstride, 2 + (lane >> 4));
         }
         __syncwarp();
 
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
                 }
                 cc[bg * PS + bp] = coef;
             }
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the previous bulk copies have left Kst
+            if (lane < G) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the previous bulk copies have left Kst
         }
         __syncwarp();
 
@@ -364,29 +367,33 @@ __global__ void __launch_bounds__(32 * Q8_WARPS, Q8_CTAS) qua8_kernel(const Inte
         }
 
         // ---- phase D: ship ---------------------------------------------------------------------------------------------------
+        // runs of blocks that are consecutive in the output leave as one copy (always one, on single-kind meshes): lane k < nv owns
+        // cell k, the first lane of a run issues its copy (bulk groups are per thread: that lane also waits for it)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const unsigned long long o1 = __shfl_sync(0xffffffffu, off, 1), o2 = __shfl_sync(0xffffffffu, off, 2);
-        if (lane == 0) {
-            // runs of blocks that are consecutive in the output leave as one copy (always, on single-kind meshes)
-            const bool c01 = nv > 1 && o1 == off + KB, c12 = nv > 2 && o2 == o1 + KB;
-            auto ship = [&](unsigned long long o, int first, int count) {
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(p.out + o),
-                             "r"(q8_smem_u32(Kst + first * KB)), "r"((unsigned)(count * KB * sizeof(double))), "l"(pol)
+        __syncwarp();
+        {
+            const unsigned long long prev = __shfl_up_sync(0xffffffffu, off, 1);
+            const bool start = lane < nv && (lane == 0 || off != prev + KB);
+            const unsigned starts = __ballot_sync(0xffffffffu, start);
+            if (start) {
+                const unsigned above = starts >> (lane + 1);
+                const int next = above ? lane + __ffs(above) : nv;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(p.out + off),
+                             "r"(q8_smem_u32(Kst + lane * KB)), "r"((unsigned)((next - lane) * KB * sizeof(double))), "l"(pol)
                              : "memory");
-            };
-            ship(off, 0, 1 + (c01 ? 1 : 0) + (c01 && c12 ? 1 : 0));
-            if (nv > 1 && !c01) ship(o1, 1, 1 + (c12 ? 1 : 0));
-            if (nv > 2 && !c12) ship(o2, 2, 1);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (lane < G) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         __syncwarp();
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane < G) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <int NN, bool AXI>
 int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, bool drec, void *stream) {
-    const size_t smem = sizeof(double) * (size_t)Q8_WARPS * (drec ? Qua8Dims<NN, AXI, true>::WSZ : Qua8Dims<NN, AXI, false>::WSZ);
+    const int warps = drec ? Qua8Dims<NN, AXI, true>::WARPS : Qua8Dims<NN, AXI, false>::WARPS;
+    constexpr int G = Qua8Dims<NN, AXI>::G;
+    const size_t smem = sizeof(double) * (size_t)warps * (drec ? Qua8Dims<NN, AXI, true>::WSZ : Qua8Dims<NN, AXI, false>::WSZ);
     typedef void (*kern_t)(const IntegParams, const Qua8Consts, const Qua8Extra);
     auto pick = [&](int pt) -> kern_t {
         if (drec) return pt == 2 ? qua8_kernel<NN, AXI, 2, false, true> : qua8_kernel<NN, AXI, 0, false, true>;
@@ -396,10 +403,10 @@ int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned long long ntriple = (p.hi - p.lo + Q8_G - 1) / Q8_G;
+    const unsigned long long ntriple = (p.hi - p.lo + G - 1) / G;
     unsigned long long grid = (unsigned long long)nsm * Q8_CTAS; // persistent: warps stride over the triples
     if (const char *e = tuning_env("GL_QUA8_GRID")) grid = (unsigned long long)atoi(e);
-    const unsigned long long need = (ntriple + Q8_WARPS - 1) / Q8_WARPS;
+    const unsigned long long need = (ntriple + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid == 0) return 0;
     // records whose structure only the device knows: both variants are enqueued, the probe's verdict selects the one that runs
@@ -410,7 +417,7 @@ int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const
     for (int pt = probe ? 0 : pat; pt <= (probe ? 2 : pat); pt += 2) {
         kern_t kern = pick(pt);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        kern<<<(unsigned)grid, 32 * Q8_WARPS, smem, (cudaStream_t)stream>>>(q, cst, x);
+        kern<<<(unsigned)grid, 32 * warps, smem, (cudaStream_t)stream>>>(q, cst, x);
         nl++;
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
@@ -427,7 +434,7 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
     if (p.scatter_pos != nullptr || p.sigma != nullptr) return 0; // fused assembly: gl_kernels_bdb.cu
     const bool drec = p.coef != nullptr;
     if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 16 || extra != nullptr)) return 0; // one modulus per Gauss point: gl_kernels_bdb.cu
-    if (Q8_G * p.ng > 32) return 0;
+    if ((p.nnode == 6 && !p.axisym ? 4 : 3) * p.ng > 32) return 0;
     const unsigned ndof = 2u * (unsigned)p.nnode;
     if (p.size_r != ndof || p.size_c != ndof) return 0;
     const bool tight = p.nrow == ndof && p.ncol == ndof && p.ii0 == 0 && p.jj0 == 0;
