@@ -78,18 +78,21 @@ constexpr int Q8_PS = 12;      // V is stored dof-major, Vt[col][p] at col PS + 
                                // (4 columns x 4 Gauss points) hit 16 distinct bank pairs
 constexpr int Q8_XS = 18;      // coordinates of a cell (16 doubles + 2): the three cells of a warp read distinct banks
 
-// NN = 8 (Qua8) or 6 (Tri6: its six nodes occupy the first six of the eight node slots of a tile; the two padding columns of V are
-// never written and only reach entries of P that nobody reads -- an MMA output depends on its own row and column alone)
+// NN = 8 (Qua8) or 6 (Tri6: its six nodes occupy the first six of the eight node slots of a tile; what the fragment lanes of the two
+// other slots read only reaches entries of P that nobody reads -- an MMA output depends on its own row and column alone)
 template <int NN, bool AXI, bool DREC = false>
 struct Qua8Dims {
     static constexpr int NDOF = 2 * NN;
     static constexpr int KB = NDOF * NDOF;    // element block (doubles)
-    // cells per warp: G x ng geometry lanes (27 of 32 with the 9-point Qua8 rule, 28 with the 7-point Tri6 rule).  Axisymmetric Tri6
-    // keeps three: four would leave room for seven warps per CTA only, measured slower (2.00 against 2.05 G el/s)
-    static constexpr int G = (NN == 6 && !AXI) ? 4 : 3;
+    // cells per warp: G x ng geometry lanes (27 of 32 with the 9-point Qua8 rule, 28 with the 7-point Tri6 rule)
+    static constexpr int G = NN == 6 ? 4 : 3;
     static constexpr int VD = AXI ? 3 : 2;
-    static constexpr int NV = 8 * VD;
-    static constexpr int CS = NV * Q8_PS + 9; // = 9 (mod 16): the (cell, Gauss point) lanes of a half-warp store one column conflict-free
+    static constexpr int NS = NN;             // columns of V per component: V[p][NS k + m].  The fragment lanes of the node slots a Tri6
+                                              // tile does not have (ar = 6, 7) read the first columns of the next component instead
+    static constexpr int NV = NS * VD;
+    // cell stride = ng (mod 16) for the default rule (9 points Qua8, 7 points Tri6): the (cell, Gauss point) lanes of a half-warp
+    // store one column conflict-free
+    static constexpr int CS = NV * Q8_PS + ((NN == 8 ? 9 : 7) + 16 - (NV * Q8_PS) % 16) % 16;
     static constexpr int VSZ = (G * CS + 1) & ~1;
     static constexpr int WSZ = G * KB + VSZ + G * Q8_PS + G * Q8_XS + (DREC ? G * 16 : 0); // doubles per warp (even)
     // warps per CTA: eight if two CTAs of eight fit an SM (228 KB, 1 KB reserved per CTA), else seven
@@ -105,12 +108,12 @@ template <int NN, bool AXI, int PAT, bool EXTRA, bool DREC = false>
 __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst, const Qua8Extra x) {
     if (DREC && p.coef_pat_dev != nullptr && (*p.coef_pat_dev == 2 ? 2 : 0) != PAT) return;
     using T = Qua8Dims<NN, AXI, DREC>;
-    constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = T::G, XS = Q8_XS, KB = T::KB, NDOF = T::NDOF, WARPS = T::WARPS;
+    constexpr int VD = T::VD, CS = T::CS, PS = Q8_PS, G = T::G, XS = Q8_XS, KB = T::KB, NDOF = T::NDOF, WARPS = T::WARPS, NS = T::NS;
 
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *Kst = smem + warp * T::WSZ; // [G][KB]   staged element blocks (16-byte aligned: bulk copy source)
-    double *V = Kst + G * KB;           // [G][CS]   Vt[cell][8k + m][p]
+    double *V = Kst + G * KB;           // [G][CS]   Vt[cell][NS k + m][p]
     double *cc = V + T::VSZ;            // [G][PS]   c'_p
     double *Xs = cc + G * PS;           // [G][XS]   X[2m + j]
     double *Dc = Xs + G * XS;           // [G][16]   d' of the cell, row-major (DREC only)
@@ -238,8 +241,8 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
 #pragma unroll
                 for (int m = 0; m < NN; m++) {
                     Vq[m * PS] = fma(l[2 * m + 1], Ji[1][0], l[2 * m] * Ji[0][0]);
-                    Vq[(8 + m) * PS] = fma(l[2 * m + 1], Ji[1][1], l[2 * m] * Ji[0][1]);
-                    if constexpr (AXI) Vq[(16 + m) * PS] = nsh[m] * rinv;
+                    Vq[(NS + m) * PS] = fma(l[2 * m + 1], Ji[1][1], l[2 * m] * Ji[0][1]);
+                    if constexpr (AXI) Vq[(2 * NS + m) * PS] = nsh[m] * rinv;
                 }
                 cc[bg * PS + bp] = coef;
             }
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
             if ((x.mask & 8) && lane < NN * G && ag < nv) {
                 const double *v0 = V + ag * CS + am * PS;
                 double sum = 0.0;
-                for (int q = 0; q < ng; q++) sum = fma(cc[ag * PS + q], fma(x.w1, v0[8 * PS + q], x.w0 * v0[q]), sum);
+                for (int q = 0; q < ng; q++) sum = fma(cc[ag * PS + q], fma(x.w1, v0[NS * PS + q], x.w0 * v0[q]), sum);
                 x.out_v03[vo + am] = sum;
             }
         }
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
                 double v[VD], vs[VD];
 #pragma unroll
                 for (int k = 0; k < VD; k++) {
-                    v[k] = ok ? vr[8 * k * PS] : 0.0;
+                    v[k] = ok ? vr[NS * k * PS] : 0.0;
                     vs[k] = v[k] * c;
                 }
                 // C[r][q] += sum_k A[r][k] B[k][q] with A[r][k] = V[k][8J + r], B[k][q] = c_k V[k][8I + q]: C[r][q] = P[I][J](m = q, n = r)
@@ -290,9 +293,9 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
                 double gm[VD][2], gn[VD];
 #pragma unroll
                 for (int k = 0; k < VD; k++) {
-                    gn[k] = vq[(8 * k + ar) * PS] * c;
-                    gm[k][0] = vq[(8 * k + 2 * ak) * PS];
-                    gm[k][1] = vq[(8 * k + 2 * ak + 1) * PS];
+                    gn[k] = vq[(NS * k + ar) * PS] * c;
+                    gm[k][0] = vq[(NS * k + 2 * ak) * PS];
+                    gm[k][1] = vq[(NS * k + 2 * ak + 1) * PS];
                 }
 #pragma unroll
                 for (int I = 0; I < VD; I++)
@@ -434,7 +437,7 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
     if (p.scatter_pos != nullptr || p.sigma != nullptr) return 0; // fused assembly: gl_kernels_bdb.cu
     const bool drec = p.coef != nullptr;
     if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 16 || extra != nullptr)) return 0; // one modulus per Gauss point: gl_kernels_bdb.cu
-    if ((p.nnode == 6 && !p.axisym ? 4 : 3) * p.ng > 32) return 0;
+    if ((p.nnode == 6 ? 4 : 3) * p.ng > 32) return 0;
     const unsigned ndof = 2u * (unsigned)p.nnode;
     if (p.size_r != ndof || p.size_c != ndof) return 0;
     const bool tight = p.nrow == ndof && p.ncol == ndof && p.ii0 == 0 && p.jj0 == 0;
