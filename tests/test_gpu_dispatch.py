@@ -260,6 +260,51 @@ def test_stiffness_plus_scalar_cases_in_one_call_3d(ctx, kind):
             assert rel_err(o.cpu().numpy(), ref, np.arange(mesh.ncell + 1) * bs) <= TOL, op
 
 
+def mixed_tri6_qua8(n=6, seed=6):
+    """Stripes of Qua8 cells and of Tri6 pairs over one Qua9 lattice (a Qua8 is the Qua9's first eight nodes; the Tri6 take its centre)."""
+    q9 = Block.new_square(2.0).set_ndiv([n, n]).subdivide(GeoKind.Qua9)
+    q9.coords[:, 0] += 1.0
+    c = q9.conn_matrix()
+    cells = []
+    for e in range(q9.ncell):
+        if (e // n) % 2 == 0:
+            cells.append((GeoKind.Qua8, c[e, :8]))
+        else:
+            cells.append((GeoKind.Tri6, c[e, [0, 1, 2, 4, 5, 8]]))
+            cells.append((GeoKind.Tri6, c[e, [0, 2, 3, 8, 6, 7]]))
+    return g.jitter_interior_points(Mesh.from_cells(2, q9.coords, cells), 0.01, seed)
+
+
+@pytest.mark.parametrize("axisymmetric", [False, True])
+def test_tensor_core_kernels_on_a_mixed_tri6_qua8_mesh(ctx, axisymmetric):
+    """Both kinds of a mixed quadratic mesh on the DMMA kernel: blocks of 144 and 256 doubles interleave in the output, so the warps
+    (three Qua8 / four Tri6 cells each) ship runs that start and end inside stripes; stiffness alone and with the scalar by-products."""
+    import torch
+    mesh = mixed_tri6_qua8()
+    dmesh = ctx.upload(mesh)
+    args = CommonArgs(axisymmetric=axisymmetric)
+    kw = {"axisymmetric": True} if axisymmetric else {}
+    coefs = {"mat_10_bdb": iso(2), "mat_03_btb": np.array([2.0, 3.5, 0.0, 0.75]), "vec_03_bv": np.array([1.0, -2.0])}
+    for b, e in [(0, mesh.ncell), (2, mesh.ncell - 3), (5, 17), (7, 8)]:
+        sub = mesh.permuted(np.arange(b, e))
+        off = integ.out_offsets(dmesh, "mat_10_bdb", (b, e), args)
+        buf = torch.full((int(off[-1]) + 32,), 4.5, dtype=torch.float64, device="cuda")
+        integ.mat_10_bdb(ctx, dmesh, (b, e), args, Coef.uniform(coefs["mat_10_bdb"]), out=buf[16:-16])
+        got = buf.cpu().numpy()
+        assert np.all(got[:16] == 4.5) and np.all(got[-16:] == 4.5)
+        assert rel_err(got[16:-16], oracle_integ("mat_10_bdb", sub, coefs["mat_10_bdb"], **kw), off) <= TOL, f"{b}:{e}"
+        ops = ["mat_10_bdb", "mat_03_btb", "vec_03_bv"]
+        offs = [integ.out_offsets(dmesh, op, (b, e), args) for op in ops]
+        outs = [torch.full((int(o[-1]) + 16,), 3.25, dtype=torch.float64, device="cuda") for o in offs]
+        integ.fused(ctx, dmesh, (b, e), args, [(op, Coef.uniform(coefs[op]), o[8:-8]) for op, o in zip(ops, outs)])
+        ran = ctx.last_kernel().split(" + ")
+        assert all(k.startswith(("qua8_dmma<", "tri6_dmma<")) and k.endswith(",fused=10>") for k in ran), ran
+        for op, o, of in zip(ops, outs, offs):
+            res = o.cpu().numpy()
+            assert np.all(res[:8] == 3.25) and np.all(res[-8:] == 3.25), op
+            assert rel_err(res[8:-8], oracle_integ(op, sub, coefs[op], **kw), of) <= TOL, f"{op} {b}:{e}"
+
+
 def test_hex20_general_blocks_and_accumulation(ctx):
     """nrow / ncol / ii0 / jj0 and clear = false in the store epilogue of the tensor-core kernel (CommonArgs,
     src/integ/common_args.rs:5-43; kk.fill(0.0) clears the WHOLE block, mat_10_bdb.rs:141-143)."""
