@@ -1,31 +1,33 @@
-// gl_kernels_qua8.cu -- Qua8 (and Tri6) stiffness on the FP64 TENSOR CORES, plane and axisymmetric: integ::mat_10_bdb
-// (src/integ/mat_10_bdb.rs:121-233, the axisymmetric branch :213-233) with a uniform modulus D.  The heavier half of
-// BASELINE.json configs[4] (mixed Tri3 / Qua8, axisymmetric).
+// gl_kernels_qua8.cu -- Qua8 and Tri6 stiffness on the FP64 TENSOR CORES, plane and axisymmetric: integ::mat_10_bdb
+// (src/integ/mat_10_bdb.rs:121-233, the axisymmetric branch :213-233) with a modulus D that does not vary inside a cell (uniform, or
+// one record per marker / per cell).  Qua8 is the heavier half of BASELINE.json configs[4] (mixed Tri3 / Qua8, axisymmetric).
 //
 // Algebra (gl_kernels_bdb.cu): with the per-node vector g(m) = (B(m,0), B(m,1) [, N(m)/r]) and c' = det.w.alpha [.r],
 //     P[k][l](m,n) = sum_p c'_p g_p(m)[k] g_p(n)[l],        K(2m+i, 2n+j) = sum_kl D'_(ik)(jl) P[k][l](m,n)   (once per node pair).
 // The register-blocked kernel accumulates P with DFMA from per-node records in shared memory and is bound by the shared-memory
 // pipe (ncu, profiles/r02_ncu_full_qua8_axisym_bdb_summary.json: LDS wavefronts 78 % of peak, FP64 pipe 35 %, a quarter of the
 // stall samples at CTA barriers).  Here P = V^T diag(c') V is formed by mma.sync.m8n8k4.f64 with the columns of V ordered
-// COMPONENT-MAJOR, V[p][8k + m] = g_p(m)[k]: Qua8 has exactly eight nodes, so the 8 x 8 tile (I, J) of P is P[I][J](., .) and its
+// COMPONENT-MAJOR, V[p][NS k + m] = g_p(m)[k]: Qua8 has exactly eight nodes, so the 8 x 8 tile (I, J) of P is P[I][J](., .) and its
 // accumulator fragment gives lane (ar, ak) the entries (m, n) = (2ak + e, ar), e = 0, 1, of EVERY component pair -- the lane owns
 // the complete geometric tensors of two node pairs and contracts them with D' in registers (compile-time sparsity pattern); no
 // second trip through shared memory, no pair table.  Only the upper tiles (I <= J) are computed (6 of 9 axisymmetric, 3 of 4
 // plane); P[J][I](m,n) = P[I][J](n,m) sits in lane (2ak + e, ar >> 1) as element ar & 1 and is fetched with shuffles.
 //
-// Mapping: ONE WARP PER THREE CELLS, no barrier wider than a warp, 8 warps per CTA, 2 CTAs per SM.  Per triple:
-//   A  gather (Mesh::set_pad, src/mesh/mesh.rs:448-456): lane = (cell, node); point ids two triples ahead, coordinates one;
+// Mapping: ONE WARP PER G CELLS (three Qua8, four Tri6), no barrier wider than a warp, 8 warps per CTA, 2 CTAs per SM.  Per group
+// ("triple" below) of cells:
+//   A  gather (Mesh::set_pad, src/mesh/mesh.rs:448-456): lane = (cell, node); point ids two groups ahead, coordinates one;
 //   B  geometry, lane = (cell, Gauss point), in the ORACLE'S operation order (gl_geom.cuh): J = Xt.L, closed-form inverse, det,
 //      r = sum N.x0; B = L.inv(J), N/r -> V (shared memory, dof-major, conflict-free strides), c';
-//   C  per cell: k-steps of 6 (3) DMMA over four Gauss points each (a single leftover point by DFMA), the scaled operand c' V formed in
-//      registers; transposed tiles by shuffle;
-//      contraction with D'; the lane's two 2 x 2 blocks go to the staged element block as 16-byte stores (odd fragment rows
-//      store their upper half first: conflict-free);
-//   D  the triple (3 x 2,048 contiguous bytes on single-kind meshes; runs of consecutive blocks on mixed ones) leaves with bulk
-//      async copies (L2 evict-first).
-// Tri6 runs on the same template with its six nodes in the first six node slots of the tiles.
-// Covered: uniform D or one record per marker / per cell (any pattern), rules of at most 10 points, tight blocks that overwrite a
-// 16-byte aligned buffer; everything else (one modulus per Gauss point, general blocks, fused assembly) stays on gl_kernels_bdb.cu.
+//   C  per cell: k-steps of 6 (3) DMMA over four Gauss points each (a single leftover point by DFMA), the scaled operand c' V formed
+//      in registers; transposed tiles by shuffle; contraction with D'; the lane's two 2 x 2 blocks go to the staged element block
+//      as 16-byte stores (odd fragment rows store their upper half first: conflict-free for Qua8);
+//   D  the group (G contiguous blocks on single-kind meshes; runs of consecutive blocks on mixed ones) leaves with bulk async copies
+//      (L2 evict-first), issued by the lane that owns the first cell of a run.
+// Tri6 runs on the same template with its six nodes in the first six node slots of the tiles.  gl_integ_fused can ask for the
+// conductivity matrix and the flux vector of the same cells as by-products (Qua8Extra).
+// Covered: uniform D or one record per marker / per cell (any pattern), rules of at most 10 (Tri6: 8) points, tight blocks that
+// overwrite a 16-byte aligned buffer; everything else (one modulus per Gauss point, general blocks, fused assembly) stays on
+// gl_kernels_bdb.cu.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -57,7 +59,7 @@ struct Qua8Extra {
     int mask; // 2: mat_03_btb, 8: vec_03_bv (the bits of ScalarFused::mask)
     double t00, t11, t01, w0, w1;
     double *out_m03, *out_v03;
-    const unsigned long long *moff, *voff; // mixed meshes: bucket-local cell -> absolute offset of its 8 x 8 block / 8-vector
+    const unsigned long long *moff, *voff; // mixed meshes: bucket-local cell -> absolute offset of its NN x NN block / NN-vector
     unsigned long long mbase, vbase;
 };
 
@@ -76,7 +78,7 @@ __device__ __forceinline__ double q8_select(int c, double a, double b) { // c ? 
 constexpr int Q8_CTAS = 2;     // CTAs per SM
 constexpr int Q8_PS = 12;      // V is stored dof-major, Vt[col][p] at col PS + p; PS = 12 (mod 16): the fragment loads of a half-warp
                                // (4 columns x 4 Gauss points) hit 16 distinct bank pairs
-constexpr int Q8_XS = 18;      // coordinates of a cell (16 doubles + 2): the three cells of a warp read distinct banks
+constexpr int Q8_XS = 18;      // coordinates of a cell (up to 16 doubles, + 2): the cells of a warp read distinct banks
 
 // NN = 8 (Qua8) or 6 (Tri6: its six nodes occupy the first six of the eight node slots of a tile; what the fragment lanes of the two
 // other slots read only reaches entries of P that nobody reads -- an MMA output depends on its own row and column alone)
