@@ -1066,6 +1066,7 @@ static int launch_range(gl_ctx *ctx, gl_mesh *mesh, int op, uint64_t b, uint64_t
             p.scatter_pos = sc_pos;
             p.scatter_vals = sc_vals;
             nl = launch_hex8_bdb(p, ctx->stream);
+            if (nl == 0) nl = launch_bdb_qua8(p, mesh->ndim, ctx->stream);
             if (nl == 0) nl = launch_bdb(p, mesh->ndim, ctx->stream);
             if (nl == 0) return fail(ctx, GL_ERR_INVALID_ARG, "internal: no kernel with a scatter epilogue took the configuration");
             if (nl < 0) return cuda_fail(ctx, cudaGetLastError(), "kernel launch");

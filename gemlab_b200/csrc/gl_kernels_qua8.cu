@@ -26,8 +26,8 @@
 // Tri6 runs on the same template with its six nodes in the first six node slots of the tiles.  gl_integ_fused can ask for the
 // conductivity matrix and the flux vector of the same cells as by-products (Qua8Extra).
 // Covered: uniform D or one record per marker / per cell (any pattern), rules of at most 10 (Tri6: 8) points, tight blocks that
-// overwrite a 16-byte aligned buffer; everything else (one modulus per Gauss point, general blocks, fused assembly) stays on
-// gl_kernels_bdb.cu.
+// overwrite a 16-byte aligned buffer, and the fused assembly (scatter epilogue) with a symmetric modulus pattern; everything else
+// (one modulus per Gauss point, general blocks, fused assembly with a general D) stays on gl_kernels_bdb.cu.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -106,7 +106,10 @@ struct Qua8Dims {
 // DREC = one modulus record per marker or per cell (multi-material meshes) instead of a uniform D: the records of the next triple are
 // fetched one iteration ahead (their indices two ahead), scaled into d' and staged per cell; with device-resident records whose
 // structure only the probe knows, every pattern variant is enqueued and all but the matching one return at once (gl_kernels_bdb.cu)
-template <int NN, bool AXI, int PAT, bool EXTRA, bool DREC = false>
+// SCATTER = fused assembly (gl_assemble_planned): instead of leaving as element blocks, every staged entry is added to its slot of the
+// global matrix through the plan's position map (IntegParams::scatter_pos / scatter_vals, RED.ADD.F64); the element-matrix slab is
+// never written.  Only with a symmetric pattern (PAT 2): the map is indexed row-major, the staged block is column-major, K = K^T.
+template <int NN, bool AXI, int PAT, bool EXTRA, bool DREC = false, bool SCATTER = false>
 __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst, const Qua8Extra x) {
     if (DREC && p.coef_pat_dev != nullptr && (*p.coef_pat_dev == 2 ? 2 : 0) != PAT) return;
     using T = Qua8Dims<NN, AXI, DREC>;
@@ -372,6 +375,25 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
         }
 
         // ---- phase D: ship ---------------------------------------------------------------------------------------------------
+        if constexpr (SCATTER) {
+            static_assert(!SCATTER || PAT == 2, "the scatter epilogue reads the staged block through its transpose");
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const unsigned long long base = __shfl_sync(0xffffffffu, off, g);
+                if (g < nv) {
+                    constexpr int NIT = (KB + 31) / 32;
+                    unsigned int pos[NIT];
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) pos[it] = lane + 32 * it < KB ? p.scatter_pos[base + lane + 32 * it] : 0xffffffffu;
+#pragma unroll
+                    for (int it = 0; it < NIT; it++)
+                        if (pos[it] != 0xffffffffu) atomicAdd(p.scatter_vals + pos[it], Kst[g * KB + lane + 32 * it]);
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         // runs of blocks that are consecutive in the output leave as one copy (always one, on single-kind meshes): lane k < nv owns
         // cell k, the first lane of a run issues its copy (bulk groups are per thread: that lane also waits for it)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -395,12 +417,13 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
 }
 
 template <int NN, bool AXI>
-int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, bool drec, void *stream) {
+int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, bool drec, bool scatter, void *stream) {
     const int warps = drec ? Qua8Dims<NN, AXI, true>::WARPS : Qua8Dims<NN, AXI, false>::WARPS;
     constexpr int G = Qua8Dims<NN, AXI>::G;
     const size_t smem = sizeof(double) * (size_t)warps * (drec ? Qua8Dims<NN, AXI, true>::WSZ : Qua8Dims<NN, AXI, false>::WSZ);
     typedef void (*kern_t)(const IntegParams, const Qua8Consts, const Qua8Extra);
     auto pick = [&](int pt) -> kern_t {
+        if (scatter) return drec ? qua8_kernel<NN, AXI, 2, false, true, true> : qua8_kernel<NN, AXI, 2, false, false, true>;
         if (drec) return pt == 2 ? qua8_kernel<NN, AXI, 2, false, true> : qua8_kernel<NN, AXI, 0, false, true>;
         if (x.mask) return pt == 2 ? qua8_kernel<NN, AXI, 2, true> : qua8_kernel<NN, AXI, 0, true>;
         return pt == 2 ? qua8_kernel<NN, AXI, 2, false> : qua8_kernel<NN, AXI, 0, false>;
@@ -428,7 +451,7 @@ int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const
     if (cudaGetLastError() != cudaSuccess) return -1;
     const char *family = NN == 8 ? "qua8_dmma" : "tri6_dmma";
     if (x.mask) note_kernel("%s<axi=%d,pat=%d,fused=%d>", family, AXI ? 1 : 0, pat, x.mask);
-    else note_kernel("%s<axi=%d,pat=%d%s>", family, AXI ? 1 : 0, pat, drec ? ",rec" : "");
+    else note_kernel("%s<axi=%d,pat=%d%s%s>", family, AXI ? 1 : 0, pat, drec ? ",rec" : "", scatter ? ",scatter" : "");
     return nl;
 }
 
@@ -436,14 +459,17 @@ int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const
 
 int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFused *extra) {
     if (sd != 2 || p.op != GL_OP_MAT_10_BDB || (p.nnode != 8 && p.nnode != 6)) return 0;
-    if (p.scatter_pos != nullptr || p.sigma != nullptr) return 0; // fused assembly: gl_kernels_bdb.cu
+    if (p.sigma != nullptr) return 0;
+    const bool scatter = p.scatter_pos != nullptr; // fused assembly: symmetric patterns only (below)
     const bool drec = p.coef != nullptr;
     if (drec && (p.coef_gp_stride != 0 || p.coef_cell_stride != 16 || extra != nullptr)) return 0; // one modulus per Gauss point: gl_kernels_bdb.cu
     if ((p.nnode == 6 ? 4 : 3) * p.ng > 32) return 0;
     const unsigned ndof = 2u * (unsigned)p.nnode;
     if (p.size_r != ndof || p.size_c != ndof) return 0;
     const bool tight = p.nrow == ndof && p.ncol == ndof && p.ii0 == 0 && p.jj0 == 0;
-    if (!(tight && p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) return 0; // general store epilogue: gl_kernels_bdb.cu
+    if (!tight) return 0;
+    if (!scatter && !(p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) return 0; // general store epilogue: gl_kernels_bdb.cu
+    if (scatter && extra != nullptr) return 0;
     if (tuning_env("GL_DISABLE_QUA8")) return 0;
 
     Qua8Consts cst;
@@ -466,6 +492,7 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
     if (const char *e = tuning_env("GL_BDB_PATTERN")) {
         if (atoi(e) < pat) pat = 0;
     }
+    if (scatter && (pat != 2 || (drec && p.coef_pat_dev != nullptr))) return 0; // general D, or records only the device has seen: gl_kernels_bdb.cu
     Qua8Extra x;
     std::memset(&x, 0, sizeof(x));
     if (extra) { // mat_03_btb and / or vec_03_bv from the same pass (uniform coefficients, tight blocks, device outputs: checked by the caller)
@@ -484,8 +511,8 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
         x.vbase = extra->vbase;
     }
     if (p.nnode == 6)
-        return p.axisym ? launch_qua8_kind<6, true>(p, cst, pat, x, drec, stream) : launch_qua8_kind<6, false>(p, cst, pat, x, drec, stream);
-    return p.axisym ? launch_qua8_kind<8, true>(p, cst, pat, x, drec, stream) : launch_qua8_kind<8, false>(p, cst, pat, x, drec, stream);
+        return p.axisym ? launch_qua8_kind<6, true>(p, cst, pat, x, drec, scatter, stream) : launch_qua8_kind<6, false>(p, cst, pat, x, drec, scatter, stream);
+    return p.axisym ? launch_qua8_kind<8, true>(p, cst, pat, x, drec, scatter, stream) : launch_qua8_kind<8, false>(p, cst, pat, x, drec, scatter, stream);
 }
 
 } // namespace gl

@@ -1,5 +1,5 @@
-"""Times the assembly hand-off (gl_triplet_indices + gl_assemble) on an n^3 Hex8 block generated on the device.
-The CSR pattern is built on the device with torch from the triplet indices.  usage: time_assemble.py [n]"""
+"""Times the assembly hand-off (gl_triplet_indices + gl_assemble) on an n^3 Hex8 (or n^2 Qua8) block generated on the device.
+The CSR pattern is built on the device with torch from the triplet indices.  usage: time_assemble.py [n] [planned-only|all] [hex8|qua8]"""
 import sys
 import time
 from pathlib import Path
@@ -14,11 +14,13 @@ from gemlab_b200 import Coef, CommonArgs, Context, GeoKind, integ
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 planned_only = len(sys.argv) > 2 and sys.argv[2] == "planned-only"  # for profiling the fused kernel alone
 ctx = Context(0)
-dm = ctx.block(GeoKind.Hex8, (n, n, n))
+kind = sys.argv[3] if len(sys.argv) > 3 else "hex8"
+ndim = 3 if kind == "hex8" else 2
+dm = ctx.block(GeoKind.from_str(kind), (n,) * ndim)
 ncell, npoint = dm.ncell, dm.npoint
-neq = npoint * 3
+neq = npoint * ndim
 eq = torch.arange(neq, dtype=torch.int32, device="cuda")
-dd = g.mandel_matrix(g.lin_elasticity(480.0, 1.0 / 3.0, False))
+dd = g.mandel_matrix(g.lin_elasticity(480.0, 1.0 / 3.0, ndim == 2))
 t0 = time.perf_counter()
 rows, cols = integ.triplet_indices(ctx, dm, "mat_10_bdb", None, CommonArgs(), eq)
 torch.cuda.synchronize()
