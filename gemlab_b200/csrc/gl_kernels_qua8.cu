@@ -25,9 +25,10 @@
 //      (L2 evict-first), issued by the lane that owns the first cell of a run.
 // Tri6 runs on the same template with its six nodes in the first six node slots of the tiles.  gl_integ_fused can ask for the
 // conductivity matrix and the flux vector of the same cells as by-products (Qua8Extra).
-// Covered: uniform D or one record per marker / per cell (any pattern), rules of at most 10 (Tri6: 8) points, tight blocks that
-// overwrite a 16-byte aligned buffer, and the fused assembly (scatter epilogue) with a symmetric modulus pattern; everything else
-// (one modulus per Gauss point, general blocks, fused assembly with a general D) stays on gl_kernels_bdb.cu.
+// Covered: uniform D or one record per marker / per cell (any pattern), rules of at most 10 (Tri6: 8) points; tight blocks that
+// overwrite a 16-byte aligned buffer leave by bulk copy, everything else (nrow / ncol / ii0 / jj0, clear = false) through the general
+// store epilogue; the fused assembly (scatter epilogue) with a symmetric modulus pattern.  One modulus per Gauss point and the fused
+// assembly with a general D stay on gl_kernels_bdb.cu.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -109,7 +110,10 @@ struct Qua8Dims {
 // SCATTER = fused assembly (gl_assemble_planned): instead of leaving as element blocks, every staged entry is added to its slot of the
 // global matrix through the plan's position map (IntegParams::scatter_pos / scatter_vals, RED.ADD.F64); the element-matrix slab is
 // never written.  Only with a symmetric pattern (PAT 2): the map is indexed row-major, the staged block is column-major, K = K^T.
-template <int NN, bool AXI, int PAT, bool EXTRA, bool DREC = false, bool SCATTER = false>
+// GEN = general store epilogue: element blocks of nrow x ncol with the integrated window at (ii0, jj0), clear = false, 8-byte aligned
+// outputs (CommonArgs, src/integ/common_args.rs:5-43; clear = true overwrites the WHOLE block, mat_10_bdb.rs:141-143) -- e.g. the
+// displacement block of a coupled displacement-pressure element matrix.
+template <int NN, bool AXI, int PAT, bool EXTRA, bool DREC = false, bool SCATTER = false, bool GEN = false>
 __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) qua8_kernel(const IntegParams p, const Qua8Consts cst, const Qua8Extra x) {
     if (DREC && p.coef_pat_dev != nullptr && (*p.coef_pat_dev == 2 ? 2 : 0) != PAT) return;
     using T = Qua8Dims<NN, AXI, DREC>;
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
         if (lane < nv) {
             const unsigned long long cell = p.lo + c0 + lane;
             const unsigned long long rel = (p.cell_ids ? (unsigned long long)p.cell_ids[cell] : cell) - p.cell_begin;
-            off = p.out_off ? p.out_off[cell] - p.out_base : rel * (unsigned long long)KB;
+            off = p.out_off ? p.out_off[cell] - p.out_base : rel * (GEN ? (unsigned long long)p.nrow * p.ncol : (unsigned long long)KB);
             if constexpr (EXTRA) {
                 moffv = x.moff ? x.moff[cell] - x.mbase : rel * (unsigned long long)(NN * NN);
                 voffv = x.voff ? x.voff[cell] - x.vbase : rel * (unsigned long long)NN;
@@ -394,6 +398,26 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
             __syncwarp();
             continue;
         }
+        if constexpr (GEN) {
+            __syncwarp();
+            const unsigned int nrow = p.nrow, tot = p.nrow * p.ncol;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const unsigned long long base = __shfl_sync(0xffffffffu, off, g);
+                if (g < nv) {
+                    double *dst = p.out + base;
+                    for (unsigned int idx = lane; idx < tot; idx += 32) {
+                        const unsigned int jj = idx / nrow, ii = idx - jj * nrow;
+                        const bool in = ii >= p.ii0 && ii < p.ii0 + NDOF && jj >= p.jj0 && jj < p.jj0 + NDOF;
+                        const double val = in ? Kst[g * KB + (ii - p.ii0) + NDOF * (jj - p.jj0)] : 0.0;
+                        if (p.clear) dst[idx] = val;
+                        else if (in) dst[idx] += val;
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         // runs of blocks that are consecutive in the output leave as one copy (always one, on single-kind meshes): lane k < nv owns
         // cell k, the first lane of a run issues its copy (bulk groups are per thread: that lane also waits for it)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -417,13 +441,17 @@ __global__ void __launch_bounds__(32 * Qua8Dims<NN, AXI, DREC>::WARPS, Q8_CTAS) 
 }
 
 template <int NN, bool AXI>
-int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, bool drec, bool scatter, void *stream) {
+int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const Qua8Extra &x, bool drec, bool scatter, bool gen, void *stream) {
     const int warps = drec ? Qua8Dims<NN, AXI, true>::WARPS : Qua8Dims<NN, AXI, false>::WARPS;
     constexpr int G = Qua8Dims<NN, AXI>::G;
     const size_t smem = sizeof(double) * (size_t)warps * (drec ? Qua8Dims<NN, AXI, true>::WSZ : Qua8Dims<NN, AXI, false>::WSZ);
     typedef void (*kern_t)(const IntegParams, const Qua8Consts, const Qua8Extra);
     auto pick = [&](int pt) -> kern_t {
         if (scatter) return drec ? qua8_kernel<NN, AXI, 2, false, true, true> : qua8_kernel<NN, AXI, 2, false, false, true>;
+        if (gen) {
+            if (drec) return pt == 2 ? qua8_kernel<NN, AXI, 2, false, true, false, true> : qua8_kernel<NN, AXI, 0, false, true, false, true>;
+            return pt == 2 ? qua8_kernel<NN, AXI, 2, false, false, false, true> : qua8_kernel<NN, AXI, 0, false, false, false, true>;
+        }
         if (drec) return pt == 2 ? qua8_kernel<NN, AXI, 2, false, true> : qua8_kernel<NN, AXI, 0, false, true>;
         if (x.mask) return pt == 2 ? qua8_kernel<NN, AXI, 2, true> : qua8_kernel<NN, AXI, 0, true>;
         return pt == 2 ? qua8_kernel<NN, AXI, 2, false> : qua8_kernel<NN, AXI, 0, false>;
@@ -451,7 +479,7 @@ int launch_qua8_kind(const IntegParams &p, const Qua8Consts &cst, int pat, const
     if (cudaGetLastError() != cudaSuccess) return -1;
     const char *family = NN == 8 ? "qua8_dmma" : "tri6_dmma";
     if (x.mask) note_kernel("%s<axi=%d,pat=%d,fused=%d>", family, AXI ? 1 : 0, pat, x.mask);
-    else note_kernel("%s<axi=%d,pat=%d%s%s>", family, AXI ? 1 : 0, pat, drec ? ",rec" : "", scatter ? ",scatter" : "");
+    else note_kernel("%s<axi=%d,pat=%d%s%s>", family, AXI ? 1 : 0, pat, drec ? ",rec" : "", scatter ? ",scatter" : (gen ? ",gen" : ""));
     return nl;
 }
 
@@ -467,9 +495,9 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
     const unsigned ndof = 2u * (unsigned)p.nnode;
     if (p.size_r != ndof || p.size_c != ndof) return 0;
     const bool tight = p.nrow == ndof && p.ncol == ndof && p.ii0 == 0 && p.jj0 == 0;
-    if (!tight) return 0;
-    if (!scatter && !(p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) return 0; // general store epilogue: gl_kernels_bdb.cu
-    if (scatter && extra != nullptr) return 0;
+    if (scatter && !tight) return 0;
+    const bool gen = !scatter && !(tight && p.clear && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0); // general store epilogue
+    if ((scatter || gen) && extra != nullptr) return 0;
     if (tuning_env("GL_DISABLE_QUA8")) return 0;
 
     Qua8Consts cst;
@@ -511,8 +539,8 @@ int launch_bdb_qua8(const IntegParams &p, int sd, void *stream, const ScalarFuse
         x.vbase = extra->vbase;
     }
     if (p.nnode == 6)
-        return p.axisym ? launch_qua8_kind<6, true>(p, cst, pat, x, drec, scatter, stream) : launch_qua8_kind<6, false>(p, cst, pat, x, drec, scatter, stream);
-    return p.axisym ? launch_qua8_kind<8, true>(p, cst, pat, x, drec, scatter, stream) : launch_qua8_kind<8, false>(p, cst, pat, x, drec, scatter, stream);
+        return p.axisym ? launch_qua8_kind<6, true>(p, cst, pat, x, drec, scatter, gen, stream) : launch_qua8_kind<6, false>(p, cst, pat, x, drec, scatter, gen, stream);
+    return p.axisym ? launch_qua8_kind<8, true>(p, cst, pat, x, drec, scatter, gen, stream) : launch_qua8_kind<8, false>(p, cst, pat, x, drec, scatter, gen, stream);
 }
 
 } // namespace gl

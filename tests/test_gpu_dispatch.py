@@ -44,7 +44,9 @@ FAMILIES = [
     ("qua8", "mat_10_bdb", {}, "qua8_dmma<axi=0,pat=2>"),
     ("qua8", "mat_10_bdb", {"axisymmetric": True}, "qua8_dmma<axi=1,pat=2>"),
     ("qua8", "mat_10_bdb", {"ngauss": 16}, "bdb<nn=8,sd=2,axi=0"),
-    ("qua8", "mat_10_bdb", {"axisymmetric": True, "clear": False}, "bdb<nn=8,sd=2,axi=1,pat=2,gen>"),
+    ("qua8", "mat_10_bdb", {"axisymmetric": True, "clear": False}, "qua8_dmma<axi=1,pat=2,gen>"),
+    ("tri6", "mat_10_bdb", {"ii0": 1, "jj0": 2, "nrow": 15, "ncol": 16}, "tri6_dmma<axi=0,pat=2,gen>"),
+    ("qua8", "mat_10_bdb", {"ngauss": 16, "clear": False}, "bdb<nn=8,sd=2,axi=0,pat=2,gen>"),
     ("qua9", "mat_10_bdb", {}, "bdb<nn=9,sd=2"),
     ("tri6", "mat_10_bdb", {}, "tri6_dmma<axi=0,pat=2>"),
     ("tri6", "mat_10_bdb", {"axisymmetric": True}, "tri6_dmma<axi=1,pat=2>"),
