@@ -220,5 +220,8 @@ struct gl_ctx {
     double *h_coef = nullptr; // pinned staging of PER_MARKER tables (keeps those calls asynchronous)
     size_t h_coef_bytes = 0;
     void *ev_coef = nullptr;  // completion of the last copy out of h_coef
+    // host-resident PER_CELL / PER_GAUSS records go through two pinned bounce buffers (upload_records, gl_api.cu)
+    double *h_rec[2] = {nullptr, nullptr};
+    void *ev_rec[2] = {nullptr, nullptr};
     void *ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
