@@ -1532,7 +1532,8 @@ int gl_integ_fused(gl_ctx *ctx, const gl_mesh *cmesh, uint64_t b, uint64_t e, co
             const size_t sig_bytes = (size_t)(e - b) * 8 * 6 * sizeof(double);
             if (id->coef->location != GL_DEVICE) {
                 CUDA_TRY(ctx, pool_alloc_t(ctx, &tmp, sig_bytes));
-                CUDA_TRY(ctx, cudaMemcpyAsync(tmp, id->coef->data, sig_bytes, cudaMemcpyHostToDevice, (cudaStream_t)ctx->stream));
+                int stu = upload_records(ctx, id->coef->data, sig_bytes / sizeof(double), tmp, 0, nullptr);
+                if (stu) return stu;
                 d_sigma = tmp;
             }
             bool done = false;
