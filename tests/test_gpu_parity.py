@@ -383,6 +383,37 @@ def test_host_path_chunking_matches_device_path(ctx):
     np.testing.assert_allclose(k0, k0.T, rtol=0, atol=1e-12 * np.max(np.abs(k0)))
 
 
+def test_pageable_and_pinned_host_outputs_agree_with_the_device_path(ctx):
+    """Host outputs in pageable memory (a numpy array, a Rust Vec) are drained through pinned bounce buffers in 16 MB pieces, one
+    128 MiB chunk behind the kernels; pinned outputs take the direct copy.  On a jittered mesh (no two element matrices alike) both
+    must equal the device-resident result bit for bit, also when accumulating (clear = false reads the destination first)."""
+    import torch
+
+    mesh = g.jitter_interior_points(Block.new_cube(1.0).set_ndiv([40, 40, 35]).subdivide(GeoKind.Hex8), 0.2 / 40, 17)  # 258 MB: 3 chunks
+    dmesh = ctx.upload(mesh)
+    dd = Coef.uniform(g.mandel_matrix(g.lin_elasticity(480.0, 1 / 3, False)))
+    dev = torch.empty(mesh.ncell * 576, dtype=torch.float64, device="cuda")
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), dd, out=dev)
+    ctx.sync()
+    ref = dev.cpu().numpy()
+    pageable = np.full(ref.size, -3.0)
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), dd, out=pageable)
+    np.testing.assert_array_equal(pageable, ref)
+    pinned = torch.full((ref.size,), -3.0, dtype=torch.float64).pin_memory()
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(), dd, out=pinned)
+    np.testing.assert_array_equal(pinned.numpy(), ref)
+    acc = np.full(ref.size, 0.5)
+    integ.mat_10_bdb(ctx, dmesh, None, CommonArgs(clear=False), dd, out=acc)
+    np.testing.assert_allclose(acc, ref + 0.5, rtol=1e-13, atol=1e-13 * float(np.abs(ref).max()))
+    # a ragged range through the packed path (upper triangles) into pageable memory
+    b, e = 7, mesh.ncell - 5
+    packed = integ.mat_10_bdb(ctx, dmesh, (b, e), CommonArgs(packed=True), dd)
+    jj = np.concatenate([np.full(j + 1, j) for j in range(24)])  # packed order: column by column, rows 0 .. j
+    ii = np.concatenate([np.arange(j + 1) for j in range(24)])
+    full = ref.reshape(mesh.ncell, 24, 24)[b:e]  # column-major blocks: [cell][col][row]
+    np.testing.assert_array_equal(packed.reshape(e - b, 300), full[:, jj, ii])
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # 4. error behaviour (the reference's strings)
 # ---------------------------------------------------------------------------------------------------------------
