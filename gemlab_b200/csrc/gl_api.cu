@@ -494,6 +494,10 @@ uint64_t gl_op_coef_size(int op, int ndim) { return coef_len(op, ndim); }
 
 } // extern "C" (reopened below)
 
+// host -> device on the ctx stream: straight from pinned memory (asynchronous), through the pinned bounce buffers from pageable memory
+// (defined next to upload_records)
+int gl_h2d_any(gl_ctx *ctx, void *dst, const void *src, size_t bytes);
+
 // ---- device-side structure-of-arrays transposition (upload path of homogeneous meshes) -----------------------------------
 namespace {
 
@@ -552,12 +556,16 @@ int upload_homogeneous_begin(gl_ctx *ctx, gl_mesh *mesh, gl_mesh_bucket &bk, con
     CUDA_TRY(ctx, pool_alloc_t(ctx, &pu.d_bad, sizeof(int)));
     CUDA_TRY(ctx, cudaMemsetAsync(pu.d_bad, 0, sizeof(int), st));
     CUDA_TRY(ctx, pool_alloc_t(ctx, &mesh->d_coords, coord_bytes));
-    CUDA_TRY(ctx, cudaMemcpyAsync(pu.d_raw, coords, coord_bytes, cudaMemcpyHostToDevice, st));
+    {
+        int rc = gl_h2d_any(ctx, pu.d_raw, coords, coord_bytes);
+        if (rc) return rc;
+    }
     coords_to_soa_kernel<<<1184, 256, 0, st>>>((const double *)pu.d_raw, mesh->d_coords, mesh->npoint, mesh->ndim);
     if (bk.ncell) {
         char *d_conn_raw = (char *)pu.d_raw + conn_at;
         CUDA_TRY(ctx, pool_alloc_t(ctx, &bk.d_conn, (size_t)bk.ncell * bk.nnode * sizeof(uint32_t)));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_conn_raw, conn, conn_bytes, cudaMemcpyHostToDevice, st));
+        int rc = gl_h2d_any(ctx, d_conn_raw, conn, conn_bytes);
+        if (rc) return rc;
         conn_to_soa_kernel<IdT><<<1184, 256, 0, st>>>((const IdT *)d_conn_raw, bk.d_conn, bk.ncell, bk.nnode, mesh->npoint, pu.d_bad);
     }
     ctx->launches += bk.ncell ? 2 : 1;
@@ -1254,6 +1262,21 @@ static int upload_records(gl_ctx *ctx, const double *src, uint64_t ndoubles, dou
 }
 
 } // extern "C"
+
+int gl_h2d_any(gl_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    if (bytes < ((size_t)1 << 20) || host_pointer_is_pinned(src)) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return GL_OK;
+    }
+    const size_t n8 = bytes / sizeof(double);
+    int rc = upload_records(ctx, (const double *)src, n8, (double *)dst, 0, nullptr);
+    if (rc) return rc;
+    if (bytes > n8 * sizeof(double))
+        CUDA_TRY(ctx, cudaMemcpyAsync((char *)dst + n8 * sizeof(double), (const char *)src + n8 * sizeof(double), bytes - n8 * sizeof(double),
+                                      cudaMemcpyHostToDevice, st));
+    return GL_OK;
+}
 
 // modulus_pattern() for records that live on the device: *pat starts at 2 and is lowered by the records that break a pattern.
 // The verdict stays on the device -- the stiffness launchers enqueue all three pattern variants and the two that do not
