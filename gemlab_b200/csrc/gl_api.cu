@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <thread>
 
 #include "gl_internal.hpp"
@@ -1166,6 +1167,26 @@ static int ensure_bounce(gl_ctx *ctx) {
     return GL_OK;
 }
 
+// work(0) .. work(nthr - 1), on up to nthr host threads; a thread that cannot be started (resource limits) has its share done inline
+// -- nothing may throw across the C ABI
+static void run_parallel(int nthr, const std::function<void(int)> &work) {
+    std::thread th[7];
+    bool started[7] = {false, false, false, false, false, false, false};
+    for (int t = 1; t < nthr && t <= 7; t++) {
+        try {
+            th[t - 1] = std::thread(work, t);
+            started[t - 1] = true;
+        } catch (...) {
+            started[t - 1] = false;
+        }
+    }
+    work(0);
+    for (int t = 1; t < nthr && t <= 7; t++) {
+        if (started[t - 1]) th[t - 1].join();
+        else work(t);
+    }
+}
+
 static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
     const unsigned hw = std::thread::hardware_concurrency();
     const int nthr = bytes < ((size_t)4 << 20) ? 1 : (int)std::max(1u, std::min(8u, hw ? hw : 1u));
@@ -1177,10 +1198,7 @@ static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
         const size_t a = (bytes * (size_t)t / nthr) & ~(size_t)63, b = t == nthr - 1 ? bytes : (bytes * (size_t)(t + 1) / nthr) & ~(size_t)63;
         std::memcpy((char *)dst + a, (const char *)src + a, b - a);
     };
-    std::thread th[7];
-    for (int t = 1; t < nthr; t++) th[t - 1] = std::thread(work, t);
-    work(0);
-    for (int t = 1; t < nthr; t++) th[t - 1].join();
+    run_parallel(nthr, work);
 }
 
 static bool host_pointer_is_pinned(const void *p) {
@@ -1249,10 +1267,7 @@ static int upload_records(gl_ctx *ctx, const double *src, uint64_t ndoubles, dou
             std::memcpy(buf + d0, src + off + d0, (d1 - d0) * sizeof(double));
             if (ns > 0 && pats[t] > 0) pats[t] = std::min(pats[t], modulus_pattern(buf + d0, r1 - r0, ns));
         };
-        std::thread th[7];
-        for (int t = 1; t < nthr; t++) th[t - 1] = std::thread(work, t);
-        work(0);
-        for (int t = 1; t < nthr; t++) th[t - 1].join();
+        run_parallel(nthr, work);
         CUDA_TRY(ctx, cudaMemcpyAsync(dst + off, buf, n * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)ctx->stream));
         CUDA_TRY(ctx, cudaEventRecord((cudaEvent_t)ctx->ev_rec[k & 1], (cudaStream_t)ctx->stream));
     }
